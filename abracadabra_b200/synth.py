@@ -1,0 +1,548 @@
+"""Synthetic DAB mode I ensemble modulator (transmitter side) with known payloads.
+
+Test/benchmark tooling: builds the IQ files the receive path is exercised on (SURVEY.md sec. 7 step 2,
+sec. 8(d) configs 1-5).  Everything here follows ETSI EN 300 401 (mode I) and TS 102 563 (DAB+) with the
+constants of SURVEY.md Appendix A, each of which libdabsdr 4.0.1 has been shown to decode.
+
+The modulator returns the ground truth alongside the samples: FIBs, per-sub-channel logical frames
+(the bytes a receiver obtains after Viterbi + energy dispersal), DAB+ access units, TII ids.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import dabconst as C
+
+
+# ============================================================================ configuration
+@dataclass
+class SubChannel:
+    subchid: int
+    start_cu: int
+    kind: str                     # 'dabplus' | 'mp2' | 'data'
+    bitrate: int                  # kbit/s
+    prot: Tuple                   # ('EEP', level 1..4, 'A'|'B')  or ('UEP', table index 0..63)
+    seed: int = 0
+
+    def profile(self):
+        if self.prot[0] == "EEP":
+            segs, size = C.eep_profile(self.bitrate, self.prot[1], self.prot[2])
+            return segs, size, 0
+        segs, size, pad, br = C.uep_profile(self.prot[1])
+        assert br == self.bitrate, "UEP table index does not match bitrate"
+        return segs, size, pad
+
+    @property
+    def size_cu(self) -> int:
+        return self.profile()[1]
+
+    @property
+    def frame_bytes(self) -> int:   # logical frame (24 ms) size
+        return self.bitrate * 3
+
+
+@dataclass
+class Service:
+    sid: int
+    label: str
+    subchid: int
+
+
+@dataclass
+class TiiTx:
+    main: int
+    sub: int
+    amp: float = 1.0
+    delay: int = 0                # samples
+    phase: float = 0.0
+
+
+@dataclass
+class EnsembleConfig:
+    eid: int = 0x1001
+    ecc: int = 0xE1
+    label: str = "B200 TEST MUX"
+    lto: int = 2
+    subchannels: List[SubChannel] = field(default_factory=list)
+    services: List[Service] = field(default_factory=list)
+    tii: List[TiiTx] = field(default_factory=list)
+    tii_every_null: bool = False  # debugging: put TII in every null instead of every second one
+    cif_count0: int = 0           # CIF counter of the first CIF (multiple of 4 keeps frames aligned)
+
+    def check(self):
+        used = np.zeros(864, dtype=int)
+        for s in self.subchannels:
+            used[s.start_cu:s.start_cu + s.size_cu] += 1
+            assert s.start_cu + s.size_cu <= 864, "sub-channel exceeds CIF"
+        assert used.max() <= 1, "sub-channels overlap"
+
+
+@dataclass
+class Impairments:
+    snr_db: Optional[float] = 40.0     # None = no noise
+    cfo_hz: float = 0.0
+    cfo_drift_hz_per_s: float = 0.0
+    taps: List[Tuple[int, complex]] = field(default_factory=list)   # extra multipath taps (delay samples, gain)
+    lead_in: int = 49152               # samples of noise before the first frame (24 ms)
+    rms: float = 28.0                  # target RMS in output LSB (u8: 28, s16: ~7000)
+    sample_offset_ppm: float = 0.0     # not modelled (kept 0); placeholder for config 5
+    seed: int = 1
+
+
+def config1_ensemble(seed: int = 1000) -> EnsembleConfig:
+    """BASELINE.json configs[0]: FIC + one DAB+ 96 kbps EEP-3A sub-channel, TII (12,5)."""
+    return EnsembleConfig(
+        subchannels=[SubChannel(3, 0, "dabplus", 96, ("EEP", 3, "A"), seed=seed)],
+        services=[Service(0x1001, "SERVICE ONE", 3)],
+        tii=[TiiTx(12, 5, 1.0)],
+    )
+
+
+def full_ensemble(seed: int = 2000) -> EnsembleConfig:
+    """BASELINE.json configs[1]: FIC + 12 sub-channels filling 864 CU (mixed DAB+ EEP and MP2 UEP)."""
+    plan = [  # kind, bitrate, prot
+        ("dabplus", 96, ("EEP", 3, "A")),    # 72
+        ("dabplus", 96, ("EEP", 3, "A")),    # 72
+        ("dabplus", 80, ("EEP", 3, "A")),    # 60
+        ("dabplus", 72, ("EEP", 3, "A")),    # 54
+        ("dabplus", 64, ("EEP", 3, "A")),    # 48
+        ("dabplus", 48, ("EEP", 3, "A")),    # 36
+        ("dabplus", 64, ("EEP", 2, "A")),    # 64
+        ("dabplus", 64, ("EEP", 3, "B")),    # 36
+        ("mp2", 128, ("UEP", 35)),           # 96
+        ("mp2", 160, ("UEP", 40)),           # 116
+        ("mp2", 192, ("UEP", 44)),           # 116
+        ("mp2", 128, ("UEP", 34)),           # 84
+    ]
+    subs, svcs, cu = [], [], 0
+    for i, (kind, br, prot) in enumerate(plan):
+        sc = SubChannel(i + 1, cu, kind, br, prot, seed=seed + i)
+        subs.append(sc)
+        svcs.append(Service(0x2000 + i + 1, f"SVC {i + 1:02d} {kind.upper()}", i + 1))
+        cu += sc.size_cu
+    assert cu <= 864, cu
+    ens = EnsembleConfig(eid=0x2002, label="B200 FULL MUX", subchannels=subs, services=svcs,
+                         tii=[TiiTx(20, 7, 1.0), TiiTx(20, 11, 0.5, delay=40)])
+    ens.check()
+    return ens
+
+
+# ============================================================================ coding primitives
+def bytes_to_bits(b: np.ndarray) -> np.ndarray:
+    return np.unpackbits(np.asarray(b, dtype=np.uint8), axis=-1)
+
+
+def bits_to_bytes(bits: np.ndarray) -> np.ndarray:
+    return np.packbits(np.asarray(bits, dtype=np.uint8), axis=-1)
+
+
+def conv_encode(bits: np.ndarray) -> np.ndarray:
+    """Rate 1/4 K=7 mother code, zero-terminated.  bits [R, n] -> [R, 4*(n+6)]."""
+    bits = np.atleast_2d(bits).astype(np.uint8)
+    r, n = bits.shape
+    a = np.zeros((r, n + 12), dtype=np.uint8)      # 6 zeros history + data + 6 tail zeros
+    a[:, 6:6 + n] = bits
+    out = np.zeros((r, n + 6, 4), dtype=np.uint8)
+    for j, poly in enumerate(C.POLYS):
+        acc = np.zeros((r, n + 6), dtype=np.uint8)
+        for d in range(7):                           # tap on a[i-d] is bit (6-d) of the polynomial
+            if (poly >> (6 - d)) & 1:
+                acc ^= a[:, 6 - d:6 - d + n + 6]
+        out[:, :, j] = acc
+    return out.reshape(r, 4 * (n + 6))
+
+
+def encode_protected(frames: np.ndarray, segs, pad: int) -> np.ndarray:
+    """Energy-dispersed bits [R, n] -> punctured code bits [R, size]."""
+    n = frames.shape[1]
+    keep = C.punct_keep_mask(segs, n)
+    enc = conv_encode(frames)[:, keep]
+    if pad:
+        enc = np.concatenate([enc, np.zeros((enc.shape[0], pad), dtype=np.uint8)], axis=1)
+    return enc
+
+
+# GF(256) for RS(120,110) -- poly 0x11D, generator roots alpha^0..alpha^9
+def _gf_tables():
+    exp = np.zeros(512, dtype=np.int64)
+    log = np.zeros(256, dtype=np.int64)
+    x = 1
+    for i in range(255):
+        exp[i] = x
+        log[x] = i
+        x <<= 1
+        if x & 0x100:
+            x ^= 0x11D
+    exp[255:510] = exp[:255]
+    return exp, log
+
+
+GF_EXP, GF_LOG = _gf_tables()
+
+
+def _rs_generator():
+    g = [1]
+    for i in range(10):
+        ng = [0] * (len(g) + 1)
+        for j, c in enumerate(g):           # multiply by (x + alpha^i); g stored highest degree first
+            ng[j] ^= c
+            if c:
+                ng[j + 1] ^= int(GF_EXP[GF_LOG[c] + i])
+        g = ng
+    return g                                  # length 11, g[0] = 1
+
+
+RS_GEN = _rs_generator()
+
+
+def rs_parity(data: np.ndarray) -> np.ndarray:
+    """Systematic RS(120,110) parity; data [R, 110] uint8 -> [R, 10] (shortening zeros are implicit)."""
+    data = np.atleast_2d(data).astype(np.int64)
+    r = data.shape[0]
+    rem = np.zeros((r, 10), dtype=np.int64)
+    glog = np.array([GF_LOG[c] if c else -1 for c in RS_GEN[1:]], dtype=np.int64)
+    for i in range(data.shape[1]):
+        fb = data[:, i] ^ rem[:, 0]
+        rem[:, :-1] = rem[:, 1:]
+        rem[:, -1] = 0
+        nz = fb != 0
+        if nz.any():
+            lf = GF_LOG[fb[nz]]
+            for j in range(10):
+                if glog[j] >= 0:
+                    rem[nz, j] ^= GF_EXP[lf + glog[j]]
+    return rem.astype(np.uint8)
+
+
+def crc16_np(rows: np.ndarray) -> np.ndarray:
+    """CRC-16 (poly 0x1021, init 0xFFFF, inverted) of each row of a uint8 matrix."""
+    rows = np.atleast_2d(rows).astype(np.uint32)
+    tbl = _crc_table(0x1021)
+    crc = np.full(rows.shape[0], 0xFFFF, dtype=np.uint32)
+    for i in range(rows.shape[1]):
+        crc = ((crc << 8) & 0xFFFF) ^ tbl[((crc >> 8) ^ rows[:, i]) & 0xFF]
+    return (crc ^ 0xFFFF).astype(np.uint16)
+
+
+_CRC_TABLES: Dict[int, np.ndarray] = {}
+
+
+def _crc_table(poly: int) -> np.ndarray:
+    if poly not in _CRC_TABLES:
+        t = np.zeros(256, dtype=np.uint32)
+        for i in range(256):
+            c = i << 8
+            for _ in range(8):
+                c = ((c << 1) ^ poly) & 0xFFFF if c & 0x8000 else (c << 1) & 0xFFFF
+            t[i] = c
+        _CRC_TABLES[poly] = t
+    return _CRC_TABLES[poly]
+
+
+# ============================================================================ payload builders
+def dabplus_superframes(sc: SubChannel, n_sf: int, rng: np.random.Generator):
+    """Build n_sf DAB+ audio superframes for sub-channel `sc`.
+
+    Returns (bytes [n_sf, 120*s], list of access units (bytes, without CRC) in stream order).
+    HE-AAC v1 24 kHz core: dac_rate=1, sbr=1, stereo -> 3 AUs per superframe, header byte 0x70.
+    """
+    s = sc.bitrate // 8
+    size = 110 * s
+    num_aus, first = 3, 6
+    body = size - first
+    lens = [body // num_aus] * num_aus
+    lens[-1] += body - sum(lens)
+    starts = [first]
+    for ln in lens[:-1]:
+        starts.append(starts[-1] + ln)
+    sf = np.zeros((n_sf, 120 * s), dtype=np.uint8)
+    aus: List[bytes] = []
+    for f in range(n_sf):
+        buf = np.zeros(size, dtype=np.uint8)
+        buf[2] = 0x70
+        buf[3] = (starts[1] >> 4) & 0xFF
+        buf[4] = ((starts[1] & 0xF) << 4) | ((starts[2] >> 8) & 0xF)
+        buf[5] = starts[2] & 0xFF
+        fc = C.firecode(bytes(buf[2:11]))      # bytes 2..10; bytes 6..10 belong to AU 0 and are filled below
+        for a in range(num_aus):
+            payload = rng.integers(0, 256, lens[a] - 2, dtype=np.uint8)
+            crc = C.crc16(bytes(payload))
+            buf[starts[a]:starts[a] + lens[a] - 2] = payload
+            buf[starts[a] + lens[a] - 2] = crc >> 8
+            buf[starts[a] + lens[a] - 1] = crc & 0xFF
+            aus.append(bytes(payload))
+        fc = C.firecode(bytes(buf[2:11]))
+        buf[0], buf[1] = fc >> 8, fc & 0xFF
+        # RS: codeword j = bytes j + s*i
+        data = buf.reshape(110, s).T            # [s, 110]
+        par = rs_parity(data)                   # [s, 10]
+        sf[f, :size] = buf
+        sf[f, size:] = par.T.reshape(-1)
+    return sf, aus
+
+
+def mp2_frames(sc: SubChannel, n: int, rng: np.random.Generator) -> np.ndarray:
+    """MPEG-1 Layer II 48 kHz frames (24 ms) with a valid header and random body (body CRC is NOT valid)."""
+    fb = sc.frame_bytes
+    frames = rng.integers(0, 256, (n, fb), dtype=np.uint8)
+    br_idx = {32: 1, 48: 2, 56: 3, 64: 4, 80: 5, 96: 6, 112: 7, 128: 8, 160: 9, 192: 10, 224: 11, 256: 12,
+              320: 13, 384: 14}[sc.bitrate]
+    frames[:, 0] = 0xFF
+    frames[:, 1] = 0xFC            # MPEG-1, layer II, CRC protected
+    frames[:, 2] = (br_idx << 4) | (1 << 2)   # 48 kHz
+    frames[:, 3] = 0x00
+    return frames
+
+
+# ============================================================================ FIC
+def _fig(type_: int, body: bytes) -> bytes:
+    assert len(body) <= 29
+    return bytes([(type_ << 5) | len(body)]) + body
+
+
+def fig0_0(ens: EnsembleConfig, cif_count: int) -> bytes:
+    hi, lo = (cif_count // 250) % 20, cif_count % 250
+    return _fig(0, bytes([0x00, ens.eid >> 8, ens.eid & 0xFF, hi & 0x1F, lo]))
+
+
+def fig0_1_entry(sc: SubChannel) -> bytes:
+    b = bytes([(sc.subchid << 2) | (sc.start_cu >> 8), sc.start_cu & 0xFF])
+    if sc.prot[0] == "UEP":
+        return b + bytes([sc.prot[1] & 0x3F])
+    opt = 0 if sc.prot[2] == "A" else 1
+    lvl = sc.prot[1] - 1
+    size = sc.size_cu
+    return b + bytes([0x80 | (opt << 4) | (lvl << 2) | (size >> 8), size & 0xFF])
+
+
+def fig0_2_entry(ens: EnsembleConfig, sv: Service) -> bytes:
+    sc = next(s for s in ens.subchannels if s.subchid == sv.subchid)
+    ascty = 63 if sc.kind == "dabplus" else 0
+    return bytes([sv.sid >> 8, sv.sid & 0xFF, 0x01, (0 << 6) | ascty, (sc.subchid << 2) | 0x02])
+
+
+def fig0_9(ens: EnsembleConfig) -> bytes:
+    return _fig(0, bytes([0x09, ens.lto & 0x3F, ens.ecc, 0x01]))
+
+
+def fig1(ext: int, ident: int, label: str) -> bytes:
+    txt = label.encode("ascii")[:16].ljust(16, b" ")
+    return _fig(1, bytes([ext, ident >> 8, ident & 0xFF]) + txt + bytes([0xFF, 0x00]))
+
+
+def _pack_rotating(entries: List[bytes], ext_byte: int, room: int, start: int):
+    """Take as many entries as fit into `room` bytes (incl. 2 header bytes) starting at index `start` (cyclic)."""
+    if not entries:
+        return b"", start
+    body = bytes([ext_byte])
+    taken = 0
+    idx = start % len(entries)
+    while taken < len(entries) and len(body) + len(entries[idx]) + 1 <= room and len(body) + len(entries[idx]) <= 29:
+        body += entries[idx]
+        idx = (idx + 1) % len(entries)
+        taken += 1
+    if taken == 0:
+        return b"", start
+    return _fig(0, body), idx
+
+
+def make_fib(figs: bytes) -> bytes:
+    assert len(figs) <= 30, len(figs)
+    data = figs
+    if len(data) < 30:
+        data += b"\xFF"
+        data = data.ljust(30, b"\x00")
+    crc = C.crc16(data)
+    return data + bytes([crc >> 8, crc & 0xFF])
+
+
+class FicBuilder:
+    def __init__(self, ens: EnsembleConfig):
+        self.ens = ens
+        self.e01 = [fig0_1_entry(s) for s in ens.subchannels]
+        self.e02 = [fig0_2_entry(ens, sv) for sv in ens.services]
+        self.labels = [fig1(0, ens.eid, ens.label)] + [fig1(1, sv.sid, sv.label) for sv in ens.services]
+        self.i01 = self.i02 = self.ilab = 0
+
+    def cif_fibs(self, cif_count: int) -> bytes:
+        """Three FIBs (96 bytes) for one CIF."""
+        f00 = fig0_0(self.ens, cif_count)
+        f01, self.i01 = _pack_rotating(self.e01, 0x01, 30 - len(f00), self.i01)
+        fib0 = make_fib(f00 + f01)
+        f02, self.i02 = _pack_rotating(self.e02, 0x02, 30, self.i02)
+        fib1 = make_fib(f02)
+        lab = self.labels[self.ilab % len(self.labels)]
+        self.ilab += 1
+        fib2 = make_fib(lab + fig0_9(self.ens))
+        return fib0 + fib1 + fib2
+
+
+# ============================================================================ modulator
+_PHASE8 = np.exp(1j * np.pi / 4 * np.arange(8)).astype(np.complex64)
+
+
+@dataclass
+class SynthResult:
+    iq: np.ndarray                       # complex64 baseband before quantisation (None if not kept)
+    n_frames: int
+    fibs: np.ndarray                     # [n_cif, 96] uint8
+    logical: Dict[int, np.ndarray]       # subchid -> [n_cif, bitrate*3] uint8 logical frames (pre-scrambling)
+    aus: Dict[int, List[bytes]]          # subchid -> DAB+ access units in stream order
+    superframes: Dict[int, np.ndarray]   # subchid -> [n_sf, 120*s]
+    ens: EnsembleConfig = None
+    frame0: int = 0                      # sample index of the first null symbol
+    cfo_hz: float = 0.0
+
+
+def build_cif_bits(ens: EnsembleConfig, n_cif: int, seed: int):
+    """Payloads -> per-CIF code bits.  Returns (fic_bits [n_cif, 2304], msc_bits [n_cif, 55296], truth dicts)."""
+    rng = np.random.default_rng(seed)
+    ens.check()
+    # ---- FIC
+    fb = FicBuilder(ens)
+    fibs = np.zeros((n_cif, 96), dtype=np.uint8)
+    for c in range(n_cif):
+        fibs[c] = np.frombuffer(fb.cif_fibs((ens.cif_count0 + c) % 5000), dtype=np.uint8)
+    fic_in = bytes_to_bits(fibs) ^ C.prbs_bits(768)[None, :]
+    fic_bits = encode_protected(fic_in, [(21, 16), (3, 15)], 0)
+    assert fic_bits.shape[1] == C.FIC_PUNCT_BITS
+    # ---- MSC
+    msc_pre = rng.integers(0, 2, (n_cif, C.CIF_BITS), dtype=np.uint8)   # filler in unused CUs
+    logical, aus, sfs = {}, {}, {}
+    for sc in ens.subchannels:
+        srng = np.random.default_rng(sc.seed + 77)
+        segs, size_cu, pad = sc.profile()
+        if sc.kind == "dabplus":
+            n_sf = (n_cif + 4) // 5
+            sf, au = dabplus_superframes(sc, n_sf, srng)
+            frames = sf.reshape(n_sf * 5, sc.frame_bytes)[:n_cif]
+            aus[sc.subchid] = au
+            sfs[sc.subchid] = sf
+        elif sc.kind == "mp2":
+            frames = mp2_frames(sc, n_cif, srng)
+        else:
+            frames = srng.integers(0, 256, (n_cif, sc.frame_bytes), dtype=np.uint8)
+        logical[sc.subchid] = frames
+        nb = sc.frame_bytes * 8
+        scr = bytes_to_bits(frames) ^ C.prbs_bits(nb)[None, :]
+        enc = encode_protected(scr, segs, pad)
+        assert enc.shape[1] == size_cu * 64, (enc.shape, size_cu)
+        msc_pre[:, sc.start_cu * 64:(sc.start_cu + size_cu) * 64] = enc
+    # ---- time interleaving: out[r][i] = in[r - D(i mod 16)][i]
+    msc = np.zeros_like(msc_pre)
+    for j, d in enumerate(C.TIME_DEINT_DELAY):
+        if d == 0:
+            msc[:, j::16] = msc_pre[:, j::16]
+        elif d < n_cif:
+            msc[d:, j::16] = msc_pre[:n_cif - d, j::16]
+    return fic_bits, msc, dict(fibs=fibs, logical=logical, aus=aus, superframes=sfs)
+
+
+def tii_symbol(ens: EnsembleConfig) -> np.ndarray:
+    """Null-symbol TII signal (2656 samples, useful part last), unit carrier amplitude * amp."""
+    spec = np.zeros(C.NFFT, dtype=np.complex128)
+    prs = C.prs_carriers()
+    kk = C.carrier_k()
+    cidx = {int(k): i for i, k in enumerate(kk)}
+    for tx in ens.tii:
+        s = np.zeros(C.NFFT, dtype=np.complex128)
+        for k in C.tii_carriers(tx.main, tx.sub):
+            ph = prs[cidx[k]]
+            s[k % C.NFFT] += ph
+            s[(k + 1) % C.NFFT] += ph
+        if tx.delay:
+            f = np.fft.fftfreq(C.NFFT, 1.0 / C.NFFT)
+            s *= np.exp(-2j * np.pi * f * tx.delay / C.NFFT)
+        spec += tx.amp * np.exp(1j * tx.phase) * s
+    t = np.fft.ifft(spec) * C.NFFT / np.sqrt(C.NCARR)
+    return np.concatenate([t[-(C.T_NULL - C.NFFT):], t]).astype(np.complex64)
+
+
+def modulate(ens: EnsembleConfig, n_frames: int, seed: int = 1) -> Tuple[np.ndarray, dict]:
+    """Return (clean complex64 baseband of n_frames transmission frames at unit mean symbol power, truth)."""
+    n_cif = 4 * n_frames
+    fic_bits, msc_bits, truth = build_cif_bits(ens, n_cif, seed)
+    prs_q = C.prs_quarter_phase()
+    fidx = C.freq_interleave_index()        # QPSK symbol n -> carrier index
+    bins = C.carrier_bins()
+    tii = tii_symbol(ens) if ens.tii else None
+    out = np.zeros(n_frames * C.T_FRAME, dtype=np.complex64)
+    scale = C.NFFT / np.sqrt(C.NCARR)
+    # QPSK phase index (units of pi/4): bits (re, im): 00->1, 10->3, 11->5, 01->7
+    qmap = np.array([[1, 7], [3, 5]], dtype=np.int64)
+    for f in range(n_frames):
+        bits = np.concatenate([fic_bits[4 * f:4 * f + 4].reshape(-1), msc_bits[4 * f:4 * f + 4].reshape(-1)])
+        bits = bits.reshape(75, C.BITS_PER_SYM)
+        q = qmap[bits[:, :C.NCARR], bits[:, C.NCARR:]]            # [75, 1536] by QPSK symbol index n
+        y = np.zeros((75, C.NCARR), dtype=np.int64)
+        y[:, fidx] = q                                            # by carrier index
+        ph = np.concatenate([2 * prs_q[None, :], y], axis=0)
+        ph = np.cumsum(ph, axis=0) & 7                            # differential modulation
+        spec = np.zeros((C.NSYM, C.NFFT), dtype=np.complex64)
+        spec[:, bins] = _PHASE8[ph]
+        t = (np.fft.ifft(spec, axis=1) * scale).astype(np.complex64)
+        sym = np.concatenate([t[:, -C.T_CP:], t], axis=1).reshape(-1)
+        base = f * C.T_FRAME
+        cif0 = ens.cif_count0 + 4 * f
+        if tii is not None and (ens.tii_every_null or cif0 % 8 == 0):
+            out[base:base + C.T_NULL] = tii
+        out[base + C.T_NULL:base + C.T_FRAME] = sym
+    return out, truth
+
+
+def impair(x: np.ndarray, imp: Impairments, tail: int = 0) -> np.ndarray:
+    """Apply multipath, CFO (+drift), lead-in, AWGN.  Output has unit mean symbol power before noise."""
+    rng = np.random.default_rng(imp.seed)
+    if imp.taps:
+        y = x.copy()
+        for d, g in imp.taps:
+            y[d:] += np.complex64(g) * x[:len(x) - d]
+        x = y
+    x = np.concatenate([np.zeros(imp.lead_in, dtype=np.complex64), x, np.zeros(tail, dtype=np.complex64)])
+    n = x.size
+    if imp.cfo_hz or imp.cfo_drift_hz_per_s:
+        # phase(t) = 2 pi (f0 t + 0.5 a t^2); evaluated in float64 in chunks to bound memory
+        step = 1 << 22
+        for s in range(0, n, step):
+            t = np.arange(s, min(n, s + step), dtype=np.float64) / C.FS
+            phs = 2 * np.pi * (imp.cfo_hz * t + 0.5 * imp.cfo_drift_hz_per_s * t * t)
+            x[s:s + step] *= np.exp(1j * phs).astype(np.complex64)
+    if imp.snr_db is not None:
+        sigma = np.sqrt(0.5 * 10 ** (-imp.snr_db / 10))
+        step = 1 << 22
+        for s in range(0, n, step):
+            m = min(n, s + step) - s
+            x[s:s + m] += (sigma * (rng.standard_normal(m) + 1j * rng.standard_normal(m))).astype(np.complex64)
+    return x
+
+
+def quantize(x: np.ndarray, fmt: str, rms: float) -> np.ndarray:
+    """Complex baseband -> interleaved IQ in the raw-file formats RawFileInput reads
+    (reference: src/input/rawfileinput.h:42-46, conversion rawfileinput.cpp:643-711), plus f32."""
+    iq = np.empty(2 * x.size, dtype=np.float32)
+    iq[0::2] = x.real
+    iq[1::2] = x.imag
+    iq *= np.float32(rms)     # symbol power is 1 => I and Q each have rms/sqrt(2); 'rms' is the complex RMS
+    if fmt == "u8":
+        return np.clip(np.rint(iq) + 128, 0, 255).astype(np.uint8)
+    if fmt == "s16":
+        return np.clip(np.rint(iq), -32768, 32767).astype(np.int16)
+    if fmt == "f32":
+        return iq
+    raise ValueError(fmt)
+
+
+def synthesize(ens: EnsembleConfig, n_frames: int, fmt: str = "u8", imp: Optional[Impairments] = None,
+               seed: int = 1, tail: int = 0):
+    """Full chain: returns (raw interleaved IQ array in `fmt`, SynthResult)."""
+    imp = imp or Impairments()
+    clean, truth = modulate(ens, n_frames, seed)
+    x = impair(clean, imp, tail)
+    rms = imp.rms if fmt != "s16" or imp.rms > 200 else imp.rms * 250.0
+    raw = quantize(x, fmt, rms if fmt != "f32" else 1.0)
+    res = SynthResult(iq=None, n_frames=n_frames, fibs=truth["fibs"], logical=truth["logical"], aus=truth["aus"],
+                      superframes=truth["superframes"], ens=ens, frame0=imp.lead_in, cfo_hz=imp.cfo_hz)
+    return raw, res
