@@ -1,0 +1,861 @@
+// b200dab.cu -- host side of libb200dab.so: context, device memory, stage orchestration and the C ABI of include/b200dab.h.
+//
+// The pipeline is the B200-native stand-in for the reference's closed receiver core (libdabsdr 4.0.1; interface
+// lib/linux_x86_64/dabsdr.h:397-429): it is fed with what RawFileInput/InputDevice deliver (raw u8/s16 IQ, or the float
+// stream of getSamples: src/input/inputdevice.cpp:70-108) and produces what RadioControl receives (FIBs -> ensemble
+// structures, access units, statistics, TII lists).  No CPU fallback exists: without a CUDA device creation fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "k_sync.cuh"
+#include "k_ofdm.cuh"
+#include "k_viterbi.cuh"
+#include "k_dabplus.cuh"
+#include "k_tii.cuh"
+#include "tables.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(#x, e_); return -1; } } while (0)
+#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->set_error(#x, e_); return -1; } } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct b200dab_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int launches = 0;
+    // constant tables on the device
+    DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf;
+    // pipeline buffers
+    DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
+    DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_fic_out, d_fib_ok, d_msc_out;
+    DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
+    DevBuf d_tmp_a, d_tmp_b;
+    HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc;
+    // result storage
+    std::vector<int64_t> r_tf;
+    std::vector<float> r_cfo, r_cir;
+    std::vector<b200dab_subch_t> r_subch;
+    std::vector<const uint8_t*> r_frames;
+    std::vector<int32_t> r_rows;
+    std::vector<b200dab_au_t> r_aus;
+    std::vector<b200dab_tii_t> r_tii;
+
+    void set_error(const char* what, cudaError_t e)
+    {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        err = buf;
+    }
+    void set_error(const char* what) { err = what; }
+
+    int init_tables();
+    // device-side stages (all asynchronous on `stream` unless noted)
+    int upload_raw(const void* iq, uint64_t n, int fmt, int mem, const void** d_out);
+    int coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, int* max_cand_out);
+    int fine(const void* d_iq, uint64_t n, int fmt, int n_cand);
+    int demod(const void* d_iq, uint64_t n, int fmt, const FrameInfo* h_fr, int n_frames, int n_slots, bool symstat);
+    int run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out);
+    int fic(int n_slots);
+    int msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std::vector<size_t>& out_off, size_t* total);
+    int dabplus(uint8_t* d_frames, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows);
+};
+
+static size_t fmt_bytes(int fmt) { return fmt == B200DAB_FMT_U8 ? 2 : fmt == B200DAB_FMT_S16 ? 4 : 8; }
+
+int b200dab_ctx::init_tables()
+{
+    std::vector<float> tw(4096);
+    dabtab::twiddles(tw.data());
+    CK(d_tw.ensure(tw.size() * 4));
+    CK(cudaMemcpy(d_tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int16_t> c_of_n(DAB_NCARR);
+    dabtab::freq_deint(c_of_n.data());
+    std::vector<uint16_t> pos(DAB_NCARR);
+    for (int n = 0; n < DAB_NCARR; n++) pos[n] = (uint16_t)fft_phys(fft_pos(carrier_bin(c_of_n[n])));
+    CK(d_fdi_pos.ensure(pos.size() * 2));
+    CK(cudaMemcpy(d_fdi_pos.p, pos.data(), pos.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<int8_t> prs(DAB_NCARR);
+    dabtab::prs_quarter(prs.data());
+    CK(d_prs_q.ensure(prs.size()));
+    CK(cudaMemcpy(d_prs_q.p, prs.data(), prs.size(), cudaMemcpyHostToDevice));
+    std::vector<uint32_t> pw(512);
+    dabtab::prbs_words(pw.data(), 512);
+    CK(d_prbs_w.ensure(pw.size() * 4));
+    CK(cudaMemcpy(d_prbs_w.p, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
+    GfTables gf;
+    dabtab::gf_tables(gf.exp, gf.log);
+    CK(d_gf.ensure(sizeof gf));
+    CK(cudaMemcpy(d_gf.p, &gf, sizeof gf, cudaMemcpyHostToDevice));
+    uint8_t pat[70];
+    dabtab::tii_patterns(pat);
+    CK(cudaMemcpyToSymbol(c_tii_pattern, pat, 70));
+    return 0;
+}
+
+int b200dab_ctx::upload_raw(const void* iq, uint64_t n, int fmt, int mem, const void** d_out)
+{
+    if (mem == B200DAB_MEM_DEVICE) { *d_out = iq; return 0; }
+    const size_t bytes = (size_t)n * fmt_bytes(fmt);
+    CK(d_raw.ensure(bytes + 64));
+    CK(cudaMemcpyAsync(d_raw.p, iq, bytes, cudaMemcpyHostToDevice, stream));
+    *d_out = d_raw.p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ coarse sync
+int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, int* max_cand_out)
+{
+    const int64_t nblk = (int64_t)(n / SYNC_BLK);
+    const int max_cand = (int)(nblk / SYNC_WIN) + 2;
+    *max_cand_out = max_cand;
+    *n_cand_out = 0;
+    if (nblk <= 0) return 0;
+    CK(d_P.ensure((size_t)nblk * 4));
+    CK(d_S.ensure((size_t)nblk * 4));
+    CK(d_cand_raw.ensure((size_t)max_cand * 8));
+    CK(d_cand.ensure((size_t)max_cand * 8));
+    CK(d_ncand.ensure(4));
+    CK(cudaMemsetAsync(d_ncand.p, 0, 4, stream));
+    const unsigned grid = (unsigned)((nblk + 255) / 256);
+    if (fmt == B200DAB_FMT_U8) k_block_power<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    else if (fmt == B200DAB_FMT_S16) k_block_power<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    else k_block_power<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    k_window_sum<<<grid, 256, 0, stream>>>(d_P.as<float>(), nblk, d_S.as<float>());
+    k_candidates<<<grid, 256, 0, stream>>>(d_S.as<float>(), nblk, (int64_t)n, d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand);
+    k_sort_small<<<1, 256, 0, stream>>>(d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand, d_cand.as<long long>());
+    launches += 4;
+    CK(cudaGetLastError());
+    int nc = 0;
+    CK(cudaMemcpyAsync(&nc, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (nc > max_cand) nc = max_cand;
+    *n_cand_out = nc;
+    return 0;
+}
+
+int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
+{
+    if (n_cand <= 0) return 0;
+    CK(d_fine.ensure((size_t)n_cand * sizeof(FineOut)));
+    const float2* tw = d_tw.as<float2>();
+    const int8_t* prs = d_prs_q.as<int8_t>();
+    if (fmt == B200DAB_FMT_U8)
+        k_fine_sync<B200DAB_FMT_U8><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+    else if (fmt == B200DAB_FMT_S16)
+        k_fine_sync<B200DAB_FMT_S16><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+    else
+        k_fine_sync<B200DAB_FMT_F32><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+    launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// keep sharp PRS correlations, at most one per frame period; slot = frame number relative to the first accepted frame
+static int chain_frames(const FineOut* f, int n, std::vector<FrameInfo>& out, std::vector<float>& cir)
+{
+    out.clear(); cir.clear();
+    long long t0 = 0, last = 0;
+    for (int i = 0; i < n; i++) {
+        if (!(f[i].cir_ratio >= SYNC_CIR_MIN)) continue;
+        if (!out.empty() && f[i].t_f - last < (long long)(DAB_T_FRAME * 9 / 10)) continue;
+        if (out.empty()) t0 = f[i].t_f;
+        FrameInfo fi;
+        fi.t_f = f[i].t_f; fi.cfo_hz = f[i].cfo_hz;
+        fi.slot = (int)((f[i].t_f - t0 + DAB_T_FRAME / 2) / DAB_T_FRAME);
+        out.push_back(fi);
+        cir.push_back(f[i].cir_ratio);
+        last = f[i].t_f;
+    }
+    return out.empty() ? 0 : out.back().slot + 1;
+}
+
+// ------------------------------------------------------------------------------------------------ OFDM demod
+int b200dab_ctx::demod(const void* d_iq, uint64_t n, int fmt, const FrameInfo* h_fr, int n_frames, int n_slots, bool want_stat)
+{
+    if (n_frames <= 0) return 0;
+    CK(d_frames.ensure((size_t)n_frames * sizeof(FrameInfo)));
+    CK(cudaMemcpyAsync(d_frames.p, h_fr, (size_t)n_frames * sizeof(FrameInfo), cudaMemcpyHostToDevice, stream));
+    CK(d_soft.ensure((size_t)n_slots * DAB_FRAME_SOFT + 256));
+    if (n_frames < n_slots) CK(cudaMemsetAsync(d_soft.p, 0, (size_t)n_slots * DAB_FRAME_SOFT, stream));   // lost frames = erasures
+    float* st = nullptr;
+    if (want_stat) {
+        CK(d_symstat.ensure((size_t)n_slots * 150 * 4));
+        CK(cudaMemsetAsync(d_symstat.p, 0, (size_t)n_slots * 150 * 4, stream));
+        st = d_symstat.as<float>();
+    }
+    const unsigned grid = (unsigned)n_frames * OFDM_GROUPS;
+    const float2* tw = d_tw.as<float2>();
+    const uint16_t* fp = d_fdi_pos.as<uint16_t>();
+    if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
+    else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
+    else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
+    launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Viterbi (gather + ACS + traceback)
+// jobs_in: vin_off/dec_off are filled here; out_off, row0, ... by the caller.  Soft bits are read from d_soft.
+int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out)
+{
+    std::vector<VitJob> jobs = jobs_in;
+    std::vector<VitGroup> groups;
+    size_t words = 0;
+    int max_steps = 0;
+    for (size_t j = 0; j < jobs.size(); j++) {
+        const int ng = (jobs[j].n_rows + 31) / 32;
+        jobs[j].vin_off = (long long)words;
+        jobs[j].dec_off = (long long)words;
+        words += (size_t)ng * 32 * jobs[j].steps;
+        for (int g = 0; g < ng; g++) groups.push_back(VitGroup{(int)j, g});
+        max_steps = std::max(max_steps, jobs[j].steps);
+    }
+    if (groups.empty()) return 0;
+    std::stable_sort(groups.begin(), groups.end(), [&](const VitGroup& a, const VitGroup& b) { return jobs[a.job].steps > jobs[b.job].steps; });
+    CK(d_jobs.ensure(jobs.size() * sizeof(VitJob)));
+    CK(d_groups.ensure(groups.size() * sizeof(VitGroup)));
+    CK(d_stepinfo.ensure(stepinfo.size() * 4));
+    CK(d_vin.ensure(words * 4));
+    CK(d_dec.ensure(words * 8));
+    CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(VitJob), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_groups.p, groups.data(), groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_stepinfo.p, stepinfo.data(), stepinfo.size() * 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));      // the host vectors above go out of scope
+    dim3 ggrid((unsigned)groups.size(), (unsigned)((max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
+    k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
+    k_viterbi<<<(unsigned)groups.size(), 32, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
+                                                       d_prbs_w.as<uint32_t>(), d_out);
+    launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static VitJob make_job(const b200dab_subch_t& sc, int kind, int n_rows, int max_row, int stepinfo_off, long long out_off)
+{
+    VitJob j;
+    memset(&j, 0, sizeof j);
+    j.kind = kind;
+    j.n_info = sc.bitrate * 24;
+    j.steps = j.n_info + 6;
+    j.n_rows = n_rows;
+    j.row0 = 0;
+    j.max_row = max_row;
+    j.stepinfo_off = stepinfo_off;
+    j.out_off = out_off;
+    j.out_pitch = j.n_info / 8;
+    if (kind == 0) { j.soft_base = 0; j.row_pitch = DAB_FIC_PUNCT; j.use_tdi = 0; }
+    else { j.soft_base = DAB_FIC_SOFT + (long long)sc.start_cu * 64; j.row_pitch = DAB_CIF_BITS; j.use_tdi = 1; }
+    return j;
+}
+
+int b200dab_ctx::fic(int n_slots)
+{
+    b200dab_subch_t ficp;
+    memset(&ficp, 0, sizeof ficp);
+    ficp.bitrate = 32; ficp.n_seg = 2; ficp.seg_len[0] = 21; ficp.seg_pi[0] = 16; ficp.seg_len[1] = 3; ficp.seg_pi[1] = 15;
+    std::vector<uint32_t> si;
+    if (dabtab::build_stepinfo(ficp, si) != DAB_FIC_PUNCT) { set_error("FIC puncturing table inconsistent"); return -1; }
+    const int n_rows = 4 * n_slots;
+    std::vector<VitJob> jobs(1, make_job(ficp, 0, n_rows, n_rows - 1, 0, 0));
+    CK(d_fic_out.ensure((size_t)(n_rows + 32) * 96));
+    CK(d_fib_ok.ensure((size_t)n_rows * 3 + 64));
+    if (run_viterbi(jobs, si, d_fic_out.as<uint8_t>())) return -1;
+    const int n_fib = n_rows * 3;
+    k_fib_crc<<<(n_fib + 255) / 256, 256, 0, stream>>>(d_fic_out.as<uint8_t>(), n_fib, d_fib_ok.as<uint8_t>());
+    launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200dab_ctx::msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std::vector<size_t>& out_off, size_t* total)
+{
+    const int n_cif = 4 * n_slots, n_rows = n_cif - (DAB_TDI_DEPTH - 1);
+    out_off.assign(subch.size(), 0);
+    *total = 0;
+    if (n_rows <= 0 || subch.empty()) return 0;
+    std::vector<uint32_t> si;
+    std::vector<VitJob> jobs;
+    size_t off = 0;
+    for (size_t i = 0; i < subch.size(); i++) {
+        const int si_off = (int)si.size();
+        const int np = dabtab::build_stepinfo(subch[i], si);
+        if (np < 0 || np > subch[i].size_cu * 64 || subch[i].start_cu < 0 || subch[i].start_cu + subch[i].size_cu > 864) {
+            set_error("sub-channel protection profile inconsistent with its size");
+            return -1;
+        }
+        out_off[i] = off;
+        jobs.push_back(make_job(subch[i], 1, n_rows, n_cif - 1, si_off, (long long)off));
+        off += (size_t)((n_rows + 31) / 32 * 32) * (size_t)(subch[i].bitrate * 3);
+    }
+    *total = off;
+    CK(d_msc_out.ensure(off + 256));
+    return run_viterbi(jobs, si, d_msc_out.as<uint8_t>());
+}
+
+int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows)
+{
+    if (jobs.empty() || total_sf <= 0) return 0;
+    CK(d_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob)));
+    CK(d_flags.ensure((size_t)total_rows + 64));
+    CK(d_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
+    CK(d_residue.ensure(jobs.size() * 4));
+    CK(cudaMemcpyAsync(d_dpjobs.p, jobs.data(), jobs.size() * sizeof(DabPlusJob), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    int max_rows = 0, max_sf = 0, max_cw = 0;
+    for (auto& j : jobs) { max_rows = std::max(max_rows, j.n_rows); max_sf = std::max(max_sf, j.max_sf); max_cw = std::max(max_cw, j.max_sf * j.s); }
+    const unsigned nj = (unsigned)jobs.size();
+    k_firecode_scan<<<dim3((max_rows + 255) / 256, nj), 256, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>());
+    k_sf_align<<<nj, 32, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>());
+    k_rs_decode<<<dim3((max_cw + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<GfTables>());
+    k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
+    launches += 4;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ FIG 0/1 + 0/2 (sub-channel discovery)
+static int parse_subch_impl(const uint8_t* fibs, const uint8_t* ok, int n_fibs, b200dab_subch_t* out, int max_out)
+{
+    struct Ent { bool have = false; b200dab_subch_t sc; bool dabplus = false; bool audio = false; };
+    std::vector<Ent> tab(64);
+    for (int f = 0; f < n_fibs; f++) {
+        if (ok && !ok[f]) continue;
+        const uint8_t* p = fibs + (size_t)f * 32;
+        int i = 0;
+        while (i < 30) {
+            const uint8_t h = p[i];
+            if (h == 0xFF) break;
+            const int type = h >> 5, len = h & 31;
+            if (len == 0 || i + 1 + len > 30) break;
+            const uint8_t* d = p + i + 1;
+            if (type == 0) {
+                const int ext = d[0] & 31, pd = (d[0] >> 5) & 1;
+                int k = 1;
+                if (ext == 1) {
+                    while (k + 3 <= len) {
+                        const int id = d[k] >> 2, start = ((d[k] & 3) << 8) | d[k + 1];
+                        b200dab_subch_t sc;
+                        memset(&sc, 0, sizeof sc);
+                        sc.subch_id = id; sc.start_cu = start;
+                        int okp = -1;
+                        if (d[k + 2] & 0x80) {
+                            if (k + 4 > len) break;
+                            const int opt = (d[k + 2] >> 4) & 7, lvl = (d[k + 2] >> 2) & 3, size = ((d[k + 2] & 3) << 8) | d[k + 3];
+                            int bitrate = 0;
+                            if (opt == 0) { static const int div[4] = {12, 8, 6, 4}; bitrate = size / div[lvl] * 8; }
+                            else if (opt == 1) { static const int div[4] = {27, 21, 18, 15}; bitrate = size / div[lvl] * 32; }
+                            if (bitrate > 0) okp = dabtab::profile_eep(bitrate, lvl + 1, opt, &sc);
+                            if (okp == 0 && sc.size_cu != size) okp = -1;
+                            k += 4;
+                        } else {
+                            okp = dabtab::profile_uep(d[k + 2] & 0x3F, &sc);
+                            k += 3;
+                        }
+                        if (okp == 0) { sc.subch_id = id; sc.start_cu = start; tab[id].have = true; bool dp = tab[id].dabplus; tab[id].sc = sc; tab[id].dabplus = dp; }
+                    }
+                } else if (ext == 2) {
+                    while (k < len) {
+                        const int sidlen = pd ? 4 : 2;
+                        if (k + sidlen + 1 > len) break;
+                        k += sidlen;
+                        const int ncomp = d[k] & 0x0F;
+                        k++;
+                        for (int c = 0; c < ncomp && k + 2 <= len; c++, k += 2) {
+                            const int tmid = d[k] >> 6;
+                            if (tmid == 0) {
+                                const int ascty = d[k] & 0x3F, id = d[k + 1] >> 2;
+                                tab[id].audio = true;
+                                tab[id].dabplus = (ascty == 63);
+                            }
+                        }
+                    }
+                }
+            }
+            i += 1 + len;
+        }
+    }
+    int n = 0;
+    for (int id = 0; id < 64 && n < max_out; id++)
+        if (tab[id].have) { out[n] = tab[id].sc; out[n].kind = tab[id].dabplus ? 1 : 0; n++; }
+    std::sort(out, out + n, [](const b200dab_subch_t& a, const b200dab_subch_t& b) { return a.start_cu < b.start_cu; });
+    return n;
+}
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int b200dab_version(void) { return 0x000100; }
+
+int b200dab_create(b200dab_ctx** out, int device)
+{
+    if (!out) return -1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return -2;      // no CPU fallback
+    if (device < 0 || device >= ndev) return -3;
+    if (cudaSetDevice(device) != cudaSuccess) return -4;
+    b200dab_ctx* ctx = new b200dab_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
+    if (ctx->init_tables()) { fprintf(stderr, "b200dab: %s\n", ctx->err.c_str()); cudaStreamDestroy(ctx->stream); delete ctx; return -6; }
+    *out = ctx;
+    return 0;
+}
+
+void b200dab_destroy(b200dab_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
+                    &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
+                    &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b};
+    for (auto* b : db) b->release();
+    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc};
+    for (auto* b : hb) b->release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* b200dab_last_error(b200dab_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void* b200dab_stream(b200dab_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int b200dab_profile_eep(int bitrate, int level, int option, b200dab_subch_t* out)
+{
+    if (!out) return -1;
+    return dabtab::profile_eep(bitrate, level, option, out);
+}
+int b200dab_profile_uep(int idx, b200dab_subch_t* out)
+{
+    if (!out) return -1;
+    return dabtab::profile_uep(idx, out);
+}
+int b200dab_parse_subch(const uint8_t* fibs, const uint8_t* fib_ok, int n_fibs, b200dab_subch_t* out, int max_out)
+{
+    if (!fibs || !out) return -1;
+    return parse_subch_impl(fibs, fib_ok, n_fibs, out, max_out);
+}
+
+// ------------------------------------------------------------------------------------------------ whole path
+int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int mem, const b200dab_subch_t* subch_in, int n_subch_in,
+                   uint32_t flags, b200dab_result_t* res)
+{
+    if (!ctx || !iq || !res || fmt < 0 || fmt > 2) return -1;
+    cudaSetDevice(ctx->device);
+    memset(res, 0, sizeof *res);
+    ctx->launches = 0;
+    ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
+    const void* d_iq = nullptr;
+    if (ctx->upload_raw(iq, n, fmt, mem, &d_iq)) return -1;
+    // ---- sync
+    int n_cand = 0, max_cand = 0;
+    if (ctx->coarse(d_iq, n, fmt, &n_cand, &max_cand)) return -1;
+    res->n_candidates = n_cand;
+    if (ctx->fine(d_iq, n, fmt, n_cand)) return -1;
+    std::vector<FrameInfo> frames;
+    std::vector<float> cir;
+    int n_slots = 0;
+    if (n_cand > 0) {
+        CKC(ctx->h_fine.ensure((size_t)n_cand * sizeof(FineOut)));
+        CKC(cudaMemcpyAsync(ctx->h_fine.p, ctx->d_fine.p, (size_t)n_cand * sizeof(FineOut), cudaMemcpyDeviceToHost, ctx->stream));
+        CKC(cudaStreamSynchronize(ctx->stream));
+        n_slots = chain_frames(ctx->h_fine.as<FineOut>(), n_cand, frames, cir);
+    }
+    const int n_frames = (int)frames.size();
+    res->n_frames = n_frames; res->n_slots = n_slots;
+    ctx->r_tf.assign(n_slots, -1); ctx->r_cfo.assign(n_slots, 0.f); ctx->r_cir.assign(n_slots, 0.f);
+    for (int i = 0; i < n_frames; i++) { ctx->r_tf[frames[i].slot] = frames[i].t_f; ctx->r_cfo[frames[i].slot] = frames[i].cfo_hz; ctx->r_cir[frames[i].slot] = cir[i]; }
+    res->t_f = ctx->r_tf.data(); res->cfo_hz = ctx->r_cfo.data(); res->cir_ratio = ctx->r_cir.data();
+    if (n_frames == 0) { res->gpu_launches = ctx->launches; return 0; }
+    // ---- OFDM demod -> soft bits
+    CKC(ctx->h_frames.ensure((size_t)n_frames * sizeof(FrameInfo)));
+    memcpy(ctx->h_frames.p, frames.data(), (size_t)n_frames * sizeof(FrameInfo));
+    const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
+    if (ctx->demod(d_iq, n, fmt, ctx->h_frames.as<FrameInfo>(), n_frames, n_slots, want_stat)) return -1;
+    // ---- TII fold runs on the raw samples, independent of the decoding chain
+    const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
+    if (want_tii) {
+        CKC(ctx->d_fold.ensure((size_t)n_slots * TII_SPECTRUM_BINS * 4));
+        CKC(ctx->d_norm.ensure((size_t)n_slots * 4));
+        CKC(cudaMemsetAsync(ctx->d_fold.p, 0, (size_t)n_slots * TII_SPECTRUM_BINS * 4, ctx->stream));
+        CKC(cudaMemsetAsync(ctx->d_norm.p, 0, (size_t)n_slots * 4, ctx->stream));
+        const float2* tw = ctx->d_tw.as<float2>();
+        if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
+        else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
+        else k_tii_fold<B200DAB_FMT_F32><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
+        ctx->launches += 1;
+        CKC(cudaGetLastError());
+    }
+    // ---- FIC
+    if (ctx->fic(n_slots)) return -1;
+    const size_t fib_bytes = (size_t)n_slots * 12 * 32;
+    CKC(ctx->h_fibs.ensure(fib_bytes));
+    CKC(ctx->h_fib_ok.ensure((size_t)n_slots * 12));
+    CKC(cudaMemcpyAsync(ctx->h_fibs.p, ctx->d_fic_out.p, fib_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->h_fib_ok.p, ctx->d_fib_ok.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    res->fibs = ctx->h_fibs.as<uint8_t>(); res->fib_ok = ctx->h_fib_ok.as<uint8_t>();
+    // ---- sub-channel organisation: given by the caller or discovered from FIG 0/1, 0/2
+    if (subch_in && n_subch_in > 0) ctx->r_subch.assign(subch_in, subch_in + n_subch_in);
+    else {
+        ctx->r_subch.resize(B200DAB_MAX_SUBCH);
+        int ns = parse_subch_impl(res->fibs, res->fib_ok, n_slots * 12, ctx->r_subch.data(), B200DAB_MAX_SUBCH);
+        ctx->r_subch.resize(ns);
+    }
+    res->n_subch = (int)ctx->r_subch.size();
+    res->subch = ctx->r_subch.data();
+    // ---- MSC
+    std::vector<size_t> out_off;
+    size_t msc_bytes = 0;
+    const int n_rows = 4 * n_slots - (DAB_TDI_DEPTH - 1);
+    std::vector<DabPlusJob> dpjobs;
+    std::vector<int> dp_subch;
+    int total_sf = 0, total_rows = 0;
+    if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
+        if (ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes)) return -1;
+        for (size_t i = 0; i < ctx->r_subch.size(); i++) {
+            if (ctx->r_subch[i].kind != 1) continue;
+            DabPlusJob j;
+            j.frames_off = (long long)out_off[i]; j.n_rows = n_rows; j.pitch = ctx->r_subch[i].bitrate * 3; j.s = ctx->r_subch[i].bitrate / 8;
+            j.sf_off = total_sf; j.max_sf = n_rows / 5; j.flag_off = total_rows;
+            total_sf += j.max_sf; total_rows += n_rows;
+            dpjobs.push_back(j); dp_subch.push_back((int)i);
+        }
+        if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows)) return -1;
+        CKC(ctx->h_msc.ensure(msc_bytes + 64));
+        CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (total_sf > 0) {
+            CKC(ctx->h_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
+            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    // ---- TII detection needs to know which nulls carry TII: CIF counter (FIG 0/0) = 0 mod 8
+    int n_win = 0;
+    if (want_tii) {
+        std::vector<int> sign(n_slots, 0);
+        for (int s = 0; s < n_slots; s++) {
+            if (ctx->r_tf[s] < 0) continue;
+            const uint8_t* fib = res->fibs + (size_t)s * 384;          // FIB 0 of the first CIF carries FIG 0/0 first
+            if (res->fib_ok[(size_t)s * 12] && (fib[0] >> 5) == 0 && (fib[1] & 31) == 0 && (fib[0] & 31) >= 5) {
+                const int cif = ((fib[4] & 0x1F) * 250 + fib[5]);
+                sign[s] = (cif % 8 == 0) ? 1 : (cif % 8 == 4 ? -1 : 0);
+            }
+        }
+        // frames whose FIG 0/0 was lost: alternate from a decoded neighbour
+        for (int s = 1; s < n_slots; s++) if (!sign[s] && sign[s - 1] && ctx->r_tf[s] >= 0) sign[s] = -sign[s - 1];
+        for (int s = n_slots - 2; s >= 0; s--) if (!sign[s] && sign[s + 1] && ctx->r_tf[s] >= 0) sign[s] = -sign[s + 1];
+        std::vector<int2> wins;
+        for (int w = 0; w + TII_NOTIFY_FRAMES <= n_slots; w += TII_NOTIFY_FRAMES) wins.push_back(make_int2(w, w + TII_NOTIFY_FRAMES));
+        if (wins.empty()) wins.push_back(make_int2(0, n_slots & ~1));
+        n_win = (int)wins.size();
+        CKC(ctx->d_sign.ensure((size_t)n_slots * 4));
+        CKC(ctx->d_windows.ensure(wins.size() * sizeof(int2)));
+        CKC(ctx->d_tii.ensure(wins.size() * sizeof(TiiResult)));
+        CKC(cudaMemcpyAsync(ctx->d_sign.p, sign.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CKC(cudaMemcpyAsync(ctx->d_windows.p, wins.data(), wins.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        CKC(cudaStreamSynchronize(ctx->stream));
+        k_tii_detect<<<n_win, 384, 0, ctx->stream>>>(ctx->d_fold.as<float>(), ctx->d_norm.as<float>(), ctx->d_sign.as<int>(), ctx->d_windows.as<int2>(),
+                                                     6.0f, ctx->d_tii.as<TiiResult>());
+        ctx->launches += 1;
+        CKC(cudaGetLastError());
+        CKC(ctx->h_tii.ensure(wins.size() * sizeof(TiiResult)));
+        CKC(cudaMemcpyAsync(ctx->h_tii.p, ctx->d_tii.p, wins.size() * sizeof(TiiResult), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (want_stat) {
+        CKC(ctx->h_symstat.ensure((size_t)n_slots * 150 * 4));
+        CKC(cudaMemcpyAsync(ctx->h_symstat.p, ctx->d_symstat.p, (size_t)n_slots * 150 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CKC(cudaStreamSynchronize(ctx->stream));
+    // ---- assemble the result
+    if (msc_bytes > 0) {
+        for (size_t i = 0; i < ctx->r_subch.size(); i++) { ctx->r_frames.push_back(ctx->h_msc.as<uint8_t>() + out_off[i]); ctx->r_rows.push_back(n_rows); }
+        res->frames = ctx->r_frames.data(); res->frame_rows = ctx->r_rows.data();
+        const SfInfo* sf = ctx->h_sf.as<SfInfo>();
+        for (size_t k = 0; k < dpjobs.size(); k++) {
+            const DabPlusJob& j = dpjobs[k];
+            for (int m = 0; m < j.max_sf; m++) {
+                const SfInfo& s = sf[j.sf_off + m];
+                if (!s.valid) continue;
+                res->superframes++;
+                res->rs_corrected += s.rs_corrected; res->rs_bit_errors += s.rs_bit_errors; res->rs_uncorrectable += s.rs_uncorrectable;
+                if (!s.firecode_ok) res->firecode_fail++;
+                for (int a = 0; a < s.n_aus; a++) {
+                    b200dab_au_t au;
+                    au.subch_index = dp_subch[k]; au.superframe = m; au.cif = s.row;
+                    au.offset = s.row * j.pitch + s.au_off[a]; au.length = s.au_len[a]; au.crc_ok = s.au_ok[a]; au.header = s.header;
+                    ctx->r_aus.push_back(au);
+                }
+            }
+        }
+        res->n_aus = (int)ctx->r_aus.size(); res->aus = ctx->r_aus.data();
+    }
+    if (want_tii && n_win > 0) {
+        static_assert(sizeof(TiiResult) == sizeof(b200dab_tii_t), "TII result layout");
+        ctx->r_tii.resize(n_win);
+        memcpy(ctx->r_tii.data(), ctx->h_tii.p, (size_t)n_win * sizeof(TiiResult));
+        res->n_tii = n_win; res->tii = ctx->r_tii.data();
+    }
+    if (want_stat) {
+        res->symstat = ctx->h_symstat.as<float>();
+        double snr_acc = 0; int cnt = 0;
+        for (int s = 0; s < n_slots; s++) {
+            if (ctx->r_tf[s] < 0) continue;
+            for (int l = 0; l < 75; l++) {
+                const float mu = res->symstat[((size_t)s * 75 + l) * 2], m2 = res->symstat[((size_t)s * 75 + l) * 2 + 1];
+                const double var = (double)m2 - (double)mu * mu;
+                if (mu > 0 && var > 0) { snr_acc += (double)mu * mu / var; cnt++; }
+            }
+        }
+        res->snr_db = cnt ? (float)(10.0 * log10(snr_acc / cnt)) : 0.f;
+    }
+    res->gpu_launches = ctx->launches;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stage entry points
+int b200dab_stage_coarse(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, float* P, float* S, int64_t* cand, int32_t* n_cand, int max_cand_out)
+{
+    if (!ctx || !iq) return -1;
+    cudaSetDevice(ctx->device);
+    const void* d_iq;
+    if (ctx->upload_raw(iq, n, fmt, B200DAB_MEM_HOST, &d_iq)) return -1;
+    int nc = 0, mc = 0;
+    if (ctx->coarse(d_iq, n, fmt, &nc, &mc)) return -1;
+    const size_t nblk = n / SYNC_BLK;
+    if (P) CKC(cudaMemcpy(P, ctx->d_P.p, nblk * 4, cudaMemcpyDeviceToHost));
+    if (S) CKC(cudaMemcpy(S, ctx->d_S.p, nblk * 4, cudaMemcpyDeviceToHost));
+    if (nc > max_cand_out) nc = max_cand_out;
+    if (cand && nc > 0) CKC(cudaMemcpy(cand, ctx->d_cand.p, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    if (n_cand) *n_cand = nc;
+    return 0;
+}
+
+int b200dab_stage_fine(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, const int64_t* cand, int n_cand, int64_t* t_f, float* cfo, float* metric)
+{
+    if (!ctx || !iq || !cand || n_cand <= 0) return -1;
+    cudaSetDevice(ctx->device);
+    const void* d_iq;
+    if (ctx->upload_raw(iq, n, fmt, B200DAB_MEM_HOST, &d_iq)) return -1;
+    CKC(ctx->d_cand.ensure((size_t)n_cand * 8));
+    CKC(ctx->d_ncand.ensure(4));
+    CKC(cudaMemcpyAsync(ctx->d_cand.p, cand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_ncand.p, &n_cand, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    if (ctx->fine(d_iq, n, fmt, n_cand)) return -1;
+    std::vector<FineOut> f(n_cand);
+    CKC(cudaMemcpyAsync(f.data(), ctx->d_fine.p, (size_t)n_cand * sizeof(FineOut), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_cand; i++) {
+        if (t_f) t_f[i] = f[i].t_f;
+        if (cfo) cfo[i] = f[i].cfo_hz;
+        if (metric) { metric[4 * i] = f[i].cp_mag; metric[4 * i + 1] = f[i].cfo_ratio; metric[4 * i + 2] = f[i].cir_ratio; metric[4 * i + 3] = f[i].tau1; }
+    }
+    return 0;
+}
+
+int b200dab_stage_demod(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, const int64_t* t_f, const float* cfo, int n_frames, int8_t* soft)
+{
+    if (!ctx || !iq || !t_f || !cfo || n_frames <= 0 || !soft) return -1;
+    cudaSetDevice(ctx->device);
+    const void* d_iq;
+    if (ctx->upload_raw(iq, n, fmt, B200DAB_MEM_HOST, &d_iq)) return -1;
+    CKC(ctx->h_frames.ensure((size_t)n_frames * sizeof(FrameInfo)));
+    FrameInfo* fr = ctx->h_frames.as<FrameInfo>();
+    for (int i = 0; i < n_frames; i++) { fr[i].t_f = t_f[i]; fr[i].cfo_hz = cfo[i]; fr[i].slot = i; }
+    if (ctx->demod(d_iq, n, fmt, fr, n_frames, n_frames, false)) return -1;
+    CKC(cudaMemcpyAsync(soft, ctx->d_soft.p, (size_t)n_frames * DAB_FRAME_SOFT, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// raw Viterbi on already de-punctured soft bits: packs them into the kernel's [group][step][lane] layout on the host
+int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int steps, uint8_t* bits)
+{
+    if (!ctx || !soft4 || n_cw <= 0 || steps < 38 || ((steps - 6) % 32) != 0 || !bits) { if (ctx) ctx->set_error("stage_viterbi: steps-6 must be a multiple of 32"); return -1; }
+    cudaSetDevice(ctx->device);
+    const int ng = (n_cw + 31) / 32;
+    std::vector<uint32_t> vin((size_t)ng * steps * 32, 0);
+    for (int c = 0; c < n_cw; c++)
+        for (int t = 0; t < steps; t++) {
+            uint32_t w;
+            memcpy(&w, soft4 + ((size_t)c * steps + t) * 4, 4);
+            vin[((size_t)(c / 32) * steps + t) * 32 + (c % 32)] = w;
+        }
+    VitJob job;
+    memset(&job, 0, sizeof job);
+    job.n_rows = n_cw; job.steps = steps; job.n_info = steps - 6; job.out_pitch = job.n_info / 8;
+    std::vector<VitGroup> groups;
+    for (int g = 0; g < ng; g++) groups.push_back(VitGroup{0, g});
+    const size_t words = vin.size();
+    std::vector<uint32_t> zero_prbs(512, 0);
+    CKC(ctx->d_jobs.ensure(sizeof job));
+    CKC(ctx->d_groups.ensure(groups.size() * sizeof(VitGroup)));
+    CKC(ctx->d_vin.ensure(words * 4));
+    CKC(ctx->d_dec.ensure(words * 8));
+    CKC(ctx->d_tmp_a.ensure(512 * 4));
+    CKC(ctx->d_tmp_b.ensure((size_t)ng * 32 * job.out_pitch + 64));
+    CKC(cudaMemcpyAsync(ctx->d_jobs.p, &job, sizeof job, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_groups.p, groups.data(), groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_vin.p, vin.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, zero_prbs.data(), 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_viterbi<<<ng, 32, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint2>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
+                                         ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>());
+    ctx->launches += 1;
+    CKC(cudaGetLastError());
+    std::vector<uint8_t> packed((size_t)n_cw * job.out_pitch);
+    CKC(cudaMemcpyAsync(packed.data(), ctx->d_tmp_b.p, packed.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < n_cw; c++)
+        for (int i = 0; i < job.n_info; i++) bits[(size_t)c * job.n_info + i] = (packed[(size_t)c * job.out_pitch + i / 8] >> (7 - (i & 7))) & 1;
+    return 0;
+}
+
+static int upload_soft(b200dab_ctx* ctx, const int8_t* soft, int n_frames)
+{
+    CKC(ctx->d_soft.ensure((size_t)n_frames * DAB_FRAME_SOFT + 256));
+    CKC(cudaMemcpyAsync(ctx->d_soft.p, soft, (size_t)n_frames * DAB_FRAME_SOFT, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int b200dab_stage_fic(b200dab_ctx* ctx, const int8_t* soft, int n_frames, uint8_t* fibs, uint8_t* fib_ok)
+{
+    if (!ctx || !soft || n_frames <= 0) return -1;
+    cudaSetDevice(ctx->device);
+    if (upload_soft(ctx, soft, n_frames)) return -1;
+    if (ctx->fic(n_frames)) return -1;
+    if (fibs) CKC(cudaMemcpyAsync(fibs, ctx->d_fic_out.p, (size_t)n_frames * 384, cudaMemcpyDeviceToHost, ctx->stream));
+    if (fib_ok) CKC(cudaMemcpyAsync(fib_ok, ctx->d_fib_ok.p, (size_t)n_frames * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200dab_stage_msc(b200dab_ctx* ctx, const int8_t* soft, int n_frames, const b200dab_subch_t* sc, uint8_t* frames)
+{
+    if (!ctx || !soft || !sc || !frames || n_frames < 4) return -1;
+    cudaSetDevice(ctx->device);
+    if (upload_soft(ctx, soft, n_frames)) return -1;
+    std::vector<b200dab_subch_t> v(1, *sc);
+    std::vector<size_t> off;
+    size_t total = 0;
+    if (ctx->msc(n_frames, v, off, &total)) return -1;
+    const int n_rows = 4 * n_frames - 15;
+    CKC(cudaMemcpyAsync(frames, ctx->d_msc_out.p, (size_t)n_rows * sc->bitrate * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200dab_stage_dabplus(b200dab_ctx* ctx, uint8_t* frames, int n_rows, int bitrate, b200dab_au_t* aus, int32_t* n_aus, int max_aus, int64_t* stats)
+{
+    if (!ctx || !frames || n_rows < 5 || bitrate % 8) return -1;
+    cudaSetDevice(ctx->device);
+    const int pitch = bitrate * 3;
+    CKC(ctx->d_msc_out.ensure((size_t)n_rows * pitch + 256));
+    CKC(cudaMemcpyAsync(ctx->d_msc_out.p, frames, (size_t)n_rows * pitch, cudaMemcpyHostToDevice, ctx->stream));
+    DabPlusJob j;
+    j.frames_off = 0; j.n_rows = n_rows; j.pitch = pitch; j.s = bitrate / 8; j.sf_off = 0; j.max_sf = n_rows / 5; j.flag_off = 0;
+    std::vector<DabPlusJob> jobs(1, j);
+    if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), jobs, j.max_sf, n_rows)) return -1;
+    std::vector<SfInfo> sf(j.max_sf);
+    CKC(cudaMemcpyAsync(frames, ctx->d_msc_out.p, (size_t)n_rows * pitch, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(sf.data(), ctx->d_sf.p, sf.size() * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    int64_t st[5] = {0, 0, 0, 0, 0};
+    for (int m = 0; m < j.max_sf; m++) {
+        const SfInfo& s = sf[m];
+        if (!s.valid) continue;
+        st[0]++; st[1] += s.rs_corrected; st[2] += s.rs_bit_errors; st[3] += s.rs_uncorrectable; st[4] += s.firecode_ok ? 0 : 1;
+        for (int a = 0; a < s.n_aus && n < max_aus; a++) {
+            b200dab_au_t au;
+            au.subch_index = 0; au.superframe = m; au.cif = s.row; au.offset = s.row * pitch + s.au_off[a]; au.length = s.au_len[a];
+            au.crc_ok = s.au_ok[a]; au.header = s.header;
+            if (aus) aus[n] = au;
+            n++;
+        }
+    }
+    if (n_aus) *n_aus = n;
+    if (stats) memcpy(stats, st, sizeof st);
+    return 0;
+}
+
+int b200dab_stage_tii_fold(b200dab_ctx* ctx, const float* nulls, int n, float* fold)
+{
+    if (!ctx || !nulls || n <= 0 || !fold) return -1;
+    cudaSetDevice(ctx->device);
+    CKC(ctx->d_tmp_a.ensure((size_t)n * DAB_NFFT * 8));
+    CKC(ctx->d_fold.ensure((size_t)n * TII_SPECTRUM_BINS * 4));
+    CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, nulls, (size_t)n * DAB_NFFT * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_tii_fold_nulls<<<n, 256, 0, ctx->stream>>>(ctx->d_tmp_a.as<float2>(), ctx->d_tw.as<float2>(), ctx->d_fold.as<float>());
+    ctx->launches += 1;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(fold, ctx->d_fold.p, (size_t)n * TII_SPECTRUM_BINS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200dab_stage_tii_detect(b200dab_ctx* ctx, const float* fold, const float* norm, const int32_t* sign, int n, float thr_k, b200dab_tii_t* out)
+{
+    if (!ctx || !fold || !norm || !sign || n <= 0 || !out) return -1;
+    cudaSetDevice(ctx->device);
+    CKC(ctx->d_fold.ensure((size_t)n * TII_SPECTRUM_BINS * 4));
+    CKC(ctx->d_norm.ensure((size_t)n * 4));
+    CKC(ctx->d_sign.ensure((size_t)n * 4));
+    CKC(ctx->d_windows.ensure(sizeof(int2)));
+    CKC(ctx->d_tii.ensure(sizeof(TiiResult)));
+    const int2 win = make_int2(0, n);
+    CKC(cudaMemcpyAsync(ctx->d_fold.p, fold, (size_t)n * TII_SPECTRUM_BINS * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_norm.p, norm, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_sign.p, sign, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_windows.p, &win, sizeof win, cudaMemcpyHostToDevice, ctx->stream));
+    k_tii_detect<<<1, 384, 0, ctx->stream>>>(ctx->d_fold.as<float>(), ctx->d_norm.as<float>(), ctx->d_sign.as<int>(), ctx->d_windows.as<int2>(), thr_k,
+                                            ctx->d_tii.as<TiiResult>());
+    ctx->launches += 1;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(out, ctx->d_tii.p, sizeof(TiiResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// k_dabplus.cuh -- FIB CRC, DAB+ superframe synchronisation (fire code), RS(120,110) correction, AU split + CRC.
+//
+// Replaces the reference core's FIB CRC check, firecode search, libfec decode_rs_char calls and AU CRC check
+// (observable through dabsdrNtfPeriodic_t fibErrorCntr/rs*/mscCrc* (dabsdr.h:151-166) and the
+// access units handed to the audio callback (dabsdr.h:71-78)).
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ uint16_t crc16_ccitt_dev(const uint8_t* __restrict__ p, int n, uint16_t init, uint16_t poly)
+{
+    uint32_t crc = init;
+    for (int i = 0; i < n; i++) {
+        crc ^= (uint32_t)p[i] << 8;
+#pragma unroll
+        for (int b = 0; b < 8; b++) crc = (crc & 0x8000u) ? ((crc << 1) ^ poly) & 0xffffu : (crc << 1) & 0xffffu;
+    }
+    return (uint16_t)crc;
+}
+
+// one thread per FIB (32 bytes): ok[i] = CRC-16 (0x1021, init 0xFFFF, inverted) matches
+__global__ void __launch_bounds__(256) k_fib_crc(const uint8_t* __restrict__ fibs, int n_fib, uint8_t* __restrict__ ok)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_fib) return;
+    const uint8_t* f = fibs + (size_t)i * 32;
+    uint16_t crc = (uint16_t)~crc16_ccitt_dev(f, 30, 0xFFFF, 0x1021);
+    ok[i] = crc == (uint16_t)((f[30] << 8) | f[31]);
+}
+
+struct DabPlusJob {
+    long long frames_off;   // byte offset of row 0 of this sub-channel's logical frames
+    int n_rows;             // logical frames available
+    int pitch;              // bytes per logical frame = 24 * s
+    int s;                  // RS codewords per superframe = bitrate / 8
+    int sf_off;             // index of this job's first superframe slot in the per-superframe arrays
+    int max_sf;             // slots reserved = n_rows / 5
+    int flag_off;           // index into the per-row firecode flag array
+};
+struct SfInfo {             // per superframe slot
+    int valid;              // 1 = slot used (inside the aligned run)
+    int row;                // first logical frame
+    int rs_corrected, rs_bit_errors, rs_uncorrectable;
+    int firecode_ok;
+    int n_aus;
+    int au_off[6], au_len[6], au_ok[6];
+    int header;             // superframe byte 2
+};
+
+// firecode over bytes 2..10 of every logical frame (pre-RS, like the reference, which needs it to find alignment)
+__global__ void __launch_bounds__(256) k_firecode_scan(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
+                                                       uint8_t* __restrict__ flags)
+{
+    const DabPlusJob job = jobs[blockIdx.y];
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= job.n_rows) return;
+    const uint8_t* f = frames + job.frames_off + (size_t)r * job.pitch;
+    uint16_t fc = crc16_ccitt_dev(f + 2, 9, 0, 0x782F);
+    flags[job.flag_off + r] = (fc == (uint16_t)((f[0] << 8) | f[1])) && ((f[0] | f[1] | f[2]) != 0);
+}
+
+// one warp per job: pick the residue (row mod 5) with most firecode hits; mark the superframe slots
+__global__ void __launch_bounds__(32) k_sf_align(const DabPlusJob* __restrict__ jobs, const uint8_t* __restrict__ flags,
+                                                 SfInfo* __restrict__ sf, int* __restrict__ residue_out)
+{
+    const DabPlusJob job = jobs[blockIdx.x];
+    const int lane = threadIdx.x;
+    int cnt[5] = {0, 0, 0, 0, 0};
+    for (int r = lane; r < job.n_rows; r += 32)
+        if (flags[job.flag_off + r]) cnt[r % 5]++;
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+    int best = -1, bc = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) if (cnt[k] > bc) { bc = cnt[k]; best = k; }
+    if (lane == 0) residue_out[blockIdx.x] = best;
+    for (int m = lane; m < job.max_sf; m += 32) {
+        SfInfo* o = sf + job.sf_off + m;
+        const int row = best + 5 * m;
+        o->valid = (best >= 0 && row + 5 <= job.n_rows) ? 1 : 0;
+        o->row = row;
+        o->rs_corrected = o->rs_bit_errors = o->rs_uncorrectable = 0;
+        o->firecode_ok = 0; o->n_aus = 0; o->header = 0;
+    }
+}
+
+// ---- GF(2^8) / 0x11D
+struct GfTables { uint8_t exp[512]; uint8_t log[256]; };
+__device__ __forceinline__ uint8_t gf_mul(const GfTables& g, uint8_t a, uint8_t b) { return (a && b) ? g.exp[g.log[a] + g.log[b]] : 0; }
+__device__ __forceinline__ uint8_t gf_inv(const GfTables& g, uint8_t a) { return g.exp[255 - g.log[a]]; }
+
+// one thread per RS codeword; grid (ceil(max_sf * s / 128), n_jobs), 128 threads
+__global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
+                                                   SfInfo* __restrict__ sf, const GfTables* __restrict__ gf_g)
+{
+    __shared__ GfTables gf;
+    for (int i = threadIdx.x; i < (int)sizeof(GfTables); i += blockDim.x) reinterpret_cast<uint8_t*>(&gf)[i] = reinterpret_cast<const uint8_t*>(gf_g)[i];
+    __syncthreads();
+    const DabPlusJob job = jobs[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= job.max_sf * job.s) return;
+    const int m = idx / job.s, j = idx - m * job.s;
+    SfInfo* info = sf + job.sf_off + m;
+    if (!info->valid) return;
+    uint8_t* base = frames + job.frames_off + (size_t)info->row * job.pitch;
+    const int s = job.s, n = 120, nroots = 10;
+    uint8_t S[10];
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < nroots; i++) S[i] = 0;
+    for (int k = 0; k < n; k++) {
+        const uint8_t c = base[j + s * k];
+#pragma unroll
+        for (int i = 0; i < nroots; i++) {
+            uint8_t v = S[i];
+            v = v ? gf.exp[gf.log[v] + i] : 0;            // * alpha^i
+            S[i] = v ^ c;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < nroots; i++) nz |= S[i];
+    if (!nz) return;
+    // Berlekamp-Massey
+    uint8_t Lm[12], B[12], T[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { Lm[i] = 0; B[i] = 0; }
+    Lm[0] = 1; B[0] = 1;
+    int el = 0, mm = 1; uint8_t bb = 1;
+    for (int r = 0; r < nroots; r++) {
+        uint8_t d = S[r];
+        for (int i = 1; i <= el; i++) d ^= gf_mul(gf, Lm[i], S[r - i]);
+        if (d == 0) { mm++; continue; }
+        for (int i = 0; i < 12; i++) T[i] = Lm[i];
+        const uint8_t coef = gf_mul(gf, d, gf_inv(gf, bb));
+        for (int i = 0; i + mm < 12; i++) Lm[i + mm] ^= gf_mul(gf, coef, B[i]);
+        if (2 * el <= r) { el = r + 1 - el; for (int i = 0; i < 12; i++) B[i] = T[i]; bb = d; mm = 1; } else mm++;
+    }
+    if (el > nroots / 2) { atomicAdd(&info->rs_uncorrectable, 1); return; }
+    // Chien search over the 120 positions
+    int pos[5], np = 0;
+    for (int k = 0; k < n; k++) {
+        const int p = n - 1 - k;
+        const uint8_t xinv = gf.exp[(255 - p) % 255];
+        uint8_t v = 0, xp = 1;
+        for (int i = 0; i <= el; i++) { v ^= gf_mul(gf, Lm[i], xp); xp = gf_mul(gf, xp, xinv); }
+        if (v == 0) { if (np < 5) pos[np] = k; np++; }
+    }
+    if (np != el) { atomicAdd(&info->rs_uncorrectable, 1); return; }
+    // Forney (first root alpha^0): e = X * Omega(X^-1) / Lambda'(X^-1)
+    uint8_t Om[10];
+    for (int i = 0; i < nroots; i++) {
+        uint8_t v = 0;
+        for (int k = 0; k <= i && k <= el; k++) v ^= gf_mul(gf, Lm[k], S[i - k]);
+        Om[i] = v;
+    }
+    uint8_t ev[5];
+    for (int e = 0; e < np; e++) {
+        const int p = n - 1 - pos[e];
+        const uint8_t X = gf.exp[p % 255], xinv = gf.exp[(255 - p) % 255];
+        uint8_t num = 0, xp = 1;
+        for (int i = 0; i < nroots; i++) { num ^= gf_mul(gf, Om[i], xp); xp = gf_mul(gf, xp, xinv); }
+        uint8_t den = 0;
+        for (int i = 1; i <= el; i += 2) {
+            uint8_t pw = 1;
+            for (int k = 0; k < i - 1; k++) pw = gf_mul(gf, pw, xinv);
+            den ^= gf_mul(gf, Lm[i], pw);
+        }
+        if (den == 0) { atomicAdd(&info->rs_uncorrectable, 1); return; }
+        ev[e] = gf_mul(gf, gf_mul(gf, X, num), gf_inv(gf, den));
+    }
+    int be = 0;
+    for (int e = 0; e < np; e++) { base[j + s * pos[e]] ^= ev[e]; be += __popc((unsigned)ev[e]); }
+    atomicAdd(&info->rs_corrected, np);
+    atomicAdd(&info->rs_bit_errors, be);
+}
+
+// one thread per superframe slot: firecode after RS, header parse, AU CRCs
+__global__ void __launch_bounds__(64) k_au_split(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs, SfInfo* __restrict__ sf)
+{
+    const DabPlusJob job = jobs[blockIdx.y];
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= job.max_sf) return;
+    SfInfo* info = sf + job.sf_off + m;
+    if (!info->valid) return;
+    const uint8_t* p = frames + job.frames_off + (size_t)info->row * job.pitch;
+    const int s = job.s;
+    const uint16_t fc = crc16_ccitt_dev(p + 2, 9, 0, 0x782F);
+    const int fok = (fc == (uint16_t)((p[0] << 8) | p[1])) && ((p[0] | p[1] | p[2]) != 0);
+    info->firecode_ok = fok;
+    info->header = p[2];
+    if (!fok) return;
+    const int dac = (p[2] >> 6) & 1, sbr = (p[2] >> 5) & 1;
+    const int num = dac ? (sbr ? 3 : 6) : (sbr ? 2 : 4);
+    const int first = dac ? (sbr ? 6 : 11) : (sbr ? 5 : 8);
+    int st[7];
+    st[0] = first;
+    for (int i = 1; i < num; i++) {
+        const int bitpos = 24 + 12 * (i - 1), byte = bitpos >> 3;
+        st[i] = (bitpos & 7) ? (((p[byte] & 0x0F) << 8) | p[byte + 1]) : ((p[byte] << 4) | (p[byte + 1] >> 4));
+    }
+    st[num] = 110 * s;
+    for (int i = 0; i < num; i++) if (st[i + 1] <= st[i] + 2 || st[i + 1] > 110 * s) return;
+    for (int i = 0; i < num; i++) {
+        const int len = st[i + 1] - st[i];
+        info->au_off[i] = st[i];
+        info->au_len[i] = len - 2;
+        const uint16_t crc = (uint16_t)~crc16_ccitt_dev(p + st[i], len - 2, 0xFFFF, 0x1021);
+        info->au_ok[i] = crc == (uint16_t)((p[st[i] + len - 2] << 8) | p[st[i] + len - 1]);
+    }
+    info->n_aus = num;
+}

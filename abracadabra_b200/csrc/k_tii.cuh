@@ -1,0 +1,156 @@
+// k_tii.cuh -- Transmitter Identification Information: null-symbol FFT, carrier-pair fold, comb search.
+//
+// Replaces the TII detector inside the reference core, whose results reach RadioControl as DABSDR_NID_TII
+// (dabsdrNtfTii_t, dabsdr.h:372-384; consumer src/radiocontrol.cpp:2479-2493, src/tii/tiibackend.cpp:70-88) and whose
+// carrier layout is restated in the open source at src/dabtables.cpp:2338-2444 (pattern table, pair = 24 b + sub).
+// Black-box behaviour reproduced: TII lives in the nulls of frames whose CIF
+// counter is 0 mod 8; the other nulls are subtracted as noise reference; 384-bin spectrum = 192 pairs x 2 carriers
+// folded over the four 384-carrier quarters; levels are linear in amplitude and relative to the data carriers.
+#pragma once
+#include "common.cuh"
+#include "k_ofdm.cuh"
+
+// one CTA per frame: fold[f][2p+e] = sum over the 4 quarters of |N[k]|, k = 384 q + 2p + e ; norm[f] = rms PRS carrier magnitude
+template <int FMT>
+__global__ void __launch_bounds__(256) k_tii_fold(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+                                                  const float2* __restrict__ tw, float* __restrict__ fold, float* __restrict__ norm)
+{
+    __shared__ float2 buf[FFT_BUF_LEN];
+    __shared__ float red[32];
+    const int t = threadIdx.x;
+    const FrameInfo fr = frames[blockIdx.x];
+    const double cyc_per = (double)fr.cfo_hz / (double)DAB_FS;
+    const float cpp = (float)cyc_per;
+    // PRS symbol -> reference carrier magnitude
+    load_symbol<FMT>(buf, raw, nsamp, fr.t_f, 0.f, cpp);
+    fft2048_smem(buf, tw);
+    float acc = 0.f;
+    for (int c = t; c < DAB_NCARR; c += 256) {
+        float2 v = buf[fft_phys(fft_pos(carrier_bin(c)))];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    acc = block_sum(acc, red);
+    if (t == 0) norm[fr.slot] = sqrtf(acc / (float)DAB_NCARR);
+    __syncthreads();
+    // null symbol: its useful part ends where the PRS cyclic prefix begins
+    double base = cyc_per * (double)(-(int64_t)DAB_T_SYM);
+    base -= floor(base);
+    load_symbol<FMT>(buf, raw, nsamp, fr.t_f - DAB_T_SYM, (float)base, cpp);
+    fft2048_smem(buf, tw);
+    float* o = fold + (size_t)fr.slot * TII_SPECTRUM_BINS;
+    for (int i = t; i < TII_SPECTRUM_BINS; i += 256) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float2 v = buf[fft_phys(fft_pos(carrier_bin(384 * q + i)))];
+            a += sqrtf(v.x * v.x + v.y * v.y);
+        }
+        o[i] = a;
+    }
+}
+
+// stage variant for pre-cut null symbols: in [n][2048] complex64 -> fold [n][384]
+__global__ void __launch_bounds__(256) k_tii_fold_nulls(const float2* __restrict__ nulls, const float2* __restrict__ tw, float* __restrict__ fold)
+{
+    __shared__ float2 buf[FFT_BUF_LEN];
+    const int t = threadIdx.x;
+    const float2* src = nulls + (size_t)blockIdx.x * DAB_NFFT;
+#pragma unroll
+    for (int r = 0; r < 8; r++) buf[fft_phys(t + 256 * r)] = __ldg(src + t + 256 * r);
+    fft2048_smem(buf, tw);
+    float* o = fold + (size_t)blockIdx.x * TII_SPECTRUM_BINS;
+    for (int i = t; i < TII_SPECTRUM_BINS; i += 256) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float2 v = buf[fft_phys(fft_pos(carrier_bin(384 * q + i)))];
+            a += sqrtf(v.x * v.x + v.y * v.y);
+        }
+        o[i] = a;
+    }
+}
+
+struct TiiResult {
+    int n_ids;
+    int n_tii_frames;
+    float norm;                 // sum of the reference magnitudes of the TII frames * 4
+    float noise;
+    unsigned char main_id[TII_MAX_IDS];
+    unsigned char sub_id[TII_MAX_IDS];
+    float level[TII_MAX_IDS];
+    float spectrum[TII_SPECTRUM_BINS];
+};
+
+__constant__ unsigned char c_tii_pattern[70];
+
+// one CTA (384 threads) per window of frames [w0, w1): acc = sum sign[f] * fold[f]; then the comb search.
+// sign[f]: +1 TII null, -1 reference null, 0 unusable.
+__global__ void __launch_bounds__(384) k_tii_detect(const float* __restrict__ fold, const float* __restrict__ norm, const int* __restrict__ sign,
+                                                    const int2* __restrict__ windows, float thr_k, TiiResult* __restrict__ res)
+{
+    __shared__ float spec[TII_SPECTRUM_BINS];
+    __shared__ float pair[TII_PAIRS];
+    __shared__ float sorted_rank[TII_PAIRS];
+    __shared__ float s_noise, s_norm, s_peak;
+    __shared__ int s_ntii, s_count;
+    __shared__ unsigned short found[24 * 70];
+    const int t = threadIdx.x;
+    const int2 win = windows[blockIdx.x];
+    float a = 0.f;
+    for (int f = win.x; f < win.y; f++) {
+        const int sg = sign[f];
+        if (sg) a += (float)sg * fold[(size_t)f * TII_SPECTRUM_BINS + t];
+    }
+    spec[t] = a;
+    if (t == 0) {
+        float nm = 0.f; int nt = 0;
+        for (int f = win.x; f < win.y; f++) if (sign[f] > 0) { nm += norm[f]; nt++; }
+        s_norm = nm * 4.f; s_ntii = nt; s_count = 0;
+    }
+    __syncthreads();
+    if (t < TII_PAIRS) pair[t] = spec[2 * t] + spec[2 * t + 1];
+    __syncthreads();
+    // noise level: median of |pair| (rank selection, 192 values)
+    if (t < TII_PAIRS) {
+        const float v = fabsf(pair[t]);
+        int rank = 0;
+        for (int j = 0; j < TII_PAIRS; j++) { float u = fabsf(pair[j]); rank += (u < v || (u == v && j < t)) ? 1 : 0; }
+        sorted_rank[rank] = v;
+    }
+    __syncthreads();
+    if (t == 0) { s_noise = sorted_rank[TII_PAIRS / 2]; s_peak = sorted_rank[TII_PAIRS - 1]; }
+    __syncthreads();
+    const float thr = fmaxf(thr_k * s_noise, 0.05f * s_peak);
+    // comb search: thread (sub, main) tests whether all four blocks of the pattern are lit
+    for (int i = t; i < 24 * 70; i += 384) {
+        const int sub = i / 70, m = i - sub * 70;
+        const unsigned pat = c_tii_pattern[m];
+        unsigned mask = 0; float mn = 1e30f, mx = 0.f, sum_all = 0.f; int cnt = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const float v = pair[24 * b + sub];
+            if (v > thr) { mask |= 0x80u >> b; cnt++; }
+            if (pat & (0x80u >> b)) { mn = fminf(mn, v); mx = fmaxf(mx, v); sum_all += v; }
+        }
+        bool hit = (mask & pat) == pat;
+        if (hit && cnt > 4) hit = mn >= 0.5f * mx;      // several transmitters share this sub id: keep consistent combs only
+        found[i] = hit ? 1 : 0;
+    }
+    __syncthreads();
+    if (t == 0) {
+        TiiResult* r = res + blockIdx.x;
+        int n = 0;
+        for (int sub = 0; sub < 24 && n < TII_MAX_IDS; sub++)
+            for (int m = 0; m < 70 && n < TII_MAX_IDS; m++)
+                if (found[sub * 70 + m]) {
+                    const unsigned pat = c_tii_pattern[m];
+                    float sum = 0.f;
+                    for (int b = 0; b < 8; b++) if (pat & (0x80u >> b)) sum += pair[24 * b + sub];
+                    r->main_id[n] = (unsigned char)m; r->sub_id[n] = (unsigned char)sub;
+                    r->level[n] = s_norm > 0.f ? (sum / 8.f) / s_norm : 0.f;
+                    n++;
+                }
+        r->n_ids = n; r->n_tii_frames = s_ntii; r->norm = s_norm; r->noise = s_noise;
+    }
+    res[blockIdx.x].spectrum[t] = fmaxf(spec[t], 0.f);
+}

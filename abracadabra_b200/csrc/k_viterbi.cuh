@@ -1,0 +1,194 @@
+// k_viterbi.cuh -- time de-interleave + de-puncture (gather) and K=7 rate-1/4 Viterbi decoding with full traceback.
+//
+// Replaces the reference core's time de-interleaver, de-puncturer, float Viterbi decoder and energy-dispersal
+// descrambler (code: polynomials 133,171,145,133, puncturing vectors PI 1..24 + tail,
+// 16-CIF delay table {0,8,4,12,...}).
+//
+// Layout: codewords of one sub-channel (one per CIF) are decoded 32 at a time, one codeword per thread, so every
+// global access is a coalesced 128/256-byte row:
+//   vin [group][step][32 lanes] uint32 : the 4 de-punctured int8 soft bits of that trellis step (0 = punctured)
+//   dec [group][step][32 lanes] uint2  : the 64 survivor decisions of that step
+// Path metrics are int16, two states per 32-bit register ((j, j+16) and (j+32, j+48)), updated with the packed
+// VIADD.16x2 / VIMNMX.S16x2 instructions; VIMNMX delivers both decision predicates of a register pair for free.
+#pragma once
+#include "common.cuh"
+
+struct VitJob {
+    long long soft_base;   // byte offset of column 0 of row 0 inside a frame's soft block
+    long long vin_off;     // uint32 index of this job's first group in vin
+    long long dec_off;     // uint2 index in dec
+    long long out_off;     // byte offset in out
+    int row_pitch;         // bytes between the (up to 4) rows inside one frame's soft block
+    int use_tdi;           // 1: bit p comes from row r + delay[p & 15]
+    int row0;              // absolute row (CIF / FIC vector index) of codeword 0
+    int max_row;           // last absolute row that exists in the soft buffer
+    int n_rows;            // number of codewords
+    int steps;             // trellis steps = n_info + 6
+    int n_info;
+    int stepinfo_off;      // index into the stepinfo table; entry [steps] is the sentinel (total punctured bits << 4)
+    int out_pitch;         // bytes per decoded row = n_info / 8
+    int kind;              // 0 FIC, 1 MSC
+    int pad_[2];
+};
+struct VitGroup { int job; int g_in_job; };
+
+__constant__ int c_tdi_delay[16] = {0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15};
+
+#define GATHER_STEPS 64
+#define GATHER_PITCHW 67
+
+// grid (n_groups, ceil(max_steps / 64)), 256 threads
+__global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ soft, const VitJob* __restrict__ jobs,
+                                                const VitGroup* __restrict__ groups, const uint32_t* __restrict__ stepinfo,
+                                                uint32_t* __restrict__ vin)
+{
+    __shared__ uint32_t tile[47 * GATHER_PITCHW];
+    const VitGroup grp = groups[blockIdx.x];
+    const VitJob job = jobs[grp.job];
+    const int s0 = blockIdx.y * GATHER_STEPS;
+    if (s0 >= job.steps) return;
+    const int s1 = min(s0 + GATHER_STEPS, job.steps);
+    const uint32_t* si = stepinfo + job.stepinfo_off;
+    const int p0 = (int)(__ldg(si + s0) >> 4), p1 = (int)(__ldg(si + s1) >> 4);
+    const int p0a = p0 & ~3;
+    const int nwords = (p1 - p0a + 3) >> 2;              // <= 65
+    const int nrows = job.use_tdi ? 47 : 32;
+    const int rbase = job.row0 + grp.g_in_job * 32;
+    for (int idx = threadIdx.x; idx < nrows * nwords; idx += 256) {
+        const int row = idx / nwords, w = idx - row * nwords;
+        int r = rbase + row;
+        if (r > job.max_row) r = job.max_row;
+        const size_t addr = (size_t)(r >> 2) * DAB_FRAME_SOFT + (size_t)job.soft_base + (size_t)(r & 3) * job.row_pitch + p0a + 4 * w;
+        tile[row * GATHER_PITCHW + w] = __ldg(reinterpret_cast<const uint32_t*>(soft + addr));
+    }
+    __syncthreads();
+    const int8_t* tb = reinterpret_cast<const int8_t*>(tile);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* out = vin + job.vin_off + ((size_t)grp.g_in_job * job.steps) * 32 + lane;
+    for (int s = s0 + warp; s < s1; s += 8) {
+        const uint32_t info = __ldg(si + s);
+        int p = (int)(info >> 4);
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (info & (1u << q)) {
+                const int d = job.use_tdi ? c_tdi_delay[p & 15] : 0;
+                const uint32_t b = (uint8_t)tb[(lane + d) * (GATHER_PITCHW * 4) + (p - p0a)];
+                word |= b << (8 * q);
+                p++;
+            }
+        }
+        out[(size_t)s * 32] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ ACS
+__host__ __device__ constexpr int vit_parity7(int x) { return (x ^ (x >> 1) ^ (x >> 2) ^ (x >> 3) ^ (x >> 4) ^ (x >> 5) ^ (x >> 6)) & 1; }
+// code bit q (0..2; bit 3 repeats bit 0) for state j (newest input = LSB) and input 0; polynomials bit-reversed so that
+// bit d of the window (state << 1 | input) is a[i-d]
+__host__ __device__ constexpr int vit_cbit(int j, int q) { return vit_parity7((j << 1) & (q == 0 ? 0155 : q == 1 ? 0117 : 0123)); }
+
+template <int J>
+__device__ __forceinline__ void vit_bfly(const uint32_t (&L)[16], const uint32_t (&H)[16], uint32_t (&E)[16], uint32_t (&O)[16],
+                                         const uint32_t (&BP)[8], uint32_t& dlo, uint32_t& dhi)
+{
+    // low halves: butterfly of states (J, J+32) -> (2J, 2J+1); high halves: (J+16, J+48) -> (2J+32, 2J+33)
+    constexpr int k = vit_cbit(J, 0) * 4 + vit_cbit(J, 1) * 2 + vit_cbit(J, 2);   // BP[k] = +beta, BP[7-k] = -beta
+    bool ph, pl;
+    const uint32_t t0 = __vadd2(L[J], BP[k]), t1 = __vadd2(H[J], BP[7 - k]);
+    E[J] = __vibmax_s16x2(t0, t1, &ph, &pl);          // predicate = (t0 >= t1): survivor from the lower predecessor
+    if (!pl) dlo |= 1u << (2 * J);
+    if (!ph) dhi |= 1u << (2 * J);
+    const uint32_t u0 = __vadd2(L[J], BP[7 - k]), u1 = __vadd2(H[J], BP[k]);
+    O[J] = __vibmax_s16x2(u0, u1, &ph, &pl);
+    if (!pl) dlo |= 1u << (2 * J + 1);
+    if (!ph) dhi |= 1u << (2 * J + 1);
+}
+template <int J> struct VitUnroll {
+    static __device__ __forceinline__ void run(const uint32_t (&L)[16], const uint32_t (&H)[16], uint32_t (&E)[16], uint32_t (&O)[16],
+                                               const uint32_t (&BP)[8], uint32_t& dlo, uint32_t& dhi)
+    {
+        VitUnroll<J - 1>::run(L, H, E, O, BP, dlo, dhi);
+        vit_bfly<J>(L, H, E, O, BP, dlo, dhi);
+    }
+};
+template <> struct VitUnroll<-1> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[16], const uint32_t (&)[16], uint32_t (&)[16], uint32_t (&)[16],
+                                               const uint32_t (&)[8], uint32_t&, uint32_t&) {}
+};
+
+// one warp per group of 32 codewords; grid = n_groups (longest groups first)
+__global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin, uint2* __restrict__ dec, const VitJob* __restrict__ jobs,
+                                                const VitGroup* __restrict__ groups, const uint32_t* __restrict__ prbs_w,
+                                                uint8_t* __restrict__ out)
+{
+    const VitGroup grp = groups[blockIdx.x];
+    const VitJob job = jobs[grp.job];
+    const int lane = threadIdx.x;
+    const int steps = job.steps;
+    const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
+    uint2* d = dec + job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
+
+    uint32_t L[16], H[16], E[16], O[16];
+    const uint32_t PEN = 0xE000E000u;                 // VIT_START_PENALTY = -8192 in both halves
+#pragma unroll
+    for (int j = 0; j < 16; j++) { L[j] = PEN; H[j] = PEN; }
+    L[0] = 0xE0000000u;                               // state 0 starts at 0, state 16 at the penalty
+
+    uint32_t w_next = __ldg(in);
+    for (int t = 0; t < steps; t++) {
+        const uint32_t w = w_next;
+        if (t + 1 < steps) w_next = __ldg(in + (size_t)(t + 1) * 32);
+        if ((t & (VIT_NORM_PERIOD - 1)) == 0) {
+            const uint32_t m0 = __byte_perm(L[0], 0, 0x1010);       // (M[0], M[0])
+            const uint32_t nm = __vneg2(m0);
+#pragma unroll
+            for (int j = 0; j < 16; j++) { L[j] = __vadd2(L[j], nm); H[j] = __vadd2(H[j], nm); }
+        }
+        const int a0 = (int8_t)(w), a1 = (int8_t)(w >> 8), a2 = (int8_t)(w >> 16), a3 = (int8_t)(w >> 24);
+        const int T = a0 + a3, X1 = a1 + a2, X2 = a1 - a2;
+        // BP[k], k = c0*4 + c1*2 + c2 (1 = code bit 1 = negative contribution): low half  (1-2c0) T + x,
+        //                                                                      high half -(1-2c0) T + x  (state + 16 flips c0, c3)
+        uint32_t BP[8];
+        const int xs[4] = {X1, X2, -X2, -X1};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            BP[i] = __byte_perm((uint32_t)(T + xs[i]), (uint32_t)(-T + xs[i]), 0x5410);
+            BP[4 + i] = __byte_perm((uint32_t)(-T + xs[i]), (uint32_t)(T + xs[i]), 0x5410);
+        }
+        uint32_t dlo = 0, dhi = 0;
+        VitUnroll<15>::run(L, H, E, O, BP, dlo, dhi);
+        d[(size_t)t * 32] = make_uint2(dlo, dhi);
+        // re-pair: L'[m] = (new[m], new[m+16]), H'[m] = (new[m+32], new[m+48])
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            L[2 * j] = __byte_perm(E[j], E[j + 8], 0x5410);     H[2 * j] = __byte_perm(E[j], E[j + 8], 0x7632);
+            L[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x5410); H[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x7632);
+        }
+    }
+
+    // ---- traceback from state 0 (zero-terminated code); decisions of one step: bit s of (dlo | dhi << 32)
+    const int row = grp.g_in_job * 32 + lane;
+    int s = 0;
+    int t = steps - 1;
+    for (; t >= job.n_info; t--) {                     // tail bits: no output
+        const uint2 dd = d[(size_t)t * 32];
+        const uint32_t wsel = (s & 32) ? dd.y : dd.x;
+        const int bit = (wsel >> (s & 31)) & 1;
+        s = (s >> 1) | (bit << 5);
+    }
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + job.out_off + (size_t)row * job.out_pitch);
+    const bool live = row < job.n_rows;
+    for (int c = job.n_info / 32 - 1; c >= 0; c--) {
+        uint32_t word = 0;
+#pragma unroll 8
+        for (int i = 31; i >= 0; i--) {
+            const uint2 dd = d[(size_t)(32 * c + i) * 32];
+            word |= (uint32_t)(s & 1) << (31 - i);
+            const uint32_t wsel = (s & 32) ? dd.y : dd.x;
+            const int bit = (wsel >> (s & 31)) & 1;
+            s = (s >> 1) | (bit << 5);
+        }
+        if (live) orow[c] = __byte_perm(word, 0, 0x0123) ^ __ldg(prbs_w + c);
+    }
+}

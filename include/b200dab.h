@@ -1,0 +1,142 @@
+/*
+ * b200dab.h -- C ABI of the B200-native DAB mode I receive path (libb200dab.so).
+ *
+ * This is the thin layer the host side calls into CUDA through: plain pointers and sizes, no C++ or torch types.
+ * It is the batch form of what the reference obtains from its closed core through the pull interface
+ *     dabsdrRegisterInputFcn / dabsdrRegisterDummyInputFcn      (lib/linux_x86_64/dabsdr.h:405-406, feed:
+ *                                                                src/input/inputdevice.cpp:70-131 getSamples/skipSamples)
+ * and receives back through the five callbacks                  (dabsdr.h:390-394, src/radiocontrol.cpp:2235-2609).
+ * The drop-in with the reference's own 24 entry points (include/dabsdr_abi.h, libdabsdr.so.4) is built on top of
+ * these calls in abracadabra_b200/csrc/dabsdr_shim.cpp; INTEGRATION.md shows both bindings.
+ *
+ * Every function returns 0 on success and a negative value on failure (b200dab_last_error gives the text).
+ * There is no CPU fallback: b200dab_create fails when no CUDA device is present.
+ */
+#ifndef B200DAB_H
+#define B200DAB_H
+#include <stdint.h>
+#include "b200dab_spec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200DAB_API __attribute__((visibility("default")))
+#else
+#define B200DAB_API
+#endif
+
+typedef struct b200dab_ctx b200dab_ctx;
+
+/* Sub-channel organisation: what FIG 0/1 carries and RadioControl sees as SubChAddr/SubChSize/protection in
+ * dabsdrServiceCompListItem_t (dabsdr.h:194-243).  The protection profile is given explicitly as up to four segments
+ * of L 128-bit blocks with puncturing index PI (EN 300 401 11.3) so that EEP-A/B and UEP share one code path. */
+typedef struct {
+    int32_t subch_id;
+    int32_t start_cu;        /* 0..863 */
+    int32_t size_cu;
+    int32_t bitrate;         /* kbit/s; information bits per 24 ms logical frame = 24 * bitrate */
+    int32_t n_seg;
+    int32_t seg_len[4];
+    int32_t seg_pi[4];
+    int32_t kind;            /* 0 = DAB (MP2) audio / data, 1 = DAB+ audio (superframes, RS, AUs) */
+    int32_t uep_index;       /* -1 for EEP */
+    int32_t prot_level;      /* EEP: 0..3 (+4 for option B); UEP: level 1..5 */
+} b200dab_subch_t;
+
+#define B200DAB_MAX_SUBCH 64
+#define B200DAB_MEM_HOST   0
+#define B200DAB_MEM_DEVICE 1
+
+/* option flags of b200dab_decode */
+#define B200DAB_OPT_TII        1u    /* run the TII detector */
+#define B200DAB_OPT_NO_MSC     2u    /* stop after the FIC (ensemble discovery only) */
+#define B200DAB_OPT_SYMSTAT    4u    /* keep per-symbol soft-bit statistics (SNR estimate) */
+
+/* per access unit (DAB+), in stream order per sub-channel */
+typedef struct {
+    int32_t subch_index;     /* index into the sub-channel table of the result */
+    int32_t superframe;      /* superframe number within the sub-channel */
+    int32_t cif;             /* logical frame (CIF row) the superframe starts at */
+    int32_t offset;          /* byte offset of the payload inside that sub-channel's frame buffer */
+    int32_t length;          /* payload bytes (CRC stripped) */
+    int32_t crc_ok;
+    int32_t header;          /* superframe byte 2 (dac_rate, sbr, channel mode, ps, surround) */
+} b200dab_au_t;
+
+typedef struct {
+    int32_t n_ids;
+    int32_t n_tii_frames;
+    float norm, noise;
+    uint8_t main_id[TII_MAX_IDS];
+    uint8_t sub_id[TII_MAX_IDS];
+    float level[TII_MAX_IDS];
+    float spectrum[TII_SPECTRUM_BINS];
+} b200dab_tii_t;
+
+/* All pointers below refer to pinned host memory owned by the context; valid until the next decode/destroy. */
+typedef struct {
+    int32_t n_candidates;            /* null-symbol candidates examined */
+    int32_t n_frames;                /* frames accepted */
+    int32_t n_slots;                 /* frame slots spanned (n_slots - n_frames = lost frames) */
+    const int64_t *t_f;              /* [n_slots] FFT window start of symbol 0, -1 for a lost slot */
+    const float *cfo_hz;             /* [n_slots] */
+    const float *cir_ratio;          /* [n_slots] PRS correlation sharpness */
+    const uint8_t *fibs;             /* [n_slots * 12][32] */
+    const uint8_t *fib_ok;           /* [n_slots * 12] */
+    int32_t n_subch;
+    const b200dab_subch_t *subch;    /* [n_subch] as used for MSC decoding (given or discovered from FIG 0/1) */
+    const uint8_t *const *frames;    /* [n_subch] -> [n_rows][24 * s] logical frames (RS-corrected in place for DAB+) */
+    const int32_t *frame_rows;       /* [n_subch] rows = n_cif - 15 */
+    int32_t n_aus;
+    const b200dab_au_t *aus;         /* [n_aus] */
+    int64_t rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail, superframes;
+    int32_t n_tii;
+    const b200dab_tii_t *tii;        /* [n_tii] one per 40-frame window */
+    const float *symstat;            /* [n_slots * 75 * 2] mean |soft|, mean soft^2 before scaling (OPT_SYMSTAT) */
+    float snr_db;                    /* decision-directed estimate over all frames (OPT_SYMSTAT) */
+    int32_t gpu_launches;            /* kernels launched by this call */
+} b200dab_result_t;
+
+B200DAB_API int b200dab_version(void);
+B200DAB_API int b200dab_create(b200dab_ctx **out, int device);
+B200DAB_API void b200dab_destroy(b200dab_ctx *ctx);
+B200DAB_API const char *b200dab_last_error(b200dab_ctx *ctx);
+B200DAB_API void *b200dab_stream(b200dab_ctx *ctx);                 /* cudaStream_t the context launches on */
+
+/* protection profile helpers (EN 300 401 tables 7/8 and 11.3.2); fill seg_len/seg_pi/size_cu/bitrate */
+B200DAB_API int b200dab_profile_eep(int bitrate, int level /*1..4*/, int option /*0=A,1=B*/, b200dab_subch_t *out);
+B200DAB_API int b200dab_profile_uep(int table_index, b200dab_subch_t *out);
+/* parse FIBs (CRC-checked by the caller) into a sub-channel table: FIG 0/1 + FIG 0/2 (ASCTy 63 = DAB+) */
+B200DAB_API int b200dab_parse_subch(const uint8_t *fibs, const uint8_t *fib_ok, int n_fibs, b200dab_subch_t *out, int max_out);
+
+/* Whole hot path over one recording (or chunk): sync -> FFT -> DQPSK -> de-interleave -> Viterbi -> FIB CRC ->
+ * [FIG 0/1 discovery] -> MSC Viterbi -> RS/AU -> TII.  iq: interleaved I,Q in `fmt`; mem says where it lives. */
+B200DAB_API int b200dab_decode(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, int mem,
+                               const b200dab_subch_t *subch, int n_subch, uint32_t flags, b200dab_result_t *res);
+
+/* ---- stage entry points (host buffers in, host buffers out): the kernels of the path one by one, for parity tests
+ *      against oracle/ and for profiling.  They launch exactly the kernels b200dab_decode launches. */
+B200DAB_API int b200dab_stage_coarse(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, float *P /* n/32 */,
+                                     float *S /* n/32 */, int64_t *cand, int32_t *n_cand, int max_cand);
+B200DAB_API int b200dab_stage_fine(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, const int64_t *cand, int n_cand,
+                                   int64_t *t_f, float *cfo_hz, float *metric /* [n_cand][4] */);
+B200DAB_API int b200dab_stage_demod(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, const int64_t *t_f,
+                                    const float *cfo_hz, int n_frames, int8_t *soft /* [n_frames][230400] */);
+B200DAB_API int b200dab_stage_viterbi(b200dab_ctx *ctx, const int8_t *soft4 /* [n_cw][4*steps] */, int n_cw, int steps,
+                                      uint8_t *bits /* [n_cw][steps-6] one bit per byte, before descrambling */);
+B200DAB_API int b200dab_stage_fic(b200dab_ctx *ctx, const int8_t *soft /* [n_frames][230400] */, int n_frames,
+                                  uint8_t *fibs /* [n_frames*12][32] */, uint8_t *fib_ok);
+B200DAB_API int b200dab_stage_msc(b200dab_ctx *ctx, const int8_t *soft /* [n_frames][230400] */, int n_frames,
+                                  const b200dab_subch_t *sc, uint8_t *frames /* [4*n_frames-15][24*bitrate/8] */);
+B200DAB_API int b200dab_stage_dabplus(b200dab_ctx *ctx, uint8_t *frames /* [n_rows][pitch], corrected in place */, int n_rows,
+                                      int bitrate, b200dab_au_t *aus, int32_t *n_aus, int max_aus, int64_t *stats /* [5] */);
+B200DAB_API int b200dab_stage_tii_fold(b200dab_ctx *ctx, const float *nulls /* [n][2048] complex64 */, int n, float *fold /* [n][384] */);
+B200DAB_API int b200dab_stage_tii_detect(b200dab_ctx *ctx, const float *fold /* [n][384] */, const float *norm /* [n] */,
+                                         const int32_t *sign /* [n] */, int n, float thr_k, b200dab_tii_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI (libb200dab.so), against the CPU checker
+(oracle/daboracle.c) on the same seeded inputs.  Bit-exact for integer/byte/index results; floating-point results
+within the tolerance written next to each comparison."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_coarse_sync_bit_exact(receiver, oracle):
+    for fmt in ("u8", "s16", "f32"):
+        raw, res = cases.config1(6, fmt)
+        P, S, cand = receiver.stage_coarse(raw, fmt)
+        Po = oracle.block_power(raw, fmt)
+        assert np.array_equal(P, Po), fmt                 # same summation order, explicit fma: bit-exact
+        q = oracle.null_metric(Po)
+        co = oracle.candidates(q, oracle.nsamples(raw, fmt))
+        assert np.array_equal(cand, co), fmt
+        assert res.frame0 in cand
+
+
+def test_fine_sync_matches_oracle(receiver, oracle):
+    raw, res = cases.config1(6, "u8")
+    _, _, cand = receiver.stage_coarse(raw, "u8")
+    t_f, cfo, met = receiver.stage_fine(raw, "u8", cand)
+    for i, c in enumerate(cand):
+        to, co, mo = oracle.frame_sync(raw, "u8", c)
+        if mo[2] < 40:      # not a frame (noise candidate): nothing to compare
+            assert met[i, 2] < 40
+            continue
+        assert t_f[i] == to                                # integer timing decision
+        assert abs(cfo[i] - co) <= 0.05                    # Hz; float accumulation order differs
+        assert abs(met[i, 2] - mo[2]) <= 1e-3 * mo[2]
+        assert abs(cfo[i] - res.cfo_hz) < 2.0
+
+
+def test_demod_soft_bits(receiver, oracle):
+    raw, res = cases.config1(6, "u8")
+    _, _, cand = receiver.stage_coarse(raw, "u8")
+    t_f, cfo, met = receiver.stage_fine(raw, "u8", cand)
+    keep = met[:, 2] >= 40
+    t_f, cfo = t_f[keep][:3], cfo[keep][:3]
+    soft = receiver.stage_demod(raw, "u8", t_f, cfo)
+    for i in range(len(t_f)):
+        so = oracle.demod_frame(raw, "u8", t_f[i], cfo[i])
+        d = np.abs(soft[i].astype(np.int32) - so.astype(np.int32))
+        # tolerance: +-1 LSB of the int8 soft bit (FFT rounding and gain reduction order), on at most 0.5 % of the bits
+        assert d.max() <= 1
+        assert (d > 0).mean() < 5e-3
+
+
+def test_viterbi_bit_exact(receiver, oracle):
+    rng = np.random.default_rng(5)
+    for steps, n_cw in ((774, 40), (2310, 33), (1158, 7)):
+        # noisy soft bits around a valid codeword plus pure-noise codewords: decisions (incl. ties) must be identical
+        from abracadabra_b200 import synth
+        info = rng.integers(0, 2, (n_cw, steps - 6), dtype=np.uint8)
+        code = synth.conv_encode(info).astype(np.int32)
+        soft = (1 - 2 * code) * 40 + rng.normal(0, 45, code.shape)
+        soft[n_cw // 2:] = rng.normal(0, 60, soft[n_cw // 2:].shape)
+        punct = rng.random(soft.shape) < 0.3
+        soft[punct] = 0
+        soft = np.clip(np.rint(soft), -127, 127).astype(np.int8)
+        got = receiver.stage_viterbi(soft)
+        for c in range(n_cw):
+            assert np.array_equal(got[c], oracle.viterbi(soft[c])), (steps, c)
+
+
+def test_fic_and_msc_bit_exact(receiver, oracle):
+    raw, res = cases.multi(8, "u8")
+    from abracadabra_b200 import pipeline
+    _, _, cand = receiver.stage_coarse(raw, "u8")
+    t_f, cfo, met = receiver.stage_fine(raw, "u8", cand)
+    keep = met[:, 2] >= 40
+    soft = receiver.stage_demod(raw, "u8", t_f[keep], cfo[keep])
+    nf = soft.shape[0]
+    assert nf == 8
+    fibs, ok = receiver.stage_fic(soft)
+    for f in range(nf):
+        fo, oo = oracle.fic_decode(soft[f, :9216])
+        assert np.array_equal(fibs[12 * f:12 * f + 12], fo)
+        assert np.array_equal(ok[12 * f:12 * f + 12], oo)
+    assert ok.all()
+    assert np.array_equal(fibs.reshape(-1, 96), res.fibs[:nf * 4])
+    cifs = soft[:, 9216:].reshape(nf * 4, 55296)
+    for sc in res.ens.subchannels:
+        got = receiver.stage_msc(soft, pipeline.subch_from_synth(sc))
+        exp = oracle.msc_decode(cifs, oracle.subch_struct(sc))
+        assert np.array_equal(got, exp), sc.subchid
+        assert np.array_equal(got, res.logical[sc.subchid][:got.shape[0]]), sc.subchid
+
+
+def test_dabplus_rs_and_aus(receiver, oracle):
+    raw, res = cases.config1(10, "u8")
+    sc = res.ens.subchannels[0]
+    frames = res.logical[sc.subchid][3:38].copy()        # starts mid-superframe: alignment must be found
+    rng = np.random.default_rng(3)
+    # inject byte errors: up to 5 per RS codeword in some superframes, 6+ (uncorrectable) in one codeword
+    flat = frames.reshape(-1)
+    s = sc.bitrate // 8
+    base = 2 * frames.shape[1]                            # superframe starts at row 2 (global row 5)
+    for sfi in range(3):
+        off = base + sfi * 120 * s
+        for j in range(s):
+            for k in rng.choice(120, size=rng.integers(0, 6), replace=False):
+                flat[off + j + s * k] ^= rng.integers(1, 256)
+    off = base + 4 * 120 * s
+    for k in rng.choice(120, size=8, replace=False):
+        flat[off + 3 + s * k] ^= rng.integers(1, 256)
+    aus, stats, corrected = receiver.stage_dabplus(frames, sc.bitrate)
+    # oracle on the same aligned superframes
+    exp_aus, exp_stats = [], dict(rs_corrected=0, rs_bit_errors=0, rs_uncorrectable=0)
+    n_sf = (frames.shape[0] - 2) // 5
+    for m in range(n_sf):
+        r = oracle.superframe(frames[2 + 5 * m:7 + 5 * m].reshape(-1), s)
+        exp_stats["rs_corrected"] += r["corrected"]; exp_stats["rs_bit_errors"] += r["bit_errors"]
+        exp_stats["rs_uncorrectable"] += r["uncorrectable"]
+        exp_aus += list(zip(r["aus"], r["crc_ok"]))
+        assert np.array_equal(corrected[2 + 5 * m:7 + 5 * m].reshape(-1), r["data"])
+    assert stats["superframes"] == n_sf
+    for k in exp_stats:
+        assert stats[k] == exp_stats[k], k
+    assert stats["rs_uncorrectable"] == 1
+    assert [(a.data, int(a.crc_ok)) for a in aus] == [(d, int(o)) for d, o in exp_aus]
+    truth = res.aus[sc.subchid]
+    good = [a.data for a in aus if a.crc_ok]
+    assert len(good) >= 3 * (n_sf - 1) and all(g in truth for g in good)
+
+
+def test_whole_path_against_truth_and_oracle(receiver, oracle):
+    for fmt, snr in (("u8", 30.0), ("s16", 12.0), ("f32", 8.0)):
+        raw, res = cases.config1(12, fmt, snr, -4321.0, 7)
+        dec = receiver.decode(raw, fmt, tii=True, symstat=True)
+        assert dec.n_frames == 12 and dec.n_slots == 12
+        assert dec.fib_ok.all()
+        assert np.array_equal(dec.fibs.reshape(-1, 96), res.fibs[:48])
+        assert np.all(np.abs(dec.cfo_hz - res.cfo_hz) < 3.0)
+        assert len(dec.subch) == 1 and dec.subch[0].start_cu == 0 and dec.subch[0].size_cu == 72 and dec.subch[0].kind == 1
+        sc = res.ens.subchannels[0]
+        o = oracle.decode(raw, fmt, [oracle.subch_struct(sc)])
+        assert o["nf"] == 12 and np.array_equal(o["t_f"], dec.t_f)
+        if snr >= 12:
+            assert np.array_equal(dec.frames[0], res.logical[sc.subchid][:33])
+        truth = res.aus[sc.subchid]
+        got = [a.data for a in dec.aus if a.crc_ok]
+        assert len(got) >= 15
+        i0 = truth.index(got[0])
+        assert got == truth[i0:i0 + len(got)]
+        assert dec.gpu_launches >= 10
+
+
+def test_tii_ids(receiver):
+    from abracadabra_b200 import synth
+    ens = synth.config1_ensemble()
+    ens.tii = [synth.TiiTx(12, 5, 1.0), synth.TiiTx(33, 17, 0.5, delay=30), synth.TiiTx(60, 2, 0.25, delay=100)]
+    raw, res = synth.synthesize(ens, 41, "u8", synth.Impairments(snr_db=25, cfo_hz=50.0), tail=150000)
+    dec = receiver.decode(raw, "u8", tii=True, no_msc=True)
+    assert len(dec.tii) == 1
+    ids = dec.tii[0].ids
+    assert [(m, s) for m, s, _ in ids] == [(60, 2), (12, 5), (33, 17)]      # ascending sub id, like the reference
+    lv = {(m, s): l for m, s, l in ids}
+    # levels are linear in amplitude: ratios within 0.5 dB of the transmitted 6 / 12 dB steps
+    assert abs(20 * np.log10(lv[(33, 17)] / lv[(12, 5)]) + 6.02) < 0.5
+    assert abs(20 * np.log10(lv[(60, 2)] / lv[(12, 5)]) + 12.04) < 1.0
+    assert 0.85 < lv[(12, 5)] < 1.1
+    sp = dec.tii[0].spectrum
+    assert int(np.argmax(sp)) // 2 in [b * 24 + 5 for b in (2, 3, 4, 7)]
