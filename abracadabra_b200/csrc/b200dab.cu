@@ -81,6 +81,25 @@ struct b200dab_ctx {
     std::vector<b200dab_au_t> r_aus;
     std::vector<b200dab_tii_t> r_tii;
 
+    // optional per-kernel timing (CUDA events on `stream`), enabled by b200dab_set_profiling
+    bool profile = false;
+    struct ProfEv { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfEv> prof;
+    size_t prof_used = 0;
+    void prof_begin(const char* name)
+    {
+        if (!profile) return;
+        if (prof_used == prof.size()) { ProfEv e; e.name = name; cudaEventCreate(&e.a); cudaEventCreate(&e.b); prof.push_back(e); }
+        prof[prof_used].name = name;
+        cudaEventRecord(prof[prof_used].a, stream);
+    }
+    void prof_end()
+    {
+        if (!profile) return;
+        cudaEventRecord(prof[prof_used].b, stream);
+        prof_used++;
+    }
+
     void set_error(const char* what, cudaError_t e)
     {
         char buf[512];
@@ -158,12 +177,16 @@ int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, 
     CK(d_ncand.ensure(4));
     CK(cudaMemsetAsync(d_ncand.p, 0, 4, stream));
     const unsigned grid = (unsigned)((nblk + 255) / 256);
+    prof_begin("k_block_power");
     if (fmt == B200DAB_FMT_U8) k_block_power<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
     else if (fmt == B200DAB_FMT_S16) k_block_power<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
     else k_block_power<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    prof_end();
+    prof_begin("k_window_sum+k_candidates+k_sort_small");
     k_window_sum<<<grid, 256, 0, stream>>>(d_P.as<float>(), nblk, d_S.as<float>());
     k_candidates<<<grid, 256, 0, stream>>>(d_S.as<float>(), nblk, (int64_t)n, d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand);
     k_sort_small<<<1, 256, 0, stream>>>(d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand, d_cand.as<long long>());
+    prof_end();
     launches += 4;
     CK(cudaGetLastError());
     int nc = 0;
@@ -180,12 +203,14 @@ int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
     CK(d_fine.ensure((size_t)n_cand * sizeof(FineOut)));
     const float2* tw = d_tw.as<float2>();
     const int8_t* prs = d_prs_q.as<int8_t>();
+    prof_begin("k_fine_sync");
     if (fmt == B200DAB_FMT_U8)
         k_fine_sync<B200DAB_FMT_U8><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
     else if (fmt == B200DAB_FMT_S16)
         k_fine_sync<B200DAB_FMT_S16><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
     else
         k_fine_sync<B200DAB_FMT_F32><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+    prof_end();
     launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -227,9 +252,11 @@ int b200dab_ctx::demod(const void* d_iq, uint64_t n, int fmt, const FrameInfo* h
     const unsigned grid = (unsigned)n_frames * OFDM_GROUPS;
     const float2* tw = d_tw.as<float2>();
     const uint16_t* fp = d_fdi_pos.as<uint16_t>();
+    prof_begin("k_ofdm_demod");
     if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
     else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
     else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
+    prof_end();
     launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -263,9 +290,13 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     CK(cudaMemcpyAsync(d_stepinfo.p, stepinfo.data(), stepinfo.size() * 4, cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));      // the host vectors above go out of scope
     dim3 ggrid((unsigned)groups.size(), (unsigned)((max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
+    prof_begin(jobs[0].kind == 0 ? "k_gather(fic)" : "k_gather(msc)");
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
+    prof_end();
+    prof_begin(jobs[0].kind == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
     k_viterbi<<<(unsigned)groups.size(), 32, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
                                                        d_prbs_w.as<uint32_t>(), d_out);
+    prof_end();
     launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -302,7 +333,9 @@ int b200dab_ctx::fic(int n_slots)
     CK(d_fib_ok.ensure((size_t)n_rows * 3 + 64));
     if (run_viterbi(jobs, si, d_fic_out.as<uint8_t>())) return -1;
     const int n_fib = n_rows * 3;
+    prof_begin("k_fib_crc");
     k_fib_crc<<<(n_fib + 255) / 256, 256, 0, stream>>>(d_fic_out.as<uint8_t>(), n_fib, d_fib_ok.as<uint8_t>());
+    prof_end();
     launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -345,10 +378,16 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     int max_rows = 0, max_sf = 0, max_cw = 0;
     for (auto& j : jobs) { max_rows = std::max(max_rows, j.n_rows); max_sf = std::max(max_sf, j.max_sf); max_cw = std::max(max_cw, j.max_sf * j.s); }
     const unsigned nj = (unsigned)jobs.size();
+    prof_begin("k_firecode_scan+k_sf_align");
     k_firecode_scan<<<dim3((max_rows + 255) / 256, nj), 256, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>());
     k_sf_align<<<nj, 32, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>());
+    prof_end();
+    prof_begin("k_rs_decode");
     k_rs_decode<<<dim3((max_cw + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<GfTables>());
+    prof_end();
+    prof_begin("k_au_split");
     k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
+    prof_end();
     launches += 4;
     CK(cudaGetLastError());
     return 0;
@@ -478,6 +517,32 @@ int b200dab_parse_subch(const uint8_t* fibs, const uint8_t* fib_ok, int n_fibs, 
     return parse_subch_impl(fibs, fib_ok, n_fibs, out, max_out);
 }
 
+int b200dab_set_profiling(b200dab_ctx* ctx, int on)
+{
+    if (!ctx) return -1;
+    ctx->profile = on != 0;
+    return 0;
+}
+
+// per-kernel device times of the last b200dab_decode (CUDA events on the context stream); names are ';'-separated
+int b200dab_get_kernel_times(b200dab_ctx* ctx, char* names, int names_cap, float* ms, int max_n)
+{
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    int n = 0;
+    std::string all;
+    for (size_t i = 0; i < ctx->prof_used && n < max_n; i++, n++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->prof[i].a, ctx->prof[i].b) != cudaSuccess) t = -1.f;
+        if (ms) ms[n] = t;
+        if (!all.empty()) all += ";";
+        all += ctx->prof[i].name;
+    }
+    if (names && names_cap > 0) { strncpy(names, all.c_str(), (size_t)names_cap - 1); names[names_cap - 1] = 0; }
+    return n;
+}
+
 // ------------------------------------------------------------------------------------------------ whole path
 int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int mem, const b200dab_subch_t* subch_in, int n_subch_in,
                    uint32_t flags, b200dab_result_t* res)
@@ -486,6 +551,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     cudaSetDevice(ctx->device);
     memset(res, 0, sizeof *res);
     ctx->launches = 0;
+    ctx->prof_used = 0;
     ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
     const void* d_iq = nullptr;
     if (ctx->upload_raw(iq, n, fmt, mem, &d_iq)) return -1;
@@ -522,9 +588,11 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(cudaMemsetAsync(ctx->d_fold.p, 0, (size_t)n_slots * TII_SPECTRUM_BINS * 4, ctx->stream));
         CKC(cudaMemsetAsync(ctx->d_norm.p, 0, (size_t)n_slots * 4, ctx->stream));
         const float2* tw = ctx->d_tw.as<float2>();
+        ctx->prof_begin("k_tii_fold");
         if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
         else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
         else k_tii_fold<B200DAB_FMT_F32><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
+        ctx->prof_end();
         ctx->launches += 1;
         CKC(cudaGetLastError());
     }

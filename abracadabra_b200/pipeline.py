@@ -85,6 +85,8 @@ def lib():
         L.b200dab_profile_uep.argtypes = [i32, ct.POINTER(SubCh)]
         L.b200dab_parse_subch.argtypes = [vp, vp, i32, ct.POINTER(SubCh), i32]
         L.b200dab_decode.argtypes = [vp, vp, u64, i32, i32, ct.POINTER(SubCh), i32, ct.c_uint32, ct.POINTER(Result)]
+        L.b200dab_set_profiling.argtypes = [vp, i32]
+        L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
         L.b200dab_stage_coarse.argtypes = [vp, vp, u64, i32, vp, vp, vp, ct.POINTER(i32), i32]
         L.b200dab_stage_fine.argtypes = [vp, vp, u64, i32, vp, i32, vp, vp, vp]
         L.b200dab_stage_demod.argtypes = [vp, vp, u64, i32, vp, vp, i32, vp]
@@ -99,7 +101,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -211,6 +213,17 @@ class Receiver:
     @property
     def stream(self) -> int:
         return int(lib().b200dab_stream(self._h) or 0)
+
+    def set_profiling(self, on: bool) -> None:
+        lib().b200dab_set_profiling(self._h, int(on))
+
+    def kernel_times(self):
+        """[(kernel name, ms)] of the last decode (needs set_profiling(True) before it)."""
+        names = ct.create_string_buffer(4096)
+        ms = np.zeros(64, np.float32)
+        n = lib().b200dab_get_kernel_times(self._h, names, 4096, ms.ctypes.data, 64)
+        nm = names.value.decode().split(";") if n > 0 else []
+        return list(zip(nm, ms[:n].tolist()))
 
     # ------------------------------------------------------------------ whole path
     def decode_raw(self, ptr: int, n_samples: int, fmt: str, on_device: bool, subch: Optional[Sequence[SubCh]] = None,

@@ -217,14 +217,16 @@ def rs_parity(data: np.ndarray) -> np.ndarray:
     return rem.astype(np.uint8)
 
 
-def crc16_np(rows: np.ndarray) -> np.ndarray:
-    """CRC-16 (poly 0x1021, init 0xFFFF, inverted) of each row of a uint8 matrix."""
+def crc16_np(rows: np.ndarray, poly: int = 0x1021, init: int = 0xFFFF, invert: bool = True) -> np.ndarray:
+    """CRC-16 of each row of a uint8 matrix (default: poly 0x1021, init 0xFFFF, inverted)."""
     rows = np.atleast_2d(rows).astype(np.uint32)
-    tbl = _crc_table(0x1021)
-    crc = np.full(rows.shape[0], 0xFFFF, dtype=np.uint32)
+    tbl = _crc_table(poly)
+    crc = np.full(rows.shape[0], init, dtype=np.uint32)
     for i in range(rows.shape[1]):
         crc = ((crc << 8) & 0xFFFF) ^ tbl[((crc >> 8) ^ rows[:, i]) & 0xFF]
-    return (crc ^ 0xFFFF).astype(np.uint16)
+    if invert:
+        crc = crc ^ 0xFFFF
+    return crc.astype(np.uint16)
 
 
 _CRC_TABLES: Dict[int, np.ndarray] = {}
@@ -244,7 +246,7 @@ def _crc_table(poly: int) -> np.ndarray:
 
 # ============================================================================ payload builders
 def dabplus_superframes(sc: SubChannel, n_sf: int, rng: np.random.Generator):
-    """Build n_sf DAB+ audio superframes for sub-channel `sc`.
+    """Build n_sf DAB+ audio superframes for sub-channel `sc` (vectorised over superframes).
 
     Returns (bytes [n_sf, 120*s], list of access units (bytes, without CRC) in stream order).
     HE-AAC v1 24 kHz core: dac_rate=1, sbr=1, stereo -> 3 AUs per superframe, header byte 0x70.
@@ -258,29 +260,30 @@ def dabplus_superframes(sc: SubChannel, n_sf: int, rng: np.random.Generator):
     starts = [first]
     for ln in lens[:-1]:
         starts.append(starts[-1] + ln)
-    sf = np.zeros((n_sf, 120 * s), dtype=np.uint8)
+    buf = np.zeros((n_sf, size), dtype=np.uint8)
+    buf[:, 2] = 0x70
+    buf[:, 3] = (starts[1] >> 4) & 0xFF
+    buf[:, 4] = ((starts[1] & 0xF) << 4) | ((starts[2] >> 8) & 0xF)
+    buf[:, 5] = starts[2] & 0xFF
+    payloads = []
+    for a in range(num_aus):
+        pl = rng.integers(0, 256, (n_sf, lens[a] - 2), dtype=np.uint8)
+        crc = crc16_np(pl)
+        buf[:, starts[a]:starts[a] + lens[a] - 2] = pl
+        buf[:, starts[a] + lens[a] - 2] = crc >> 8
+        buf[:, starts[a] + lens[a] - 1] = crc & 0xFF
+        payloads.append(pl)
+    fc = crc16_np(buf[:, 2:11], poly=0x782F, init=0, invert=False)      # fire code over bytes 2..10
+    buf[:, 0] = fc >> 8
+    buf[:, 1] = fc & 0xFF
     aus: List[bytes] = []
     for f in range(n_sf):
-        buf = np.zeros(size, dtype=np.uint8)
-        buf[2] = 0x70
-        buf[3] = (starts[1] >> 4) & 0xFF
-        buf[4] = ((starts[1] & 0xF) << 4) | ((starts[2] >> 8) & 0xF)
-        buf[5] = starts[2] & 0xFF
-        fc = C.firecode(bytes(buf[2:11]))      # bytes 2..10; bytes 6..10 belong to AU 0 and are filled below
         for a in range(num_aus):
-            payload = rng.integers(0, 256, lens[a] - 2, dtype=np.uint8)
-            crc = C.crc16(bytes(payload))
-            buf[starts[a]:starts[a] + lens[a] - 2] = payload
-            buf[starts[a] + lens[a] - 2] = crc >> 8
-            buf[starts[a] + lens[a] - 1] = crc & 0xFF
-            aus.append(bytes(payload))
-        fc = C.firecode(bytes(buf[2:11]))
-        buf[0], buf[1] = fc >> 8, fc & 0xFF
-        # RS: codeword j = bytes j + s*i
-        data = buf.reshape(110, s).T            # [s, 110]
-        par = rs_parity(data)                   # [s, 10]
-        sf[f, :size] = buf
-        sf[f, size:] = par.T.reshape(-1)
+            aus.append(payloads[a][f].tobytes())
+    # RS: codeword j of a superframe = bytes j + s*i
+    data = buf.reshape(n_sf, 110, s).transpose(0, 2, 1).reshape(n_sf * s, 110)
+    par = rs_parity(data).reshape(n_sf, s, 10).transpose(0, 2, 1).reshape(n_sf, 10 * s)
+    sf = np.concatenate([buf, par], axis=1)
     return sf, aus
 
 
@@ -505,17 +508,24 @@ def impair(x: np.ndarray, imp: Impairments, tail: int = 0) -> np.ndarray:
     n = x.size
     if imp.cfo_hz or imp.cfo_drift_hz_per_s:
         # phase(t) = 2 pi (f0 t + 0.5 a t^2); evaluated in float64 in chunks to bound memory
-        step = 1 << 22
+        step = 1 << 20
+        k = np.arange(step, dtype=np.float64)
         for s in range(0, n, step):
-            t = np.arange(s, min(n, s + step), dtype=np.float64) / C.FS
-            phs = 2 * np.pi * (imp.cfo_hz * t + 0.5 * imp.cfo_drift_hz_per_s * t * t)
-            x[s:s + step] *= np.exp(1j * phs).astype(np.complex64)
+            m = min(n, s + step) - s
+            # phase(s + k) = phi0 + w k + 0.5 a (k/fs)^2 ; chunk-local terms stay small enough for float32 sincos
+            t0 = s / C.FS
+            phi0 = 2 * np.pi * (imp.cfo_hz * t0 + 0.5 * imp.cfo_drift_hz_per_s * t0 * t0)
+            w = 2 * np.pi * (imp.cfo_hz + imp.cfo_drift_hz_per_s * t0) / C.FS
+            ph = np.mod(w * k[:m] + np.pi * imp.cfo_drift_hz_per_s * (k[:m] / C.FS) ** 2, 2 * np.pi).astype(np.float32)
+            rot = (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64) * np.complex64(np.exp(1j * (phi0 % (2 * np.pi))))
+            x[s:s + m] *= rot
     if imp.snr_db is not None:
         sigma = np.sqrt(0.5 * 10 ** (-imp.snr_db / 10))
         step = 1 << 22
         for s in range(0, n, step):
             m = min(n, s + step) - s
-            x[s:s + m] += (sigma * (rng.standard_normal(m) + 1j * rng.standard_normal(m))).astype(np.complex64)
+            nz = rng.standard_normal(2 * m, dtype=np.float32) * np.float32(sigma)
+            x[s:s + m] += nz.view(np.complex64)
     return x
 
 

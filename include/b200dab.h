@@ -116,6 +116,10 @@ B200DAB_API int b200dab_parse_subch(const uint8_t *fibs, const uint8_t *fib_ok, 
 B200DAB_API int b200dab_decode(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, int mem,
                                const b200dab_subch_t *subch, int n_subch, uint32_t flags, b200dab_result_t *res);
 
+/* per-kernel device times (CUDA events on the context stream) of the last b200dab_decode; names ';'-separated */
+B200DAB_API int b200dab_set_profiling(b200dab_ctx *ctx, int on);
+B200DAB_API int b200dab_get_kernel_times(b200dab_ctx *ctx, char *names, int names_cap, float *ms, int max_n);
+
 /* ---- stage entry points (host buffers in, host buffers out): the kernels of the path one by one, for parity tests
  *      against oracle/ and for profiling.  They launch exactly the kernels b200dab_decode launches. */
 B200DAB_API int b200dab_stage_coarse(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, float *P /* n/32 */,

@@ -38,8 +38,8 @@
 #define SYNC_FRAME_MARGIN 160         /* samples a frame may extend beyond its nominal end (fine timing slack) */
 
 /* --- fine sync */
-#define CP_CORR_LO        64          /* cyclic-prefix correlation uses CP samples [LO, HI) of every symbol */
-#define CP_CORR_HI        440
+#define CP_CORR_LO        160         /* cyclic-prefix correlation uses CP samples [LO, HI) of every symbol */
+#define CP_CORR_HI        344
 #define PRS_WIN_EARLY     252         /* the PRS analysis window starts this many samples before the nominal useful part */
 #define CFO_INT_RANGE     16          /* integer CFO search +-16 carriers (+-16 kHz) */
 #define FINE_BACKOFF      24          /* FFT windows start this many samples before the first detected path */

@@ -15,7 +15,7 @@
  * The ABI types are declared in include/dabsdr_abi.h (this repo's own restatement of lib/linux_x86_64/dabsdr.h).
  *
  * usage: ref_harness <iqfile> <u8|s16|f32> <out.jsonl|-> [--tii MODE] [--service N | --sid HEX] [--spectrum]
- *                    [--freq KHZ] [--tail-frames N] [--no-au-data] [--second N]
+ *                    [--freq KHZ] [--tail-frames N] [--no-au-data] [--second N] [--free-run]
  */
 #define _GNU_SOURCE
 #include <pthread.h>
@@ -84,6 +84,7 @@ static void wait_main_idle(void)
 }
 
 static uint64_t g_next_tick = 196608;
+static int g_free_run;     /* --free-run: no lock-step gating (throughput measurements) */
 
 static void advance(uint64_t n)
 {
@@ -109,7 +110,7 @@ static void advance(uint64_t n)
 
 static void input_fn(float buf[], uint16_t n)
 {
-    wait_main_idle();
+    if (!g_free_run) wait_main_idle();
     uint64_t p = g_pos;
     uint64_t avail = p < g_nsamples ? g_nsamples - p : 0;
     uint32_t m = n < avail ? n : (uint32_t)avail;
@@ -129,7 +130,7 @@ static void input_fn(float buf[], uint16_t n)
 static void dummy_fn(float buf[], uint16_t n)
 {
     (void)buf;
-    wait_main_idle();
+    if (!g_free_run) wait_main_idle();
     advance(n);
 }
 
@@ -373,6 +374,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--freq") && i + 1 < argc) g_freq = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "--tail-frames") && i + 1 < argc) g_tail_samples = 196608ull * atoi(argv[++i]);
         else if (!strcmp(argv[i], "--no-au-data")) g_log_au_data = 0;
+        else if (!strcmp(argv[i], "--free-run")) g_free_run = 1;
     }
     int fd = open(path, O_RDONLY);
     if (fd < 0) { perror(path); return 1; }
