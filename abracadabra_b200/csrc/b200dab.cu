@@ -808,8 +808,11 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     CKC(cudaMemcpyAsync(ctx->d_groups.p, groups.data(), groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->d_vin.p, vin.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, zero_prbs.data(), 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof_used = 0;
+    ctx->prof_begin("k_viterbi(stage)");
     k_viterbi<<<ng, 32, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint2>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
                                          ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>());
+    ctx->prof_end();
     ctx->launches += 1;
     CKC(cudaGetLastError());
     std::vector<uint8_t> packed((size_t)n_cw * job.out_pitch);

@@ -155,6 +155,47 @@ __device__ __forceinline__ void fft2048_smem(float2* __restrict__ buf, const flo
 // carrier index c (0..1535, ascending k = -768..-1, 1..768) -> FFT bin
 __device__ __host__ __forceinline__ int carrier_bin(int c) { return c < 768 ? c + 1280 : c - 767; }
 
+// raw samples of one symbol held in registers between the (early) global load and the (late) conversion, so that the
+// next symbol's loads are in flight while the current symbol is transformed
+template <int FMT> struct RawSym;
+template <> struct RawSym<B200DAB_FMT_U8> { uchar2 v[8]; };
+template <> struct RawSym<B200DAB_FMT_S16> { short2 v[8]; };
+template <> struct RawSym<B200DAB_FMT_F32> { float2 v[8]; };
+
+template <int FMT>
+__device__ __forceinline__ void fetch_symbol(RawSym<FMT>& r, const void* __restrict__ raw, int64_t nsamp, int64_t start)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int64_t n = start + t + 256 * i;
+        const bool ok = n >= 0 && n < nsamp;
+        if (!ok) n = 0;
+        if (FMT == B200DAB_FMT_U8) { uchar2 x = __ldg(reinterpret_cast<const uchar2*>(raw) + n); if (!ok) x = make_uchar2(128, 128); reinterpret_cast<uchar2*>(r.v)[i] = x; }
+        else if (FMT == B200DAB_FMT_S16) { short2 x = __ldg(reinterpret_cast<const short2*>(raw) + n); if (!ok) x = make_short2(0, 0); reinterpret_cast<short2*>(r.v)[i] = x; }
+        else { float2 x = __ldg(reinterpret_cast<const float2*>(raw) + n); if (!ok) x = make_float2(0.f, 0.f); reinterpret_cast<float2*>(r.v)[i] = x; }
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_symbol(float2* __restrict__ buf, const RawSym<FMT>& r, float base_cyc, float cpp)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int m = t + 256 * i;
+        float2 x;
+        if (FMT == B200DAB_FMT_U8) { uchar2 v = reinterpret_cast<const uchar2*>(r.v)[i]; x = make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+        else if (FMT == B200DAB_FMT_S16) { short2 v = reinterpret_cast<const short2*>(r.v)[i]; x = make_float2((float)v.x, (float)v.y); }
+        else x = reinterpret_cast<const float2*>(r.v)[i];
+        float cyc = base_cyc + cpp * (float)m;
+        float ph = -6.283185307179586f * (cyc - rintf(cyc));
+        float s, c;
+        __sincosf(ph, &s, &c);
+        buf[fft_phys(m)] = make_float2(x.x * c - x.y * s, x.x * s + x.y * c);
+    }
+}
+
 // load 2048 samples starting at `start` into buf (natural order), de-rotated: x[m] * exp(-2 pi i (base_cyc + cpp * m))
 template <int FMT>
 __device__ __forceinline__ void load_symbol(float2* __restrict__ buf, const void* __restrict__ raw, int64_t nsamp, int64_t start,

@@ -18,7 +18,7 @@ struct FrameInfo {
 
 // fdi_pos[n] = physical shared-memory index of the FFT output that carries QPSK symbol n
 template <int FMT>
-__global__ void __launch_bounds__(256) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+__global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
                                                     const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_pos,
                                                     int8_t* __restrict__ soft, float* __restrict__ symstat)
 {
@@ -37,10 +37,13 @@ __global__ void __launch_bounds__(256) k_ofdm_demod(const void* __restrict__ raw
     float2* prev = bufB;
     int8_t* out_frame = soft + (size_t)fr.slot * DAB_FRAME_SOFT;
 
+    RawSym<FMT> rs;
+    fetch_symbol<FMT>(rs, raw, nsamp, fr.t_f + (int64_t)DAB_T_SYM * l_ref);
     for (int l = l_ref; l <= l_end; l++) {
         double base = cyc_per * (double)((int64_t)DAB_T_SYM * l);
         base -= floor(base);
-        load_symbol<FMT>(cur, raw, nsamp, fr.t_f + (int64_t)DAB_T_SYM * l, (float)base, cpp);
+        store_symbol<FMT>(cur, rs, (float)base, cpp);
+        if (l < l_end) fetch_symbol<FMT>(rs, raw, nsamp, fr.t_f + (int64_t)DAB_T_SYM * (l + 1));   // in flight during the FFT
         fft2048_smem(cur, tw);
         if (l > l_ref) {
             // DQPSK against the previous symbol, de-interleaved order: thread handles n = 4t..4t+3 and (t < 128) 1024+4t..

@@ -90,31 +90,33 @@ __host__ __device__ constexpr int vit_cbit(int j, int q) { return vit_parity7((j
 
 template <int J>
 __device__ __forceinline__ void vit_bfly(const uint32_t (&L)[16], const uint32_t (&H)[16], uint32_t (&E)[16], uint32_t (&O)[16],
-                                         const uint32_t (&BP)[8], uint32_t& dlo, uint32_t& dhi)
+                                         const uint32_t (&BP)[8], uint32_t (&dl)[4], uint32_t (&dh)[4])
 {
     // low halves: butterfly of states (J, J+32) -> (2J, 2J+1); high halves: (J+16, J+48) -> (2J+32, 2J+33)
+    uint32_t& dlo = dl[J & 3];          // four partial decision words: independent chains instead of one serial one
+    uint32_t& dhi = dh[J & 3];
     constexpr int k = vit_cbit(J, 0) * 4 + vit_cbit(J, 1) * 2 + vit_cbit(J, 2);   // BP[k] = +beta, BP[7-k] = -beta
     bool ph, pl;
-    const uint32_t t0 = __vadd2(L[J], BP[k]), t1 = __vadd2(H[J], BP[7 - k]);
+    const uint32_t t0 = L[J] + BP[k], t1 = H[J] + BP[7 - k];       // plain 32-bit adds: see the bias note in k_viterbi
     E[J] = __vibmax_s16x2(t0, t1, &ph, &pl);          // predicate = (t0 >= t1): survivor from the lower predecessor
     if (!pl) dlo |= 1u << (2 * J);
     if (!ph) dhi |= 1u << (2 * J);
-    const uint32_t u0 = __vadd2(L[J], BP[7 - k]), u1 = __vadd2(H[J], BP[k]);
+    const uint32_t u0 = L[J] + BP[7 - k], u1 = H[J] + BP[k];
     O[J] = __vibmax_s16x2(u0, u1, &ph, &pl);
     if (!pl) dlo |= 1u << (2 * J + 1);
     if (!ph) dhi |= 1u << (2 * J + 1);
 }
 template <int J> struct VitUnroll {
     static __device__ __forceinline__ void run(const uint32_t (&L)[16], const uint32_t (&H)[16], uint32_t (&E)[16], uint32_t (&O)[16],
-                                               const uint32_t (&BP)[8], uint32_t& dlo, uint32_t& dhi)
+                                               const uint32_t (&BP)[8], uint32_t (&dl)[4], uint32_t (&dh)[4])
     {
-        VitUnroll<J - 1>::run(L, H, E, O, BP, dlo, dhi);
-        vit_bfly<J>(L, H, E, O, BP, dlo, dhi);
+        VitUnroll<J - 1>::run(L, H, E, O, BP, dl, dh);
+        vit_bfly<J>(L, H, E, O, BP, dl, dh);
     }
 };
 template <> struct VitUnroll<-1> {
     static __device__ __forceinline__ void run(const uint32_t (&)[16], const uint32_t (&)[16], uint32_t (&)[16], uint32_t (&)[16],
-                                               const uint32_t (&)[8], uint32_t&, uint32_t&) {}
+                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t (&)[4]) {}
 };
 
 // one warp per group of 32 codewords; grid = n_groups (longest groups first)
@@ -129,41 +131,72 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
     const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
     uint2* d = dec + job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
 
+    // Path metrics are kept BIASED: each 16-bit half holds metric + 16384 and stays inside [0, 32767] (start penalty
+    // -8192, spread <= 6096, growth <= 16 * 508 between re-referencings).  With non-negative halves a packed add of the
+    // signed pair (b_lo, b_hi) is one ordinary 32-bit add of the constant b_hi * 65536 + b_lo -- the borrow of a negative
+    // b_lo is already folded into the constant -- so the adds are free to issue on the FMA pipe (IMAD.IADD) while
+    // VIMNMX/PRMT keep the ALU pipe busy.  Comparisons are unaffected by the bias, so decisions equal the checker's.
     uint32_t L[16], H[16], E[16], O[16];
-    const uint32_t PEN = 0xE000E000u;                 // VIT_START_PENALTY = -8192 in both halves
+    constexpr uint32_t BIAS = 16384u;
+    constexpr uint32_t PEN = (BIAS + VIT_START_PENALTY) * 65537u;
 #pragma unroll
     for (int j = 0; j < 16; j++) { L[j] = PEN; H[j] = PEN; }
-    L[0] = 0xE0000000u;                               // state 0 starts at 0, state 16 at the penalty
+    L[0] = ((BIAS + VIT_START_PENALTY) << 16) | BIAS;  // state 0 starts at 0, state 16 at the penalty
 
-    uint32_t w_next = __ldg(in);
-    for (int t = 0; t < steps; t++) {
-        const uint32_t w = w_next;
-        if (t + 1 < steps) w_next = __ldg(in + (size_t)(t + 1) * 32);
-        if ((t & (VIT_NORM_PERIOD - 1)) == 0) {
-            const uint32_t m0 = __byte_perm(L[0], 0, 0x1010);       // (M[0], M[0])
-            const uint32_t nm = __vneg2(m0);
+    // The soft words stream from HBM (the array is far larger than L2).  Each lane copies its own column of the next
+    // 16 steps into shared memory with cp.async (LDGSTS, no register staging) while the current 16 steps are decoded,
+    // so one memory latency is paid per 16 trellis steps instead of per step, and the loop body stays I-cache sized.
+    constexpr int PF = VIT_NORM_PERIOD;
+    __shared__ uint32_t ring[2][PF][32];
+    auto prefetch = [&](int buf, int t0) {
 #pragma unroll
-            for (int j = 0; j < 16; j++) { L[j] = __vadd2(L[j], nm); H[j] = __vadd2(H[j], nm); }
+        for (int i = 0; i < PF; i++) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][i][lane]);
+            const uint32_t* src = in + (size_t)min(t0 + i, steps - 1) * 32;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
         }
-        const int a0 = (int8_t)(w), a1 = (int8_t)(w >> 8), a2 = (int8_t)(w >> 16), a3 = (int8_t)(w >> 24);
-        const int T = a0 + a3, X1 = a1 + a2, X2 = a1 - a2;
-        // BP[k], k = c0*4 + c1*2 + c2 (1 = code bit 1 = negative contribution): low half  (1-2c0) T + x,
-        //                                                                      high half -(1-2c0) T + x  (state + 16 flips c0, c3)
-        uint32_t BP[8];
-        const int xs[4] = {X1, X2, -X2, -X1};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            BP[i] = __byte_perm((uint32_t)(T + xs[i]), (uint32_t)(-T + xs[i]), 0x5410);
-            BP[4 + i] = __byte_perm((uint32_t)(-T + xs[i]), (uint32_t)(T + xs[i]), 0x5410);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < steps; t0 += PF, buf ^= 1) {
+        if (t0 + PF < steps) {
+            prefetch(buf ^ 1, t0 + PF);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        uint32_t dlo = 0, dhi = 0;
-        VitUnroll<15>::run(L, H, E, O, BP, dlo, dhi);
-        d[(size_t)t * 32] = make_uint2(dlo, dhi);
-        // re-pair: L'[m] = (new[m], new[m+16]), H'[m] = (new[m+32], new[m+48])
+        {   // re-reference all metrics to state 0 (every VIT_NORM_PERIOD steps, same rule as the checker)
+            const int nm = (int)BIAS - (int)(L[0] & 0xffffu);       // brings state 0 back to the bias
+            const uint32_t c = (uint32_t)(nm * 65537);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            L[2 * j] = __byte_perm(E[j], E[j + 8], 0x5410);     H[2 * j] = __byte_perm(E[j], E[j + 8], 0x7632);
-            L[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x5410); H[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x7632);
+            for (int j = 0; j < 16; j++) { L[j] += c; H[j] += c; }
+        }
+        const int nst = min(PF, steps - t0);
+#pragma unroll 2
+        for (int i = 0; i < nst; i++) {
+            const int t = t0 + i;
+            const uint32_t w = ring[buf][i][lane];
+            const int a0 = (int8_t)(w), a1 = (int8_t)(w >> 8), a2 = (int8_t)(w >> 16), a3 = (int8_t)(w >> 24);
+            const int T = a0 + a3, X1 = a1 + a2, X2 = a1 - a2;
+            // BP[k], k = c0*4 + c1*2 + c2 (1 = code bit 1 = negative contribution): low half  (1-2c0) T + x,
+            //                                                                      high half -(1-2c0) T + x  (state + 16 flips c0, c3)
+            uint32_t BP[8];
+            const int xs[4] = {X1, X2, -X2, -X1};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                BP[q] = (uint32_t)((-T + xs[q]) * 65536 + (T + xs[q]));
+                BP[4 + q] = (uint32_t)((T + xs[q]) * 65536 + (-T + xs[q]));
+            }
+            uint32_t dl[4] = {0, 0, 0, 0}, dh[4] = {0, 0, 0, 0};
+            VitUnroll<15>::run(L, H, E, O, BP, dl, dh);
+            d[(size_t)t * 32] = make_uint2((dl[0] | dl[1]) | (dl[2] | dl[3]), (dh[0] | dh[1]) | (dh[2] | dh[3]));
+            // re-pair: L'[m] = (new[m], new[m+16]), H'[m] = (new[m+32], new[m+48])
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                L[2 * j] = __byte_perm(E[j], E[j + 8], 0x5410);     H[2 * j] = __byte_perm(E[j], E[j + 8], 0x7632);
+                L[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x5410); H[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x7632);
+            }
         }
     }
 
