@@ -71,7 +71,8 @@ struct b200dab_ctx {
     DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_fic_out, d_fib_ok, d_msc_out;
     DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
     DevBuf d_tmp_a, d_tmp_b;
-    HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc;
+    HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
+    std::vector<int32_t> r_sign;
     // result storage
     std::vector<int64_t> r_tf;
     std::vector<float> r_cfo, r_cir;
@@ -149,6 +150,7 @@ int b200dab_ctx::init_tables()
     uint8_t pat[70];
     dabtab::tii_patterns(pat);
     CK(cudaMemcpyToSymbol(c_tii_pattern, pat, 70));
+    CK(cudaMemcpyToSymbol(c_tii_gain, B200DAB_TII_GAIN, sizeof(B200DAB_TII_GAIN)));
     return 0;
 }
 
@@ -492,7 +494,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
                     &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b};
     for (auto* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc};
+    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm};
     for (auto* b : hb) b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -642,7 +644,8 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     // ---- TII detection needs to know which nulls carry TII: CIF counter (FIG 0/0) = 0 mod 8
     int n_win = 0;
     if (want_tii) {
-        std::vector<int> sign(n_slots, 0);
+        ctx->r_sign.assign(n_slots, 0);
+        std::vector<int32_t>& sign = ctx->r_sign;
         for (int s = 0; s < n_slots; s++) {
             if (ctx->r_tf[s] < 0) continue;
             const uint8_t* fib = res->fibs + (size_t)s * 384;          // FIB 0 of the first CIF carries FIG 0/0 first
@@ -670,6 +673,11 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(cudaGetLastError());
         CKC(ctx->h_tii.ensure(wins.size() * sizeof(TiiResult)));
         CKC(cudaMemcpyAsync(ctx->h_tii.p, ctx->d_tii.p, wins.size() * sizeof(TiiResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CKC(ctx->h_fold.ensure((size_t)n_slots * TII_SPECTRUM_BINS * 4));
+        CKC(ctx->h_norm.ensure((size_t)n_slots * 4));
+        CKC(cudaMemcpyAsync(ctx->h_fold.p, ctx->d_fold.p, (size_t)n_slots * TII_SPECTRUM_BINS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CKC(cudaMemcpyAsync(ctx->h_norm.p, ctx->d_norm.p, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        res->tii_fold = ctx->h_fold.as<float>(); res->tii_norm = ctx->h_norm.as<float>(); res->tii_sign = ctx->r_sign.data();
     }
     if (want_stat) {
         CKC(ctx->h_symstat.ensure((size_t)n_slots * 150 * 4));

@@ -53,7 +53,7 @@ struct Database {
     int cif_count = -1;                 // of the last FIG 0/0 seen
     SubCh subch[64];
     std::vector<Service> services;      // in order of first appearance
-    uint32_t date_hours_minutes = 0;    // raw FIG 0/10: MJD(17) << 15 | hours(5) << 10 | minutes(6) << 4 ... packed below
+    uint32_t date_hours_minutes = 0;    // FIG 0/10: MJD << 14 | LSI << 13 | hours << 6 | minutes
     uint16_t sec_msec = 0;
     uint64_t version = 0;               // bumps when something changed
 
@@ -135,7 +135,7 @@ struct Database {
                 if (ok == 0) {
                     sc.subch_id = id; sc.start_cu = start;
                     if (!subch[id].valid || subch[id].p.start_cu != start || subch[id].p.size_cu != sc.size_cu || subch[id].p.bitrate != sc.bitrate) {
-                        sc.kind = subch[id].valid ? subch[id].p.kind : 0;
+                        sc.kind = subch[id].p.kind;        // FIG 0/2 may have told us already
                         subch[id].p = sc; subch[id].valid = true; version++;
                     }
                 }
@@ -229,7 +229,8 @@ struct Database {
                 const uint32_t mjd = ((uint32_t)(d[1] & 0x7F) << 10) | ((uint32_t)d[2] << 2) | (d[3] >> 6);
                 const int utc = (d[3] >> 3) & 1;
                 const uint32_t hours = ((d[3] & 7) << 2) | (d[4] >> 6), minutes = d[4] & 0x3F;
-                date_hours_minutes = (mjd << 11) | (hours << 6) | minutes;      // same packing RadioControl unpacks (dabtables.cpp:124-157)
+                const uint32_t lsi = (d[3] >> 5) & 1;
+                date_hours_minutes = (mjd << 14) | (lsi << 13) | (hours << 6) | minutes;   // packing RadioControl unpacks (src/dabtables.cpp:124-157)
                 if (utc && len >= 7) sec_msec = (uint16_t)(((d[5] >> 2) << 10) | (((d[5] & 3) << 8) | d[6]));
                 else sec_msec = 0;
             }

@@ -9,6 +9,10 @@
 #pragma once
 #include "common.cuh"
 #include "k_ofdm.cuh"
+#include "../../include/b200dab_tii_gain.h"
+
+// per-bin gain of the reference core's TII spectrum (measured, see the header); applied when folding
+__constant__ float c_tii_gain[TII_SPECTRUM_BINS];
 
 // one CTA per frame: fold[f][2p+e] = sum over the 4 quarters of |N[k]|, k = 384 q + 2p + e ; norm[f] = rms PRS carrier magnitude
 template <int FMT>
@@ -45,7 +49,7 @@ __global__ void __launch_bounds__(256) k_tii_fold(const void* __restrict__ raw, 
             float2 v = buf[fft_phys(fft_pos(carrier_bin(384 * q + i)))];
             a += sqrtf(v.x * v.x + v.y * v.y);
         }
-        o[i] = a;
+        o[i] = a * c_tii_gain[i];
     }
 }
 
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(256) k_tii_fold_nulls(const float2* __restrict
             float2 v = buf[fft_phys(fft_pos(carrier_bin(384 * q + i)))];
             a += sqrtf(v.x * v.x + v.y * v.y);
         }
-        o[i] = a;
+        o[i] = a * c_tii_gain[i];
     }
 }
 
@@ -91,9 +95,10 @@ __global__ void __launch_bounds__(384) k_tii_detect(const float* __restrict__ fo
     __shared__ float spec[TII_SPECTRUM_BINS];
     __shared__ float pair[TII_PAIRS];
     __shared__ float sorted_rank[TII_PAIRS];
-    __shared__ float s_noise, s_norm, s_peak;
+    __shared__ float s_noise, s_norm, s_peak, s_binmax;
     __shared__ int s_ntii, s_count;
-    __shared__ unsigned short found[24 * 70];
+    __shared__ unsigned short hits[64];
+    __shared__ float warp_max[12];
     const int t = threadIdx.x;
     const int2 win = windows[blockIdx.x];
     float a = 0.f;
@@ -118,38 +123,53 @@ __global__ void __launch_bounds__(384) k_tii_detect(const float* __restrict__ fo
         sorted_rank[rank] = v;
     }
     __syncthreads();
-    if (t == 0) { s_noise = sorted_rank[TII_PAIRS / 2]; s_peak = sorted_rank[TII_PAIRS - 1]; }
+    // strongest bin of the spectrum (level reference), block-wide maximum
+    {
+        float bm = spec[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        if ((t & 31) == 0) warp_max[t >> 5] = bm;
+    }
+    __syncthreads();
+    if (t == 0) {
+        s_noise = sorted_rank[TII_PAIRS / 2]; s_peak = sorted_rank[TII_PAIRS - 1];
+        float bm = 0.f;
+        for (int i = 0; i < 12; i++) bm = fmaxf(bm, warp_max[i]);
+        s_binmax = bm;
+    }
     __syncthreads();
     const float thr = fmaxf(thr_k * s_noise, 0.05f * s_peak);
-    // comb search: thread (sub, main) tests whether all four blocks of the pattern are lit
+    // comb search: thread (sub, main) tests whether all four blocks of the pattern are lit; hits go to a short list
     for (int i = t; i < 24 * 70; i += 384) {
         const int sub = i / 70, m = i - sub * 70;
         const unsigned pat = c_tii_pattern[m];
-        unsigned mask = 0; float mn = 1e30f, mx = 0.f, sum_all = 0.f; int cnt = 0;
+        unsigned mask = 0; float mn = 1e30f, mx = 0.f; int cnt = 0;
 #pragma unroll
         for (int b = 0; b < 8; b++) {
             const float v = pair[24 * b + sub];
             if (v > thr) { mask |= 0x80u >> b; cnt++; }
-            if (pat & (0x80u >> b)) { mn = fminf(mn, v); mx = fmaxf(mx, v); sum_all += v; }
+            if (pat & (0x80u >> b)) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
         }
         bool hit = (mask & pat) == pat;
         if (hit && cnt > 4) hit = mn >= 0.5f * mx;      // several transmitters share this sub id: keep consistent combs only
-        found[i] = hit ? 1 : 0;
+        if (hit) { const int k = atomicAdd(&s_count, 1); if (k < 64) hits[k] = (unsigned short)i; }
     }
     __syncthreads();
     if (t == 0) {
         TiiResult* r = res + blockIdx.x;
+        int nh = min(s_count, 64);
+        for (int i = 1; i < nh; i++) { unsigned short v = hits[i]; int j = i - 1; while (j >= 0 && hits[j] > v) { hits[j + 1] = hits[j]; j--; } hits[j + 1] = v; }
         int n = 0;
-        for (int sub = 0; sub < 24 && n < TII_MAX_IDS; sub++)
-            for (int m = 0; m < 70 && n < TII_MAX_IDS; m++)
-                if (found[sub * 70 + m]) {
-                    const unsigned pat = c_tii_pattern[m];
-                    float sum = 0.f;
-                    for (int b = 0; b < 8; b++) if (pat & (0x80u >> b)) sum += pair[24 * b + sub];
-                    r->main_id[n] = (unsigned char)m; r->sub_id[n] = (unsigned char)sub;
-                    r->level[n] = s_norm > 0.f ? (sum / 8.f) / s_norm : 0.f;
-                    n++;
-                }
+        for (int k = 0; k < nh && n < TII_MAX_IDS; k++) {      // index = sub * 70 + main: ascending sub, then main (order of the reference)
+            const int sub = hits[k] / 70, m = hits[k] - sub * 70;
+            const unsigned pat = c_tii_pattern[m];
+            float sum = 0.f;
+            for (int b = 0; b < 8; b++) if (pat & (0x80u >> b)) sum += pair[24 * b + sub];
+            r->main_id[n] = (unsigned char)m; r->sub_id[n] = (unsigned char)sub;
+            // like the reference: mean of the transmitter's 8 bins relative to the strongest bin of the spectrum
+            r->level[n] = s_binmax > 0.f ? (sum / 8.f) / s_binmax : 0.f;
+            n++;
+        }
         r->n_ids = n; r->n_tii_frames = s_ntii; r->norm = s_norm; r->noise = s_noise;
     }
     res[blockIdx.x].spectrum[t] = fmaxf(spec[t], 0.f);

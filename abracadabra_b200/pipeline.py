@@ -53,7 +53,8 @@ class Result(ct.Structure):
                 ("rs_corrected", ct.c_int64), ("rs_bit_errors", ct.c_int64), ("rs_uncorrectable", ct.c_int64),
                 ("firecode_fail", ct.c_int64), ("superframes", ct.c_int64),
                 ("n_tii", ct.c_int32), ("tii", ct.POINTER(Tii)),
-                ("symstat", ct.POINTER(ct.c_float)), ("snr_db", ct.c_float), ("gpu_launches", ct.c_int32)]
+                ("symstat", ct.POINTER(ct.c_float)), ("snr_db", ct.c_float), ("gpu_launches", ct.c_int32),
+                ("tii_fold", ct.POINTER(ct.c_float)), ("tii_norm", ct.POINTER(ct.c_float)), ("tii_sign", ct.POINTER(ct.c_int32))]
 
 
 def build(verbose: bool = False) -> None:

@@ -97,6 +97,10 @@ typedef struct {
     const float *symstat;            /* [n_slots * 75 * 2] mean |soft|, mean soft^2 before scaling (OPT_SYMSTAT) */
     float snr_db;                    /* decision-directed estimate over all frames (OPT_SYMSTAT) */
     int32_t gpu_launches;            /* kernels launched by this call */
+    /* per-frame TII material for streaming callers (OPT_TII): folded null spectra, reference magnitude, TII/reference sign */
+    const float *tii_fold;           /* [n_slots][384] */
+    const float *tii_norm;           /* [n_slots] */
+    const int32_t *tii_sign;         /* [n_slots] +1 TII null, -1 reference null, 0 unknown */
 } b200dab_result_t;
 
 B200DAB_API int b200dab_version(void);

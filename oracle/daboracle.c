@@ -7,6 +7,7 @@
  * logs of the binary.  The sample conversion follows src/input/rawfileinput.cpp:643-711 (u8: x-128, s16: x).
  */
 #include "daboracle.h"
+#include "../include/b200dab_tii_gain.h"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -559,23 +560,19 @@ void orc_tii_null(const void *raw, int fmt, uint64_t nsamp, int64_t t_f, float c
     orc_fft2048(spec, 0);
 }
 
-void orc_tii_fold(const float *spec_tii, const float *spec_ref, float *acc)
+void orc_tii_fold(const float *spec, float *fold)
 {
     init_tables();
-    /* carrier pair p (0..191) of comb quarter qd (0..3): carriers c0 = 384*qd + 2p and c0+1 (ascending-k index);
-     * both carry the PRS phase of the lower carrier.  bin 2p+e accumulates the power of member e over the 4 quarters,
-     * minus the power seen in the TII-free reference null. */
-    for (int p = 0; p < TII_PAIRS; p++)
-        for (int e = 0; e < 2; e++) {
-            float a = 0.f;
-            for (int qd = 0; qd < 4; qd++) {
-                int b = g_c_bin[384 * qd + 2 * p + e];
-                float pw = spec_tii[2 * b] * spec_tii[2 * b] + spec_tii[2 * b + 1] * spec_tii[2 * b + 1];
-                if (spec_ref) pw -= spec_ref[2 * b] * spec_ref[2 * b] + spec_ref[2 * b + 1] * spec_ref[2 * b + 1];
-                a += pw;
-            }
-            acc[2 * p + e] += a;
+    /* carrier pair p (0..191) of comb quarter qd (0..3): carriers 384*qd + 2p and + 2p + 1 (ascending-k index).
+     * fold[2p + e] = sum over the four quarters of |N[k]| -- magnitudes, as the reference's levels are linear in amplitude */
+    for (int i = 0; i < TII_SPECTRUM_BINS; i++) {
+        float a = 0.f;
+        for (int qd = 0; qd < 4; qd++) {
+            int b = g_c_bin[384 * qd + i];
+            a += sqrtf(spec[2 * b] * spec[2 * b] + spec[2 * b + 1] * spec[2 * b + 1]);
         }
+        fold[i] = a * B200DAB_TII_GAIN[i];
+    }
 }
 
 static int tii_pattern(int main_id)
@@ -585,40 +582,57 @@ static int tii_pattern(int main_id)
     return 0;
 }
 
-int orc_tii_detect(const float *acc, int n_acc, uint8_t *mains, uint8_t *subs, float *levels, int max_ids)
+/* accumulate sign[f] * fold[f] over n frames (+1 = TII null, -1 = TII-free reference null), then the comb search.
+ * norm[f] = rms PRS carrier magnitude of frame f.  Returns the number of ids; ids ordered by sub then main. */
+int orc_tii_detect(const float *fold, const float *norm, const int32_t *sign, int n, float thr_k, uint8_t *mains, uint8_t *subs,
+                   float *levels, int max_ids, float *spectrum /* 384 */)
 {
-    /* pair power E[b][sub] = acc[2p] + acc[2p+1], p = 24 b + sub.  A transmitter (main, sub) lights 4 of the 8 comb
-     * blocks b.  Noise floor = median-like estimate from the weakest half of all pairs. */
-    float E[8][24];
-    float sorted[TII_PAIRS];
-    for (int p = 0; p < TII_PAIRS; p++) { float v = (acc[2 * p] + acc[2 * p + 1]) / (float)(n_acc > 0 ? n_acc : 1); E[p / 24][p % 24] = v; sorted[p] = v; }
-    for (int i = 1; i < TII_PAIRS; i++) { float v = sorted[i]; int j = i - 1; while (j >= 0 && sorted[j] > v) { sorted[j + 1] = sorted[j]; j--; } sorted[j + 1] = v; }
-    float floor_ = sorted[TII_PAIRS / 4];
-    if (floor_ < 0.f) floor_ = 0.f;
-    float peak = sorted[TII_PAIRS - 1];
-    float thr = floor_ * 8.f + peak * 0.01f;
-    int n = 0;
-    for (int sub = 0; sub < 24 && n < max_ids; sub++) {
-        int mask = 0, cnt = 0;
-        for (int b = 0; b < 8; b++) if (E[b][sub] > thr) { mask |= 0x80 >> b; cnt++; }
-        if (cnt < 4) continue;
-        /* enumerate patterns contained in mask, strongest first is not needed for cnt == 4 */
-        for (int m = 0; m < 70 && n < max_ids; m++) {
-            int pat = tii_pattern(m);
-            if ((pat & mask) != pat) continue;
-            if (cnt > 4) {
-                /* overlapping transmitters: accept a pattern only if its four blocks are the consistent ones */
-                float mn = 1e30f, mx = 0.f;
-                for (int b = 0; b < 8; b++) if (pat & (0x80 >> b)) { if (E[b][sub] < mn) mn = E[b][sub]; if (E[b][sub] > mx) mx = E[b][sub]; }
-                if (mn < 0.25f * mx) continue;
-            }
-            float lv = 0.f;
-            for (int b = 0; b < 8; b++) if (pat & (0x80 >> b)) lv += E[b][sub];
-            mains[n] = (uint8_t)m; subs[n] = (uint8_t)sub; levels[n] = sqrtf(lv / 4.f);
-            n++;
-        }
+    float spec[TII_SPECTRUM_BINS], pair[TII_PAIRS], absv[TII_PAIRS];
+    for (int t = 0; t < TII_SPECTRUM_BINS; t++) {
+        float a = 0.f;
+        for (int f = 0; f < n; f++) if (sign[f]) a += (float)sign[f] * fold[(size_t)f * TII_SPECTRUM_BINS + t];
+        spec[t] = a;
     }
-    return n;
+    float nm = 0.f;
+    for (int f = 0; f < n; f++) if (sign[f] > 0) nm += norm[f];
+    nm *= 4.f;
+    for (int p = 0; p < TII_PAIRS; p++) { pair[p] = spec[2 * p] + spec[2 * p + 1]; absv[p] = fabsf(pair[p]); }
+    /* median and maximum of |pair| */
+    for (int i = 1; i < TII_PAIRS; i++) { float v = absv[i]; int j = i - 1; while (j >= 0 && absv[j] > v) { absv[j + 1] = absv[j]; j--; } absv[j + 1] = v; }
+    float noise = absv[TII_PAIRS / 2], peak = absv[TII_PAIRS - 1];
+    float thr = fmaxf(thr_k * noise, 0.05f * peak);
+    float binmax = 0.f;
+    for (int t = 0; t < TII_SPECTRUM_BINS; t++) binmax = fmaxf(binmax, spec[t]);
+    int cnt = 0;
+    for (int sub = 0; sub < 24 && cnt < max_ids; sub++)
+        for (int m = 0; m < 70 && cnt < max_ids; m++) {
+            unsigned pat = (unsigned)tii_pattern(m), mask = 0;
+            int lit = 0; float mn = 1e30f, mx = 0.f, sum = 0.f;
+            for (int b = 0; b < 8; b++) {
+                float v = pair[24 * b + sub];
+                if (v > thr) { mask |= 0x80u >> b; lit++; }
+                if (pat & (0x80u >> b)) { mn = fminf(mn, v); mx = fmaxf(mx, v); sum += v; }
+            }
+            int hit = (mask & pat) == pat;
+            if (hit && lit > 4) hit = mn >= 0.5f * mx;
+            if (!hit) continue;
+            mains[cnt] = (uint8_t)m; subs[cnt] = (uint8_t)sub; levels[cnt] = binmax > 0.f ? (sum / 8.f) / binmax : 0.f;
+            cnt++;
+        }
+    if (spectrum) for (int t = 0; t < TII_SPECTRUM_BINS; t++) spectrum[t] = fmaxf(spec[t], 0.f);
+    return cnt;
+}
+
+/* rms magnitude of the PRS carriers of a frame (TII level reference) */
+float orc_prs_rms(const void *raw, int fmt, uint64_t nsamp, int64_t t_f, float cfo_hz)
+{
+    init_tables();
+    static float X[2 * DAB_NFFT];
+    load_derot(raw, fmt, nsamp, t_f, (double)cfo_hz, 0, X);
+    orc_fft2048(X, 0);
+    float acc = 0.f;
+    for (int c = 0; c < DAB_NCARR; c++) { int b = g_c_bin[c]; acc += X[2 * b] * X[2 * b] + X[2 * b + 1] * X[2 * b + 1]; }
+    return sqrtf(acc / (float)DAB_NCARR);
 }
 
 /* ======================================================================= whole chain */

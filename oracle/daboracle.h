@@ -59,9 +59,11 @@ int  orc_superframe(uint8_t *sf, int s, int *au_off, int *au_len, int *au_crc_ok
                     int *rs_uncorrectable, int *firecode_ok);
 /* ---- TII */
 void orc_tii_null(const void *raw, int fmt, uint64_t nsamp, int64_t t_f, float cfo_hz, float *spec2048 /* re,im interleaved 4096 */);
-/* fold one TII null spectrum (minus optional reference null) into 384 bins */
-void orc_tii_fold(const float *spec_tii, const float *spec_ref, float *acc384);
-int  orc_tii_detect(const float *acc384, int n_acc, uint8_t *mains, uint8_t *subs, float *levels, int max_ids);
+/* fold one null-symbol spectrum into 384 bins: sum over the four carrier quarters of |N[k]| */
+void orc_tii_fold(const float *spec2048, float *fold384);
+int  orc_tii_detect(const float *fold, const float *norm, const int32_t *sign, int n, float thr_k, uint8_t *mains, uint8_t *subs,
+                    float *levels, int max_ids, float *spectrum384);
+float orc_prs_rms(const void *raw, int fmt, uint64_t nsamp, int64_t t_f, float cfo_hz);
 /* ---- whole chain (CPU baseline "port"): returns number of frames decoded */
 int  orc_decode(const void *raw, int fmt, uint64_t nsamp, const orc_subch_t *sc, int n_sc,
                 uint8_t *fibs /* [4*max_frames][96] */, uint8_t *fib_ok /* [12*max_frames] */,

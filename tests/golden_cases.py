@@ -1,0 +1,51 @@
+"""Seeded definitions of the golden-fixture inputs (shared by tests/golden/make_golden.py and the tests)."""
+import gzip
+import hashlib
+import json
+from pathlib import Path
+
+from abracadabra_b200 import synth
+
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
+
+CASES = {
+    # BASELINE.json configs[0] in small: FIC + one DAB+ 96 kbps EEP-3A sub-channel, TII (12,5), u8
+    "c1_u8_40db": dict(kind="config1", n_frames=46, fmt="u8", snr=40.0, cfo=123.4, seed=1, tii=[(12, 5, 1.0, 0)], tii_mode=1, service=0),
+    # near the decoding threshold: RS has work to do
+    "c1_u8_4p5db": dict(kind="config1", n_frames=30, fmt="u8", snr=4.5, cfo=-3456.7, seed=5, tii=[], tii_mode=None, service=0),
+    # s16 samples, large negative CFO
+    "c1_s16_12db": dict(kind="config1", n_frames=24, fmt="s16", snr=12.0, cfo=-8765.4, seed=9, tii=[], tii_mode=None, service=0),
+    # three overlapping transmitters with different amplitude and delay
+    "tii3_u8_25db": dict(kind="config1", n_frames=46, fmt="u8", snr=25.0, cfo=50.0, seed=3,
+                         tii=[(12, 5, 1.0, 0), (33, 17, 0.5, 30), (60, 2, 0.25, 100)], tii_mode=1, service=None),
+    # several sub-channels with different protection (EEP-A/B, UEP); the reference decodes the selected one
+    "multi_u8_25db": dict(kind="multi", n_frames=22, fmt="u8", snr=25.0, cfo=-2345.6, seed=21, tii=[(3, 9, 1.0, 0)], tii_mode=None, service=2),
+}
+
+
+def build_case(spec):
+    if spec["kind"] == "config1":
+        ens = synth.config1_ensemble(seed=1000 + spec["seed"])
+        ens.tii = [synth.TiiTx(m, s, a, delay=d) for m, s, a, d in spec["tii"]]
+    else:
+        seed = spec["seed"]
+        subs = [synth.SubChannel(1, 0, "dabplus", 96, ("EEP", 3, "A"), seed=seed),
+                synth.SubChannel(2, 72, "dabplus", 64, ("EEP", 2, "A"), seed=seed + 1),
+                synth.SubChannel(5, 140, "dabplus", 64, ("EEP", 3, "B"), seed=seed + 2),
+                synth.SubChannel(9, 200, "mp2", 128, ("UEP", 35), seed=seed + 3),
+                synth.SubChannel(11, 300, "dabplus", 32, ("EEP", 1, "A"), seed=seed + 4)]
+        svcs = [synth.Service(0x3000 + i, f"MULTI {i}", s.subchid) for i, s in enumerate(subs)]
+        ens = synth.EnsembleConfig(eid=0x3003, label="B200 MULTI", subchannels=subs, services=svcs,
+                                   tii=[synth.TiiTx(m, s, a, delay=d) for m, s, a, d in spec["tii"]])
+    imp = synth.Impairments(snr_db=spec["snr"], cfo_hz=spec["cfo"], seed=spec["seed"])
+    raw, res = synth.synthesize(ens, spec["n_frames"], spec["fmt"], imp, seed=spec["seed"], tail=150000)
+    return raw, res
+
+
+def load_golden(name):
+    with gzip.open(GOLDEN_DIR / f"{name}.json.gz", "rt") as f:
+        return json.load(f)
+
+
+def raw_matches(raw, golden) -> bool:
+    return hashlib.sha1(raw.tobytes()).hexdigest() == golden["raw_sha1"]

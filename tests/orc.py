@@ -73,9 +73,11 @@ def lib():
         L.orc_superframe.argtypes = [vp, i32, vp, vp, vp, ct.POINTER(i32), ct.POINTER(i32), ct.POINTER(i32), ct.POINTER(i32)]
         L.orc_superframe.restype = i32
         L.orc_tii_null.argtypes = [vp, i32, u64, i64, ct.c_float, vp]
-        L.orc_tii_fold.argtypes = [vp, vp, vp]
-        L.orc_tii_detect.argtypes = [vp, i32, vp, vp, vp, i32]
+        L.orc_tii_fold.argtypes = [vp, vp]
+        L.orc_tii_detect.argtypes = [vp, vp, vp, i32, ct.c_float, vp, vp, vp, i32, vp]
         L.orc_tii_detect.restype = i32
+        L.orc_prs_rms.argtypes = [vp, i32, u64, i64, ct.c_float]
+        L.orc_prs_rms.restype = ct.c_float
         L.orc_decode.argtypes = [vp, i32, u64, ct.POINTER(SubCh), i32, vp, vp, ct.POINTER(vp), vp, vp, i32]
         L.orc_decode.restype = i32
         _lib = L
@@ -192,6 +194,33 @@ def superframe(sf: np.ndarray, s: int):
     aus = [bytes(sf[off[i]:off[i] + ln[i]]) for i in range(n)]
     return dict(n=n, aus=aus, crc_ok=ok[:n].tolist(), corrected=c.value, bit_errors=b.value, uncorrectable=u.value,
                 firecode_ok=f.value, data=sf)
+
+
+def tii_null_spectrum(raw, fmt, t_f, cfo):
+    spec = np.zeros(2048, dtype=np.complex64)
+    lib().orc_tii_null(_p(raw), FMT[fmt], nsamples(raw, fmt), int(t_f), float(cfo), _p(spec))
+    return spec
+
+
+def tii_fold(spec: np.ndarray) -> np.ndarray:
+    spec = np.ascontiguousarray(spec, dtype=np.complex64)
+    fold = np.zeros(384, dtype=np.float32)
+    lib().orc_tii_fold(_p(spec), _p(fold))
+    return fold
+
+
+def prs_rms(raw, fmt, t_f, cfo) -> float:
+    return float(lib().orc_prs_rms(_p(raw), FMT[fmt], nsamples(raw, fmt), int(t_f), float(cfo)))
+
+
+def tii_detect(fold, norm, sign, thr_k=6.0):
+    fold = np.ascontiguousarray(fold, dtype=np.float32)
+    norm = np.ascontiguousarray(norm, dtype=np.float32)
+    sign = np.ascontiguousarray(sign, dtype=np.int32)
+    mains = np.zeros(24, np.uint8); subs = np.zeros(24, np.uint8); lv = np.zeros(24, np.float32)
+    spec = np.zeros(384, np.float32)
+    n = lib().orc_tii_detect(_p(fold), _p(norm), _p(sign), fold.shape[0], float(thr_k), _p(mains), _p(subs), _p(lv), 24, _p(spec))
+    return [(int(mains[i]), int(subs[i]), float(lv[i])) for i in range(n)], spec
 
 
 def decode(raw, fmt, subchs, max_frames=None):

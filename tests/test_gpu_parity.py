@@ -168,3 +168,35 @@ def test_tii_ids(receiver):
     assert 0.85 < lv[(12, 5)] < 1.1
     sp = dec.tii[0].spectrum
     assert int(np.argmax(sp)) // 2 in [b * 24 + 5 for b in (2, 3, 4, 7)]
+
+
+def test_tii_fold_and_detect_match_oracle(receiver, oracle):
+    """BASELINE.json configs[2] at kernel level: a batch of null symbols with 1-8 overlapping transmitters, CFO already
+    removed; fold within 1e-4 relative of the checker, ids exact, levels within 1e-4."""
+    from abracadabra_b200 import synth
+    rng = np.random.default_rng(12)
+    n_sets, per = 12, 20
+    for k in range(n_sets):
+        n_tx = 1 + (k % 8)
+        subs = rng.choice(np.arange(1, 24), n_tx, replace=False)
+        ens = synth.EnsembleConfig(tii=[synth.TiiTx(int(rng.integers(0, 70)), int(s), float(rng.uniform(0.2, 1.0)), delay=int(rng.integers(0, 300)),
+                                                    phase=float(rng.uniform(0, 6.28))) for s in subs])
+        sym = synth.tii_symbol(ens)[-2048:]
+        nulls = np.zeros((2 * per, 2048), np.complex64)
+        sigma = 10 ** (-rng.uniform(10, 30) / 20) * np.sqrt(0.5)
+        noise = (rng.standard_normal((2 * per, 2048)) + 1j * rng.standard_normal((2 * per, 2048))) * sigma
+        nulls[0::2] = sym
+        nulls += noise.astype(np.complex64)
+        fold = receiver.stage_tii_fold(nulls)
+        fo = np.array([oracle.tii_fold(oracle.fft2048(x)) for x in nulls])
+        assert np.allclose(fold, fo, rtol=1e-4, atol=1e-3 * fo.max())
+        norm = np.full(2 * per, 1.0, np.float32)
+        sign = np.tile(np.array([1, -1], np.int32), per)
+        got = receiver.stage_tii_detect(fo, norm, sign)           # same fold in: the integer decisions must be identical
+        ids_o, spec_o = oracle.tii_detect(fo, norm, sign)
+        assert [(m, s) for m, s, _ in got.ids] == [(m, s) for m, s, _ in ids_o]
+        assert np.allclose([l for _, _, l in got.ids], [l for _, _, l in ids_o], rtol=1e-4)
+        assert np.allclose(got.spectrum, spec_o, rtol=1e-5, atol=1e-3)
+        want = sorted((tx.sub, tx.main) for tx in ens.tii if tx.amp >= 0.3)
+        have = [(s, m) for m, s, _ in got.ids]
+        assert all(w in have for w in want), (want, have)

