@@ -312,7 +312,7 @@ bool handle_request(dabsdr_s* h, const Request& r)
         h->tii_on = r.a != 0; h->tii_mode = r.c;
         h->tii_fold.clear(); h->tii_norm.clear(); h->tii_sign.clear();
         std::fill(h->tii_spectrum.begin(), h->tii_spectrum.end(), 0.f);
-        if (h->tii_on) send_tii(h, nullptr);
+        if (h->tii_on && h->freq != 0) send_tii(h, nullptr);     // untuned: the empty list follows NID_RESET of the next tune
         break;
     case R_SPECTRUM:
         h->spectrum_on = r.a != 0;
@@ -480,13 +480,12 @@ void* worker(void* arg)
             }
         }
         if (h->freq == 0 || !h->in || !h->gpu) continue;
-        // pull what is missing to fill the window (blocks inside the input function = flow control)
-        while (h->have < WIN_SAMPLES) {
+        // pull one chunk (blocks inside the input function = flow control); requests are looked at again after every chunk,
+        // i.e. every 8 ms of signal, so a request/notification round trip costs less than one transmission frame
+        {
             const int64_t n = std::min<int64_t>(16384, WIN_SAMPLES - h->have);
             h->in(h->win.data() + 2 * h->have, (uint16_t)n);
             h->have += n;
-            std::lock_guard<std::mutex> lk(h->mx);
-            if (!h->q.empty() && (h->q.front().type == R_EXIT || h->q.front().type == R_TUNE)) break;
         }
         if (h->have < WIN_SAMPLES) continue;
         process_window(h);

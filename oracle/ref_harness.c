@@ -196,6 +196,8 @@ static void spectrum_cb(const float *p, dabsdrSpectrum_t type, void *ctx)
     g_n_spec++;
 }
 
+static void log_notification(const ev_t *e);
+
 static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
 {
     (void)ctx;
@@ -205,6 +207,8 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
     e->payload_len = -1;
     if (p->pData) {
         int n = p->len < sizeof e->payload ? p->len : (int)sizeof e->payload;
+        /* TUNE / RESET: the caller dereferences pData as a 32-bit value whatever `len` says (src/radiocontrol.cpp:2261, :2437) */
+        if ((p->nid == DABSDR_NID_TUNE || p->nid == DABSDR_NID_RESET) && n < 4) n = 4;
         memcpy(e->payload, p->pData, n);
         e->payload_len = n;
     }
@@ -261,6 +265,8 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
         pthread_mutex_unlock(&g_logmx);
 #undef g_log
     }
+    e->pos = g_pos;
+    log_notification(e);
     post_event(e);
 }
 
@@ -274,20 +280,62 @@ static int g_need_ensemble, g_have_ensemble, g_selected, g_selected2, g_fic_sync
 static uint32_t g_retry_sid; static int g_retry_ticks;
 static uint64_t g_fib_err, g_rs_bit, g_rs_unc, g_crc_ok, g_crc_err, g_n_periodic;
 
-static void handle_event(ev_t *e)
+/* logging happens inside the callback (exact callback order); handle_event only runs the RadioControl-like protocol */
+static void log_notification(const ev_t *e)
 {
     FILE *f = g_log;
-    if (f) pthread_mutex_lock(&g_logmx);
+    if (!f) return;
+    pthread_mutex_lock(&g_logmx);
+    switch (e->kind) {
+    case DABSDR_NID_SYNC_STATUS: {
+        const dabsdrNtfSyncStatus_t *s = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"sync\",\"pos\":%llu,\"level\":%d,\"snr10\":%d}\n", (unsigned long long)e->pos, (int)s->syncLevel, s->snr10);
+        break; }
+    case DABSDR_NID_TUNE:
+        fprintf(f, "{\"ev\":\"tune\",\"pos\":%llu,\"freq\":%u}\n", (unsigned long long)e->pos, e->payload_len >= 4 ? *(const uint32_t *)e->payload : 0);
+        break;
+    case DABSDR_NID_RESET:
+        fprintf(f, "{\"ev\":\"reset\",\"pos\":%llu,\"flag\":%d}\n", (unsigned long long)e->pos, e->payload_len >= 4 ? *(const int *)e->payload : -1);
+        break;
+    case DABSDR_NID_ENSEMBLE_INFO: {
+        const dabsdrNtfEnsemble_t *en = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"ensemble\",\"pos\":%llu,\"status\":%d,\"freq\":%u,\"ueid\":%u,\"lto\":%d,\"inttable\":%u,\"alarm\":%u,",
+                (unsigned long long)e->pos, e->status, en->frequency, en->ueid, en->LTO, en->intTable, en->alarm);
+        log_label(f, &en->label);
+        fprintf(f, "}\n");
+        break; }
+    case DABSDR_NID_SERVICE_SELECTION: {
+        const dabsdrNtfServiceSelection_t *s = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"selection\",\"pos\":%llu,\"status\":%d,\"sid\":%u,\"scids\":%u,\"id\":%d}\n",
+                (unsigned long long)e->pos, e->status, s->SId, s->SCIdS, (int)s->id);
+        break; }
+    case DABSDR_NID_PERIODIC: {
+        if (e->payload_len < 0) { fprintf(f, "{\"ev\":\"periodic\",\"pos\":%llu,\"null\":1}\n", (unsigned long long)e->pos); break; }
+        const dabsdrNtfPeriodic_t *pp = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"periodic\",\"pos\":%llu,\"level\":%d,\"snr10\":%d,\"freqOffset\":%d,\"date\":%u,\"secmsec\":%u,\"fibErr\":%u,"
+                   "\"crcOk\":%u,\"crcErr\":%u,\"audioBytes\":%u,\"padBytes\":%u,\"rsUnc\":%u,\"rsBitErr\":%u,\"rsBytes\":%u}\n",
+                (unsigned long long)e->pos, (int)pp->syncLevel, pp->snr10, pp->freqOffset, pp->dateHoursMinutes, pp->secMsec,
+                pp->fibErrorCntr, pp->mscCrcOkCntr, pp->mscCrcErrorCntr, pp->audioServiceBytes, pp->padBytes,
+                pp->rsUncorrectableCntr, pp->rsBitErrors, pp->rsBytes);
+        break; }
+    case DABSDR_NID_SERVICE_LIST: case DABSDR_NID_SERVICE_COMPONENT_LIST: case DABSDR_NID_TII:
+        break;                      /* logged with their accessor data in notif_cb */
+    default:
+        fprintf(f, "{\"ev\":\"other\",\"pos\":%llu,\"nid\":%d,\"status\":%d,\"len\":%d}\n", (unsigned long long)e->pos, e->kind, e->status, e->payload_len);
+        break;
+    }
+    pthread_mutex_unlock(&g_logmx);
+}
+
+static void handle_event(ev_t *e)
+{
     switch (e->kind) {
     case -1: /* tick, once per frame of signal */
         if (g_need_ensemble && g_fic_sync && !g_have_ensemble) dabsdrRequest_GetEnsemble(g_h);
         if (g_retry_ticks > 0 && --g_retry_ticks == 0) dabsdrRequest_GetServiceComponents(g_h, g_retry_sid);
         break;
-    case -2:
-        break;
     case DABSDR_NID_SYNC_STATUS: {
         const dabsdrNtfSyncStatus_t *s = (const void *)e->payload;
-        if (f) fprintf(f, "{\"ev\":\"sync\",\"pos\":%llu,\"level\":%d,\"snr10\":%d}\n", (unsigned long long)e->pos, (int)s->syncLevel, s->snr10);
         if (s->syncLevel == DABSDR_SYNC_LEVEL_FIC && !g_fic_sync) {
             g_fic_sync = 1;
             dabsdrRequest_SetPeriodicNotify(g_h, 3, 0);
@@ -295,20 +343,8 @@ static void handle_event(ev_t *e)
         }
         if (s->syncLevel == DABSDR_SYNC_LEVEL_NO_SYNC) g_fic_sync = 0;
         break; }
-    case DABSDR_NID_TUNE:
-        if (f) fprintf(f, "{\"ev\":\"tune\",\"pos\":%llu,\"freq\":%u}\n", (unsigned long long)e->pos, e->payload_len >= 4 ? *(uint32_t *)e->payload : 0);
-        break;
-    case DABSDR_NID_RESET:
-        if (f) fprintf(f, "{\"ev\":\"reset\",\"pos\":%llu,\"flag\":%d}\n", (unsigned long long)e->pos, e->payload_len >= 4 ? *(int *)e->payload : -1);
-        break;
     case DABSDR_NID_ENSEMBLE_INFO: {
         const dabsdrNtfEnsemble_t *en = (const void *)e->payload;
-        if (f) {
-            fprintf(f, "{\"ev\":\"ensemble\",\"pos\":%llu,\"status\":%d,\"freq\":%u,\"ueid\":%u,\"lto\":%d,\"inttable\":%u,\"alarm\":%u,",
-                    (unsigned long long)e->pos, e->status, en->frequency, en->ueid, en->LTO, en->intTable, en->alarm);
-            log_label(f, &en->label);
-            fprintf(f, "}\n");
-        }
         /* accepted only once ECC != 0 and label non-empty (reference: src/radiocontrol.cpp:1396) */
         if (e->payload_len > 0 && ((en->ueid >> 16) & 0xFF) != 0 && en->label.str[0] != 0 && !g_have_ensemble) {
             g_have_ensemble = 1; g_need_ensemble = 0;
@@ -334,29 +370,15 @@ static void handle_event(ev_t *e)
             } else { g_retry_sid = e->sc_sid; g_retry_ticks = 2; }
         }
         break; }
-    case DABSDR_NID_SERVICE_SELECTION: {
-        const dabsdrNtfServiceSelection_t *s = (const void *)e->payload;
-        if (f) fprintf(f, "{\"ev\":\"selection\",\"pos\":%llu,\"status\":%d,\"sid\":%u,\"scids\":%u,\"id\":%d}\n",
-                       (unsigned long long)e->pos, e->status, s->SId, s->SCIdS, (int)s->id);
-        break; }
     case DABSDR_NID_PERIODIC: {
-        if (e->payload_len < 0) { if (f) fprintf(f, "{\"ev\":\"periodic\",\"pos\":%llu,\"null\":1}\n", (unsigned long long)e->pos); break; }
+        if (e->payload_len < 0) break;
         const dabsdrNtfPeriodic_t *pp = (const void *)e->payload;
         g_fib_err += pp->fibErrorCntr; g_rs_bit += pp->rsBitErrors; g_rs_unc += pp->rsUncorrectableCntr;
         g_crc_ok += pp->mscCrcOkCntr; g_crc_err += pp->mscCrcErrorCntr; g_n_periodic++;
-        if (f) fprintf(f, "{\"ev\":\"periodic\",\"pos\":%llu,\"level\":%d,\"snr10\":%d,\"freqOffset\":%d,\"date\":%u,\"secmsec\":%u,\"fibErr\":%u,"
-                          "\"crcOk\":%u,\"crcErr\":%u,\"audioBytes\":%u,\"padBytes\":%u,\"rsUnc\":%u,\"rsBitErr\":%u,\"rsBytes\":%u}\n",
-                       (unsigned long long)e->pos, (int)pp->syncLevel, pp->snr10, pp->freqOffset, pp->dateHoursMinutes, pp->secMsec,
-                       pp->fibErrorCntr, pp->mscCrcOkCntr, pp->mscCrcErrorCntr, pp->audioServiceBytes, pp->padBytes,
-                       pp->rsUncorrectableCntr, pp->rsBitErrors, pp->rsBytes);
         break; }
-    case DABSDR_NID_TII:
-        break;
     default:
-        if (f) fprintf(f, "{\"ev\":\"other\",\"pos\":%llu,\"nid\":%d,\"status\":%d,\"len\":%d}\n", (unsigned long long)e->pos, e->kind, e->status, e->payload_len);
         break;
     }
-    if (f) pthread_mutex_unlock(&g_logmx);
 }
 
 int main(int argc, char **argv)
