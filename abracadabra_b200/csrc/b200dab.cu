@@ -114,7 +114,14 @@ struct b200dab_ctx {
     int upload_raw(const void* iq, uint64_t n, int fmt, int mem, const void** d_out);
     int coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, int* max_cand_out);
     int fine(const void* d_iq, uint64_t n, int fmt, int n_cand);
-    int demod(const void* d_iq, uint64_t n, int fmt, const FrameInfo* h_fr, int n_frames, int n_slots, bool symstat);
+    int prepare_slots(int max_slots, bool want_stat, bool want_tii);
+    int demod(const void* d_iq, uint64_t n_visible, int fmt, int first, int count, bool want_stat, bool want_tii);
+    int front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len, bool want_stat, bool want_tii, int max_slots);
+    // front-end state across the ranges of one decode
+    size_t fe_frames = 0; long long fe_t0 = 0, fe_last = 0; int fe_candidates = 0;
+    std::vector<float> fe_cir;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
     int run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out);
     int fic(int n_slots);
     int msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std::vector<size_t>& out_off, size_t* total);
@@ -122,6 +129,7 @@ struct b200dab_ctx {
 };
 
 static size_t fmt_bytes(int fmt) { return fmt == B200DAB_FMT_U8 ? 2 : fmt == B200DAB_FMT_S16 ? 4 : 8; }
+#define FRONT_CHUNK_FRAMES 64     /* host uploads are pipelined in chunks of 64 transmission frames (25 MB of u8) */
 
 int b200dab_ctx::init_tables()
 {
@@ -218,50 +226,87 @@ int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
     return 0;
 }
 
-// keep sharp PRS correlations, at most one per frame period; slot = frame number relative to the first accepted frame
-static int chain_frames(const FineOut* f, int n, std::vector<FrameInfo>& out, std::vector<float>& cir)
+// ------------------------------------------------------------------------------------------------ OFDM demod
+// soft-bit / statistics / TII buffers for up to max_slots frames; cleared once so that lost frames read as erasures
+int b200dab_ctx::prepare_slots(int max_slots, bool want_stat, bool want_tii)
 {
-    out.clear(); cir.clear();
-    long long t0 = 0, last = 0;
-    for (int i = 0; i < n; i++) {
-        if (!(f[i].cir_ratio >= SYNC_CIR_MIN)) continue;
-        if (!out.empty() && f[i].t_f - last < (long long)(DAB_T_FRAME * 9 / 10)) continue;
-        if (out.empty()) t0 = f[i].t_f;
-        FrameInfo fi;
-        fi.t_f = f[i].t_f; fi.cfo_hz = f[i].cfo_hz;
-        fi.slot = (int)((f[i].t_f - t0 + DAB_T_FRAME / 2) / DAB_T_FRAME);
-        out.push_back(fi);
-        cir.push_back(f[i].cir_ratio);
-        last = f[i].t_f;
+    CK(d_frames.ensure((size_t)max_slots * sizeof(FrameInfo)));
+    CK(h_frames.ensure((size_t)max_slots * sizeof(FrameInfo)));
+    CK(d_soft.ensure((size_t)max_slots * DAB_FRAME_SOFT + 256));
+    CK(cudaMemsetAsync(d_soft.p, 0, (size_t)max_slots * DAB_FRAME_SOFT, stream));
+    if (want_stat) {
+        CK(d_symstat.ensure((size_t)max_slots * 150 * 4));
+        CK(cudaMemsetAsync(d_symstat.p, 0, (size_t)max_slots * 150 * 4, stream));
     }
-    return out.empty() ? 0 : out.back().slot + 1;
+    if (want_tii) {
+        CK(d_fold.ensure((size_t)max_slots * TII_SPECTRUM_BINS * 4));
+        CK(d_norm.ensure((size_t)max_slots * 4));
+        CK(cudaMemsetAsync(d_fold.p, 0, (size_t)max_slots * TII_SPECTRUM_BINS * 4, stream));
+        CK(cudaMemsetAsync(d_norm.p, 0, (size_t)max_slots * 4, stream));
+    }
+    return 0;
 }
 
-// ------------------------------------------------------------------------------------------------ OFDM demod
-int b200dab_ctx::demod(const void* d_iq, uint64_t n, int fmt, const FrameInfo* h_fr, int n_frames, int n_slots, bool want_stat)
+// OFDM demodulation (and TII fold) of frames [first, first + count) of h_frames; n_visible = samples valid in d_iq
+int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int first, int count, bool want_stat, bool want_tii)
 {
-    if (n_frames <= 0) return 0;
-    CK(d_frames.ensure((size_t)n_frames * sizeof(FrameInfo)));
-    CK(cudaMemcpyAsync(d_frames.p, h_fr, (size_t)n_frames * sizeof(FrameInfo), cudaMemcpyHostToDevice, stream));
-    CK(d_soft.ensure((size_t)n_slots * DAB_FRAME_SOFT + 256));
-    if (n_frames < n_slots) CK(cudaMemsetAsync(d_soft.p, 0, (size_t)n_slots * DAB_FRAME_SOFT, stream));   // lost frames = erasures
-    float* st = nullptr;
-    if (want_stat) {
-        CK(d_symstat.ensure((size_t)n_slots * 150 * 4));
-        CK(cudaMemsetAsync(d_symstat.p, 0, (size_t)n_slots * 150 * 4, stream));
-        st = d_symstat.as<float>();
-    }
-    const unsigned grid = (unsigned)n_frames * OFDM_GROUPS;
+    if (count <= 0) return 0;
+    FrameInfo* dfr = d_frames.as<FrameInfo>() + first;
+    CK(cudaMemcpyAsync(dfr, h_frames.as<FrameInfo>() + first, (size_t)count * sizeof(FrameInfo), cudaMemcpyHostToDevice, stream));
+    float* st = want_stat ? d_symstat.as<float>() : nullptr;
+    const unsigned grid = (unsigned)count * OFDM_GROUPS;
     const float2* tw = d_tw.as<float2>();
     const uint16_t* fp = d_fdi_pos.as<uint16_t>();
+    const int64_t n = (int64_t)n_visible;
     prof_begin("k_ofdm_demod");
-    if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
-    else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
-    else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_frames.as<FrameInfo>(), tw, fp, d_soft.as<int8_t>(), st);
+    if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
+    else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
+    else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
     prof_end();
     launches += 1;
+    if (want_tii) {
+        prof_begin("k_tii_fold");
+        if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+        else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+        else k_tii_fold<B200DAB_FMT_F32><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+        prof_end();
+        launches += 1;
+    }
     CK(cudaGetLastError());
     return 0;
+}
+
+// Front end over the sample range [off, off + len) of the device buffer: coarse sync, fine sync, host-side chaining with the
+// frames found so far, OFDM demodulation of the new frames.  Ranges must come in ascending order and overlap by more than
+// one frame so that a frame cut by a range boundary is found whole in the next range.
+int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len, bool want_stat, bool want_tii, int max_slots)
+{
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(d_iq) + off * fmt_bytes(fmt);
+    int n_cand = 0, max_cand = 0;
+    if (coarse(base, len, fmt, &n_cand, &max_cand)) return -1;
+    fe_candidates += n_cand;
+    if (n_cand <= 0) return 0;
+    if (fine(base, len, fmt, n_cand)) return -1;
+    CK(h_fine.ensure((size_t)n_cand * sizeof(FineOut)));
+    CK(cudaMemcpyAsync(h_fine.p, d_fine.p, (size_t)n_cand * sizeof(FineOut), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const FineOut* f = h_fine.as<FineOut>();
+    FrameInfo* hf = h_frames.as<FrameInfo>();
+    const int first_new = (int)fe_frames;
+    for (int i = 0; i < n_cand; i++) {
+        if (!(f[i].cir_ratio >= SYNC_CIR_MIN)) continue;
+        const long long t_abs = f[i].t_f + (long long)off;
+        if (fe_frames > 0 && t_abs - fe_last < (long long)(DAB_T_FRAME * 9 / 10)) continue;       // seen already / too close
+        if (fe_frames == 0) fe_t0 = t_abs;
+        const int slot = (int)((t_abs - fe_t0 + DAB_T_FRAME / 2) / DAB_T_FRAME);
+        if (slot >= max_slots) break;
+        FrameInfo fi;
+        fi.t_f = t_abs; fi.cfo_hz = f[i].cfo_hz; fi.slot = slot;
+        hf[fe_frames++] = fi;
+        fe_cir.push_back(f[i].cir_ratio);
+        fe_last = t_abs;
+    }
+    return demod(d_iq, off + len, fmt, first_new, (int)fe_frames - first_new, want_stat, want_tii);
 }
 
 // ------------------------------------------------------------------------------------------------ Viterbi (gather + ACS + traceback)
@@ -496,6 +541,9 @@ void b200dab_destroy(b200dab_ctx* ctx)
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm};
     for (auto* b : hb) b->release();
+    for (auto e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -555,49 +603,49 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     ctx->launches = 0;
     ctx->prof_used = 0;
     ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
-    const void* d_iq = nullptr;
-    if (ctx->upload_raw(iq, n, fmt, mem, &d_iq)) return -1;
-    // ---- sync
-    int n_cand = 0, max_cand = 0;
-    if (ctx->coarse(d_iq, n, fmt, &n_cand, &max_cand)) return -1;
-    res->n_candidates = n_cand;
-    if (ctx->fine(d_iq, n, fmt, n_cand)) return -1;
-    std::vector<FrameInfo> frames;
-    std::vector<float> cir;
-    int n_slots = 0;
-    if (n_cand > 0) {
-        CKC(ctx->h_fine.ensure((size_t)n_cand * sizeof(FineOut)));
-        CKC(cudaMemcpyAsync(ctx->h_fine.p, ctx->d_fine.p, (size_t)n_cand * sizeof(FineOut), cudaMemcpyDeviceToHost, ctx->stream));
-        CKC(cudaStreamSynchronize(ctx->stream));
-        n_slots = chain_frames(ctx->h_fine.as<FineOut>(), n_cand, frames, cir);
+    const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
+    const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
+    const int max_slots = (int)(n / DAB_T_FRAME) + 2;
+    ctx->fe_frames = 0; ctx->fe_t0 = 0; ctx->fe_last = 0; ctx->fe_candidates = 0; ctx->fe_cir.clear();
+    if (ctx->prepare_slots(max_slots, want_stat, want_tii)) return -1;
+    // ---- front end: sync + OFDM demodulation.  A host buffer is uploaded in chunks on a second stream and each chunk is
+    //      synchronised and demodulated while the next one is still crossing PCIe; a device buffer is done in one range.
+    const void* d_iq = iq;
+    const uint64_t chunk = (uint64_t)FRONT_CHUNK_FRAMES * DAB_T_FRAME;
+    const uint64_t lap = (uint64_t)DAB_T_FRAME + 2 * DAB_T_NULL + SYNC_FRAME_MARGIN + 4 * SYNC_WIN * SYNC_BLK;
+    if (mem == B200DAB_MEM_HOST && n > 2 * chunk) {
+        const size_t bps = fmt_bytes(fmt);
+        CKC(ctx->d_raw.ensure((size_t)n * bps + 64));
+        d_iq = ctx->d_raw.p;
+        if (!ctx->copy_stream) CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        const int n_chunks = (int)((n + chunk - 1) / chunk);
+        while ((int)ctx->copy_events.size() < n_chunks) { cudaEvent_t e; CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->copy_events.push_back(e); }
+        for (int c = 0; c < n_chunks; c++) {
+            const uint64_t a0 = (uint64_t)c * chunk, a1 = std::min<uint64_t>(n, a0 + chunk);
+            CKC(cudaMemcpyAsync((uint8_t*)ctx->d_raw.p + a0 * bps, (const uint8_t*)iq + a0 * bps, (size_t)(a1 - a0) * bps, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CKC(cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
+        }
+        for (int c = 0; c < n_chunks; c++) {
+            const uint64_t a1 = std::min<uint64_t>(n, (uint64_t)(c + 1) * chunk);
+            uint64_t a0 = (uint64_t)c * chunk;
+            a0 = a0 > lap ? a0 - lap : 0;
+            a0 &= ~(uint64_t)(SYNC_BLK * 8 - 1);                    // keep 128-bit loads of the block-power kernel aligned
+            CKC(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[c], 0));
+            if (ctx->front_end(d_iq, fmt, a0, a1 - a0, want_stat, want_tii, max_slots)) return -1;
+        }
+    } else {
+        if (ctx->upload_raw(iq, n, fmt, mem, &d_iq)) return -1;
+        if (ctx->front_end(d_iq, fmt, 0, n, want_stat, want_tii, max_slots)) return -1;
     }
-    const int n_frames = (int)frames.size();
+    res->n_candidates = ctx->fe_candidates;
+    const int n_frames = (int)ctx->fe_frames;
+    const FrameInfo* frames = ctx->h_frames.as<FrameInfo>();
+    const int n_slots = n_frames ? frames[n_frames - 1].slot + 1 : 0;
     res->n_frames = n_frames; res->n_slots = n_slots;
     ctx->r_tf.assign(n_slots, -1); ctx->r_cfo.assign(n_slots, 0.f); ctx->r_cir.assign(n_slots, 0.f);
-    for (int i = 0; i < n_frames; i++) { ctx->r_tf[frames[i].slot] = frames[i].t_f; ctx->r_cfo[frames[i].slot] = frames[i].cfo_hz; ctx->r_cir[frames[i].slot] = cir[i]; }
+    for (int i = 0; i < n_frames; i++) { ctx->r_tf[frames[i].slot] = frames[i].t_f; ctx->r_cfo[frames[i].slot] = frames[i].cfo_hz; ctx->r_cir[frames[i].slot] = ctx->fe_cir[i]; }
     res->t_f = ctx->r_tf.data(); res->cfo_hz = ctx->r_cfo.data(); res->cir_ratio = ctx->r_cir.data();
     if (n_frames == 0) { res->gpu_launches = ctx->launches; return 0; }
-    // ---- OFDM demod -> soft bits
-    CKC(ctx->h_frames.ensure((size_t)n_frames * sizeof(FrameInfo)));
-    memcpy(ctx->h_frames.p, frames.data(), (size_t)n_frames * sizeof(FrameInfo));
-    const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
-    if (ctx->demod(d_iq, n, fmt, ctx->h_frames.as<FrameInfo>(), n_frames, n_slots, want_stat)) return -1;
-    // ---- TII fold runs on the raw samples, independent of the decoding chain
-    const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
-    if (want_tii) {
-        CKC(ctx->d_fold.ensure((size_t)n_slots * TII_SPECTRUM_BINS * 4));
-        CKC(ctx->d_norm.ensure((size_t)n_slots * 4));
-        CKC(cudaMemsetAsync(ctx->d_fold.p, 0, (size_t)n_slots * TII_SPECTRUM_BINS * 4, ctx->stream));
-        CKC(cudaMemsetAsync(ctx->d_norm.p, 0, (size_t)n_slots * 4, ctx->stream));
-        const float2* tw = ctx->d_tw.as<float2>();
-        ctx->prof_begin("k_tii_fold");
-        if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
-        else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
-        else k_tii_fold<B200DAB_FMT_F32><<<n_frames, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_frames.as<FrameInfo>(), tw, ctx->d_fold.as<float>(), ctx->d_norm.as<float>());
-        ctx->prof_end();
-        ctx->launches += 1;
-        CKC(cudaGetLastError());
-    }
     // ---- FIC
     if (ctx->fic(n_slots)) return -1;
     const size_t fib_bytes = (size_t)n_slots * 12 * 32;
@@ -777,10 +825,10 @@ int b200dab_stage_demod(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, c
     cudaSetDevice(ctx->device);
     const void* d_iq;
     if (ctx->upload_raw(iq, n, fmt, B200DAB_MEM_HOST, &d_iq)) return -1;
-    CKC(ctx->h_frames.ensure((size_t)n_frames * sizeof(FrameInfo)));
+    if (ctx->prepare_slots(n_frames, false, false)) return -1;
     FrameInfo* fr = ctx->h_frames.as<FrameInfo>();
     for (int i = 0; i < n_frames; i++) { fr[i].t_f = t_f[i]; fr[i].cfo_hz = cfo[i]; fr[i].slot = i; }
-    if (ctx->demod(d_iq, n, fmt, fr, n_frames, n_frames, false)) return -1;
+    if (ctx->demod(d_iq, n, fmt, 0, n_frames, false, false)) return -1;
     CKC(cudaMemcpyAsync(soft, ctx->d_soft.p, (size_t)n_frames * DAB_FRAME_SOFT, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -220,11 +220,14 @@ class Receiver:
 
     def kernel_times(self):
         """[(kernel name, ms)] of the last decode (needs set_profiling(True) before it)."""
-        names = ct.create_string_buffer(4096)
-        ms = np.zeros(64, np.float32)
-        n = lib().b200dab_get_kernel_times(self._h, names, 4096, ms.ctypes.data, 64)
+        names = ct.create_string_buffer(32768)
+        ms = np.zeros(1024, np.float32)
+        n = lib().b200dab_get_kernel_times(self._h, names, 32768, ms.ctypes.data, 1024)
         nm = names.value.decode().split(";") if n > 0 else []
-        return list(zip(nm, ms[:n].tolist()))
+        tot = {}
+        for k, v in zip(nm, ms[:n].tolist()):      # a kernel may be launched several times per decode (chunked front end)
+            tot[k] = tot.get(k, 0.0) + v
+        return list(tot.items())
 
     # ------------------------------------------------------------------ whole path
     def decode_raw(self, ptr: int, n_samples: int, fmt: str, on_device: bool, subch: Optional[Sequence[SubCh]] = None,
