@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "common.cuh"
 #include "k_sync.cuh"
@@ -59,8 +60,13 @@ struct HostBuf {
 
 }  // namespace
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool g_trace = getenv("B200DAB_TRACE") != nullptr;
+#define TRACE(msg) do { if (g_trace) fprintf(stderr, "[trace] %-28s %.3f ms\n", msg, now_ms() - ctx->t_trace0); } while (0)
+
 struct b200dab_ctx {
     int device = 0;
+    double t_trace0 = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     int launches = 0;
@@ -72,7 +78,9 @@ struct b200dab_ctx {
     DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
     DevBuf d_tmp_a, d_tmp_b;
     HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
+    HostBuf h_jobs[2], h_groups[2], h_stepinfo[2], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
     std::vector<int32_t> r_sign;
+    std::vector<std::pair<b200dab_subch_t, std::vector<uint32_t>>> stepinfo_cache;   // de-puncturing tables by protection profile
     // result storage
     std::vector<int64_t> r_tf;
     std::vector<float> r_cfo, r_cir;
@@ -178,7 +186,7 @@ int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, 
     const int64_t nblk = (int64_t)(n / SYNC_BLK);
     const int max_cand = (int)(nblk / SYNC_WIN) + 2;
     *max_cand_out = max_cand;
-    *n_cand_out = 0;
+    if (n_cand_out) *n_cand_out = 0;
     if (nblk <= 0) return 0;
     CK(d_P.ensure((size_t)nblk * 4));
     CK(d_S.ensure((size_t)nblk * 4));
@@ -199,11 +207,13 @@ int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, 
     prof_end();
     launches += 4;
     CK(cudaGetLastError());
-    int nc = 0;
-    CK(cudaMemcpyAsync(&nc, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    if (nc > max_cand) nc = max_cand;
-    *n_cand_out = nc;
+    if (n_cand_out) {                     // stage entry point: the caller wants the count now
+        int nc = 0;
+        CK(cudaMemcpyAsync(&nc, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (nc > max_cand) nc = max_cand;
+        *n_cand_out = nc;
+    }
     return 0;
 }
 
@@ -251,8 +261,9 @@ int b200dab_ctx::prepare_slots(int max_slots, bool want_stat, bool want_tii)
 int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int first, int count, bool want_stat, bool want_tii)
 {
     if (count <= 0) return 0;
-    FrameInfo* dfr = d_frames.as<FrameInfo>() + first;
-    CK(cudaMemcpyAsync(dfr, h_frames.as<FrameInfo>() + first, (size_t)count * sizeof(FrameInfo), cudaMemcpyHostToDevice, stream));
+    // The kernels read the (16-byte) frame descriptors straight from pinned host memory (unified addressing): an H2D copy
+    // here would queue on the copy engine behind the bulk IQ upload and serialise the whole front end with it.
+    const FrameInfo* dfr = h_frames.as<FrameInfo>() + first;
     float* st = want_stat ? d_symstat.as<float>() : nullptr;
     const unsigned grid = (unsigned)count * OFDM_GROUPS;
     const float2* tw = d_tw.as<float2>();
@@ -283,13 +294,25 @@ int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len
 {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(d_iq) + off * fmt_bytes(fmt);
     int n_cand = 0, max_cand = 0;
-    if (coarse(base, len, fmt, &n_cand, &max_cand)) return -1;
+    if (coarse(base, len, fmt, nullptr, &max_cand)) return -1;
+    if (max_cand <= 0) return 0;
+    // fine sync is launched for an upper bound of candidates (CTAs beyond the device-side count exit at once), so the
+    // candidate count and the results come back with a single synchronisation
+    int bound = std::min(max_cand, 2 * (int)(len / DAB_T_FRAME) + 64);
+    for (int pass = 0; pass < 2; pass++) {
+        if (fine(base, len, fmt, bound)) return -1;
+        CK(h_fine.ensure((size_t)bound * sizeof(FineOut) + 16));
+        CK(h_misc.ensure(64));
+        CK(cudaMemcpyAsync(h_misc.p, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(h_fine.p, d_fine.p, (size_t)bound * sizeof(FineOut), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        if (g_trace) fprintf(stderr, "[trace] %-28s %.3f ms\n", "fine synced", now_ms() - t_trace0);
+        n_cand = std::min(*h_misc.as<int>(), max_cand);
+        if (n_cand <= bound) break;
+        bound = n_cand;                   // rare: far more candidates than frames (noise-like input); run again on all of them
+    }
     fe_candidates += n_cand;
     if (n_cand <= 0) return 0;
-    if (fine(base, len, fmt, n_cand)) return -1;
-    CK(h_fine.ensure((size_t)n_cand * sizeof(FineOut)));
-    CK(cudaMemcpyAsync(h_fine.p, d_fine.p, (size_t)n_cand * sizeof(FineOut), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
     const FineOut* f = h_fine.as<FineOut>();
     FrameInfo* hf = h_frames.as<FrameInfo>();
     const int first_new = (int)fe_frames;
@@ -332,10 +355,17 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     CK(d_stepinfo.ensure(stepinfo.size() * 4));
     CK(d_vin.ensure(words * 4));
     CK(d_dec.ensure(words * 8));
-    CK(cudaMemcpyAsync(d_jobs.p, jobs.data(), jobs.size() * sizeof(VitJob), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_groups.p, groups.data(), groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_stepinfo.p, stepinfo.data(), stepinfo.size() * 4, cudaMemcpyHostToDevice, stream));
-    CK(cudaStreamSynchronize(stream));      // the host vectors above go out of scope
+    // small tables go through pinned staging owned by the context (one set per call site), so no stream sync is needed here
+    const int st = jobs[0].kind == 0 ? 0 : 1;
+    CK(h_jobs[st].ensure(jobs.size() * sizeof(VitJob)));
+    CK(h_groups[st].ensure(groups.size() * sizeof(VitGroup)));
+    CK(h_stepinfo[st].ensure(stepinfo.size() * 4));
+    memcpy(h_jobs[st].p, jobs.data(), jobs.size() * sizeof(VitJob));
+    memcpy(h_groups[st].p, groups.data(), groups.size() * sizeof(VitGroup));
+    memcpy(h_stepinfo[st].p, stepinfo.data(), stepinfo.size() * 4);
+    CK(cudaMemcpyAsync(d_jobs.p, h_jobs[st].p, jobs.size() * sizeof(VitJob), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_groups.p, h_groups[st].p, groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_stepinfo.p, h_stepinfo[st].p, stepinfo.size() * 4, cudaMemcpyHostToDevice, stream));
     dim3 ggrid((unsigned)groups.size(), (unsigned)((max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
     prof_begin(jobs[0].kind == 0 ? "k_gather(fic)" : "k_gather(msc)");
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
@@ -399,7 +429,23 @@ int b200dab_ctx::msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std
     size_t off = 0;
     for (size_t i = 0; i < subch.size(); i++) {
         const int si_off = (int)si.size();
-        const int np = dabtab::build_stepinfo(subch[i], si);
+        int np = -1;
+        {   // the table depends on bitrate and the (L, PI) segments only; ensembles rarely change between calls
+            const b200dab_subch_t& q = subch[i];
+            const std::vector<uint32_t>* hit = nullptr;
+            for (auto& e : stepinfo_cache)
+                if (e.first.bitrate == q.bitrate && e.first.n_seg == q.n_seg && !memcmp(e.first.seg_len, q.seg_len, sizeof q.seg_len) &&
+                    !memcmp(e.first.seg_pi, q.seg_pi, sizeof q.seg_pi)) { hit = &e.second; break; }
+            if (!hit) {
+                std::vector<uint32_t> t;
+                if (dabtab::build_stepinfo(q, t) >= 0) {
+                    if (stepinfo_cache.size() > 64) stepinfo_cache.clear();
+                    stepinfo_cache.emplace_back(q, std::move(t));
+                    hit = &stepinfo_cache.back().second;
+                }
+            }
+            if (hit) { si.insert(si.end(), hit->begin(), hit->end()); np = (int)(hit->back() >> 4); }
+        }
         if (np < 0 || np > subch[i].size_cu * 64 || subch[i].start_cu < 0 || subch[i].start_cu + subch[i].size_cu > 864) {
             set_error("sub-channel protection profile inconsistent with its size");
             return -1;
@@ -420,8 +466,9 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     CK(d_flags.ensure((size_t)total_rows + 64));
     CK(d_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
     CK(d_residue.ensure(jobs.size() * 4));
-    CK(cudaMemcpyAsync(d_dpjobs.p, jobs.data(), jobs.size() * sizeof(DabPlusJob), cudaMemcpyHostToDevice, stream));
-    CK(cudaStreamSynchronize(stream));
+    CK(h_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob)));
+    memcpy(h_dpjobs.p, jobs.data(), jobs.size() * sizeof(DabPlusJob));
+    CK(cudaMemcpyAsync(d_dpjobs.p, h_dpjobs.p, jobs.size() * sizeof(DabPlusJob), cudaMemcpyHostToDevice, stream));
     int max_rows = 0, max_sf = 0, max_cw = 0;
     for (auto& j : jobs) { max_rows = std::max(max_rows, j.n_rows); max_sf = std::max(max_sf, j.max_sf); max_cw = std::max(max_cw, j.max_sf * j.s); }
     const unsigned nj = (unsigned)jobs.size();
@@ -432,10 +479,11 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     prof_begin("k_rs_decode");
     k_rs_decode<<<dim3((max_cw + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<GfTables>());
     prof_end();
-    prof_begin("k_au_split");
+    prof_begin("k_au_split+k_au_crc");
     k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
+    k_au_crc<<<dim3((max_sf * 6 + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
     prof_end();
-    launches += 4;
+    launches += 5;
     CK(cudaGetLastError());
     return 0;
 }
@@ -539,7 +587,8 @@ void b200dab_destroy(b200dab_ctx* ctx)
                     &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b};
     for (auto* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm};
+    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
+                     &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -602,6 +651,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     memset(res, 0, sizeof *res);
     ctx->launches = 0;
     ctx->prof_used = 0;
+    ctx->t_trace0 = now_ms();
     ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
     const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
     const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
@@ -625,7 +675,10 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             CKC(cudaMemcpyAsync((uint8_t*)ctx->d_raw.p + a0 * bps, (const uint8_t*)iq + a0 * bps, (size_t)(a1 - a0) * bps, cudaMemcpyHostToDevice, ctx->copy_stream));
             CKC(cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
         }
+        static const bool trace = getenv("B200DAB_TRACE") != nullptr;
+        auto t_start = std::chrono::steady_clock::now();
         for (int c = 0; c < n_chunks; c++) {
+            if (trace) fprintf(stderr, "[trace] chunk %d begin %.3f ms\n", c, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
             const uint64_t a1 = std::min<uint64_t>(n, (uint64_t)(c + 1) * chunk);
             uint64_t a0 = (uint64_t)c * chunk;
             a0 = a0 > lap ? a0 - lap : 0;
@@ -633,10 +686,12 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             CKC(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[c], 0));
             if (ctx->front_end(d_iq, fmt, a0, a1 - a0, want_stat, want_tii, max_slots)) return -1;
         }
+        if (trace) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[trace] front end done %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count()); }
     } else {
         if (ctx->upload_raw(iq, n, fmt, mem, &d_iq)) return -1;
         if (ctx->front_end(d_iq, fmt, 0, n, want_stat, want_tii, max_slots)) return -1;
     }
+    TRACE("front end submitted");
     res->n_candidates = ctx->fe_candidates;
     const int n_frames = (int)ctx->fe_frames;
     const FrameInfo* frames = ctx->h_frames.as<FrameInfo>();
@@ -653,13 +708,23 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     CKC(ctx->h_fib_ok.ensure((size_t)n_slots * 12));
     CKC(cudaMemcpyAsync(ctx->h_fibs.p, ctx->d_fic_out.p, fib_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->h_fib_ok.p, ctx->d_fib_ok.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    TRACE("fic submitted");
     CKC(cudaStreamSynchronize(ctx->stream));
+    TRACE("fic synced");
     res->fibs = ctx->h_fibs.as<uint8_t>(); res->fib_ok = ctx->h_fib_ok.as<uint8_t>();
     // ---- sub-channel organisation: given by the caller or discovered from FIG 0/1, 0/2
     if (subch_in && n_subch_in > 0) ctx->r_subch.assign(subch_in, subch_in + n_subch_in);
     else {
+        // FIG 0/1 and 0/2 repeat every few frames: parse growing prefixes of the FIC until the table stops changing
         ctx->r_subch.resize(B200DAB_MAX_SUBCH);
-        int ns = parse_subch_impl(res->fibs, res->fib_ok, n_slots * 12, ctx->r_subch.data(), B200DAB_MAX_SUBCH);
+        std::vector<b200dab_subch_t> prev;
+        int ns = 0;
+        for (int upto = std::min(n_slots, 24); ; upto = std::min(n_slots, upto * 2)) {
+            ns = parse_subch_impl(res->fibs, res->fib_ok, upto * 12, ctx->r_subch.data(), B200DAB_MAX_SUBCH);
+            const bool same = (int)prev.size() == ns && (ns == 0 || !memcmp(prev.data(), ctx->r_subch.data(), (size_t)ns * sizeof(b200dab_subch_t)));
+            if (upto >= n_slots || (same && ns > 0)) break;
+            prev.assign(ctx->r_subch.begin(), ctx->r_subch.begin() + ns);
+        }
         ctx->r_subch.resize(ns);
     }
     res->n_subch = (int)ctx->r_subch.size();
@@ -689,6 +754,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
+    TRACE("msc+dab+ submitted");
     // ---- TII detection needs to know which nulls carry TII: CIF counter (FIG 0/0) = 0 mod 8
     int n_win = 0;
     if (want_tii) {
@@ -712,9 +778,12 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(ctx->d_sign.ensure((size_t)n_slots * 4));
         CKC(ctx->d_windows.ensure(wins.size() * sizeof(int2)));
         CKC(ctx->d_tii.ensure(wins.size() * sizeof(TiiResult)));
-        CKC(cudaMemcpyAsync(ctx->d_sign.p, sign.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CKC(cudaMemcpyAsync(ctx->d_windows.p, wins.data(), wins.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
-        CKC(cudaStreamSynchronize(ctx->stream));
+        CKC(ctx->h_sign.ensure((size_t)n_slots * 4));
+        CKC(ctx->h_windows.ensure(wins.size() * sizeof(int2)));
+        memcpy(ctx->h_sign.p, sign.data(), (size_t)n_slots * 4);
+        memcpy(ctx->h_windows.p, wins.data(), wins.size() * sizeof(int2));
+        CKC(cudaMemcpyAsync(ctx->d_sign.p, ctx->h_sign.p, (size_t)n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CKC(cudaMemcpyAsync(ctx->d_windows.p, ctx->h_windows.p, wins.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         k_tii_detect<<<n_win, 384, 0, ctx->stream>>>(ctx->d_fold.as<float>(), ctx->d_norm.as<float>(), ctx->d_sign.as<int>(), ctx->d_windows.as<int2>(),
                                                      6.0f, ctx->d_tii.as<TiiResult>());
         ctx->launches += 1;
@@ -731,7 +800,9 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(ctx->h_symstat.ensure((size_t)n_slots * 150 * 4));
         CKC(cudaMemcpyAsync(ctx->h_symstat.p, ctx->d_symstat.p, (size_t)n_slots * 150 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    TRACE("all submitted");
     CKC(cudaStreamSynchronize(ctx->stream));
+    TRACE("final sync");
     // ---- assemble the result
     if (msc_bytes > 0) {
         for (size_t i = 0; i < ctx->r_subch.size(); i++) { ctx->r_frames.push_back(ctx->h_msc.as<uint8_t>() + out_off[i]); ctx->r_rows.push_back(n_rows); }
@@ -775,6 +846,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         res->snr_db = cnt ? (float)(10.0 * log10(snr_acc / cnt)) : 0.f;
     }
     res->gpu_launches = ctx->launches;
+    TRACE("result assembled");
     return 0;
 }
 

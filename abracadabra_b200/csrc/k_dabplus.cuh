@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames,
     atomicAdd(&info->rs_bit_errors, be);
 }
 
-// one thread per superframe slot: firecode after RS, header parse, AU CRCs
+// one thread per superframe slot: firecode after RS, header parse -> AU offsets (the CRCs follow in k_au_crc)
 __global__ void __launch_bounds__(64) k_au_split(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs, SfInfo* __restrict__ sf)
 {
     const DabPlusJob job = jobs[blockIdx.y];
@@ -201,12 +201,31 @@ __global__ void __launch_bounds__(64) k_au_split(const uint8_t* __restrict__ fra
     }
     st[num] = 110 * s;
     for (int i = 0; i < num; i++) if (st[i + 1] <= st[i] + 2 || st[i + 1] > 110 * s) return;
-    for (int i = 0; i < num; i++) {
-        const int len = st[i + 1] - st[i];
-        info->au_off[i] = st[i];
-        info->au_len[i] = len - 2;
-        const uint16_t crc = (uint16_t)~crc16_ccitt_dev(p + st[i], len - 2, 0xFFFF, 0x1021);
-        info->au_ok[i] = crc == (uint16_t)((p[st[i] + len - 2] << 8) | p[st[i] + len - 1]);
-    }
+    for (int i = 0; i < num; i++) { info->au_off[i] = st[i]; info->au_len[i] = st[i + 1] - st[i] - 2; info->au_ok[i] = 0; }
     info->n_aus = num;
+}
+
+// one thread per (superframe, access unit): table-driven CRC-16 (0x1021, init 0xFFFF, inverted) over the AU payload
+__global__ void __launch_bounds__(128) k_au_crc(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs, SfInfo* __restrict__ sf)
+{
+    __shared__ uint16_t tbl[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = (uint32_t)i << 8;
+#pragma unroll
+        for (int b = 0; b < 8; b++) c = (c & 0x8000u) ? ((c << 1) ^ 0x1021u) & 0xffffu : (c << 1) & 0xffffu;
+        tbl[i] = (uint16_t)c;
+    }
+    __syncthreads();
+    const DabPlusJob job = jobs[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = idx / 6, a = idx - 6 * m;
+    if (m >= job.max_sf) return;
+    SfInfo* info = sf + job.sf_off + m;
+    if (!info->valid || a >= info->n_aus) return;
+    const uint8_t* p = frames + job.frames_off + (size_t)info->row * job.pitch + info->au_off[a];
+    const int len = info->au_len[a];
+    uint32_t crc = 0xFFFF;
+    for (int i = 0; i < len; i++) crc = ((crc << 8) & 0xffffu) ^ tbl[((crc >> 8) ^ p[i]) & 0xff];
+    crc = (~crc) & 0xffffu;
+    info->au_ok[a] = crc == (uint32_t)((p[len] << 8) | p[len + 1]);
 }

@@ -247,7 +247,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, k):
+    def timed(fn, k, collect):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
@@ -256,8 +256,9 @@ def main():
         last = None
         for _ in range(k):
             last = fn()
-            for nm, ms in rx.kernel_times():
-                ktimes.setdefault(nm, []).append(ms)
+            if collect:                      # per-kernel CUDA-event times of this step (device-resident run only)
+                for nm, ms in rx.kernel_times():
+                    ktimes.setdefault(nm, []).append(ms)
         e1.record(stream)
         e1.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
@@ -281,13 +282,14 @@ def main():
     for _ in range(args.warmup):
         step_device()
     clocks = ClockSampler(dev)
-    ms_dev, wall_dev, ktimes, last = timed(step_device, args.steps)
+    ms_dev, wall_dev, ktimes, last = timed(step_device, args.steps, True)
     launches = last.gpu_launches
     d2h = int(last.n_slots * 12 * 33 + sum(last.frame_rows[i] * subch[i].bitrate * 3 for i in range(last.n_subch))
               + last.n_tii * ct_sizeof_tii() + last.n_slots * 32)
     for _ in range(max(1, args.warmup // 2)):
         step_host()
-    ms_e2e, wall_e2e, _, _ = timed(step_host, args.steps)
+    rx.set_profiling(False)
+    ms_e2e, wall_e2e, _, _ = timed(step_host, args.steps, False)
     clk = clocks.stop()
 
     total_samples = n_samples * world
