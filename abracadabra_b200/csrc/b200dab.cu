@@ -371,7 +371,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
     prof_begin(jobs[0].kind == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
-    k_viterbi<<<(unsigned)groups.size(), 32, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
+    k_viterbi<<<(unsigned)groups.size(), 64, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
                                                        d_prbs_w.as<uint32_t>(), d_out);
     prof_end();
     launches += 2;
@@ -938,7 +938,7 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, zero_prbs.data(), 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->prof_used = 0;
     ctx->prof_begin("k_viterbi(stage)");
-    k_viterbi<<<ng, 32, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint2>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
+    k_viterbi<<<ng, 64, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint2>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
                                          ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>());
     ctx->prof_end();
     ctx->launches += 1;

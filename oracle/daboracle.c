@@ -365,13 +365,18 @@ int orc_depuncture_map(const orc_subch_t *sc, int32_t *map)
 
 void orc_viterbi(const int8_t *soft4, int steps, uint8_t *bits)
 {
+    /* Maximum-likelihood sequence of the zero-terminated K=7 code, found bidirectionally (same formulation as the CUDA
+     * kernel): forward recursion over steps [0, m) from state 0, backward recursion over steps [m, T) from state 0,
+     * m = steps/2 rounded down to a multiple of 32; the state maximising alpha + beta at stage m (lowest state on ties)
+     * lies on the best path.  Tie rules: forward survivor from the upper predecessor only if strictly better; backward
+     * continuation with input bit 1 only if strictly better.  With a unique best path this equals one-directional Viterbi. */
     init_tables();
+    const int m = ((steps >> 1) >> 5) << 5;
     int32_t M[64], N[64];
     uint64_t *dec = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)steps);
     for (int i = 0; i < 64; i++) M[i] = VIT_START_PENALTY;
     M[0] = 0;
-    for (int t = 0; t < steps; t++) {
-        if ((t % VIT_NORM_PERIOD) == 0) { int32_t m0 = M[0]; for (int i = 0; i < 64; i++) M[i] -= m0; }
+    for (int t = 0; t < m; t++) {
         const int8_t *s = soft4 + 4 * t;
         uint64_t d = 0;
         for (int j = 0; j < 32; j++) {
@@ -384,11 +389,36 @@ void orc_viterbi(const int8_t *soft4, int steps, uint8_t *bits)
         dec[t] = d;
         memcpy(M, N, sizeof M);
     }
-    int s = 0;
-    for (int t = steps - 1; t >= 0; t--) {
-        if (t < steps - 6) bits[t] = (uint8_t)(s & 1);
+    int32_t Bm[64], Bn[64];
+    for (int i = 0; i < 64; i++) Bm[i] = VIT_START_PENALTY;
+    Bm[0] = 0;
+    for (int t = steps - 1; t >= m; t--) {
+        const int8_t *s = soft4 + 4 * t;
+        uint64_t d = 0;
+        for (int j = 0; j < 32; j++) {
+            int32_t beta = s[0] * g_bm_sign[j][0] + s[1] * g_bm_sign[j][1] + s[2] * g_bm_sign[j][2] + s[3] * g_bm_sign[j][3];
+            /* state j: input 0 -> +beta to state 2j, input 1 -> -beta to state 2j+1; state j+32: signs flipped */
+            int32_t c0 = Bm[2 * j] + beta, c1 = Bm[2 * j + 1] - beta;
+            if (c1 > c0) { Bn[j] = c1; d |= 1ull << j; } else Bn[j] = c0;
+            c0 = Bm[2 * j] - beta; c1 = Bm[2 * j + 1] + beta;
+            if (c1 > c0) { Bn[j + 32] = c1; d |= 1ull << (j + 32); } else Bn[j + 32] = c0;
+        }
+        dec[t] = d;
+        memcpy(Bm, Bn, sizeof Bm);
+    }
+    int sm = 0; int32_t best = M[0] + Bm[0];
+    for (int q = 1; q < 64; q++) if (M[q] + Bm[q] > best) { best = M[q] + Bm[q]; sm = q; }
+    int s = sm;
+    for (int t = m - 1; t >= 0; t--) {
+        bits[t] = (uint8_t)(s & 1);
         int d = (int)((dec[t] >> s) & 1);
         s = (s >> 1) | (d << 5);
+    }
+    s = sm;
+    for (int t = m; t < steps; t++) {
+        int b = (int)((dec[t] >> s) & 1);
+        if (t < steps - 6) bits[t] = (uint8_t)b;
+        s = ((s << 1) | b) & 63;
     }
     free(dec);
 }
