@@ -23,6 +23,13 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(#x, e_); return -1; } } while (0)
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->set_error(#x, e_); return -1; } } while (0)
 
+// Small host->device table upload done by SMs reading pinned host memory (unified addressing) instead of the copy engine:
+// on the copy engine it would queue behind the bulk IQ upload of another receiver context sharing the GPU.
+__global__ void __launch_bounds__(256) k_fetch(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src_host, size_t nwords)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src_host[i];
+}
+
 namespace {
 
 struct DevBuf {
@@ -117,6 +124,15 @@ struct b200dab_ctx {
     }
     void set_error(const char* what) { err = what; }
 
+    int fetch(void* d_dst, const void* h_pinned, size_t bytes)
+    {
+        const size_t nw = (bytes + 3) / 4;
+        if (!nw) return 0;
+        const unsigned grid = (unsigned)std::min<size_t>(64, (nw + 255) / 256);
+        k_fetch<<<grid, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(d_dst), reinterpret_cast<const uint32_t*>(h_pinned), nw);
+        launches += 1;
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
     int init_tables();
     // device-side stages (all asynchronous on `stream` unless noted)
     int upload_raw(const void* iq, uint64_t n, int fmt, int mem, const void** d_out);
@@ -357,15 +373,17 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     CK(d_dec.ensure(words * 8));
     // small tables go through pinned staging owned by the context (one set per call site), so no stream sync is needed here
     const int st = jobs[0].kind == 0 ? 0 : 1;
-    CK(h_jobs[st].ensure(jobs.size() * sizeof(VitJob)));
-    CK(h_groups[st].ensure(groups.size() * sizeof(VitGroup)));
-    CK(h_stepinfo[st].ensure(stepinfo.size() * 4));
+    CK(h_jobs[st].ensure(jobs.size() * sizeof(VitJob) + 16));
+    CK(h_groups[st].ensure(groups.size() * sizeof(VitGroup) + 16));
+    CK(h_stepinfo[st].ensure(stepinfo.size() * 4 + 16));
+    CK(d_jobs.ensure(jobs.size() * sizeof(VitJob) + 16));
+    CK(d_groups.ensure(groups.size() * sizeof(VitGroup) + 16));
+    CK(d_stepinfo.ensure(stepinfo.size() * 4 + 16));
     memcpy(h_jobs[st].p, jobs.data(), jobs.size() * sizeof(VitJob));
     memcpy(h_groups[st].p, groups.data(), groups.size() * sizeof(VitGroup));
     memcpy(h_stepinfo[st].p, stepinfo.data(), stepinfo.size() * 4);
-    CK(cudaMemcpyAsync(d_jobs.p, h_jobs[st].p, jobs.size() * sizeof(VitJob), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_groups.p, h_groups[st].p, groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_stepinfo.p, h_stepinfo[st].p, stepinfo.size() * 4, cudaMemcpyHostToDevice, stream));
+    if (fetch(d_jobs.p, h_jobs[st].p, jobs.size() * sizeof(VitJob)) || fetch(d_groups.p, h_groups[st].p, groups.size() * sizeof(VitGroup)) ||
+        fetch(d_stepinfo.p, h_stepinfo[st].p, stepinfo.size() * 4)) { set_error("k_fetch launch failed"); return -1; }
     dim3 ggrid((unsigned)groups.size(), (unsigned)((max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
     prof_begin(jobs[0].kind == 0 ? "k_gather(fic)" : "k_gather(msc)");
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
@@ -462,13 +480,13 @@ int b200dab_ctx::msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std
 int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows)
 {
     if (jobs.empty() || total_sf <= 0) return 0;
-    CK(d_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob)));
+    CK(d_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob) + 16));
     CK(d_flags.ensure((size_t)total_rows + 64));
     CK(d_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
     CK(d_residue.ensure(jobs.size() * 4));
-    CK(h_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob)));
+    CK(h_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob) + 16));
     memcpy(h_dpjobs.p, jobs.data(), jobs.size() * sizeof(DabPlusJob));
-    CK(cudaMemcpyAsync(d_dpjobs.p, h_dpjobs.p, jobs.size() * sizeof(DabPlusJob), cudaMemcpyHostToDevice, stream));
+    if (fetch(d_dpjobs.p, h_dpjobs.p, jobs.size() * sizeof(DabPlusJob))) { set_error("k_fetch launch failed"); return -1; }
     int max_rows = 0, max_sf = 0, max_cw = 0;
     for (auto& j : jobs) { max_rows = std::max(max_rows, j.n_rows); max_sf = std::max(max_sf, j.max_sf); max_cw = std::max(max_cw, j.max_sf * j.s); }
     const unsigned nj = (unsigned)jobs.size();
@@ -782,8 +800,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(ctx->h_windows.ensure(wins.size() * sizeof(int2)));
         memcpy(ctx->h_sign.p, sign.data(), (size_t)n_slots * 4);
         memcpy(ctx->h_windows.p, wins.data(), wins.size() * sizeof(int2));
-        CKC(cudaMemcpyAsync(ctx->d_sign.p, ctx->h_sign.p, (size_t)n_slots * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CKC(cudaMemcpyAsync(ctx->d_windows.p, ctx->h_windows.p, wins.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->fetch(ctx->d_sign.p, ctx->h_sign.p, (size_t)n_slots * 4) || ctx->fetch(ctx->d_windows.p, ctx->h_windows.p, wins.size() * sizeof(int2))) return -1;
         k_tii_detect<<<n_win, 384, 0, ctx->stream>>>(ctx->d_fold.as<float>(), ctx->d_norm.as<float>(), ctx->d_sign.as<int>(), ctx->d_windows.as<int2>(),
                                                      6.0f, ctx->d_tii.as<TiiResult>());
         ctx->launches += 1;

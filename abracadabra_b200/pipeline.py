@@ -371,3 +371,43 @@ class Receiver:
             raise self._err("stage_tii_detect")
         ids = [(int(t.main_id[i]), int(t.sub_id[i]), float(t.level[i])) for i in range(t.n_ids)]
         return TiiWindow(ids, t.n_tii_frames, np.array(t.spectrum[:], dtype=np.float32), t.norm, t.noise)
+
+
+class ReceiverPool:
+    """Several receiver contexts on one GPU, fed from host threads: while one context runs the back end (Viterbi, RS, TII) of
+    recording k, the next context is already uploading and demodulating recording k+1, so the PCIe copy and the compute of
+    successive, independent recordings overlap.  This is the batch form of a band scan (one recording per channel,
+    reference: src/bandscanbackend.cpp:114-139); results come back in input order."""
+
+    def __init__(self, device: int = 0, depth: int = 2):
+        self.rx = [Receiver(device) for _ in range(depth)]
+
+    def close(self):
+        for r in self.rx:
+            r.close()
+
+    def map_raw(self, items, fn=None):
+        """items: sequence of (ptr, n_samples, fmt, on_device, subch, flags).  Calls decode_raw for each item on the next free
+        context; `fn(index, receiver, result)` runs right after the call, while the result buffers of that context are valid."""
+        import threading
+        out = [None] * len(items)
+        lock = threading.Lock()
+        nxt = [0]
+
+        def work(rx):
+            while True:
+                with lock:
+                    i = nxt[0]
+                    nxt[0] += 1
+                if i >= len(items):
+                    return
+                ptr, n, fmt, on_dev, subch, flags = items[i]
+                res = rx.decode_raw(ptr, n, fmt, on_dev, subch, flags)
+                out[i] = fn(i, rx, res) if fn else (res.n_frames, res.n_aus)
+
+        th = [threading.Thread(target=work, args=(r,)) for r in self.rx]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return out
