@@ -152,6 +152,69 @@ __device__ __forceinline__ void fft2048_smem(float2* __restrict__ buf, const flo
     __syncthreads();
 }
 
+// Same transform with everything that only depends on the thread hoisted out by the caller: shared-memory base offsets
+// (the padded layout makes every pass a base + constant stride) and the 21 twiddles of passes A/B/C held in registers.
+struct FftPlan {
+    int pA, pB, pC, pD0, pD1;
+    float2 twA[7], twB[7], twC[7];
+};
+__device__ __forceinline__ void fft_plan_init(FftPlan& pl, const float2* __restrict__ tw)
+{
+    const int t = threadIdx.x;
+    pl.pA = fft_phys(t);                                        // + 288 r
+    pl.pB = fft_phys(((t >> 5) << 8) + (t & 31));               // + 36 i
+    pl.pC = (t >> 2) * 36 + (t & 3);                            // + 4 i
+    pl.pD0 = fft_phys(4 * t);
+    pl.pD1 = fft_phys(4 * (t + 256));
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        pl.twA[k - 1] = __ldg(tw + ((t * k) & 2047));
+        pl.twB[k - 1] = __ldg(tw + (((t & 31) * k) << 3));
+        pl.twC[k - 1] = __ldg(tw + (((t & 3) * k) << 6));
+    }
+}
+__device__ __forceinline__ void fft2048_planned(float2* __restrict__ buf, const FftPlan& pl)
+{
+    float2 v[8];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = buf[pl.pA + 288 * r];
+    radix8(v);
+#pragma unroll
+    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], pl.twA[k - 1]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) buf[pl.pA + 288 * k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = buf[pl.pB + 36 * i];
+    radix8(v);
+#pragma unroll
+    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], pl.twB[k - 1]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) buf[pl.pB + 36 * k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = buf[pl.pC + 4 * i];
+    radix8(v);
+#pragma unroll
+    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], pl.twC[k - 1]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) buf[pl.pC + 4 * k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        float2* p = buf + (h ? pl.pD1 : pl.pD0);
+        float4 q0 = *reinterpret_cast<float4*>(p), q1 = *reinterpret_cast<float4*>(p + 2);
+        float2 x0 = make_float2(q0.x, q0.y), x1 = make_float2(q0.z, q0.w), x2 = make_float2(q1.x, q1.y), x3 = make_float2(q1.z, q1.w);
+        float2 s0 = cadd(x0, x2), d0 = csub(x0, x2), s1 = cadd(x1, x3), d1 = csub(x1, x3);
+        d1 = make_float2(d1.y, -d1.x);
+        float2 y0 = cadd(s0, s1), y2 = csub(s0, s1), y1 = cadd(d0, d1), y3 = csub(d0, d1);
+        *reinterpret_cast<float4*>(p) = make_float4(y0.x, y0.y, y1.x, y1.y);
+        *reinterpret_cast<float4*>(p + 2) = make_float4(y2.x, y2.y, y3.x, y3.y);
+    }
+    __syncthreads();
+}
+
 // carrier index c (0..1535, ascending k = -768..-1, 1..768) -> FFT bin
 __device__ __host__ __forceinline__ int carrier_bin(int c) { return c < 768 ? c + 1280 : c - 767; }
 
@@ -174,6 +237,38 @@ __device__ __forceinline__ void fetch_symbol(RawSym<FMT>& r, const void* __restr
         if (FMT == B200DAB_FMT_U8) { uchar2 x = __ldg(reinterpret_cast<const uchar2*>(raw) + n); if (!ok) x = make_uchar2(128, 128); reinterpret_cast<uchar2*>(r.v)[i] = x; }
         else if (FMT == B200DAB_FMT_S16) { short2 x = __ldg(reinterpret_cast<const short2*>(raw) + n); if (!ok) x = make_short2(0, 0); reinterpret_cast<short2*>(r.v)[i] = x; }
         else { float2 x = __ldg(reinterpret_cast<const float2*>(raw) + n); if (!ok) x = make_float2(0.f, 0.f); reinterpret_cast<float2*>(r.v)[i] = x; }
+    }
+}
+
+// whole symbol inside the buffer: no per-sample bounds checks
+template <int FMT>
+__device__ __forceinline__ void fetch_symbol_fast(RawSym<FMT>& r, const void* __restrict__ raw, int64_t start)
+{
+    const int64_t n0 = start + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (FMT == B200DAB_FMT_U8) reinterpret_cast<uchar2*>(r.v)[i] = __ldg(reinterpret_cast<const uchar2*>(raw) + n0 + 256 * i);
+        else if (FMT == B200DAB_FMT_S16) reinterpret_cast<short2*>(r.v)[i] = __ldg(reinterpret_cast<const short2*>(raw) + n0 + 256 * i);
+        else reinterpret_cast<float2*>(r.v)[i] = __ldg(reinterpret_cast<const float2*>(raw) + n0 + 256 * i);
+    }
+}
+
+// de-rotation by a rotor recurrence: one sincos per thread and symbol, then w_{r+1} = w_r * step (step = rotation over 256 samples)
+template <int FMT>
+__device__ __forceinline__ void store_symbol_rotor(float2* __restrict__ buf, int pA, const RawSym<FMT>& r, float base_cyc, float cpp, float2 step)
+{
+    float cyc = base_cyc + cpp * (float)threadIdx.x;
+    float ph = -6.283185307179586f * (cyc - rintf(cyc));
+    float2 w;
+    __sincosf(ph, &w.y, &w.x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float2 x;
+        if (FMT == B200DAB_FMT_U8) { uchar2 v = reinterpret_cast<const uchar2*>(r.v)[i]; x = make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+        else if (FMT == B200DAB_FMT_S16) { short2 v = reinterpret_cast<const short2*>(r.v)[i]; x = make_float2((float)v.x, (float)v.y); }
+        else x = reinterpret_cast<const float2*>(r.v)[i];
+        buf[pA + 288 * i] = cmul(x, w);
+        w = cmul(w, step);
     }
 }
 

@@ -18,7 +18,7 @@ struct FrameInfo {
 
 // fdi_pos[n] = physical shared-memory index of the FFT output that carries QPSK symbol n
 template <int FMT>
-__global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+__global__ void __launch_bounds__(256, 2) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
                                                     const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_pos,
                                                     int8_t* __restrict__ soft, float* __restrict__ symstat)
 {
@@ -37,14 +37,36 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
     float2* prev = bufB;
     int8_t* out_frame = soft + (size_t)fr.slot * DAB_FRAME_SOFT;
 
+    // thread-invariant pieces hoisted out of the symbol loop: FFT plan (addresses + 21 twiddles), de-interleaver positions,
+    // the rotor that advances the de-rotation by 256 samples, and whether the whole run lies inside the buffer
+    FftPlan plan;
+    fft_plan_init(plan, tw);
+    int ps[8];
+    {
+        const uint2 p0 = __ldg(reinterpret_cast<const uint2*>(fdi_pos + 4 * t));
+        const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(fdi_pos + 1024 + 4 * (t & 127)));
+        ps[0] = p0.x & 0xffff; ps[1] = p0.x >> 16; ps[2] = p0.y & 0xffff; ps[3] = p0.y >> 16;
+        ps[4] = p1.x & 0xffff; ps[5] = p1.x >> 16; ps[6] = p1.y & 0xffff; ps[7] = p1.y >> 16;
+    }
+    float2 step;
+    {
+        double c256 = cyc_per * 256.0;
+        c256 -= floor(c256 + 0.5);
+        sincospif((float)(-2.0 * c256), &step.y, &step.x);
+    }
+    const int64_t first = fr.t_f + (int64_t)DAB_T_SYM * l_ref, last = fr.t_f + (int64_t)DAB_T_SYM * l_end + DAB_NFFT;
+    const bool inside = first >= 0 && last <= nsamp;
     RawSym<FMT> rs;
-    fetch_symbol<FMT>(rs, raw, nsamp, fr.t_f + (int64_t)DAB_T_SYM * l_ref);
+    if (inside) fetch_symbol_fast<FMT>(rs, raw, first); else fetch_symbol<FMT>(rs, raw, nsamp, first);
     for (int l = l_ref; l <= l_end; l++) {
         double base = cyc_per * (double)((int64_t)DAB_T_SYM * l);
         base -= floor(base);
-        store_symbol<FMT>(cur, rs, (float)base, cpp);
-        if (l < l_end) fetch_symbol<FMT>(rs, raw, nsamp, fr.t_f + (int64_t)DAB_T_SYM * (l + 1));   // in flight during the FFT
-        fft2048_smem(cur, tw);
+        store_symbol_rotor<FMT>(cur, plan.pA, rs, (float)base, cpp, step);
+        if (l < l_end) {                                                             // in flight during the FFT
+            const int64_t nx = fr.t_f + (int64_t)DAB_T_SYM * (l + 1);
+            if (inside) fetch_symbol_fast<FMT>(rs, raw, nx); else fetch_symbol<FMT>(rs, raw, nsamp, nx);
+        }
+        fft2048_planned(cur, plan);
         if (l > l_ref) {
             // DQPSK against the previous symbol, de-interleaved order: thread handles n = 4t..4t+3 and (t < 128) 1024+4t..
             float2 y[8];
@@ -52,12 +74,9 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (h == 1 && t >= 128) break;
-                const int n0 = h * 1024 + 4 * t;
-                const uint2 pp = __ldg(reinterpret_cast<const uint2*>(fdi_pos + n0));
-                const int ps[4] = {(int)(pp.x & 0xffff), (int)(pp.x >> 16), (int)(pp.y & 0xffff), (int)(pp.y >> 16)};
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    float2 v = cmul_conj(cur[ps[i]], prev[ps[i]]);
+                    float2 v = cmul_conj(cur[ps[4 * h + i]], prev[ps[4 * h + i]]);
                     y[4 * h + i] = v;
                     sabs += fabsf(v.x) + fabsf(v.y);
                     ssq += v.x * v.x + v.y * v.y;
