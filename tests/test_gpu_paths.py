@@ -1,0 +1,125 @@
+"""GPU tests of the host-side paths around the kernels: chunked/pipelined upload vs one-range decode, lost frames, empty and
+truncated inputs, CFO drift with an SNR staircase (BASELINE.json configs[4] in small), a pool of receivers over several
+recordings (configs[3], band scan) -- all through the C ABI, checked against the modulator's payload and the CPU checker."""
+import numpy as np
+import pytest
+
+import cases
+from abracadabra_b200 import pipeline, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a: pipeline.Decoded, b: pipeline.Decoded):
+    assert a.n_frames == b.n_frames and a.n_slots == b.n_slots
+    assert np.array_equal(a.t_f, b.t_f) and np.array_equal(a.fibs, b.fibs) and np.array_equal(a.fib_ok, b.fib_ok)
+    assert np.allclose(a.cfo_hz, b.cfo_hz, atol=1e-3)
+    assert len(a.frames) == len(b.frames) and all(np.array_equal(x, y) for x, y in zip(a.frames, b.frames))
+    assert [(u.subch_index, u.cif, u.crc_ok, u.data) for u in a.aus] == [(u.subch_index, u.cif, u.crc_ok, u.data) for u in b.aus]
+
+
+def test_chunked_host_upload_equals_single_range(receiver):
+    """> 128 frames from a host buffer go through the pipelined front end (64-frame chunks with overlap); the same samples
+    as a device buffer go through one range.  Frames cut by a chunk boundary must be found exactly once."""
+    import torch
+    ens = synth.config1_ensemble(seed=5)
+    raw, res = synth.synthesize(ens, 150, "u8", synth.Impairments(snr_db=20.0, cfo_hz=-777.0, seed=4, lead_in=12345), seed=4, tail=70000)
+    host = receiver.decode(raw, "u8", tii=True)
+    d = torch.from_numpy(raw).cuda()
+    dev = receiver.decode(d.data_ptr(), "u8", tii=True, n_samples=raw.size // 2, on_device=True)
+    assert host.n_frames == 150 and host.n_slots == 150
+    _same(host, dev)
+    assert np.array_equal(host.frames[0], res.logical[3][:host.frames[0].shape[0]])
+    assert [i for i in host.tii[0].ids][0][:2] == (12, 5)
+
+
+def test_lost_frame_becomes_erasures(receiver, oracle):
+    raw, res = cases.config1(14, "u8", 30.0, 250.0, 17)
+    raw = raw.copy()
+    f0 = res.frame0 + 6 * 196608
+    rng = np.random.default_rng(1)
+    raw[2 * f0:2 * (f0 + 196608)] = rng.integers(120, 136, 2 * 196608, dtype=np.uint8)     # frame 6 replaced by noise
+    dec = receiver.decode(raw, "u8")
+    assert dec.n_slots == 14 and dec.n_frames == 13 and dec.t_f[6] == -1
+    assert dec.fib_ok.reshape(14, 12)[6].sum() == 0 and dec.fib_ok.reshape(14, 12)[[0, 5, 7, 13]].all()
+    sc = res.ens.subchannels[0]
+    o = oracle.decode(raw, "u8", [oracle.subch_struct(sc)])
+    assert o["nf"] == 14 and np.array_equal(o["t_f"], dec.t_f)
+    assert np.array_equal(dec.frames[0], o["frames"][0])           # same erasures, same decisions
+    truth = res.logical[sc.subchid][:dec.frames[0].shape[0]]
+    bad = np.nonzero((dec.frames[0] != truth).any(axis=1))[0]
+    assert set(bad) <= set(range(24 - 15, 28))                      # only rows whose interleaver span touches the lost CIFs
+
+
+def test_empty_noise_and_truncated_inputs(receiver):
+    silence = np.full(2 * 400000, 128, np.uint8)
+    d = receiver.decode(silence, "u8", tii=True)
+    assert d.n_frames == 0 and d.n_slots == 0 and d.aus == [] and d.frames == []
+    noise = np.random.default_rng(3).integers(96, 160, 2 * 600000, dtype=np.uint8)
+    assert receiver.decode(noise, "u8").n_frames == 0
+    tiny = np.full(2 * 1000, 128, np.uint8)
+    assert receiver.decode(tiny, "u8").n_frames == 0
+    ens = synth.config1_ensemble()
+    raw, res = synth.synthesize(ens, 5, "u8", synth.Impairments(snr_db=30, lead_in=777), tail=0)
+    cut = raw[:2 * (777 + 4 * 196608 + 100000)]                     # fifth frame incomplete
+    d = receiver.decode(cut, "u8")
+    assert d.n_frames == 4 and d.fib_ok.all() and d.frames[0].shape[0] == 1
+
+
+def test_cfo_drift_and_snr_staircase(receiver):
+    """configs[4] in small: s16 and f32 recordings with linear CFO drift; SNR steps 3 -> 20 dB over the recording."""
+    ens = synth.config1_ensemble(seed=9)
+    n_frames = 40
+    clean, truth = synth.modulate(ens, n_frames, seed=9)
+    x = synth.impair(clean, synth.Impairments(snr_db=None, cfo_hz=-1500.0, cfo_drift_hz_per_s=400.0, seed=2, lead_in=30000), tail=70000)
+    rng = np.random.default_rng(5)
+    snr = np.repeat(np.array([3, 5, 7, 9, 12, 15, 18, 20], float), 5)           # per frame
+    for f in range(n_frames):
+        a, b = 30000 + f * 196608, 30000 + (f + 1) * 196608
+        sg = np.sqrt(0.5 * 10 ** (-snr[f] / 10))
+        x[a:b] += (sg * (rng.standard_normal(b - a) + 1j * rng.standard_normal(b - a))).astype(np.complex64)
+    for fmt, rms in (("s16", 6000.0), ("f32", 1.0)):
+        raw = synth.quantize(x, fmt, rms)
+        d = receiver.decode(raw, fmt, symstat=True)
+        assert d.n_frames == n_frames
+        t = (d.t_f - d.t_f[0]) / 2.048e6
+        assert np.all(np.abs(d.cfo_hz - (d.cfo_hz[0] + 400.0 * t)) < 12.0)       # tracks the drift frame by frame
+        ok = d.fib_ok.reshape(n_frames, 12)
+        assert ok[10:].all()                                                     # >= 7 dB: every FIB passes
+        fr = d.frames[0]
+        want = truth["logical"][3][:fr.shape[0]]
+        good_rows = np.arange(4 * 10, fr.shape[0])                               # rows fed only by frames at >= 7 dB
+        assert np.array_equal(fr[good_rows], want[good_rows])
+        aus = [a for a in d.aus if a.cif >= 40]
+        assert aus and all(a.crc_ok for a in aus)
+        assert d.firecode_fail <= 3                                              # only the superframes at 3 dB are lost
+
+
+def test_receiver_pool_band_scan():
+    """several recordings (different ensembles / CFO, as different Band III channels) through a pool of two contexts:
+    results in input order and identical to one-by-one decoding"""
+    import torch
+    recs = []
+    for i in range(5):
+        ens = synth.config1_ensemble(seed=30 + i)
+        ens.eid = 0x4000 + i
+        ens.tii = [synth.TiiTx(5 + i, 2 + i, 1.0)]
+        raw, res = synth.synthesize(ens, 12 + i, "u8", synth.Impairments(snr_db=22.0, cfo_hz=300.0 * (i - 2), seed=i), seed=i, tail=70000)
+        recs.append((raw, res))
+    pool = pipeline.ReceiverPool(0, depth=2)
+    pinned = [torch.from_numpy(r).pin_memory() for r, _ in recs]
+    items = [(p.data_ptr(), r.size // 2, "u8", False, None, pipeline.OPT_TII) for p, (r, _) in zip(pinned, recs)]
+
+    def grab(i, rx, res):
+        fibs = np.ctypeslib.as_array(res.fibs, (res.n_slots * 12, 32)).copy()
+        fr = np.ctypeslib.as_array(res.frames[0], (res.frame_rows[0], 288)).copy()
+        return res.n_frames, fibs, fr, (int(res.tii[0].main_id[0]), int(res.tii[0].sub_id[0])) if res.n_tii else None
+
+    out = pool.map_raw(items, grab)
+    pool.close()
+    for i, ((raw, res), (nf, fibs, fr, tii)) in enumerate(zip(recs, out)):
+        assert nf == 12 + i
+        assert np.array_equal(fibs.reshape(-1, 96), res.fibs[:4 * nf])
+        assert int(fibs[0, 2]) << 8 | int(fibs[0, 3]) == 0x4000 + i              # EId of FIG 0/0: the right recording in the right slot
+        assert np.array_equal(fr, res.logical[3][:fr.shape[0]])
+    assert [o[3] for o in out] == [(5 + i, 2 + i) for i in range(5)]             # short recordings: one TII window over all frames
