@@ -78,7 +78,7 @@ struct b200dab_ctx {
     std::string err;
     int launches = 0;
     // constant tables on the device
-    DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf;
+    DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin;
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
     DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_fic_out, d_fib_ok, d_msc_out;
@@ -171,6 +171,21 @@ int b200dab_ctx::init_tables()
     dabtab::prs_quarter(prs.data());
     CK(d_prs_q.ensure(prs.size()));
     CK(cudaMemcpy(d_prs_q.p, prs.data(), prs.size(), cudaMemcpyHostToDevice));
+    {   // carrier pairs by PRS phase step (integer CFO search)
+        std::vector<uint16_t> cls;
+        int off[5] = {0, 0, 0, 0, 0};
+        for (int q = 0; q < 4; q++) {
+            off[q] = (int)cls.size();
+            for (int c = 0; c + 1 < DAB_NCARR; c++) {
+                if (c == 767) continue;                                 // the pair would straddle DC
+                if (((prs[c + 1] - prs[c]) & 3) == q) cls.push_back((uint16_t)carrier_bin(c));
+            }
+        }
+        off[4] = (int)cls.size();
+        CK(d_cls_bin.ensure(cls.size() * 2));
+        CK(cudaMemcpy(d_cls_bin.p, cls.data(), cls.size() * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyToSymbol(c_cls_off, off, sizeof off));
+    }
     std::vector<uint32_t> pw(512);
     dabtab::prbs_words(pw.data(), 512);
     CK(d_prbs_w.ensure(pw.size() * 4));
@@ -241,11 +256,11 @@ int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
     const int8_t* prs = d_prs_q.as<int8_t>();
     prof_begin("k_fine_sync");
     if (fmt == B200DAB_FMT_U8)
-        k_fine_sync<B200DAB_FMT_U8><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+        k_fine_sync<B200DAB_FMT_U8><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>());
     else if (fmt == B200DAB_FMT_S16)
-        k_fine_sync<B200DAB_FMT_S16><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+        k_fine_sync<B200DAB_FMT_S16><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>());
     else
-        k_fine_sync<B200DAB_FMT_F32><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_fine.as<FineOut>());
+        k_fine_sync<B200DAB_FMT_F32><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>());
     prof_end();
     launches += 1;
     CK(cudaGetLastError());
@@ -600,7 +615,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
+    DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b};

@@ -124,11 +124,16 @@ __global__ void __launch_bounds__(256) k_sort_small(const long long* __restrict_
     }
 }
 
+// carrier pairs (c, c+1) grouped by the PRS phase step between them (class q: PRS[c+1] = PRS[c] * exp(j pi/2 q));
+// cls_bin[i] = FFT bin of the lower carrier; cls_off[q] .. cls_off[q+1] = entries of class q
+__constant__ int c_cls_off[5];
+
 // one CTA (256 threads) per candidate null start
 template <int FMT>
 __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw, int64_t nsamp, const long long* __restrict__ cand,
                                                    const int* __restrict__ n_cand_p, int max_cand, const float2* __restrict__ tw,
-                                                   const int8_t* __restrict__ prs_q, FineOut* __restrict__ out)
+                                                   const int8_t* __restrict__ prs_q, const uint16_t* __restrict__ cls_bin,
+                                                   FineOut* __restrict__ out)
 {
     __shared__ float2 X[FFT_BUF_LEN];
     __shared__ float2 C[FFT_BUF_LEN];
@@ -143,17 +148,42 @@ __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw,
     if (ci >= n_cand) return;
     const int t = threadIdx.x;
     const int64_t null_start = cand[ci];
+    FftPlan plan;
+    fft_plan_init(plan, tw);
 
     // (a) cyclic-prefix correlation over all 76 symbols -> fractional CFO
     float sr = 0.f, si = 0.f;
-    const int span = CP_CORR_HI - CP_CORR_LO;      // 376
-    for (int i = t; i < DAB_NSYM * span; i += 256) {
-        int l = i / span, n = CP_CORR_LO + (i - l * span);
-        int64_t p = null_start + DAB_T_NULL + (int64_t)DAB_T_SYM * l + n;
-        if (p + DAB_NFFT < nsamp) {
-            float2 a = load_iq<FMT>(raw, p), b = load_iq<FMT>(raw, p + DAB_NFFT);
-            sr += a.x * b.x + a.y * b.y;
-            si += a.y * b.x - a.x * b.y;
+    const int span = CP_CORR_HI - CP_CORR_LO;      // 184
+    const int64_t cp0 = null_start + DAB_T_NULL + CP_CORR_LO;
+    if (FMT == B200DAB_FMT_U8 && (cp0 & 3) == 0 && (span & 3) == 0 &&
+        cp0 + (int64_t)DAB_T_SYM * (DAB_NSYM - 1) + span + DAB_NFFT < nsamp) {
+        // aligned fast path: four samples (8 bytes) per load
+        const int quads = span / 4;
+        for (int i = t; i < DAB_NSYM * quads; i += 256) {
+            const int l = i / quads, n = 4 * (i - l * quads);
+            const int64_t p = cp0 + (int64_t)DAB_T_SYM * l + n;
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(raw) + 2 * p));
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(raw) + 2 * (p + DAB_NFFT)));
+            const uint32_t aw[2] = {a.x, a.y}, bw[2] = {b.x, b.y};
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float ax = (float)((int)((aw[k] >> (16 * h)) & 0xff) - 128), ay = (float)((int)((aw[k] >> (16 * h + 8)) & 0xff) - 128);
+                    const float bx = (float)((int)((bw[k] >> (16 * h)) & 0xff) - 128), by = (float)((int)((bw[k] >> (16 * h + 8)) & 0xff) - 128);
+                    sr += ax * bx + ay * by;
+                    si += ay * bx - ax * by;
+                }
+        }
+    } else {
+        for (int i = t; i < DAB_NSYM * span; i += 256) {
+            int l = i / span, n = i - l * span;
+            int64_t p = cp0 + (int64_t)DAB_T_SYM * l + n;
+            if (p + DAB_NFFT < nsamp) {
+                float2 a = load_iq<FMT>(raw, p), b = load_iq<FMT>(raw, p + DAB_NFFT);
+                sr += a.x * b.x + a.y * b.y;
+                si += a.y * b.x - a.x * b.y;
+            }
         }
     }
     sr = block_sum(sr, red);
@@ -165,21 +195,27 @@ __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw,
     const int64_t w0 = null_start + DAB_T_NULL + DAB_T_CP - PRS_WIN_EARLY;
     const float cpp = (float)((double)frac / (double)DAB_FS);
     load_symbol<FMT>(X, raw, nsamp, w0, 0.f, cpp);
-    fft2048_smem(X, tw);
+    fft2048_planned(X, plan);
 
-    // integer CFO: differential correlation between adjacent carriers against the PRS, for 33 shifts
+    // integer CFO: D[b] = X[b+1] X*[b] for every bin once; then for each of the 33 shifts the sum over the carrier pairs of
+    // D[bin + s] rotated by the PRS phase step, evaluated class by class so that the inner loop is load + add only
+    for (int b = t; b < DAB_NFFT; b += 256)
+        C[b] = cmul_conj(X[fft_phys(fft_pos((b + 1) & 2047))], X[fft_phys(fft_pos(b))]);
+    __syncthreads();
     {
         const int w = t >> 5, lane = t & 31;
         for (int si_ = w; si_ < 2 * CFO_INT_RANGE + 1; si_ += 8) {
             const int s = si_ - CFO_INT_RANGE;
             float ar = 0.f, ai = 0.f;
-            for (int c = lane; c + 1 < DAB_NCARR; c += 32) {
-                if (c == 767) continue;
-                int b0 = (carrier_bin(c) + s + 2048) & 2047, b1 = (carrier_bin(c + 1) + s + 2048) & 2047;
-                float2 x0 = X[fft_phys(fft_pos(b0))], x1 = X[fft_phys(fft_pos(b1))];
-                float2 d = cmul_conj(x1, x0);
-                d = rot_mq(d, prs_q[c + 1] - prs_q[c]);
-                ar += d.x; ai += d.y;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float qr = 0.f, qi = 0.f;
+                for (int i = c_cls_off[q] + lane; i < c_cls_off[q + 1]; i += 32) {
+                    const float2 d = C[(__ldg(cls_bin + i) + s + 2048) & 2047];
+                    qr += d.x; qi += d.y;
+                }
+                const float2 r = rot_mq(make_float2(qr, qi), q);
+                ar += r.x; ai += r.y;
             }
             ar = warp_sum(ar); ai = warp_sum(ai);
             if (lane == 0) shift_m[si_] = ar * ar + ai * ai;
@@ -205,7 +241,7 @@ __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw,
         float2 x = rot_mq(X[fft_phys(fft_pos(b))], prs_q[c]);
         C[fft_phys(carrier_bin(c))] = make_float2(x.x, -x.y);          // conj -> forward FFT gives conj(IFFT)
     }
-    fft2048_smem(C, tw);
+    fft2048_planned(C, plan);
     // power profile in natural delay order, stored back into X (reuse) as floats
     float* pw = reinterpret_cast<float*>(X);
     __syncthreads();
