@@ -351,8 +351,10 @@ int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len
         if (!(f[i].cir_ratio >= SYNC_CIR_MIN)) continue;
         const long long t_abs = f[i].t_f + (long long)off;
         if (fe_frames > 0 && t_abs - fe_last < (long long)(DAB_T_FRAME * 9 / 10)) continue;       // seen already / too close
+        // slot numbers advance by the rounded distance to the previous frame (not to the first one), so a sample-clock
+        // offset that accumulates to more than half a frame over a long recording cannot shift the CIF numbering
         if (fe_frames == 0) fe_t0 = t_abs;
-        const int slot = (int)((t_abs - fe_t0 + DAB_T_FRAME / 2) / DAB_T_FRAME);
+        const int slot = fe_frames == 0 ? 0 : hf[fe_frames - 1].slot + (int)((t_abs - fe_last + DAB_T_FRAME / 2) / DAB_T_FRAME);
         if (slot >= max_slots) break;
         FrameInfo fi;
         fi.t_f = t_abs; fi.cfo_hz = f[i].cfo_hz; fi.slot = slot;

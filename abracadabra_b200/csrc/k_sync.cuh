@@ -67,11 +67,16 @@ __global__ void __launch_bounds__(256) k_block_power(const void* __restrict__ ra
 
 __global__ void __launch_bounds__(256) k_window_sum(const float* __restrict__ P, int64_t nblk, float* __restrict__ S)
 {
-    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float tile[256 + SYNC_WIN];
+    const int64_t b0 = (int64_t)blockIdx.x * 256;
+    for (int i = threadIdx.x; i < 256 + SYNC_WIN; i += 256) tile[i] = (b0 + i < nblk) ? __ldg(P + b0 + i) : 0.f;
+    __syncthreads();
+    const int64_t b = b0 + threadIdx.x;
     if (b >= nblk) return;
     float acc = 0.f;
     if (b + SYNC_WIN <= nblk) {
-        for (int j = 0; j < SYNC_WIN; j++) acc = __fadd_rn(acc, __ldg(P + b + j));   // fixed order: bit-exact vs checker
+#pragma unroll 4
+        for (int j = 0; j < SYNC_WIN; j++) acc = __fadd_rn(acc, tile[threadIdx.x + j]);   // fixed order: bit-exact vs checker
     }
     S[b] = acc;
 }

@@ -34,8 +34,8 @@ struct VitGroup { int job; int g_in_job; };
 
 __constant__ int c_tdi_delay[16] = {0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15};
 
-#define GATHER_STEPS 64
-#define GATHER_PITCHW 67
+#define GATHER_STEPS 128
+#define GATHER_PITCHW 131        /* odd: lanes reading the same column of consecutive rows hit distinct banks */
 
 // grid (n_groups, ceil(max_steps / 64)), 256 threads
 __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ soft, const VitJob* __restrict__ jobs,
@@ -51,19 +51,19 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ soft,
     const uint32_t* si = stepinfo + job.stepinfo_off;
     const int p0 = (int)(__ldg(si + s0) >> 4), p1 = (int)(__ldg(si + s1) >> 4);
     const int p0a = p0 & ~3;
-    const int nwords = (p1 - p0a + 3) >> 2;              // <= 65
+    const int nwords = (p1 - p0a + 3) >> 2;              // <= 129
     const int nrows = job.use_tdi ? 47 : 32;
     const int rbase = job.row0 + grp.g_in_job * 32;
-    for (int idx = threadIdx.x; idx < nrows * nwords; idx += 256) {
-        const int row = idx / nwords, w = idx - row * nwords;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < nrows; row += 8) {        // one warp per row: coalesced 128-byte pieces, no index division
         int r = rbase + row;
         if (r > job.max_row) r = job.max_row;
-        const size_t addr = (size_t)(r >> 2) * DAB_FRAME_SOFT + (size_t)job.soft_base + (size_t)(r & 3) * job.row_pitch + p0a + 4 * w;
-        tile[row * GATHER_PITCHW + w] = __ldg(reinterpret_cast<const uint32_t*>(soft + addr));
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(soft + (size_t)(r >> 2) * DAB_FRAME_SOFT + (size_t)job.soft_base +
+                                                                (size_t)(r & 3) * job.row_pitch + p0a);
+        for (int w = lane; w < nwords; w += 32) tile[row * GATHER_PITCHW + w] = __ldg(src + w);
     }
     __syncthreads();
     const int8_t* tb = reinterpret_cast<const int8_t*>(tile);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* out = vin + job.vin_off + ((size_t)grp.g_in_job * job.steps) * 32 + lane;
     for (int s = s0 + warp; s < s1; s += 8) {
         const uint32_t info = __ldg(si + s);

@@ -88,7 +88,7 @@ class Impairments:
     taps: List[Tuple[int, complex]] = field(default_factory=list)   # extra multipath taps (delay samples, gain)
     lead_in: int = 49152               # samples of noise before the first frame (24 ms)
     rms: float = 28.0                  # target RMS in output LSB (u8: 28, s16: ~7000)
-    sample_offset_ppm: float = 0.0     # not modelled (kept 0); placeholder for config 5
+    sample_offset_ppm: float = 0.0     # receiver sample clock error: the signal is resampled by (1 + ppm * 1e-6)
     seed: int = 1
 
 
@@ -496,6 +496,26 @@ def modulate(ens: EnsembleConfig, n_frames: int, seed: int = 1) -> Tuple[np.ndar
     return out, truth
 
 
+def resample_ppm(x: np.ndarray, ppm: float, taps: int = 16) -> np.ndarray:
+    """Sample-clock offset: y[n] = x(n * (1 + ppm 1e-6)) by a Hann-windowed-sinc fractional-delay interpolator (16 taps)."""
+    r = 1.0 + ppm * 1e-6
+    n_out = int((x.size - taps) / r)
+    out = np.zeros(n_out, dtype=np.complex64)
+    step = 1 << 20
+    half = taps // 2
+    for s0 in range(0, n_out, step):
+        pos = np.arange(s0, min(n_out, s0 + step), dtype=np.float64) * r + half
+        k = np.floor(pos).astype(np.int64)
+        mu = (pos - k).astype(np.float32)
+        acc = np.zeros(pos.size, dtype=np.complex64)
+        for m in range(-half + 1, half + 1):
+            d = m - mu
+            w = np.sinc(d) * (0.5 + 0.5 * np.cos(np.pi * d / half))
+            acc += x[k + m] * w.astype(np.float32)
+        out[s0:s0 + pos.size] = acc
+    return out
+
+
 def impair(x: np.ndarray, imp: Impairments, tail: int = 0) -> np.ndarray:
     """Apply multipath, CFO (+drift), lead-in, AWGN.  Output has unit mean symbol power before noise."""
     rng = np.random.default_rng(imp.seed)
@@ -504,6 +524,8 @@ def impair(x: np.ndarray, imp: Impairments, tail: int = 0) -> np.ndarray:
         for d, g in imp.taps:
             y[d:] += np.complex64(g) * x[:len(x) - d]
         x = y
+    if imp.sample_offset_ppm:
+        x = resample_ppm(x, imp.sample_offset_ppm)
     x = np.concatenate([np.zeros(imp.lead_in, dtype=np.complex64), x, np.zeros(tail, dtype=np.complex64)])
     n = x.size
     if imp.cfo_hz or imp.cfo_drift_hz_per_s:

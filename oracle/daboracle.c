@@ -182,13 +182,12 @@ int orc_candidates(const float *q, int64_t nblk, uint64_t nsamp, int64_t *cand, 
 int orc_chain_frames(const int64_t *t_f, const float *cir_ratio, int n, int32_t *idx, int32_t *slot)
 {
     int nf = 0;
-    int64_t t0 = 0, last = 0;
+    int64_t last = 0;
     for (int i = 0; i < n; i++) {
         if (!(cir_ratio[i] >= SYNC_CIR_MIN)) continue;
         if (nf > 0 && t_f[i] - last < (int64_t)(DAB_T_FRAME * 9 / 10)) continue;
-        if (nf == 0) t0 = t_f[i];
         idx[nf] = i;
-        slot[nf] = (int32_t)((t_f[i] - t0 + DAB_T_FRAME / 2) / DAB_T_FRAME);
+        slot[nf] = nf == 0 ? 0 : slot[nf - 1] + (int32_t)((t_f[i] - last + DAB_T_FRAME / 2) / DAB_T_FRAME);   /* relative to the previous frame: immune to clock drift */
         last = t_f[i];
         nf++;
     }

@@ -123,3 +123,15 @@ def test_receiver_pool_band_scan():
         assert int(fibs[0, 2]) << 8 | int(fibs[0, 3]) == 0x4000 + i              # EId of FIG 0/0: the right recording in the right slot
         assert np.array_equal(fr, res.logical[3][:fr.shape[0]])
     assert [o[3] for o in out] == [(5 + i, 2 + i) for i in range(5)]             # short recordings: one TII window over all frames
+
+
+def test_sample_clock_offset_and_multipath_gpu(receiver, oracle):
+    ens = synth.config1_ensemble(seed=41)
+    imp = synth.Impairments(snr_db=18.0, cfo_hz=321.0, taps=[(25, 0.5), (90, 0.3j)], sample_offset_ppm=-60.0, seed=6, lead_in=20000)
+    raw, res = synth.synthesize(ens, 14, "u8", imp, seed=6, tail=150000)
+    d = receiver.decode(raw, "u8")
+    o = oracle.decode(raw, "u8", [oracle.subch_struct(ens.subchannels[0])])
+    assert d.n_frames == 14 and d.n_slots == 14 and np.array_equal(d.t_f, o["t_f"])
+    assert np.array_equal(d.fibs.reshape(-1, 96), res.fibs[:56]) and d.fib_ok.all()
+    assert np.array_equal(d.frames[0], o["frames"][0])
+    assert np.array_equal(d.frames[0], res.logical[3][:d.frames[0].shape[0]])

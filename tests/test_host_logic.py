@@ -100,3 +100,18 @@ def test_rs_decoder_corrects_up_to_five_bytes():
             assert r == nerr and np.array_equal(out, cw[nerr % 6])
         else:
             assert r == -1 or not np.array_equal(out, cw[nerr % 6])
+
+
+def test_sample_clock_offset_and_multipath():
+    """+-60 ppm receiver clock error (frames are 196608 * (1 -+ 60e-6) samples apart) and a 3-path channel: every frame is
+    synchronised on its own, slots stay consecutive, payload exact"""
+    ens = synth.config1_ensemble(seed=41)
+    for ppm in (60.0, -60.0):
+        imp = synth.Impairments(snr_db=18.0, cfo_hz=321.0, taps=[(25, 0.5), (90, 0.3j)], sample_offset_ppm=ppm, seed=6, lead_in=20000)
+        raw, res = synth.synthesize(ens, 10, "u8", imp, seed=6, tail=150000)
+        d = orc.decode(raw, "u8", [orc.subch_struct(ens.subchannels[0])])
+        assert d["nf"] == 10 and d["fib_ok"].all() and (d["t_f"] >= 0).all()
+        spacing = np.diff(d["t_f"])
+        assert np.all(np.abs(spacing - 196608 / (1 + ppm * 1e-6)) <= 3)
+        assert np.array_equal(d["fibs"], res.fibs[:40])
+        assert np.array_equal(d["frames"][0], res.logical[3][:d["frames"][0].shape[0]])
