@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ soft,
                                                 uint32_t* __restrict__ vin)
 {
     __shared__ uint32_t tile[47 * GATHER_PITCHW];
+    __shared__ uint2 soff[GATHER_STEPS];
     const VitGroup grp = groups[blockIdx.x];
     const VitJob job = jobs[grp.job];
     const int s0 = blockIdx.y * GATHER_STEPS;
@@ -62,23 +63,30 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ soft,
                                                                 (size_t)(r & 3) * job.row_pitch + p0a);
         for (int w = lane; w < nwords; w += 32) tile[row * GATHER_PITCHW + w] = __ldg(src + w);
     }
-    __syncthreads();
-    const int8_t* tb = reinterpret_cast<const int8_t*>(tile);
-    uint32_t* out = vin + job.vin_off + ((size_t)grp.g_in_job * job.steps) * 32 + lane;
-    for (int s = s0 + warp; s < s1; s += 8) {
-        const uint32_t info = __ldg(si + s);
+    // every row gets a zero word in its last (otherwise unused) column: punctured bits read it, so the inner loop is branch-free
+    if (threadIdx.x < nrows) tile[threadIdx.x * GATHER_PITCHW + (GATHER_PITCHW - 1)] = 0;
+    // byte offsets (relative to the lane's own row) of the four soft bits of every step of this chunk, computed once
+    for (int i = threadIdx.x; i < (s1 - s0); i += 256) {
+        const uint32_t info = __ldg(si + s0 + i);
         int p = (int)(info >> 4);
-        uint32_t word = 0;
+        unsigned short o4[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             if (info & (1u << q)) {
                 const int d = job.use_tdi ? c_tdi_delay[p & 15] : 0;
-                const uint32_t b = (uint8_t)tb[(lane + d) * (GATHER_PITCHW * 4) + (p - p0a)];
-                word |= b << (8 * q);
+                o4[q] = (unsigned short)(d * (GATHER_PITCHW * 4) + (p - p0a));
                 p++;
-            }
+            } else o4[q] = (unsigned short)((GATHER_PITCHW - 1) * 4);
         }
-        out[(size_t)s * 32] = word;
+        soff[i] = make_uint2((uint32_t)o4[0] | ((uint32_t)o4[1] << 16), (uint32_t)o4[2] | ((uint32_t)o4[3] << 16));
+    }
+    __syncthreads();
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile) + lane * (GATHER_PITCHW * 4);
+    uint32_t* out = vin + job.vin_off + ((size_t)grp.g_in_job * job.steps) * 32 + lane;
+    for (int s = s0 + warp; s < s1; s += 8) {
+        const uint2 o = soff[s - s0];                                   // same for all lanes: broadcast
+        const uint32_t b0 = tb[o.x & 0xffffu], b1 = tb[o.x >> 16], b2 = tb[o.y & 0xffffu], b3 = tb[o.y >> 16];
+        out[(size_t)s * 32] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
     }
 }
 

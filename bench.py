@@ -337,10 +337,18 @@ def main():
     stages.sort(key=lambda s: -s["ms"])
     dom = stages[0] if stages else None
     roof = None
+    traffic = {}
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this very command (profiles/)
+        traffic = json.load(open(ROOT / "profiles" / "r01_traffic.json"))["bytes_per_launch"]
+    except Exception:
+        pass
+    for st in stages:
+        st["dram_traffic_ncu"] = traffic.get(st["kernel"])
     if dom:
         trellis_steps = max(4 * n_frames - 15, 0) * sum(s.bitrate * 24 + 6 for s in subch)
         roof = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": dom["frac_hbm"], "traffic": None, "ms": dom["ms"],
+                "frac": dom["frac_hbm"], "traffic": traffic.get(dom["kernel"]) if abs(args.seconds - 60.0) < 1e-6 else None, "ms": dom["ms"],
+                "algorithmic_bytes": dom["algorithmic_bytes"],
                 "note": "Viterbi ACS is issue-bound, not HBM-bound: see issue{}" if "viterbi" in dom["kernel"] else ""}
         if "viterbi(msc)" in dom["kernel"]:
             acs = trellis_steps * 64.0
