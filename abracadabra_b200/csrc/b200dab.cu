@@ -83,7 +83,8 @@ struct b200dab_ctx {
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
     DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_fic_out, d_fib_ok, d_msc_out;
     DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
-    DevBuf d_tmp_a, d_tmp_b;
+    DevBuf d_tmp_a, d_tmp_b, d_spec;
+    HostBuf h_spec;
     HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
     HostBuf h_jobs[2], h_groups[2], h_stepinfo[2], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
     std::vector<int32_t> r_sign;
@@ -620,10 +621,10 @@ void b200dab_destroy(b200dab_ctx* ctx)
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
-                    &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b};
+                    &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
-                     &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
+                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -736,6 +737,23 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     for (int i = 0; i < n_frames; i++) { ctx->r_tf[frames[i].slot] = frames[i].t_f; ctx->r_cfo[frames[i].slot] = frames[i].cfo_hz; ctx->r_cir[frames[i].slot] = ctx->fe_cir[i]; }
     res->t_f = ctx->r_tf.data(); res->cfo_hz = ctx->r_cfo.data(); res->cir_ratio = ctx->r_cir.data();
     if (n_frames == 0) { res->gpu_launches = ctx->launches; return 0; }
+    if (flags & B200DAB_OPT_SPECTRUM) {
+        CKC(ctx->d_spec.ensure((size_t)n_slots * 2 * DAB_NFFT * 4));
+        CKC(ctx->h_spec.ensure((size_t)n_slots * 2 * DAB_NFFT * 4));
+        CKC(cudaMemsetAsync(ctx->d_spec.p, 0, (size_t)n_slots * 2 * DAB_NFFT * 4, ctx->stream));
+        const FrameInfo* dfr = ctx->h_frames.as<FrameInfo>();
+        const float2* tw = ctx->d_tw.as<float2>();
+        const int64_t nn = (int64_t)n;
+        ctx->prof_begin("k_spectrum");
+        if (fmt == B200DAB_FMT_U8) k_spectrum<B200DAB_FMT_U8><<<n_frames, 256, 0, ctx->stream>>>(d_iq, nn, dfr, tw, ctx->d_spec.as<float>());
+        else if (fmt == B200DAB_FMT_S16) k_spectrum<B200DAB_FMT_S16><<<n_frames, 256, 0, ctx->stream>>>(d_iq, nn, dfr, tw, ctx->d_spec.as<float>());
+        else k_spectrum<B200DAB_FMT_F32><<<n_frames, 256, 0, ctx->stream>>>(d_iq, nn, dfr, tw, ctx->d_spec.as<float>());
+        ctx->prof_end();
+        ctx->launches += 1;
+        CKC(cudaGetLastError());
+        CKC(cudaMemcpyAsync(ctx->h_spec.p, ctx->d_spec.p, (size_t)n_slots * 2 * DAB_NFFT * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        res->spectrum = ctx->h_spec.as<float>();
+    }
     // ---- FIC
     if (ctx->fic(n_slots)) return -1;
     const size_t fib_bytes = (size_t)n_slots * 12 * 32;

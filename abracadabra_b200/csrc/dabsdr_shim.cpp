@@ -26,6 +26,7 @@
 #include "b200dab.h"
 #include "dabsdr_abi.h"
 #include "fig.h"
+#include "mp2.h"
 
 namespace {
 
@@ -333,7 +334,8 @@ void process_window(dabsdr_s* h)
             sc[n_sc].kind = h->dec[k].dabplus ? 1 : 0;
             sc_dec[n_sc++] = k;
         }
-    uint32_t flags = B200DAB_OPT_SYMSTAT | (h->tii_on ? B200DAB_OPT_TII : 0u) | (n_sc == 0 ? B200DAB_OPT_NO_MSC : 0u);
+    uint32_t flags = B200DAB_OPT_SYMSTAT | (h->tii_on ? B200DAB_OPT_TII : 0u) | (n_sc == 0 ? B200DAB_OPT_NO_MSC : 0u) |
+                     (h->spectrum_on && h->spec_cb ? B200DAB_OPT_SPECTRUM : 0u);
     b200dab_result_t r;
     if (b200dab_decode(h->gpu, h->win.data(), (uint64_t)h->have, B200DAB_FMT_F32, B200DAB_MEM_HOST, n_sc ? sc : nullptr, n_sc, flags, &r) != 0) {
         fprintf(stderr, "dabsdr(b200): GPU decode failed: %s\n", b200dab_last_error(h->gpu));
@@ -365,6 +367,13 @@ void process_window(dabsdr_s* h)
             if (r.fib_ok[(size_t)s * 12 + f]) { h->db.parse_fib(r.fibs + ((size_t)s * 12 + f) * 32); any_fic = true; }
             else h->fib_err++;
         }
+        if (r.spectrum && h->spectrum_on && h->spec_cb) {
+            // like the reference: per frame one SIGNAL spectrum and one of the null symbol (TII when that null carries TII)
+            const float* sp = r.spectrum + (size_t)s * 2 * DAB_NFFT;
+            const bool tii_null = r.tii_sign && r.tii_sign[s] > 0;
+            h->spec_cb(sp + DAB_NFFT, tii_null ? DABSDR_SPECT_TII : DABSDR_SPECT_NULL, h->spec_ctx);
+            h->spec_cb(sp, DABSDR_SPECT_SIGNAL, h->spec_ctx);
+        }
         if (h->tii_on && r.tii_fold) {
             h->tii_fold.insert(h->tii_fold.end(), r.tii_fold + (size_t)s * TII_SPECTRUM_BINS, r.tii_fold + (size_t)(s + 1) * TII_SPECTRUM_BINS);
             h->tii_norm.push_back(r.tii_norm[s]);
@@ -386,7 +395,7 @@ void process_window(dabsdr_s* h)
                     if (ar < 0 || ar <= d.last_row) continue;
                     d.last_row = ar;
                     const uint8_t* fr = r.frames[i] + (size_t)row * pitch;
-                    const bool hdr_ok = fr[0] == 0xFF && (fr[1] & 0xF0) == 0xF0;
+                    const bool hdr_ok = mp2::check_frame(fr, pitch) == 1;      // ISO 11172-3 CRC; a failing frame is delivered empty
                     if (sc_dec[i] == 0) { if (hdr_ok) h->crc_ok++; else h->crc_err++; h->audio_bytes += pitch; }
                     if (h->audio_cb) {
                         dabsdrAudioCBData_t a;

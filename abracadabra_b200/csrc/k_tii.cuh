@@ -74,6 +74,29 @@ __global__ void __launch_bounds__(256) k_tii_fold_nulls(const float2* __restrict
     }
 }
 
+// signal-spectrum callback material (dabsdr.h:393, consumer src/radiocontrol.cpp:2604-2609): per frame two 2048-bin linear power
+// spectra in natural FFT order, unnormalised |FFT|^2 of the raw samples like the reference's: [0] the PRS symbol (SIGNAL),
+// [1] the null symbol (NULL / TII).  One CTA per frame.
+template <int FMT>
+__global__ void __launch_bounds__(256) k_spectrum(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+                                                  const float2* __restrict__ tw, float* __restrict__ spec)
+{
+    __shared__ float2 buf[FFT_BUF_LEN];
+    const int t = threadIdx.x;
+    const FrameInfo fr = frames[blockIdx.x];
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+        load_symbol<FMT>(buf, raw, nsamp, which == 0 ? fr.t_f : fr.t_f - DAB_T_SYM, 0.f, 0.f);
+        fft2048_smem(buf, tw);
+        float* o = spec + ((size_t)fr.slot * 2 + which) * DAB_NFFT;
+        for (int k = t; k < DAB_NFFT; k += 256) {
+            const float2 v = buf[fft_phys(fft_pos(k))];
+            o[k] = v.x * v.x + v.y * v.y;
+        }
+        __syncthreads();
+    }
+}
+
 struct TiiResult {
     int n_ids;
     int n_tii_frames;

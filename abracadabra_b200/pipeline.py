@@ -21,7 +21,7 @@ LIB_PATH = PKG / "lib" / "libb200dab.so"
 SHIM_PATH = PKG / "lib" / "libdabsdr.so.4"
 FMT = {"u8": 0, "s16": 1, "f32": 2}
 FMT_BYTES = {"u8": 2, "s16": 4, "f32": 8}
-OPT_TII, OPT_NO_MSC, OPT_SYMSTAT = 1, 2, 4
+OPT_TII, OPT_NO_MSC, OPT_SYMSTAT, OPT_SPECTRUM = 1, 2, 4, 8
 TII_MAX_IDS, TII_BINS = 24, 384
 FRAME_SOFT = 75 * 3072
 
@@ -54,7 +54,8 @@ class Result(ct.Structure):
                 ("firecode_fail", ct.c_int64), ("superframes", ct.c_int64),
                 ("n_tii", ct.c_int32), ("tii", ct.POINTER(Tii)),
                 ("symstat", ct.POINTER(ct.c_float)), ("snr_db", ct.c_float), ("gpu_launches", ct.c_int32),
-                ("tii_fold", ct.POINTER(ct.c_float)), ("tii_norm", ct.POINTER(ct.c_float)), ("tii_sign", ct.POINTER(ct.c_int32))]
+                ("tii_fold", ct.POINTER(ct.c_float)), ("tii_norm", ct.POINTER(ct.c_float)), ("tii_sign", ct.POINTER(ct.c_int32)),
+                ("spectrum", ct.POINTER(ct.c_float))]
 
 
 def build(verbose: bool = False) -> None:

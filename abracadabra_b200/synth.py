@@ -287,8 +287,18 @@ def dabplus_superframes(sc: SubChannel, n_sf: int, rng: np.random.Generator):
     return sf, aus
 
 
-def mp2_frames(sc: SubChannel, n: int, rng: np.random.Generator) -> np.ndarray:
-    """MPEG-1 Layer II 48 kHz frames (24 ms) with a valid header and random body (body CRC is NOT valid)."""
+def _mp2_crc(crc: int, value: int, bits: int) -> int:
+    for i in range(bits - 1, -1, -1):
+        b = ((value >> i) & 1) ^ (crc >> 15)
+        crc = (crc << 1) & 0xFFFF
+        if b:
+            crc ^= 0x8005
+    return crc
+
+
+def mp2_frames(sc: SubChannel, n: int, rng: np.random.Generator, valid_crc: bool = True) -> np.ndarray:
+    """MPEG-1 Layer II, 48 kHz, stereo frames (24 ms) of the sub-channel's bitrate: valid header, random bit allocation and
+    scfsi protected by a correct ISO 11172-3 CRC-16 (poly 0x8005), random remainder (no decodable audio, DAB ScF-CRC not set)."""
     fb = sc.frame_bytes
     frames = rng.integers(0, 256, (n, fb), dtype=np.uint8)
     br_idx = {32: 1, 48: 2, 56: 3, 64: 4, 80: 5, 96: 6, 112: 7, 128: 8, 160: 9, 192: 10, 224: 11, 256: 12,
@@ -296,7 +306,29 @@ def mp2_frames(sc: SubChannel, n: int, rng: np.random.Generator) -> np.ndarray:
     frames[:, 0] = 0xFF
     frames[:, 1] = 0xFC            # MPEG-1, layer II, CRC protected
     frames[:, 2] = (br_idx << 4) | (1 << 2)   # 48 kHz
-    frames[:, 3] = 0x00
+    frames[:, 3] = 0x00            # stereo
+    if not valid_crc:
+        return frames
+    br_ch = sc.bitrate // 2
+    sbl = 8 if br_ch <= 48 else 27
+    nbal = (lambda sb: 4 if sb < 2 else 3) if br_ch <= 48 else (lambda sb: 4 if sb < 11 else 3 if sb < 23 else 2)
+    for f in range(n):
+        bits = np.unpackbits(frames[f])
+        crc = _mp2_crc(_mp2_crc(0xFFFF, int(frames[f, 2]), 8), int(frames[f, 3]), 8)
+        pos = 48
+        nz = 0
+        for sb in range(sbl):
+            nb = nbal(sb)
+            for _ch in range(2):
+                v = int("".join(map(str, bits[pos:pos + nb])), 2)
+                crc = _mp2_crc(crc, v, nb)
+                nz += v != 0
+                pos += nb
+        for _ in range(nz):
+            v = int(bits[pos]) * 2 + int(bits[pos + 1])
+            crc = _mp2_crc(crc, v, 2)
+            pos += 2
+        frames[f, 4], frames[f, 5] = crc >> 8, crc & 0xFF
     return frames
 
 

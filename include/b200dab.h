@@ -53,6 +53,7 @@ typedef struct {
 #define B200DAB_OPT_TII        1u    /* run the TII detector */
 #define B200DAB_OPT_NO_MSC     2u    /* stop after the FIC (ensemble discovery only) */
 #define B200DAB_OPT_SYMSTAT    4u    /* keep per-symbol soft-bit statistics (SNR estimate) */
+#define B200DAB_OPT_SPECTRUM   8u    /* per frame: 2048-bin power spectra of the PRS symbol and of the null symbol */
 
 /* per access unit (DAB+), in stream order per sub-channel */
 typedef struct {
@@ -101,6 +102,7 @@ typedef struct {
     const float *tii_fold;           /* [n_slots][384] */
     const float *tii_norm;           /* [n_slots] */
     const int32_t *tii_sign;         /* [n_slots] +1 TII null, -1 reference null, 0 unknown */
+    const float *spectrum;           /* [n_slots][2][2048] linear power, FFT order: [0] PRS symbol, [1] null symbol (OPT_SPECTRUM) */
 } b200dab_result_t;
 
 B200DAB_API int b200dab_version(void);

@@ -192,8 +192,18 @@ static void dg_cb(dabsdrDataGroupCBData_t *p, void *ctx)
 static uint64_t g_n_spec;
 static void spectrum_cb(const float *p, dabsdrSpectrum_t type, void *ctx)
 {
-    (void)ctx; (void)p; (void)type;
+    (void)ctx;
     g_n_spec++;
+    if (!g_log) return;
+    /* 2048 linear-power bins in FFT order (src/radiocontrol.cpp:2604-2609, src/signalbackend.cpp:383-431) */
+    double sum = 0, mx = 0; int arg = 0;
+    for (int i = 0; i < 2048; i++) { sum += p[i]; if (p[i] > mx) { mx = p[i]; arg = i; } }
+    double inband = 0;
+    for (int i = 1; i <= 768; i++) inband += p[i] + p[2048 - i];
+    pthread_mutex_lock(&g_logmx);
+    fprintf(g_log, "{\"ev\":\"spectrum\",\"pos\":%llu,\"type\":%d,\"sum\":%.6g,\"max\":%.6g,\"argmax\":%d,\"inband\":%.6g,\"b0\":%.6g,\"b1\":%.6g,\"b900\":%.6g}\n",
+            (unsigned long long)g_pos, (int)type, sum, mx, arg, inband, (double)p[0], (double)p[1], (double)p[900]);
+    pthread_mutex_unlock(&g_logmx);
 }
 
 static void log_notification(const ev_t *e);

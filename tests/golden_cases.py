@@ -20,6 +20,8 @@ CASES = {
                          tii=[(12, 5, 1.0, 0), (33, 17, 0.5, 30), (60, 2, 0.25, 100)], tii_mode=1, service=None),
     # several sub-channels with different protection (EEP-A/B, UEP); the reference decodes the selected one
     "multi_u8_25db": dict(kind="multi", n_frames=22, fmt="u8", snr=25.0, cfo=-2345.6, seed=21, tii=[(3, 9, 1.0, 0)], tii_mode=None, service=2),
+    # same ensemble, the DAB (MPEG-1 Layer II, UEP table index 35) service selected: frames with a valid ISO 11172-3 CRC
+    "multi_mp2_u8_25db": dict(kind="multi", n_frames=22, fmt="u8", snr=25.0, cfo=-2345.6, seed=21, tii=[(3, 9, 1.0, 0)], tii_mode=None, service=3),
 }
 
 

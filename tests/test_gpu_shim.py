@@ -64,3 +64,32 @@ def test_dropin_against_reference_event_log():
     assert tii and [(m, s) for m, s, _ in tii[0]["ids"]] == [(m, s) for m, s, _ in rt[0]["ids"]]
     assert abs(20 * np.log10(tii[0]["ids"][0][2] / rt[0]["ids"][0][2])) < 0.3
     assert int(np.argmax(tii[0]["spectrum"])) // 2 in [b * 24 + 5 for b in (2, 3, 4, 7)]
+
+
+def test_dropin_mp2_service_against_reference():
+    """UEP-protected DAB (MP2) service through the drop-in: same frames, same order as the reference delivers them"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("multi_mp2_u8_25db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "m.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=3, harness=harness, extra=["--tail-frames", "12", "--spectrum"])
+    me = [e for e in ev if e["ev"] == "sc_list" and e["sid"] == 0x3003][0]["items"][0]
+    rf = [e for e in g["events"] if e["ev"] == "sc_list" and e["sid"] == 0x3003][0]["items"][0]
+    assert me == rf and me["uep_fec"] == 35 and me["prot"] == 3 and me["size"] == 96 and me["bitrate"] == 128
+    got = [e for e in ev if e["ev"] == "audio"]
+    assert len(got) >= 30 and all(e["ascty"] == 0 and e["len"] == 384 and e["id"] == 0 for e in got)
+    truth = [hashlib.sha1(bytes(r)).hexdigest() for r in res.logical[9]]
+    sha = [hashlib.sha1(bytes.fromhex(e["data"])).hexdigest() for e in got]
+    i0 = truth.index(sha[0])
+    assert sha == truth[i0:i0 + len(sha)]
+    assert set(sha) & {e["sha1"] for e in g["events"] if e["ev"] == "audio"}
+    # signal-spectrum callback: two spectra per frame (null/TII + signal), Parseval-sized, energy inside the 1536 carriers
+    sp = [e for e in ev if e["ev"] == "spectrum"]
+    sig = [e for e in sp if e["type"] == 0]
+    nul = [e for e in sp if e["type"] != 0]
+    assert len(sig) >= 20 and abs(len(sig) - len(nul)) <= 1
+    ref_sum = 2048.0 * 2048.0 * 28.0 ** 2
+    assert all(0.8 * ref_sum < e["sum"] < 1.25 * ref_sum and e["inband"] > 0.98 * e["sum"] for e in sig)
+    assert np.median([e["sum"] for e in nul]) < 0.05 * ref_sum

@@ -67,6 +67,27 @@ def test_access_units_match_reference(name):
         assert 0.4 < (be / n_my_sf) / (ref_be / n_ref_sf) < 2.5
 
 
+def test_mp2_frames_match_reference():
+    """DAB (MPEG-1 Layer II) service behind UEP protection: the reference delivers every logical frame whose ISO CRC holds;
+    the checker's Viterbi output must contain exactly those bytes"""
+    g = gc.load_golden("multi_mp2_u8_25db")
+    raw, res = gc.build_case(g["spec"])
+    if not gc.raw_matches(raw, g):
+        pytest.skip("synthetic file differs from the one the fixture was made from")
+    sc = res.ens.subchannels[3]
+    assert sc.kind == "mp2" and sc.prot == ("UEP", 35)
+    d = orc.decode(raw, "u8", [orc.subch_struct(sc)])
+    mine = [hashlib.sha1(bytes(r)).hexdigest() for r in d["frames"][0]]
+    ref = [e for e in g["events"] if e["ev"] == "audio"]
+    assert len(ref) >= 30 and all(e["ascty"] == 0 and e["len"] == 384 for e in ref)
+    ref_sha = [e["sha1"] for e in ref]
+    i0 = mine.index(ref_sha[0])
+    n = min(len(mine) - i0, len(ref_sha))
+    assert n >= len(ref_sha) - 4 and mine[i0:i0 + n] == ref_sha[:n]
+    crc = [e for e in g["events"] if e["ev"] == "periodic" and e.get("crcOk")]
+    assert crc and all(e["crcErr"] == 0 for e in crc)
+
+
 @pytest.mark.parametrize("name", ["c1_u8_40db", "tii3_u8_25db"])
 def test_tii_matches_reference(name):
     g = gc.load_golden(name)
