@@ -19,6 +19,7 @@
 #include "k_dabplus.cuh"
 #include "k_tii.cuh"
 #include "tables.h"
+#include "fig.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(#x, e_); return -1; } } while (0)
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->set_error(#x, e_); return -1; } } while (0)
@@ -676,6 +677,30 @@ int b200dab_get_kernel_times(b200dab_ctx* ctx, char* names, int names_cap, float
     }
     if (names && names_cap > 0) { strncpy(names, all.c_str(), (size_t)names_cap - 1); names[names_cap - 1] = 0; }
     return n;
+}
+
+int b200dab_parse_ensemble(const uint8_t* fibs, const uint8_t* fib_ok, int n_fibs, b200dab_ensemble_t* out)
+{
+    if (!fibs || !out) return -1;
+    fig::Database db;
+    memset(out, 0, sizeof *out);
+    out->first_cif_count = -1;
+    for (int f = 0; f < n_fibs; f++) {
+        if (fib_ok && !fib_ok[f]) continue;
+        db.parse_fib(fibs + (size_t)f * 32);
+        if (out->first_cif_count < 0 && db.cif_count >= 0) out->first_cif_count = db.cif_count;
+    }
+    out->ueid = ((uint32_t)(db.have_ecc ? db.ecc : 0) << 16) | db.eid;
+    out->lto = db.lto; out->int_table = db.int_table; out->alarm = db.alarm;
+    if (db.label.valid) memcpy(out->label, db.label.str, 16);
+    for (auto& sv : db.services) {
+        if (sv.comps.empty() || out->n_services >= 64) continue;
+        b200dab_service_t& o = out->services[out->n_services++];
+        o.sid = sv.sid;
+        if (sv.label.valid) memcpy(o.label, sv.label.str, 16);
+        for (auto& c : sv.comps) if (c.tmid == 0 && o.n_components < 4) { o.subch_id[o.n_components] = (uint8_t)c.subch_id; o.ascty[o.n_components] = c.ascty_dscty; o.n_components++; }
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ whole path

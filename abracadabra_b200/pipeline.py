@@ -43,6 +43,16 @@ class Tii(ct.Structure):
                 ("level", ct.c_float * TII_MAX_IDS), ("spectrum", ct.c_float * TII_BINS)]
 
 
+class ServiceInfo(ct.Structure):
+    _fields_ = [("sid", ct.c_uint32), ("label", ct.c_char * 17), ("n_components", ct.c_uint8), ("subch_id", ct.c_uint8 * 4),
+                ("ascty", ct.c_uint8 * 4)]
+
+
+class EnsembleInfo(ct.Structure):
+    _fields_ = [("ueid", ct.c_uint32), ("lto", ct.c_int32), ("int_table", ct.c_int32), ("alarm", ct.c_int32), ("label", ct.c_char * 17),
+                ("first_cif_count", ct.c_int32), ("n_services", ct.c_int32), ("services", ServiceInfo * 64)]
+
+
 class Result(ct.Structure):
     _fields_ = [("n_candidates", ct.c_int32), ("n_frames", ct.c_int32), ("n_slots", ct.c_int32),
                 ("t_f", ct.POINTER(ct.c_int64)), ("cfo_hz", ct.POINTER(ct.c_float)), ("cir_ratio", ct.POINTER(ct.c_float)),
@@ -86,6 +96,7 @@ def lib():
         L.b200dab_profile_eep.argtypes = [i32, i32, i32, ct.POINTER(SubCh)]
         L.b200dab_profile_uep.argtypes = [i32, ct.POINTER(SubCh)]
         L.b200dab_parse_subch.argtypes = [vp, vp, i32, ct.POINTER(SubCh), i32]
+        L.b200dab_parse_ensemble.argtypes = [vp, vp, i32, ct.POINTER(EnsembleInfo)]
         L.b200dab_decode.argtypes = [vp, vp, u64, i32, i32, ct.POINTER(SubCh), i32, ct.c_uint32, ct.POINTER(Result)]
         L.b200dab_set_profiling.argtypes = [vp, i32]
         L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
@@ -103,7 +114,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -139,6 +150,19 @@ def parse_subch(fibs: np.ndarray, fib_ok: Optional[np.ndarray] = None) -> List[S
     if n < 0:
         raise RuntimeError("parse_subch failed")
     return [out[i] for i in range(n)]
+
+
+def parse_ensemble(fibs: np.ndarray, fib_ok: Optional[np.ndarray] = None) -> dict:
+    """Ensemble and service summary from decoded FIBs (what RadioControl gets as dabsdrNtfEnsemble_t + the service list)."""
+    fibs = np.ascontiguousarray(fibs, dtype=np.uint8).reshape(-1, 32)
+    ok = None if fib_ok is None else np.ascontiguousarray(fib_ok, dtype=np.uint8)
+    e = EnsembleInfo()
+    if lib().b200dab_parse_ensemble(fibs.ctypes.data, None if ok is None else ok.ctypes.data, fibs.shape[0], ct.byref(e)) != 0:
+        raise RuntimeError("parse_ensemble failed")
+    svcs = [dict(sid=s.sid, label=s.label.decode("latin1"), components=[(int(s.subch_id[i]), int(s.ascty[i])) for i in range(s.n_components)])
+            for s in (e.services[i] for i in range(e.n_services))]
+    return dict(ueid=e.ueid, eid=e.ueid & 0xFFFF, ecc=(e.ueid >> 16) & 0xFF, lto=e.lto, int_table=e.int_table, alarm=e.alarm,
+                label=e.label.decode("latin1"), first_cif_count=e.first_cif_count, services=svcs)
 
 
 @dataclass

@@ -117,6 +117,25 @@ B200DAB_API int b200dab_profile_uep(int table_index, b200dab_subch_t *out);
 /* parse FIBs (CRC-checked by the caller) into a sub-channel table: FIG 0/1 + FIG 0/2 (ASCTy 63 = DAB+) */
 B200DAB_API int b200dab_parse_subch(const uint8_t *fibs, const uint8_t *fib_ok, int n_fibs, b200dab_subch_t *out, int max_out);
 
+/* Ensemble / service summary out of decoded FIBs: the fields RadioControl receives in dabsdrNtfEnsemble_t and the service
+ * list (dabsdr.h:169-318), for batch callers that do not go through the callback interface (band scan output). */
+typedef struct {
+    uint32_t sid;
+    char label[17];
+    uint8_t n_components;
+    uint8_t subch_id[4];
+    uint8_t ascty[4];           /* 63 = DAB+, 0 = MP2 (TMId 0 components only) */
+} b200dab_service_t;
+typedef struct {
+    uint32_t ueid;              /* ECC << 16 | EId */
+    int32_t lto, int_table, alarm;
+    char label[17];
+    int32_t first_cif_count;    /* CIF counter of the first decoded FIG 0/0, -1 if none */
+    int32_t n_services;
+    b200dab_service_t services[64];
+} b200dab_ensemble_t;
+B200DAB_API int b200dab_parse_ensemble(const uint8_t *fibs, const uint8_t *fib_ok, int n_fibs, b200dab_ensemble_t *out);
+
 /* Whole hot path over one recording (or chunk): sync -> FFT -> DQPSK -> de-interleave -> Viterbi -> FIB CRC ->
  * [FIG 0/1 discovery] -> MSC Viterbi -> RS/AU -> TII.  iq: interleaved I,Q in `fmt`; mem says where it lives. */
 B200DAB_API int b200dab_decode(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, int mem,

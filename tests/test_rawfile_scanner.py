@@ -1,0 +1,129 @@
+"""Raw/UFF container rules (src/input/rawfileinput.cpp, src/input/inputdevicerecorder.cpp) and scanner CSV (src/tii/scannerbackend.cpp)."""
+import numpy as np
+import pytest
+
+from abracadabra_b200 import pipeline, rawfile, scanner, synth
+import cases
+
+
+def test_uff_roundtrip(tmp_path):
+    rng = np.random.default_rng(1)
+    for fmt, dt in (("u8", np.uint8), ("s16", np.int16)):
+        iq = rng.integers(0, 200, 2 * 5000).astype(dt)
+        p = tmp_path / f"rec_{fmt}.uff"
+        rawfile.write_uff(str(p), iq, fmt, 227360)
+        blob = p.read_bytes()
+        assert len(blob) == 2048 + iq.nbytes and blob[:5] == b"<?xml"
+        z = blob.index(b"\x00")
+        assert z < 2048 and blob[z:2048] == bytes(2048 - z)            # zero padding up to the data offset
+        data, info = rawfile.read_raw(str(p))
+        assert info.has_xml_header and info.fmt == fmt and info.frequency_khz == 227360 and info.sample_rate == 2048000
+        assert info.num_samples == 5000 and np.array_equal(data, iq)
+        assert "AbracaDABra" in info.recorder and info.time.endswith("UTC")
+
+
+def test_uff_header_fields_reference_layout(tmp_path):
+    # the element / attribute names InputDeviceRecorder writes (inputdevicerecorder.cpp:195-263)
+    import xml.etree.ElementTree as ET
+    p = tmp_path / "a.uff"
+    rawfile.write_uff(str(p), np.zeros(64, np.int16), "s16", 174928)
+    root = ET.fromstring(p.read_bytes()[:2048].rstrip(b"\x00").decode())
+    assert root.tag == "SDR" and [e.tag for e in root] == ["Recorder", "Device", "Time", "Sample", "Datablocks"]
+    ch = root.find("Sample/Channels")
+    assert ch.get("Bits") == "16" and ch.get("Container") == "int16" and ch.get("Ordering") == "LSB"
+    assert [c.get("Value") for c in ch] == ["I", "Q"]
+    blk = root.find("Datablocks/Datablock")
+    assert blk.get("Count") == "64" and blk.get("Offset") == "2048" and blk.get("Unit") == "Channel" and blk.get("Number") == "1"
+    assert blk.find("Frequency").get("Unit") == "kHz" and blk.find("Modulation").get("Value") == "DAB"
+
+
+def test_foreign_header_variants():
+    def hdr(body):
+        return (b'<?xml version="1.0"?><SDR>' + body + b"</SDR>").ljust(2048, b"\x00")
+    i = rawfile.parse_header(hdr(b'<Sample><Samplerate Value="2048" Unit="kHz"/><Channels Bits="8" Container="uint8"/></Sample>'
+                                 b'<Datablocks><Datablock Count="1000"><Frequency Value="202928000" Unit="Hz"/></Datablock></Datablocks>'))
+    assert i.sample_rate == 2048000 and i.fmt == "u8" and i.frequency_khz == 202928 and i.num_samples == 500
+    with pytest.raises(ValueError):
+        rawfile.parse_header(hdr(b'<Sample><Channels Container="float"/></Sample>'))
+    with pytest.raises(ValueError):
+        rawfile.parse_header(hdr(b'<Sample><Channels Container="int16" Ordering="MSB"/></Sample>'))
+    assert rawfile.parse_header(b"\x80" * 2048) is None                # raw samples: no zero byte / no XML
+    assert rawfile.parse_header(b"not xml\x00".ljust(2048, b"\x01")) is None
+
+
+def test_plain_raw_and_filename_frequency(tmp_path):
+    assert rawfile.frequency_from_name("/x/2024-01-01_12C_ensemble.raw") == 227360
+    assert rawfile.frequency_from_name("/x/5A.raw") == 174928
+    assert rawfile.frequency_from_name("/x/scan_13F_x.tar.raw") == 239200
+    assert rawfile.frequency_from_name("/x/nothing.raw") == 0
+    iq = (np.arange(2 * 3000 + 1) % 251).astype(np.uint8)
+    p = tmp_path / "rec_11D_test.raw"
+    iq.tofile(p)
+    data, info = rawfile.read_raw(str(p))
+    assert not info.has_xml_header and info.fmt == "u8" and info.frequency_khz == 222064 and info.num_samples == 3000
+    assert np.array_equal(data, iq[:6000])
+
+
+def test_header_count_larger_than_file(tmp_path):
+    p = tmp_path / "t.uff"
+    rawfile.write_uff(str(p), np.zeros(2000, np.uint8), "u8", 227360)
+    blob = bytearray(p.read_bytes())
+    with open(p, "wb") as f:
+        f.write(bytes(blob[:2048 + 1000]))                             # truncated recording
+    data, info = rawfile.read_raw(str(p))
+    assert data.size == 1000 and info.num_samples == 500
+
+
+def test_parse_ensemble_from_fibs():
+    ens = synth.full_ensemble()
+    ens.cif_count0 = 40
+    _, _, truth = synth.build_cif_bits(ens, 16, 5)
+    fibs = truth["fibs"].reshape(-1, 32)
+    e = pipeline.parse_ensemble(fibs)
+    assert e["eid"] == ens.eid and e["ecc"] == ens.ecc and e["label"] == ens.label.ljust(16)[:16] and e["first_cif_count"] == 40
+    assert e["lto"] == ens.lto
+    assert [s["sid"] for s in e["services"]] == [s.sid for s in ens.services]
+    assert [s["label"] for s in e["services"]] == [s.label.ljust(16)[:16] for s in ens.services]
+    assert [s["components"][0][0] for s in e["services"]] == [s.subchid for s in ens.services]
+    kind = {sc.subchid: sc.kind for sc in ens.subchannels}
+    assert [s["components"][0][1] for s in e["services"]] == [63 if kind[s.subchid] == "dabplus" else 0 for s in ens.services]
+    # FIBs flagged bad are skipped: nothing left -> empty ensemble
+    e0 = pipeline.parse_ensemble(fibs, np.zeros(fibs.shape[0], np.uint8))
+    assert e0["ueid"] == 0 and e0["services"] == [] and e0["first_cif_count"] == -1
+
+
+def test_scan_row_format():
+    r = scanner.ScanRow("2026-01-01 00:00:00", "12C", 227360, 0xE01234, "LABEL           ", 12, 23.44, 7, 3, -3.21)
+    assert r.csv() == "2026-01-01 00:00:00;12C;227360;E01234;LABEL;12;23.4;;7;3; -3.2;;;;"
+    assert scanner.HEADER.count(";") == r.csv().count(";") == 14
+    r = scanner.ScanRow("t", "5A", 174928, 0x1001, "X", 1, 9.96, None, None, None)
+    assert r.csv() == "t;5A;174928;  1001;X;1;10.0;;;;;;;;"
+
+
+@pytest.mark.gpu
+def test_scan_uff_files(tmp_path):
+    import datetime
+    specs = [("12C", 227360, dict(tii=[(7, 3, 1.0), (7, 5, 0.5)])), ("5A", 174928, dict(tii=[(21, 1, 1.0)]))]
+    paths = []
+    for k, (chn, f, kw) in enumerate(specs):
+        ens = synth.config1_ensemble()
+        ens.eid = 0x1000 + k
+        ens.label = f"SCAN {chn}"
+        ens.tii = [synth.TiiTx(*t) for t in kw["tii"]]
+        raw, _ = synth.synthesize(ens, 100, "s16", synth.Impairments(snr_db=30, cfo_hz=120.0 * (k + 1), lead_in=5000 + 1000 * k, seed=k,
+                                                                     rms=7000.0), seed=k, tail=20000)
+        p = tmp_path / f"scan_{k}.uff"
+        rawfile.write_uff(str(p), raw, "s16", f)
+        paths.append(str(p))
+    noise = (np.random.default_rng(3).normal(0, 300, 2 * 196608 * 12)).astype(np.int16)
+    p = tmp_path / "x_9B_noise.raw.s16"
+    noise.tofile(p)
+    paths.append(str(p))
+    lines = scanner.scan_files(paths)
+    assert lines[0] == scanner.HEADER
+    rows = [l.split(";") for l in lines[1:]]
+    assert [(r[1], r[2], r[3].strip(), r[4], r[8], r[9]) for r in rows] == [
+        ("12C", "227360", "E11000", "SCAN 12C", "7", "3"), ("12C", "227360", "E11000", "SCAN 12C", "7", "5"),
+        ("5A", "174928", "E11001", "SCAN 5A", "21", "1")]
+    assert float(rows[0][10]) == 0.0 and abs(float(rows[1][10]) + 6.0) < 0.3 and float(rows[2][10]) == 0.0
+    assert all(abs(float(r[6]) - 30) < 3 for r in rows) and all(r[5] == "1" for r in rows)
