@@ -78,11 +78,13 @@ struct b200dab_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int launches = 0;
+    size_t vit_dsmem = 14 * 1024;  // extra dynamic shared memory per k_viterbi CTA: caps residency at 11 one-warp CTAs per SM, so the
+                                   // shorter work items are dealt out as the long ones finish (tools/vit_residency.py sweeps this)
     // constant tables on the device
     DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin;
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
-    DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_fic_out, d_fib_ok, d_msc_out;
+    DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out;
     DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
     DevBuf d_tmp_a, d_tmp_b, d_spec;
     HostBuf h_spec;
@@ -165,8 +167,10 @@ int b200dab_ctx::init_tables()
     CK(cudaMemcpy(d_tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     std::vector<int16_t> c_of_n(DAB_NCARR);
     dabtab::freq_deint(c_of_n.data());
-    std::vector<uint16_t> pos(DAB_NCARR);
-    for (int n = 0; n < DAB_NCARR; n++) pos[n] = (uint16_t)fft_phys(fft_pos(carrier_bin(c_of_n[n])));
+    // k_ofdm_demod scatters the spectrum straight into de-interleaved order: table[p] = QPSK symbol index n of the FFT output
+    // that lands at (logical) position p of the digit-reversed result, 0xffff for the 512 unused bins
+    std::vector<uint16_t> pos(DAB_NFFT, 0xffff);
+    for (int n = 0; n < DAB_NCARR; n++) pos[fft_pos(carrier_bin(c_of_n[n]))] = (uint16_t)n;
     CK(d_fdi_pos.ensure(pos.size() * 2));
     CK(cudaMemcpy(d_fdi_pos.p, pos.data(), pos.size() * 2, cudaMemcpyHostToDevice));
     std::vector<int8_t> prs(DAB_NCARR);
@@ -407,11 +411,16 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     prof_begin(jobs[0].kind == 0 ? "k_gather(fic)" : "k_gather(msc)");
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
+    CK(d_meet.ensure(groups.size() * VIT_MEET_WORDS * sizeof(unsigned short)));
     prof_begin(jobs[0].kind == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
-    k_viterbi<<<(unsigned)groups.size(), 64, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
-                                                       d_prbs_w.as<uint32_t>(), d_out);
+    k_viterbi<<<(unsigned)groups.size() * 4, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(),
+                                                                   d_jobs.as<VitJob>(), d_groups.as<VitGroup>());
     prof_end();
-    launches += 2;
+    prof_begin(jobs[0].kind == 0 ? "k_vit_trace(fic)" : "k_vit_trace(msc)");
+    k_vit_trace<<<(unsigned)groups.size(), 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
+                                                         d_prbs_w.as<uint32_t>(), d_out);
+    prof_end();
+    launches += 3;
     CK(cudaGetLastError());
     return 0;
 }
@@ -609,6 +618,8 @@ int b200dab_create(b200dab_ctx** out, int device)
     b200dab_ctx* ctx = new b200dab_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
+    if (const char* e = getenv("B200DAB_VIT_DSMEM")) ctx->vit_dsmem = (size_t)atoi(e);
+    cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (ctx->init_tables()) { fprintf(stderr, "b200dab: %s\n", ctx->err.c_str()); cudaStreamDestroy(ctx->stream); delete ctx; return -6; }
     *out = ctx;
     return 0;
@@ -621,7 +632,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
-                    &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
@@ -1014,11 +1025,16 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     CKC(cudaMemcpyAsync(ctx->d_vin.p, vin.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, zero_prbs.data(), 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->prof_used = 0;
+    CKC(ctx->d_meet.ensure((size_t)ng * VIT_MEET_WORDS * sizeof(unsigned short)));
     ctx->prof_begin("k_viterbi(stage)");
-    k_viterbi<<<ng, 64, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint2>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
-                                         ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>());
+    k_viterbi<<<ng * 4, 32, ctx->vit_dsmem, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),
+                                                          ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>());
     ctx->prof_end();
-    ctx->launches += 1;
+    ctx->prof_begin("k_vit_trace(stage)");
+    k_vit_trace<<<ng, 64, 0, ctx->stream>>>(ctx->d_dec.as<uint2>(), ctx->d_meet.as<unsigned short>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
+                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>());
+    ctx->prof_end();
+    ctx->launches += 2;
     CKC(cudaGetLastError());
     std::vector<uint8_t> packed((size_t)n_cw * job.out_pitch);
     CKC(cudaMemcpyAsync(packed.data(), ctx->d_tmp_b.p, packed.size(), cudaMemcpyDeviceToHost, ctx->stream));

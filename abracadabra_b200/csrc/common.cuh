@@ -173,7 +173,8 @@ __device__ __forceinline__ void fft_plan_init(FftPlan& pl, const float2* __restr
         pl.twC[k - 1] = __ldg(tw + (((t & 3) * k) << 6));
     }
 }
-__device__ __forceinline__ void fft2048_planned(float2* __restrict__ buf, const FftPlan& pl)
+// passes A, B, C only: the caller finishes with its own radix-4 pass over the quadruples at pD0 / pD1
+__device__ __forceinline__ void fft2048_planned_abc(float2* __restrict__ buf, const FftPlan& pl)
 {
     float2 v[8];
     __syncthreads();
@@ -201,6 +202,10 @@ __device__ __forceinline__ void fft2048_planned(float2* __restrict__ buf, const 
 #pragma unroll
     for (int k = 0; k < 8; k++) buf[pl.pC + 4 * k] = v[k];
     __syncthreads();
+}
+__device__ __forceinline__ void fft2048_planned(float2* __restrict__ buf, const FftPlan& pl)
+{
+    fft2048_planned_abc(buf, pl);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         float2* p = buf + (h ? pl.pD1 : pl.pD0);

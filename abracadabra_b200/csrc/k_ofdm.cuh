@@ -16,14 +16,40 @@ struct FrameInfo {
 #define OFDM_SYMS_PER_CTA 19
 #define OFDM_GROUPS 4
 
-// fdi_pos[n] = physical shared-memory index of the FFT output that carries QPSK symbol n
+// Last FFT pass (radix 4 on the quadruples at pD0 / pD1) fused with the frequency de-interleaver: output X[k] goes straight to
+// spec[n], n = QPSK symbol index of carrier k (fdi_inv, 0xffff = unused bin), so the DQPSK stage reads both spectra linearly.
+// The two 16-byte halves of a quadruple are fetched in an order that depends on bit 2 of the lane: consecutive lanes are 32 bytes
+// apart, and without the swap lanes l and l+4 of a quarter-warp would hit the same banks.
+__device__ __forceinline__ void fft_pass_d_scatter(const float2* __restrict__ work, const FftPlan& pl, float2* __restrict__ spec,
+                                                   const uint32_t (&wp)[4])
+{
+    const int s = (threadIdx.x >> 2) & 1;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float2* p = work + (h ? pl.pD1 : pl.pD0);
+        const float4 qa = *reinterpret_cast<const float4*>(p + 2 * s), qb = *reinterpret_cast<const float4*>(p + 2 * (s ^ 1));
+        const float4 q0 = s ? qb : qa, q1 = s ? qa : qb;
+        float2 x0 = make_float2(q0.x, q0.y), x1 = make_float2(q0.z, q0.w), x2 = make_float2(q1.x, q1.y), x3 = make_float2(q1.z, q1.w);
+        float2 s0 = cadd(x0, x2), d0 = csub(x0, x2), s1 = cadd(x1, x3), d1 = csub(x1, x3);
+        d1 = make_float2(d1.y, -d1.x);
+        const uint32_t n0 = wp[2 * h] & 0xffffu, n1 = wp[2 * h] >> 16, n2 = wp[2 * h + 1] & 0xffffu, n3 = wp[2 * h + 1] >> 16;
+        if (n0 != 0xffffu) spec[n0] = cadd(s0, s1);
+        if (n1 != 0xffffu) spec[n1] = cadd(d0, d1);
+        if (n2 != 0xffffu) spec[n2] = csub(s0, s1);
+        if (n3 != 0xffffu) spec[n3] = csub(d0, d1);
+    }
+    __syncthreads();
+}
+
+// fdi_inv[p] = QPSK symbol index of the FFT output at logical position p of the digit-reversed result (0xffff = unused bin)
 template <int FMT>
 __global__ void __launch_bounds__(256, 2) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
-                                                    const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_pos,
+                                                    const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_inv,
                                                     int8_t* __restrict__ soft, float* __restrict__ symstat)
 {
-    __shared__ float2 bufA[FFT_BUF_LEN];
-    __shared__ float2 bufB[FFT_BUF_LEN];
+    __shared__ float2 work[FFT_BUF_LEN];
+    __shared__ float2 specA[DAB_NCARR];
+    __shared__ float2 specB[DAB_NCARR];
     __shared__ float red[32];
     const int t = threadIdx.x;
     const int fi = blockIdx.x / OFDM_GROUPS, gi = blockIdx.x % OFDM_GROUPS;
@@ -33,20 +59,19 @@ __global__ void __launch_bounds__(256, 2) k_ofdm_demod(const void* __restrict__ 
     if (l_end > DAB_NSYM - 1) l_end = DAB_NSYM - 1;
     const double cyc_per = (double)fr.cfo_hz / (double)DAB_FS;
     const float cpp = (float)cyc_per;
-    float2* cur = bufA;
-    float2* prev = bufB;
+    float2* cur = specA;
+    float2* prev = specB;
     int8_t* out_frame = soft + (size_t)fr.slot * DAB_FRAME_SOFT;
 
-    // thread-invariant pieces hoisted out of the symbol loop: FFT plan (addresses + 21 twiddles), de-interleaver positions,
-    // the rotor that advances the de-rotation by 256 samples, and whether the whole run lies inside the buffer
+    // thread-invariant pieces hoisted out of the symbol loop: FFT plan (addresses + 21 twiddles), de-interleaver targets of the
+    // thread's eight FFT outputs, the rotor that advances the de-rotation by 256 samples, whether the run lies inside the buffer
     FftPlan plan;
     fft_plan_init(plan, tw);
-    int ps[8];
+    uint32_t wp[4];
     {
-        const uint2 p0 = __ldg(reinterpret_cast<const uint2*>(fdi_pos + 4 * t));
-        const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(fdi_pos + 1024 + 4 * (t & 127)));
-        ps[0] = p0.x & 0xffff; ps[1] = p0.x >> 16; ps[2] = p0.y & 0xffff; ps[3] = p0.y >> 16;
-        ps[4] = p1.x & 0xffff; ps[5] = p1.x >> 16; ps[6] = p1.y & 0xffff; ps[7] = p1.y >> 16;
+        const uint2 p0 = __ldg(reinterpret_cast<const uint2*>(fdi_inv + 4 * t));
+        const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(fdi_inv + 1024 + 4 * t));
+        wp[0] = p0.x; wp[1] = p0.y; wp[2] = p1.x; wp[3] = p1.y;
     }
     float2 step;
     {
@@ -61,26 +86,23 @@ __global__ void __launch_bounds__(256, 2) k_ofdm_demod(const void* __restrict__ 
     for (int l = l_ref; l <= l_end; l++) {
         double base = cyc_per * (double)((int64_t)DAB_T_SYM * l);
         base -= floor(base);
-        store_symbol_rotor<FMT>(cur, plan.pA, rs, (float)base, cpp, step);
+        store_symbol_rotor<FMT>(work, plan.pA, rs, (float)base, cpp, step);
         if (l < l_end) {                                                             // in flight during the FFT
             const int64_t nx = fr.t_f + (int64_t)DAB_T_SYM * (l + 1);
             if (inside) fetch_symbol_fast<FMT>(rs, raw, nx); else fetch_symbol<FMT>(rs, raw, nsamp, nx);
         }
-        fft2048_planned(cur, plan);
+        fft2048_planned_abc(work, plan);
+        fft_pass_d_scatter(work, plan, cur, wp);
         if (l > l_ref) {
-            // DQPSK against the previous symbol, de-interleaved order: thread handles n = 4t..4t+3 and (t < 128) 1024+4t..
-            float2 y[8];
+            // DQPSK against the previous symbol: thread handles QPSK symbols n = t + 256 j
+            float2 y[6];
             float sabs = 0.f, ssq = 0.f;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (h == 1 && t >= 128) break;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float2 v = cmul_conj(cur[ps[4 * h + i]], prev[ps[4 * h + i]]);
-                    y[4 * h + i] = v;
-                    sabs += fabsf(v.x) + fabsf(v.y);
-                    ssq += v.x * v.x + v.y * v.y;
-                }
+            for (int j = 0; j < 6; j++) {
+                const float2 v = cmul_conj(cur[t + 256 * j], prev[t + 256 * j]);
+                y[j] = v;
+                sabs += fabsf(v.x) + fabsf(v.y);
+                ssq += v.x * v.x + v.y * v.y;
             }
             const float tot = block_sum(sabs, red);
             const float mean = tot / (float)DAB_BITS_PER_SYM;
@@ -92,25 +114,17 @@ __global__ void __launch_bounds__(256, 2) k_ofdm_demod(const void* __restrict__ 
                     st[0] = mean; st[1] = tsq / (float)DAB_BITS_PER_SYM;
                 }
             }
-            int8_t* o = out_frame + (size_t)(l - 1) * DAB_BITS_PER_SYM;
+            int8_t* o = out_frame + (size_t)(l - 1) * DAB_BITS_PER_SYM + t;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (h == 1 && t >= 128) break;
-                const int n0 = h * 1024 + 4 * t;
-                uint32_t wr = 0, wi = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    int a = __float2int_rn(y[4 * h + i].x * g), b = __float2int_rn(y[4 * h + i].y * g);
-                    a = max(-SOFT_MAX, min(SOFT_MAX, a));
-                    b = max(-SOFT_MAX, min(SOFT_MAX, b));
-                    wr |= (uint32_t)(a & 0xff) << (8 * i);
-                    wi |= (uint32_t)(b & 0xff) << (8 * i);
-                }
-                *reinterpret_cast<uint32_t*>(o + n0) = wr;
-                *reinterpret_cast<uint32_t*>(o + DAB_NCARR + n0) = wi;
+            for (int j = 0; j < 6; j++) {
+                int a = __float2int_rn(y[j].x * g), b = __float2int_rn(y[j].y * g);
+                a = max(-SOFT_MAX, min(SOFT_MAX, a));
+                b = max(-SOFT_MAX, min(SOFT_MAX, b));
+                o[256 * j] = (int8_t)a;                                              // a warp writes 32 consecutive bytes: one sector
+                o[DAB_NCARR + 256 * j] = (int8_t)b;
             }
         }
+        // no barrier needed here: the next writes into `prev` (as the new `cur`) come after the four barriers of the next FFT
         float2* tmp = cur; cur = prev; prev = tmp;
-        __syncthreads();
     }
 }

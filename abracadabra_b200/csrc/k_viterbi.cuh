@@ -4,12 +4,13 @@
 // descrambler (code: polynomials 133,171,145,133, puncturing vectors PI 1..24 + tail,
 // 16-CIF delay table {0,8,4,12,...}).
 //
-// Layout: codewords of one sub-channel (one per CIF) are decoded 32 at a time, one codeword per thread, so every
-// global access is a coalesced 128/256-byte row:
-//   vin [group][step][32 lanes] uint32 : the 4 de-punctured int8 soft bits of that trellis step (0 = punctured)
-//   dec [group][step][32 lanes] uint2  : the 64 survivor decisions of that step
-// Path metrics are int16, two states per 32-bit register ((j, j+16) and (j+32, j+48)), updated with the packed
-// VIADD.16x2 / VIMNMX.S16x2 instructions; VIMNMX delivers both decision predicates of a register pair for free.
+// Layout: codewords of one sub-channel (one per CIF) are handled in groups of 32, so every global access is a coalesced row:
+//   vin [group][step][32 codewords] uint32 : the 4 de-punctured int8 soft bits of that trellis step (0 = punctured)
+//   dec [group][step][32 codewords] uint2  : the 64 survivor decisions of that step (x: lane role 0, y: lane role 1)
+// Path metrics are int16, two states per 32-bit register, updated with packed 16x2 adds and VIMNMX.S16x2; VIMNMX delivers
+// both decision predicates of a register pair for free.  Each codeword is spread over TWO lanes (32 states each), and each
+// direction of the bidirectional recursion is its own one-warp CTA, so one recording yields ~4000 short work items that the
+// hardware deals to whichever SM sub-partition frees up first.
 #pragma once
 #include "common.cuh"
 
@@ -95,74 +96,95 @@ __host__ __device__ constexpr int vit_parity7(int x) { return (x ^ (x >> 1) ^ (x
 // code bit q (0..2; bit 3 repeats bit 0) for state j (newest input = LSB) and input 0; polynomials bit-reversed so that
 // bit d of the window (state << 1 | input) is a[i-d]
 __host__ __device__ constexpr int vit_cbit(int j, int q) { return vit_parity7((j << 1) & (q == 0 ? 0155 : q == 1 ? 0117 : 0123)); }
+__host__ __device__ constexpr int vit_kidx(int j) { return vit_cbit(j, 0) * 4 + vit_cbit(j, 1) * 2 + vit_cbit(j, 2); }
 
-template <int J>
-__device__ __forceinline__ void vit_bfly(const uint32_t (&L)[16], const uint32_t (&H)[16], uint32_t (&E)[16], uint32_t (&O)[16],
-                                         const uint32_t (&BP)[8], uint32_t (&dl)[4], uint32_t (&dh)[4])
+// Two lanes per codeword.  Role 0 owns the butterflies whose index has bit 3 clear; role 1 owns the others but works in
+// COMPLEMENTED coordinates (physical state = logical state ^ 63, physical input = logical input ^ 1): the trellis is invariant
+// under that map, so both roles run the same code on physical butterflies 0..7, both keep the results whose next butterfly
+// index is < 8 and hand the rest to the partner with one SHFL.xor each, and a received state index is simply the complement
+// of the sender's.  Complementing the 7-bit window flips the code bits of the odd-weight polynomials (133, 171) and leaves
+// the even-weight one (145) alone: role 1 negates soft bits 0, 1 and 3.  The tie rules (include/b200dab_spec.h) are
+// invariant under the same map, which is what makes the two roles agree with the scalar formulation bit for bit.
+//
+// forward registers : L[i] = (a[i], a[i+16]), H[i] = (a[i+32], a[i+48]), i = 0..7 (physical states)
+//   butterfly i: E[i] = (a'[2i], a'[2i+32]), O[i] = (a'[2i+1], a'[2i+33]); decision word bit (n & 15) + 16 (n >> 5) for
+//   physical new state n, 1 = survivor from physical predecessor (n >> 1) + 32
+// Decision bits are collected with predicated adds of a constant.  The ALU pipe (VIMNMX, PRMT, IADD3) is the busy one in this
+// kernel and issues one warp instruction per two cycles, the FMA pipe (IMAD) likewise: half of the bit-sets are therefore
+// written as a multiply-add by a register holding 1, which ptxas has to keep on the FMA pipe.
+__device__ __forceinline__ void vit_setbit_alu(uint32_t& d, bool p, uint32_t bit) { if (p) d |= bit; }
+__device__ __forceinline__ void vit_setbit_fma(uint32_t& d, bool p, uint32_t bit, uint32_t one)
 {
-    // low halves: butterfly of states (J, J+32) -> (2J, 2J+1); high halves: (J+16, J+48) -> (2J+32, 2J+33)
-    uint32_t& dlo = dl[J & 3];          // four partial decision words: independent chains instead of one serial one
-    uint32_t& dhi = dh[J & 3];
-    constexpr int k = vit_cbit(J, 0) * 4 + vit_cbit(J, 1) * 2 + vit_cbit(J, 2);   // BP[k] = +beta, BP[7-k] = -beta
-    bool ph, pl;
-    const uint32_t t0 = L[J] + BP[k], t1 = H[J] + BP[7 - k];       // plain 32-bit adds: see the bias note in k_viterbi
-    E[J] = __vibmax_s16x2(t0, t1, &ph, &pl);          // predicate = (t0 >= t1): survivor from the lower predecessor
-    if (!pl) dlo |= 1u << (2 * J);
-    if (!ph) dhi |= 1u << (2 * J);
-    const uint32_t u0 = L[J] + BP[7 - k], u1 = H[J] + BP[k];
-    O[J] = __vibmax_s16x2(u0, u1, &ph, &pl);
-    if (!pl) dlo |= 1u << (2 * J + 1);
-    if (!ph) dhi |= 1u << (2 * J + 1);
+    if (p) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(one), "r"(bit));
 }
-template <int J> struct VitUnroll {
-    static __device__ __forceinline__ void run(const uint32_t (&L)[16], const uint32_t (&H)[16], uint32_t (&E)[16], uint32_t (&O)[16],
-                                               const uint32_t (&BP)[8], uint32_t (&dl)[4], uint32_t (&dh)[4])
+
+template <int I>
+__device__ __forceinline__ void vit_bfly(const uint32_t (&L)[8], const uint32_t (&H)[8], uint32_t (&E)[8], uint32_t (&O)[8],
+                                         const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
+{
+    uint32_t& dd = d[I & 3];              // four partial decision words: independent chains instead of one serial one
+    constexpr int k = vit_kidx(I);        // BP[k] = +beta, BP[7-k] = -beta
+    bool ph, pl;
+    const uint32_t t0 = L[I] + BP[k], t1 = H[I] + BP[7 - k];       // plain 32-bit adds: see the bias note in k_viterbi
+    E[I] = __vibmax_s16x2(t0, t1, &ph, &pl);          // even new state: the lower predecessor survives a tie
+    vit_setbit_alu(dd, !pl, 1u << (2 * I));
+    vit_setbit_fma(dd, !ph, 1u << (2 * I + 16), one);
+    const uint32_t u0 = L[I] + BP[7 - k], u1 = H[I] + BP[k];
+    O[I] = __vibmax_s16x2(u1, u0, &ph, &pl);          // odd new state: the upper predecessor survives a tie
+    vit_setbit_alu(dd, pl, 1u << (2 * I + 1));
+    vit_setbit_fma(dd, ph, 1u << (2 * I + 17), one);
+}
+template <int I> struct VitUnroll {
+    static __device__ __forceinline__ void run(const uint32_t (&L)[8], const uint32_t (&H)[8], uint32_t (&E)[8], uint32_t (&O)[8],
+                                               const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
     {
-        VitUnroll<J - 1>::run(L, H, E, O, BP, dl, dh);
-        vit_bfly<J>(L, H, E, O, BP, dl, dh);
+        VitUnroll<I - 1>::run(L, H, E, O, BP, d, one);
+        vit_bfly<I>(L, H, E, O, BP, d, one);
     }
 };
 template <> struct VitUnroll<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[16], const uint32_t (&)[16], uint32_t (&)[16], uint32_t (&)[16],
-                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t (&)[4]) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[8], const uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8],
+                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t) {}
 };
 
-// ---- backward butterfly: packed inputs A[J] = (b'[2J], b'[2J+32]), B[J] = (b'[2J+1], b'[2J+33]) (metrics of the NEXT trellis stage),
-//      outputs X[J] = (b[J], b[J+16]), Y[J] = (b[J+32], b[J+48]); decision bit = chosen input bit of that state
-template <int J>
-__device__ __forceinline__ void vit_bfly_bwd(const uint32_t (&A)[16], const uint32_t (&B)[16], uint32_t (&X)[16], uint32_t (&Y)[16],
-                                             const uint32_t (&BP)[8], uint32_t (&dl)[4], uint32_t (&dh)[4])
+// backward registers: A[i] = (b'[2i], b'[2i+32]), B[i] = (b'[2i+1], b'[2i+33]) (metrics of the NEXT trellis stage), outputs
+//   X[i] = (b[i], b[i+16]), Y[i] = (b[i+32], b[i+48]); decision word bit 2 (s & 7) + (s >> 5) + 16 ((s >> 4) & 1) for
+//   physical state s (the forward pattern again: ptxas turns other layouts into a slower P2R sequence), 1 = the best
+//   continuation takes physical input bit 1
+template <int I>
+__device__ __forceinline__ void vit_bfly_bwd(const uint32_t (&A)[8], const uint32_t (&B)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
+                                             const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
 {
-    uint32_t& dlo = dl[J & 3];
-    uint32_t& dhi = dh[J & 3];
-    constexpr int k = vit_cbit(J, 0) * 4 + vit_cbit(J, 1) * 2 + vit_cbit(J, 2);
+    uint32_t& dd = d[I & 3];
+    constexpr int k = vit_kidx(I);
     bool ph, pl;
-    const uint32_t t0 = A[J] + BP[k], t1 = B[J] + BP[7 - k];         // state J / J+16: input 0 -> +beta, input 1 -> -beta
-    X[J] = __vibmax_s16x2(t0, t1, &ph, &pl);
-    if (!pl) dlo |= 1u << (2 * J);                                    // same bit pattern as the forward butterfly (the compiler
-    if (!ph) dhi |= 1u << (2 * J);                                    // turns it into predicated adds); decoded in the trace below
-    const uint32_t u0 = A[J] + BP[7 - k], u1 = B[J] + BP[k];         // state J+32 / J+48: all code bits flipped
-    Y[J] = __vibmax_s16x2(u0, u1, &ph, &pl);
-    if (!pl) dlo |= 1u << (2 * J + 1);
-    if (!ph) dhi |= 1u << (2 * J + 1);
+    const uint32_t t0 = A[I] + BP[k], t1 = B[I] + BP[7 - k];         // states i, i+16: input 0 -> +beta; input 0 wins a tie
+    X[I] = __vibmax_s16x2(t0, t1, &ph, &pl);
+    vit_setbit_alu(dd, !pl, 1u << (2 * I));
+    vit_setbit_fma(dd, !ph, 1u << (2 * I + 16), one);
+    const uint32_t u0 = A[I] + BP[7 - k], u1 = B[I] + BP[k];         // states i+32, i+48: code bits flipped; input 1 wins a tie
+    Y[I] = __vibmax_s16x2(u1, u0, &ph, &pl);
+    vit_setbit_alu(dd, pl, 1u << (2 * I + 1));
+    vit_setbit_fma(dd, ph, 1u << (2 * I + 17), one);
 }
-template <int J> struct VitUnrollBwd {
-    static __device__ __forceinline__ void run(const uint32_t (&A)[16], const uint32_t (&B)[16], uint32_t (&X)[16], uint32_t (&Y)[16],
-                                               const uint32_t (&BP)[8], uint32_t (&dl)[4], uint32_t (&dh)[4])
+template <int I> struct VitUnrollBwd {
+    static __device__ __forceinline__ void run(const uint32_t (&A)[8], const uint32_t (&B)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
+                                               const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
     {
-        VitUnrollBwd<J - 1>::run(A, B, X, Y, BP, dl, dh);
-        vit_bfly_bwd<J>(A, B, X, Y, BP, dl, dh);
+        VitUnrollBwd<I - 1>::run(A, B, X, Y, BP, d, one);
+        vit_bfly_bwd<I>(A, B, X, Y, BP, d, one);
     }
 };
 template <> struct VitUnrollBwd<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[16], const uint32_t (&)[16], uint32_t (&)[16], uint32_t (&)[16],
-                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t (&)[4]) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[8], const uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8],
+                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t) {}
 };
 
-__device__ __forceinline__ void vit_branch_metrics(uint32_t w, uint32_t (&BP)[8])
+// sg = +1 (role 0) or -1 (role 1)
+__device__ __forceinline__ void vit_branch_metrics(uint32_t w, int sg, uint32_t (&BP)[8])
 {
     const int a0 = (int8_t)(w), a1 = (int8_t)(w >> 8), a2 = (int8_t)(w >> 16), a3 = (int8_t)(w >> 24);
-    const int T = a0 + a3, X1 = a1 + a2, X2 = a1 - a2;
+    const int T = (a0 + a3) * sg, X1 = a1 * sg + a2, X2 = a1 * sg - a2;
     // BP[k], k = c0*4 + c1*2 + c2 (1 = code bit 1 = negative contribution): low half  (1-2c0) T + x,
     //                                                                      high half -(1-2c0) T + x  (state + 16 flips c0, c3)
     const int xs[4] = {X1, X2, -X2, -X1};
@@ -175,46 +197,43 @@ __device__ __forceinline__ void vit_branch_metrics(uint32_t w, uint32_t (&BP)[8]
 
 #define VIT_BIAS 16384u
 #define VIT_PENV ((VIT_BIAS + VIT_START_PENALTY) * 65537u)
+#define VIT_MEET_WORDS (2 * 64 * 32)        /* unsigned shorts per group: [direction][state][codeword] */
 
-struct VitSmem {
-    uint32_t ring[2][2][VIT_NORM_PERIOD][32];      // [direction][buffer][step][lane] soft words
-    unsigned short meet[2][64][32];                // [direction][state][lane] path metrics at the meeting stage
-};
-
-// Bidirectional decoding: the code is zero-terminated at BOTH ends, so warp 0 runs the trellis forward over steps [0, m) from
-// state 0 while warp 1 runs it backward over steps [m, T) from state 0; at stage m the state maximising alpha + beta lies on
-// the maximum-likelihood path, warp 0 traces back from it and warp 1 traces forward.  Same path as one-directional Viterbi
-// whenever the best path is unique; the tie rules (include/b200dab_spec.h) are mirrored by the CPU checker.  This halves the
-// latency of the longest codeword, which is what bounds the kernel, with no per-step synchronisation between the warps.
-//   decisions: dec[group][step][lane] uint2, bit s of (x | y << 32):
-//     steps <  m : 1 = the survivor into state s came from predecessor (s >> 1) + 32
-//     steps >= m : 1 = the best continuation from state s takes input bit 1; here state s sits at word (s >> 4) & 1,
-//                  bit 2 (s & 15) + (s >> 5)
-// one 64-thread CTA per group of 32 codewords; grid = n_groups (longest groups first)
-__global__ void __launch_bounds__(64) k_viterbi(const uint32_t* __restrict__ vin, uint2* __restrict__ dec, const VitJob* __restrict__ jobs,
-                                                const VitGroup* __restrict__ groups, const uint32_t* __restrict__ prbs_w,
-                                                uint8_t* __restrict__ out)
+// Bidirectional decoding: the code is zero-terminated at BOTH ends, so one work item runs the trellis forward over steps
+// [0, m) from state 0 while another runs it backward over steps [m, T) from state 0; at stage m the state maximising
+// alpha + beta lies on the maximum-likelihood path (k_vit_trace picks it, traces back over [0, m) and forward over [m, T)).
+// Same path as one-directional Viterbi whenever the best path is unique; the tie rules are mirrored by the CPU checker.
+// Metrics carry a bias of 16384 so that both halves of a register stay non-negative and a packed add is one 32-bit add.
+// grid = 4 * n_groups one-warp CTAs (longest groups first): item = (group, which 16 codewords, direction)
+__global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec, unsigned short* __restrict__ meet,
+                                                const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups)
 {
-    __shared__ VitSmem sm;
-    const VitGroup grp = groups[blockIdx.x];
+    constexpr int PF = VIT_NORM_PERIOD;
+    __shared__ uint32_t ring[2][PF][32];
+    const int item = blockIdx.x;
+    const VitGroup grp = groups[item >> 2];
     const VitJob job = jobs[grp.job];
-    const int lane = threadIdx.x & 31, dir = threadIdx.x >> 5;
+    const int lane = threadIdx.x, role = lane & 1, dir = item & 1;
+    const int cw = ((item >> 1) & 1) * 16 + (lane >> 1);
+    const int sg = role ? -1 : 1;
     const int steps = job.steps;
     const int m = ((steps >> 1) >> 5) << 5;                         // meeting stage, multiple of 32
-    const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
-    uint2* d = dec + job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
-    constexpr int PF = VIT_NORM_PERIOD;
+    const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + cw;
+    uint32_t* d = dec + (job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + cw) * 2 + role;
+    unsigned short* mt = meet + ((size_t)(item >> 2) * 2 + dir) * (64 * 32) + cw;
+    const uint32_t flip = role ? 63u : 0u;
+    const uint32_t one = job.steps > 0 ? 1u : 0u;                   // always 1, but not to the compiler: see vit_setbit_fma
 
     if (dir == 0) {
         // ------------------------------------------------------------ forward over steps [0, m)
-        uint32_t L[16], H[16], E[16], O[16];
+        uint32_t L[8], H[8], E[8], O[8];
 #pragma unroll
-        for (int j = 0; j < 16; j++) { L[j] = VIT_PENV; H[j] = VIT_PENV; }
-        L[0] = ((VIT_BIAS + VIT_START_PENALTY) << 16) | VIT_BIAS;   // state 0 starts at 0, state 16 at the penalty
+        for (int j = 0; j < 8; j++) { L[j] = VIT_PENV; H[j] = VIT_PENV; }
+        if (role == 0) L[0] = ((VIT_BIAS + VIT_START_PENALTY) << 16) | VIT_BIAS;   // state 0 starts at 0, state 16 at the penalty
         auto prefetch = [&](int buf, int t0) {
 #pragma unroll
             for (int i = 0; i < PF; i++) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.ring[0][buf][i][lane]);
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][i][lane]);
                 const uint32_t* src = in + (size_t)min(t0 + i, steps - 1) * 32;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
             }
@@ -226,41 +245,46 @@ __global__ void __launch_bounds__(64) k_viterbi(const uint32_t* __restrict__ vin
             if (t0 + PF < m) { prefetch(buf ^ 1, t0 + PF); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             {   // re-reference all metrics to state 0 (keeps the int16 range; constants do not change any decision)
-                const uint32_t c = (uint32_t)(((int)VIT_BIAS - (int)(L[0] & 0xffffu)) * 65537);
+                uint32_t c = (uint32_t)(((int)VIT_BIAS - (int)(L[0] & 0xffffu)) * 65537);
+                c = __shfl_sync(0xffffffffu, c, lane & ~1);
 #pragma unroll
-                for (int j = 0; j < 16; j++) { L[j] += c; H[j] += c; }
+                for (int j = 0; j < 8; j++) { L[j] += c; H[j] += c; }
             }
             const int nst = min(PF, m - t0);
 #pragma unroll 2
             for (int i = 0; i < nst; i++) {
                 uint32_t BP[8];
-                vit_branch_metrics(sm.ring[0][buf][i][lane], BP);
-                uint32_t dl[4] = {0, 0, 0, 0}, dh[4] = {0, 0, 0, 0};
-                VitUnroll<15>::run(L, H, E, O, BP, dl, dh);
-                d[(size_t)(t0 + i) * 32] = make_uint2((dl[0] | dl[1]) | (dl[2] | dl[3]), (dh[0] | dh[1]) | (dh[2] | dh[3]));
-                // re-pair: L'[q] = (new[q], new[q+16]), H'[q] = (new[q+32], new[q+48])
+                vit_branch_metrics(ring[buf][i][lane], sg, BP);
+                uint32_t dw[4] = {0, 0, 0, 0};
+                VitUnroll<7>::run(L, H, E, O, BP, dw, one);
+                d[(size_t)(t0 + i) * 64] = (dw[0] | dw[1]) | (dw[2] | dw[3]);
+                // E/O[0..3] stay (new states 0..7, 32..39); the partner's E/O[4..7] arrive complemented: its (8+2u+b, 40+2u+b)
+                // are my (55-2u-b, 23-2u-b)
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    L[2 * j] = __byte_perm(E[j], E[j + 8], 0x5410);     H[2 * j] = __byte_perm(E[j], E[j + 8], 0x7632);
-                    L[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x5410); H[2 * j + 1] = __byte_perm(O[j], O[j + 8], 0x7632);
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t re = __shfl_xor_sync(0xffffffffu, E[4 + u], 1), ro = __shfl_xor_sync(0xffffffffu, O[4 + u], 1);
+                    const int je = 7 - 2 * u, jo = 6 - 2 * u;           // received E -> odd slot, received O -> even slot
+                    const uint32_t own_o = O[je >> 1], own_e = E[jo >> 1];
+                    L[je] = __byte_perm(own_o, re, 0x7610); H[je] = __byte_perm(own_o, re, 0x5432);
+                    L[jo] = __byte_perm(own_e, ro, 0x7610); H[jo] = __byte_perm(own_e, ro, 0x5432);
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            sm.meet[0][j][lane] = (unsigned short)(L[j] & 0xffffu);      sm.meet[0][j + 16][lane] = (unsigned short)(L[j] >> 16);
-            sm.meet[0][j + 32][lane] = (unsigned short)(H[j] & 0xffffu); sm.meet[0][j + 48][lane] = (unsigned short)(H[j] >> 16);
+        for (int j = 0; j < 8; j++) {
+            mt[((uint32_t)j ^ flip) * 32] = (unsigned short)(L[j] & 0xffffu);        mt[((uint32_t)(j + 16) ^ flip) * 32] = (unsigned short)(L[j] >> 16);
+            mt[((uint32_t)(j + 32) ^ flip) * 32] = (unsigned short)(H[j] & 0xffffu); mt[((uint32_t)(j + 48) ^ flip) * 32] = (unsigned short)(H[j] >> 16);
         }
     } else {
         // ------------------------------------------------------------ backward over steps [m, T), T-1 first
-        uint32_t A[16], B[16], X[16], Y[16];
+        uint32_t A[8], B[8], X[8], Y[8];
 #pragma unroll
-        for (int j = 0; j < 16; j++) { A[j] = VIT_PENV; B[j] = VIT_PENV; }
-        A[0] = ((VIT_BIAS + VIT_START_PENALTY) << 16) | VIT_BIAS;   // must end in state 0: A[0] = (b[0], b[32])
+        for (int j = 0; j < 8; j++) { A[j] = VIT_PENV; B[j] = VIT_PENV; }
+        if (role == 0) A[0] = ((VIT_BIAS + VIT_START_PENALTY) << 16) | VIT_BIAS;   // must end in state 0: A[0] = (b[0], b[32])
         auto prefetch = [&](int buf, int t_hi) {                    // ring slot i holds step t_hi - i
 #pragma unroll
             for (int i = 0; i < PF; i++) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.ring[1][buf][i][lane]);
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][i][lane]);
                 const uint32_t* src = in + (size_t)max(t_hi - i, 0) * 32;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
             }
@@ -272,70 +296,103 @@ __global__ void __launch_bounds__(64) k_viterbi(const uint32_t* __restrict__ vin
             if (t_hi - PF >= m) { prefetch(buf ^ 1, t_hi - PF); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             {
-                const uint32_t c = (uint32_t)(((int)VIT_BIAS - (int)(A[0] & 0xffffu)) * 65537);
+                uint32_t c = (uint32_t)(((int)VIT_BIAS - (int)(A[0] & 0xffffu)) * 65537);
+                c = __shfl_sync(0xffffffffu, c, lane & ~1);
 #pragma unroll
-                for (int j = 0; j < 16; j++) { A[j] += c; B[j] += c; }
+                for (int j = 0; j < 8; j++) { A[j] += c; B[j] += c; }
             }
             const int nst = min(PF, t_hi - m + 1);
-#pragma unroll 2
+#pragma unroll 1
             for (int i = 0; i < nst; i++) {
                 uint32_t BP[8];
-                vit_branch_metrics(sm.ring[1][buf][i][lane], BP);
-                uint32_t dl[4] = {0, 0, 0, 0}, dh[4] = {0, 0, 0, 0};
-                VitUnrollBwd<15>::run(A, B, X, Y, BP, dl, dh);
-                d[(size_t)(t_hi - i) * 32] = make_uint2((dl[0] | dl[1]) | (dl[2] | dl[3]), (dh[0] | dh[1]) | (dh[2] | dh[3]));
-                // re-pair: A'[q] = (b[2q], b[2q+32]), B'[q] = (b[2q+1], b[2q+33]) from X[q] = (b[q], b[q+16]), Y[q] = (b[q+32], b[q+48])
+                vit_branch_metrics(ring[buf][i][lane], sg, BP);
+                uint32_t dw[4] = {0, 0, 0, 0};
+                VitUnrollBwd<7>::run(A, B, X, Y, BP, dw, one);
+                d[(size_t)(t_hi - i) * 64] = (dw[0] | dw[1]) | (dw[2] | dw[3]);
+                // low halves (states 0..7, 32..39) stay; the partner's high halves (its 16+i, 48+i) are my 47-i, 15-i:
+                // its packed (Y[i].hi, X[i].hi) is my (b[15-i], b[47-i]) = A[(15-i)/2] for odd i, B[(14-i)/2] for even i
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    A[j] = __byte_perm(X[2 * j], Y[2 * j], 0x5410);         B[j] = __byte_perm(X[2 * j + 1], Y[2 * j + 1], 0x5410);
-                    A[j + 8] = __byte_perm(X[2 * j], Y[2 * j], 0x7632);     B[j + 8] = __byte_perm(X[2 * j + 1], Y[2 * j + 1], 0x7632);
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t so = __byte_perm(Y[7 - 2 * j], X[7 - 2 * j], 0x7632), se = __byte_perm(Y[6 - 2 * j], X[6 - 2 * j], 0x7632);
+                    A[4 + j] = __shfl_xor_sync(0xffffffffu, so, 1);
+                    B[4 + j] = __shfl_xor_sync(0xffffffffu, se, 1);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    A[j] = __byte_perm(X[2 * j], Y[2 * j], 0x5410);
+                    B[j] = __byte_perm(X[2 * j + 1], Y[2 * j + 1], 0x5410);
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            sm.meet[1][2 * j][lane] = (unsigned short)(A[j] & 0xffffu);     sm.meet[1][2 * j + 32][lane] = (unsigned short)(A[j] >> 16);
-            sm.meet[1][2 * j + 1][lane] = (unsigned short)(B[j] & 0xffffu); sm.meet[1][2 * j + 33][lane] = (unsigned short)(B[j] >> 16);
+        for (int j = 0; j < 8; j++) {
+            mt[((uint32_t)(2 * j) ^ flip) * 32] = (unsigned short)(A[j] & 0xffffu);     mt[((uint32_t)(2 * j + 32) ^ flip) * 32] = (unsigned short)(A[j] >> 16);
+            mt[((uint32_t)(2 * j + 1) ^ flip) * 32] = (unsigned short)(B[j] & 0xffffu); mt[((uint32_t)(2 * j + 33) ^ flip) * 32] = (unsigned short)(B[j] >> 16);
         }
     }
-    __syncthreads();
-    // ---- meeting state: maximum of alpha + beta, lowest state on ties
-    int s = 0, best = -1;
+}
+
+// Meeting state (maximum of alpha + beta, lowest state on ties), traceback over [0, m) (warp 0) and trace forward over
+// [m, n_info) (warp 1), energy-dispersal XOR on the way out.  grid = n_groups, 64 threads, one codeword per lane.
+// With w = x | (~brev(y)) << 32 of a decision pair, the bit of logical state n is bit (n&15 | (n>>1)&16 | (n&16)<<1) of w for a
+// forward step and bit ((s&7)<<1 | s>>5 | s&16 | (s&8)<<2) for a backward step (role 1 wrote complemented positions and values).
+// The state recursion is a dependent chain, so the 32 decision pairs of the next chunk are fetched while this one is traced.
+__device__ __forceinline__ void vit_load_chunk(uint2 (&b)[32], const uint2* d, int c)
+{
+#pragma unroll
+    for (int i = 0; i < 32; i++) b[i] = __ldcs(d + (size_t)(32 * c + i) * 32);
+}
+__global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec, const unsigned short* __restrict__ meet,
+                                                  const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
+                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out)
+{
+    const VitGroup grp = groups[blockIdx.x];
+    const VitJob job = jobs[grp.job];
+    const int lane = threadIdx.x & 31, dir = threadIdx.x >> 5;
+    const int steps = job.steps;
+    const int m = ((steps >> 1) >> 5) << 5;
+    const uint2* d = dec + job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
+    const int c_first = dir == 0 ? m / 32 - 1 : m / 32, c_end = dir == 0 ? -1 : job.n_info / 32, c_step = dir == 0 ? -1 : 1;
+    uint2 cur[32], nxt[32];
+    if (c_first != c_end) vit_load_chunk(cur, d, c_first);
+    const unsigned short* mt = meet + (size_t)blockIdx.x * VIT_MEET_WORDS + lane;
+    uint32_t s = 0;
+    int best = -1;
 #pragma unroll 8
     for (int q = 0; q < 64; q++) {
-        const int v = (int)sm.meet[0][q][lane] + (int)sm.meet[1][q][lane];
-        if (v > best) { best = v; s = q; }
+        const int v = (int)mt[q * 32] + (int)mt[(64 + q) * 32];
+        if (v > best) { best = v; s = (uint32_t)q; }
     }
     const int row = grp.g_in_job * 32 + lane;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + job.out_off + (size_t)row * job.out_pitch);
     const bool live = row < job.n_rows;
-    if (dir == 0) {
-        // traceback over steps m-1 .. 0
-        for (int c = m / 32 - 1; c >= 0; c--) {
-            uint32_t word = 0;
-#pragma unroll 8
+    for (int c = c_first; c != c_end; c += c_step) {
+        const bool more = (c + c_step) != c_end;
+        if (more) vit_load_chunk(nxt, d, c + c_step);
+        uint32_t word = 0;
+        if (dir == 0) {
+            // traceback: s is the state after step 32 c + i
+#pragma unroll
             for (int i = 31; i >= 0; i--) {
-                const uint2 dd = d[(size_t)(32 * c + i) * 32];
-                word |= (uint32_t)(s & 1) << (31 - i);
-                const uint32_t wsel = (s & 32) ? dd.y : dd.x;
-                const int bit = (wsel >> (s & 31)) & 1;
-                s = (s >> 1) | (bit << 5);
+                const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
+                word |= (s & 1u) << (31 - i);
+                const uint32_t idx = (s & 15u) | ((s >> 1) & 16u) | ((s & 16u) << 1);
+                s = (s >> 1) | (((uint32_t)(w >> idx) & 1u) << 5);
             }
-            if (live) orow[c] = __byte_perm(word, 0, 0x0123) ^ __ldg(prbs_w + c);
-        }
-    } else {
-        // trace forward over steps m .. n_info-1 (the six tail steps carry no information)
-        for (int c = m / 32; c < job.n_info / 32; c++) {
-            uint32_t word = 0;
-#pragma unroll 8
+        } else {
+#pragma unroll
             for (int i = 0; i < 32; i++) {
-                const uint2 dd = d[(size_t)(32 * c + i) * 32];
-                const uint32_t wsel = (s & 16) ? dd.y : dd.x;
-                const int bit = (wsel >> (2 * (s & 15) + (s >> 5))) & 1;
-                word |= (uint32_t)bit << (31 - i);
-                s = ((s << 1) | bit) & 63;
+                const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
+                const uint32_t idx = ((s & 7u) << 1) | (s >> 5) | (s & 16u) | ((s & 8u) << 2);
+                const uint32_t bit = (uint32_t)(w >> idx) & 1u;
+                word |= bit << (31 - i);
+                s = ((s << 1) | bit) & 63u;
             }
-            if (live) orow[c] = __byte_perm(word, 0, 0x0123) ^ __ldg(prbs_w + c);
+        }
+        if (live) orow[c] = __byte_perm(word, 0, 0x0123) ^ __ldg(prbs_w + c);
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) cur[i] = nxt[i];
         }
     }
 }

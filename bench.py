@@ -156,11 +156,15 @@ def algorithmic_bytes(name: str, n_frames: int, subch, n_samples: int) -> float:
     if name == "k_gather(fic)":
         return n_cif * (2304 + 774 * 4) * 1.0
     if name == "k_viterbi(fic)":
-        return n_cif * (774 * 4 + 2 * 774 * 8 + 96) * 1.0
+        return n_cif * (774 * 4 + 774 * 8 + 2 * 64 * 2) * 1.0
+    if name == "k_vit_trace(fic)":
+        return n_cif * (774 * 8 + 2 * 64 * 2 + 96) * 1.0
     if name == "k_gather(msc)":
         return rows * (punct + steps * 4) * 1.0
     if name == "k_viterbi(msc)":
-        return rows * (steps * 4 + 2 * steps * 8 + info / 8) * 1.0            # soft words in, decisions out and back in, bytes out
+        return rows * (steps * 4 + steps * 8 + len(subch) * 2 * 64 * 2) * 1.0  # soft words in, decisions + meeting metrics out
+    if name == "k_vit_trace(msc)":
+        return rows * (steps * 8 + len(subch) * 2 * 64 * 2 + info / 8) * 1.0  # decisions + meeting metrics in, bytes out
     if name == "k_rs_decode":
         return rows * info / 8 * 1.0
     return 0.0
@@ -353,7 +357,7 @@ def main():
         if "viterbi(msc)" in dom["kernel"]:
             acs = trellis_steps * 64.0
             roof["issue"] = {"acs_per_s": acs / (dom["ms"] * 1e-3), "trellis_steps": trellis_steps,
-                             "warp_instr_per_step_per_32cw": 225, "est_issue_slots_used": round(trellis_steps / 32 * 225 / (dom["ms"] * 1e-3)
+                             "warp_instr_per_step_per_16cw": 142, "est_issue_slots_used": round(trellis_steps / 16 * 142 / (dom["ms"] * 1e-3)
                              / (148 * 4 * (clk.get("sm_mhz") or 1500) * 1e6), 4)}
 
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

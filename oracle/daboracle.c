@@ -367,8 +367,10 @@ void orc_viterbi(const int8_t *soft4, int steps, uint8_t *bits)
     /* Maximum-likelihood sequence of the zero-terminated K=7 code, found bidirectionally (same formulation as the CUDA
      * kernel): forward recursion over steps [0, m) from state 0, backward recursion over steps [m, T) from state 0,
      * m = steps/2 rounded down to a multiple of 32; the state maximising alpha + beta at stage m (lowest state on ties)
-     * lies on the best path.  Tie rules: forward survivor from the upper predecessor only if strictly better; backward
-     * continuation with input bit 1 only if strictly better.  With a unique best path this equals one-directional Viterbi. */
+     * lies on the best path.  Tie rules (include/b200dab_spec.h; chosen to be invariant under complementing all state and
+     * input bits, the symmetry the CUDA kernel's lane split relies on): forward, equal candidates into state n -> the
+     * predecessor whose oldest bit equals n & 1; backward, equal continuations from state s -> the input bit equal to
+     * s >> 5.  With a unique best path this equals one-directional Viterbi. */
     init_tables();
     const int m = ((steps >> 1) >> 5) << 5;
     int32_t M[64], N[64];
@@ -383,7 +385,7 @@ void orc_viterbi(const int8_t *soft4, int steps, uint8_t *bits)
             int32_t c0 = M[j] + beta, c1 = M[j + 32] - beta;
             if (c1 > c0) { N[2 * j] = c1; d |= 1ull << (2 * j); } else N[2 * j] = c0;
             c0 = M[j] - beta; c1 = M[j + 32] + beta;
-            if (c1 > c0) { N[2 * j + 1] = c1; d |= 1ull << (2 * j + 1); } else N[2 * j + 1] = c0;
+            if (c1 >= c0) { N[2 * j + 1] = c1; d |= 1ull << (2 * j + 1); } else N[2 * j + 1] = c0;
         }
         dec[t] = d;
         memcpy(M, N, sizeof M);
@@ -400,7 +402,7 @@ void orc_viterbi(const int8_t *soft4, int steps, uint8_t *bits)
             int32_t c0 = Bm[2 * j] + beta, c1 = Bm[2 * j + 1] - beta;
             if (c1 > c0) { Bn[j] = c1; d |= 1ull << j; } else Bn[j] = c0;
             c0 = Bm[2 * j] - beta; c1 = Bm[2 * j + 1] + beta;
-            if (c1 > c0) { Bn[j + 32] = c1; d |= 1ull << (j + 32); } else Bn[j + 32] = c0;
+            if (c1 >= c0) { Bn[j + 32] = c1; d |= 1ull << (j + 32); } else Bn[j + 32] = c0;
         }
         dec[t] = d;
         memcpy(Bm, Bn, sizeof Bm);
