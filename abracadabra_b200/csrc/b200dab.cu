@@ -20,6 +20,7 @@
 #include "k_tii.cuh"
 #include "tables.h"
 #include "fig.h"
+#include "pad.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(#x, e_); return -1; } } while (0)
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->set_error(#x, e_); return -1; } } while (0)
@@ -688,6 +689,18 @@ int b200dab_get_kernel_times(b200dab_ctx* ctx, char* names, int names_cap, float
     }
     if (names && names_cap > 0) { strncpy(names, all.c_str(), (size_t)names_cap - 1); names[names_cap - 1] = 0; }
     return n;
+}
+
+struct b200dab_pad { pad::Decoder d; };
+b200dab_pad* b200dab_pad_create(void) { return new b200dab_pad(); }
+void b200dab_pad_destroy(b200dab_pad* p) { delete p; }
+void b200dab_pad_reset(b200dab_pad* p) { if (p) p->d.reset(); }
+int b200dab_pad_feed_au(b200dab_pad* p, const uint8_t* au, int len, b200dab_pad_cb cb, void* user)
+{
+    const uint8_t* pb; int pn;
+    if (!p || !au || !pad::dabplus_pad(au, len, &pb, &pn)) return 0;
+    p->d.feed(pb, pn, [&](const uint8_t* d, int n) { if (cb) cb(user, 0, d, n); }, [&](int app, const uint8_t* d, int n) { if (cb) cb(user, app, d, n); });
+    return 1;
 }
 
 int b200dab_parse_ensemble(const uint8_t* fibs, const uint8_t* fib_ok, int n_fibs, b200dab_ensemble_t* out)

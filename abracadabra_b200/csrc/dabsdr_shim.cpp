@@ -27,6 +27,7 @@
 #include "dabsdr_abi.h"
 #include "fig.h"
 #include "mp2.h"
+#include "pad.h"
 
 namespace {
 
@@ -46,6 +47,8 @@ struct Decoder {               // one of the (up to two) audio decoder instances
     bool dabplus = false;
     int64_t last_row = -1;     // absolute logical-frame number delivered last (MP2)
     int64_t last_sf_row = -1;  // absolute row of the last delivered superframe (DAB+)
+    pad::Decoder xpad;         // X-PAD state of this audio service
+    bool xpad_app[32] = {};    // X-PAD application types started with dabsdrRequest_XPadAppStart
 };
 
 }  // namespace
@@ -300,6 +303,7 @@ bool handle_request(dabsdr_s* h, const Request& r)
         notify(h, DABSDR_NID_SERVICE_STOP, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
         break; }
     case R_XPAD: {
+        if (r.c >= 0 && r.c < 2 && r.a < 32) h->dec[r.c].xpad_app[r.a] = r.b != 0;
         dabsdrNtfXpadAppStartStop_t n;
         n.appType = (uint8_t)r.a; n.start = (int8_t)r.b;
         notify(h, DABSDR_NID_XPAD_APP_START_STOP, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
@@ -323,6 +327,21 @@ bool handle_request(dabsdr_s* h, const Request& r)
 }
 
 // ---- one GPU pass over the current window --------------------------------------------------------------------------
+// A complete, CRC-correct MSC data group arrived in the X-PAD of audio decoder `did`: hand it to the data group callback if the
+// caller started that X-PAD application (RadioControl::dabXPadAppStart, src/radiocontrol.cpp:612); the user application type is
+// the one FIG 0/13 announces for this X-PAD application type (first byte of the user application data, bits 4..0).
+void deliver_xpad_dg(dabsdr_s* h, dabsdrDecoderId_t did, Decoder& d, int app, const uint8_t* p, int n)
+{
+    if (!h->dg_cb || app < 0 || app >= 32 || !d.xpad_app[app]) return;
+    uint16_t ua_type = 0xFFFF;
+    fig::Service* s = nullptr;
+    if (fig::Component* c = find_component(h, d.sid, d.scids, &s))
+        for (auto& u : c->user_apps) if (u.data_len >= 1 && (u.data[0] & 0x1F) == app) ua_type = u.type;
+    dabsdrDataGroupCBData_t c;
+    c.id = did; c.SCId = d.scids; c.userAppType = ua_type; c.dgLen = (uint16_t)n; c.pDgData = p;
+    h->dg_cb(&c, h->dg_ctx);
+}
+
 void process_window(dabsdr_s* h)
 {
     // sub-channels to decode: those of the active decoders (none -> FIC only)
@@ -421,6 +440,18 @@ void process_window(dabsdr_s* h)
                         a.header.raw = (uint8_t)((au.header & 0x7F) | (au.crc_ok ? 0 : 0x80));       // bit 7 = concealment request
                         a.auLen = (uint16_t)au.length; a.pAuData = r.frames[i] + au.offset;
                         h->audio_cb(&a, h->audio_ctx);
+                    }
+                    // programme associated data of this AU: complete dynamic-label groups go out right after the audio callback
+                    const uint8_t* padb; int padn;
+                    if (au.crc_ok && pad::dabplus_pad(r.frames[i] + au.offset, au.length, &padb, &padn)) {
+                        const dabsdrDecoderId_t did = (dabsdrDecoderId_t)sc_dec[i];
+                        d.xpad.feed(padb, padn,
+                            [&](const uint8_t* p, int n) {
+                                if (!h->dl_cb) return;
+                                dabsdrDynamicLabelCBData_t c; c.id = did; c.len = (uint16_t)n; c.pData = p;
+                                h->dl_cb(&c, h->dl_ctx);
+                            },
+                            [&](int app, const uint8_t* p, int n) { deliver_xpad_dg(h, did, d, app, p, n); });
                     }
                 }
                 d.last_sf_row = newest;

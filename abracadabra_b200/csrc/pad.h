@@ -1,0 +1,132 @@
+// pad.h -- programme associated data of an audio frame: F-PAD / X-PAD field parsing, dynamic-label and MSC data group
+// assembly (ETSI EN 300 401 sec. 7.4; DAB+ carriage: TS 102 563 sec. 5.4).  Host-side byte work of the drop-in: the
+// reference core hands complete dynamic-label data groups (2-byte prefix + characters + CRC, CRC already verified) to
+// dabsdrDynamicLabelCBFunc_t (dabsdr.h:81-86; consumer src/data/dldecoder.cpp:82-160) and complete MSC data groups of a started
+// X-PAD user application to dabsdrDataGroupCBFunc_t (dabsdr.h:89-96; consumer src/data/mscdatagroup.cpp:30-160).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace pad {
+
+inline uint16_t crc16(const uint8_t* p, size_t n)
+{
+    uint16_t crc = 0xFFFF;
+    for (size_t i = 0; i < n; i++) {
+        crc ^= (uint16_t)p[i] << 8;
+        for (int b = 0; b < 8; b++) crc = (crc & 0x8000) ? (uint16_t)((crc << 1) ^ 0x1021) : (uint16_t)(crc << 1);
+    }
+    return (uint16_t)~crc;
+}
+inline bool crc_ok(const uint8_t* p, size_t n) { return n >= 2 && crc16(p, n - 2) == (uint16_t)((p[n - 2] << 8) | p[n - 1]); }
+
+// DAB+ access unit -> PAD bytes: the PAD travels in a data_stream_element (id 4) that is the first syntactic element of the AU
+inline bool dabplus_pad(const uint8_t* au, int len, const uint8_t** out, int* n)
+{
+    if (len < 3 || (au[0] >> 5) != 4) return false;
+    const bool align = au[0] & 1;
+    int count = au[1], pos = 2;
+    if (count == 255) { count += au[2]; pos = 3; }
+    (void)align;                                  // the element header is 16 (24) bits: the data is byte aligned either way
+    if (count < 2 || pos + count > len) return false;
+    *out = au + pos; *n = count;
+    return true;
+}
+
+static const int kXpadLen[8] = {4, 6, 8, 12, 16, 24, 32, 48};
+
+struct Decoder {
+    struct Sub { int app; int len; };
+    std::vector<Sub> last;               // sub-fields of the previous X-PAD (a field without contents indicator continues them)
+    std::vector<uint8_t> dl; bool dl_on = false;
+    std::vector<uint8_t> dg; bool dg_on = false; int dg_need = -1; int dg_app = 0;
+    std::vector<uint8_t> x;              // X-PAD in logical order
+
+    void reset() { last.clear(); dl.clear(); dg.clear(); dl_on = dg_on = false; dg_need = -1; }
+
+    static int dl_length(const std::vector<uint8_t>& d)
+    {
+        if (d.size() < 2) return -1;
+        if (!(d[0] & 0x10)) return 2 + (d[0] & 0x0F) + 1 + 2;            // message segment: prefix + characters + CRC
+        switch (d[0] & 0x0F) {
+            case 1: return 4;                                            // clear display
+            case 2: return 2 + (d[1] & 0x0F) + 1 + 2;                    // DL Plus command (TS 102 980)
+            default: return 4;
+        }
+    }
+
+    // on_dl(const uint8_t*, int) for every CRC-correct dynamic-label data group; on_dg(int xpad_app_type, const uint8_t*, int)
+    // for every CRC-correct MSC data group of X-PAD application `xpad_app_type` (the type of its start sub-field)
+    template <class DlFn, class DgFn>
+    void subfield(int app, const uint8_t* p, int n, DlFn&& on_dl, DgFn&& on_dg)
+    {
+        if (app == 1) {                                                   // data group length indicator
+            dg_need = -1; dg_on = false;
+            if (n >= 4 && crc_ok(p, 4)) dg_need = ((p[0] & 0x3F) << 8) | p[1];
+        } else if (app == 2 || app == 3) {                                // dynamic label: start / continuation
+            if (app == 2) { dl.clear(); dl_on = true; }
+            if (!dl_on) return;
+            dl.insert(dl.end(), p, p + n);
+            const int need = dl_length(dl);
+            if (need > 0 && (int)dl.size() >= need) {
+                if (crc_ok(dl.data(), (size_t)need)) on_dl(dl.data(), need);
+                dl_on = false; dl.clear();
+            }
+        } else if (app >= 4 && app < 31) {                                // user applications: even = start, odd = continuation
+            if (!(app & 1)) {
+                dg.clear(); dg_on = dg_need > 0; dg_app = app;
+            } else if (!dg_on || app != dg_app + 1) return;
+            if (!dg_on) return;
+            dg.insert(dg.end(), p, p + n);
+            if ((int)dg.size() >= dg_need) {
+                if (crc_ok(dg.data(), (size_t)dg_need)) on_dg(dg_app, dg.data(), dg_need);
+                dg_on = false; dg.clear(); dg_need = -1;
+            }
+        }
+    }
+
+    // pad: the PAD field of one audio frame in transmission order (X-PAD bytes reversed, then F-PAD byte L-1 and byte L)
+    template <class DlFn, class DgFn>
+    void feed(const uint8_t* padb, int n, DlFn&& on_dl, DgFn&& on_dg)
+    {
+        if (n < 2) return;
+        const uint8_t f0 = padb[n - 2], f1 = padb[n - 1];
+        if ((f0 >> 6) != 0) return;                                       // F-PAD type 00 only
+        const int ind = (f0 >> 4) & 3;
+        const bool ci = (f1 >> 1) & 1;
+        int nx = n - 2;
+        if (ind == 0 || nx <= 0) return;
+        if (ind == 1) { if (nx < 4) return; padb += nx - 4; nx = 4; }     // short X-PAD: the four bytes next to the F-PAD
+        else if (ind != 2) return;
+        x.resize((size_t)nx);
+        for (int i = 0; i < nx; i++) x[(size_t)i] = padb[nx - 1 - i];
+        int pos = 0;
+        std::vector<Sub> subs;
+        if (ind == 1) {
+            if (ci) { subs.push_back({x[0] & 0x1F, 3}); pos = 1; }
+            else if (!last.empty()) subs.push_back({last.back().app | 1, 4});      // continuation of the same application
+        } else if (ci) {
+            for (int k = 0; k < 4 && pos < nx; k++) {
+                const uint8_t c = x[(size_t)pos++];
+                const int app = c & 0x1F;
+                if (app == 0) break;                                      // end marker
+                if (app == 31) { pos++; continue; }                       // extended application type: not used
+                subs.push_back({app, kXpadLen[c >> 5]});
+            }
+        } else {
+            // no contents indicator: same layout as before, every sub-field continues its application
+            for (auto& s : last) subs.push_back({s.app == 1 ? 1 : (s.app | 1), s.len});
+            if (!subs.empty() && ind == 2) { int tot = 0; for (auto& s : subs) tot += s.len; if (tot > nx) subs.clear(); }
+        }
+        for (auto& s : subs) {
+            if (s.app == 0) continue;
+            if (pos + s.len > nx) break;
+            subfield(s.app, x.data() + pos, s.len, on_dl, on_dg);
+            pos += s.len;
+        }
+        if (!subs.empty()) last = subs;
+    }
+};
+
+}  // namespace pad

@@ -43,6 +43,9 @@ class Tii(ct.Structure):
                 ("level", ct.c_float * TII_MAX_IDS), ("spectrum", ct.c_float * TII_BINS)]
 
 
+PAD_CB = ct.CFUNCTYPE(None, ct.c_void_p, ct.c_int, ct.POINTER(ct.c_uint8), ct.c_int)
+
+
 class ServiceInfo(ct.Structure):
     _fields_ = [("sid", ct.c_uint32), ("label", ct.c_char * 17), ("n_components", ct.c_uint8), ("subch_id", ct.c_uint8 * 4),
                 ("ascty", ct.c_uint8 * 4)]
@@ -97,6 +100,10 @@ def lib():
         L.b200dab_profile_uep.argtypes = [i32, ct.POINTER(SubCh)]
         L.b200dab_parse_subch.argtypes = [vp, vp, i32, ct.POINTER(SubCh), i32]
         L.b200dab_parse_ensemble.argtypes = [vp, vp, i32, ct.POINTER(EnsembleInfo)]
+        L.b200dab_pad_create.restype = vp
+        L.b200dab_pad_destroy.argtypes = [vp]
+        L.b200dab_pad_reset.argtypes = [vp]
+        L.b200dab_pad_feed_au.argtypes = [vp, vp, i32, PAD_CB, vp]
         L.b200dab_decode.argtypes = [vp, vp, u64, i32, i32, ct.POINTER(SubCh), i32, ct.c_uint32, ct.POINTER(Result)]
         L.b200dab_set_profiling.argtypes = [vp, i32]
         L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
@@ -114,7 +121,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -150,6 +157,45 @@ def parse_subch(fibs: np.ndarray, fib_ok: Optional[np.ndarray] = None) -> List[S
     if n < 0:
         raise RuntimeError("parse_subch failed")
     return [out[i] for i in range(n)]
+
+
+class PadDecoder:
+    """X-PAD decoder of one DAB+ audio service: feed access units in order, get (kind, bytes) per complete data group
+    (kind 0 = dynamic label data group, kind >= 4 = MSC data group of that X-PAD application type)."""
+
+    def __init__(self):
+        self._h = lib().b200dab_pad_create()
+        self.out = []
+        self._cb = PAD_CB(lambda user, kind, data, n: self.out.append((kind, bytes(data[:n]))))
+
+    def feed(self, au: bytes) -> bool:
+        buf = (ct.c_uint8 * len(au)).from_buffer_copy(au)
+        return bool(lib().b200dab_pad_feed_au(self._h, buf, len(au), self._cb, None))
+
+    def close(self):
+        if self._h:
+            lib().b200dab_pad_destroy(self._h)
+            self._h = None
+
+
+def dynamic_label_text(groups) -> list:
+    """Assemble dynamic-label data groups into messages the way DLDecoder does (src/data/dldecoder.cpp:139-186)."""
+    msgs, cur, seg = [], None, 0
+    for g in groups:
+        if g[0] & 0x10:
+            continue
+        n = (g[0] & 0x0F) + 1
+        if g[0] & 0x40:
+            cur, seg = b"", 0
+        elif cur is None or seg != ((g[1] >> 4) & 7):
+            cur = None
+            continue
+        cur += g[2:2 + n]
+        seg += 1
+        if g[0] & 0x20:
+            msgs.append(cur.decode("latin1"))
+            cur = None
+    return msgs
 
 
 def parse_ensemble(fibs: np.ndarray, fib_ok: Optional[np.ndarray] = None) -> dict:

@@ -26,6 +26,8 @@ class SubChannel:
     bitrate: int                  # kbit/s
     prot: Tuple                   # ('EEP', level 1..4, 'A'|'B')  or ('UEP', table index 0..63)
     seed: int = 0
+    dls: Optional[List[str]] = None       # dynamic label messages carried in the X-PAD of a DAB+ sub-channel (cycled)
+    xpad_dg: Optional[List[bytes]] = None  # MSC data groups (incl. CRC) carried as X-PAD application 12/13 (MOT), cycled
 
     def profile(self):
         if self.prot[0] == "EEP":
@@ -245,6 +247,75 @@ def _crc_table(poly: int) -> np.ndarray:
 
 
 # ============================================================================ payload builders
+# ---------------------------------------------------------------------------- PAD (EN 300 401 sec. 7.4, TS 102 563 sec. 5.4)
+XPAD_LEN = (4, 6, 8, 12, 16, 24, 32, 48)
+
+
+def dl_segments(text: str, toggle: int, charset: int = 0) -> List[bytes]:
+    """Dynamic-label X-PAD data groups of one message: 2-byte prefix + up to 16 characters + CRC-16."""
+    raw = text.encode("latin1")[:128] or b" "
+    chunks = [raw[i:i + 16] for i in range(0, len(raw), 16)]
+    out = []
+    for k, ch in enumerate(chunks):
+        first, last = k == 0, k == len(chunks) - 1
+        b0 = (toggle << 7) | (first << 6) | (last << 5) | (len(ch) - 1)
+        b1 = (charset << 4) if first else (k << 4)
+        body = bytes([b0, b1]) + ch
+        crc = int(crc16_np(np.frombuffer(body, np.uint8)[None, :])[0])
+        out.append(body + bytes([crc >> 8, crc & 0xFF]))
+    return out
+
+
+class XPadStream:
+    """Variable-size X-PAD, one application sub-field per AU: dynamic label (application types 2 / 3) and, when given, MSC
+    data groups announced by a data group length indicator (application type 1) and carried as types 12 / 13."""
+
+    def __init__(self, dls: Optional[List[str]], dgs: Optional[List[bytes]], dl_len_idx: int = 3, dg_len_idx: int = 6):
+        self.q: List[Tuple[int, bytes]] = []          # (application type of the first sub-field, data group bytes)
+        self.dls, self.dgs = dls or [], dgs or []
+        self.n_dl = self.n_dg = 0
+        self.dl_len, self.dg_len = dl_len_idx, dg_len_idx
+        self.cur: Optional[Tuple[int, bytes, int]] = None
+        self.sent: List[Tuple[str, bytes]] = []       # what a receiver should report, in order
+
+    def _refill(self):
+        if self.dls:
+            for seg in dl_segments(self.dls[self.n_dl % len(self.dls)], (self.n_dl // len(self.dls)) & 1):
+                self.q.append((2, seg))
+            self.n_dl += 1
+        if self.dgs:
+            dg = self.dgs[self.n_dg % len(self.dgs)]
+            self.n_dg += 1
+            ind = bytes([(len(dg) >> 8) & 0x3F, len(dg) & 0xFF])
+            crc = int(crc16_np(np.frombuffer(ind, np.uint8)[None, :])[0])
+            self.q.append((1, ind + bytes([crc >> 8, crc & 0xFF])))
+            self.q.append((12, dg))
+
+    def next_pad(self) -> bytes:
+        """PAD bytes of one AU (X-PAD in transmission order, i.e. reversed, followed by the two F-PAD bytes)."""
+        if self.cur is None:
+            if not self.q:
+                self._refill()
+            if not self.q:
+                return bytes([0x00, 0x00])            # F-PAD only, no X-PAD
+            app, data = self.q.pop(0)
+            self.cur = (app, data, 0)
+            if app != 1:
+                self.sent.append(("dl" if app == 2 else "dg", data))
+        app, data, pos = self.cur
+        if app == 1:
+            n, ci = 4, (0 << 5) | 1                    # length indicator: 4-byte sub-field
+        else:
+            idx = self.dl_len if app == 2 else self.dg_len
+            n = XPAD_LEN[idx]
+            ci = (idx << 5) | (app if pos == 0 else app + 1)
+        piece = data[pos:pos + n].ljust(n, b"\x00")
+        pos += n
+        self.cur = None if pos >= len(data) else (app, data, pos)
+        xpad = bytes([ci, 0x00]) + piece               # CI list: one CI + end marker
+        return xpad[::-1] + bytes([0x20, 0x02])        # F-PAD: variable-size X-PAD, CI flag set
+
+
 def dabplus_superframes(sc: SubChannel, n_sf: int, rng: np.random.Generator):
     """Build n_sf DAB+ audio superframes for sub-channel `sc` (vectorised over superframes).
 
@@ -266,8 +337,19 @@ def dabplus_superframes(sc: SubChannel, n_sf: int, rng: np.random.Generator):
     buf[:, 4] = ((starts[1] & 0xF) << 4) | ((starts[2] >> 8) & 0xF)
     buf[:, 5] = starts[2] & 0xFF
     payloads = []
+    xp = XPadStream(sc.dls, sc.xpad_dg) if (sc.dls or sc.xpad_dg) else None
+    pls = [rng.integers(0, 256, (n_sf, lens[a] - 2), dtype=np.uint8) for a in range(num_aus)]
+    if xp is not None:
+        # every AU starts with a data_stream_element (id 4, instance tag 0, no byte alignment flag) that carries the PAD
+        for f in range(n_sf):
+            for a in range(num_aus):
+                pad = xp.next_pad()
+                dse = bytes([4 << 5, len(pad)]) + pad
+                pls[a][f, :len(dse)] = np.frombuffer(dse, np.uint8)
+                pls[a][f, len(dse)] = 0xE0 | (pls[a][f, len(dse)] & 0x1F)     # next element: id 7 = END
+        sc._pad_sent = xp.sent
     for a in range(num_aus):
-        pl = rng.integers(0, 256, (n_sf, lens[a] - 2), dtype=np.uint8)
+        pl = pls[a]
         crc = crc16_np(pl)
         buf[:, starts[a]:starts[a] + lens[a] - 2] = pl
         buf[:, starts[a] + lens[a] - 2] = crc >> 8

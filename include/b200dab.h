@@ -136,6 +136,17 @@ typedef struct {
 } b200dab_ensemble_t;
 B200DAB_API int b200dab_parse_ensemble(const uint8_t *fibs, const uint8_t *fib_ok, int n_fibs, b200dab_ensemble_t *out);
 
+/* Programme associated data of decoded DAB+ access units (host-side byte work; what the reference core reports through
+ * dabsdrDynamicLabelCBFunc_t / dabsdrDataGroupCBFunc_t, dabsdr.h:81-96).  Feed the AUs of one service in stream order; every
+ * complete, CRC-correct X-PAD data group is reported: kind 0 = dynamic label data group (prefix + characters + CRC),
+ * kind >= 4 = MSC data group of the X-PAD application whose start sub-field has that application type. */
+typedef struct b200dab_pad b200dab_pad;
+typedef void (*b200dab_pad_cb)(void *user, int kind, const uint8_t *data, int len);
+B200DAB_API b200dab_pad *b200dab_pad_create(void);
+B200DAB_API void b200dab_pad_destroy(b200dab_pad *p);
+B200DAB_API void b200dab_pad_reset(b200dab_pad *p);
+B200DAB_API int b200dab_pad_feed_au(b200dab_pad *p, const uint8_t *au, int len, b200dab_pad_cb cb, void *user);   /* 1 = AU carried PAD */
+
 /* Whole hot path over one recording (or chunk): sync -> FFT -> DQPSK -> de-interleave -> Viterbi -> FIB CRC ->
  * [FIG 0/1 discovery] -> MSC Viterbi -> RS/AU -> TII.  iq: interleaved I,Q in `fmt`; mem says where it lives. */
 B200DAB_API int b200dab_decode(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, int mem,

@@ -24,7 +24,10 @@ from golden_cases import CASES, build_case  # noqa: E402
 
 def main():
     assert orc.have_ref(), "reference core not built: make -C oracle ref"
+    only = set(sys.argv[1:])
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         raw, res = build_case(spec)
         with tempfile.TemporaryDirectory() as td:
             path = Path(td) / f"{name}.{spec['fmt']}"

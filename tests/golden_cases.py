@@ -22,6 +22,9 @@ CASES = {
     "multi_u8_25db": dict(kind="multi", n_frames=22, fmt="u8", snr=25.0, cfo=-2345.6, seed=21, tii=[(3, 9, 1.0, 0)], tii_mode=None, service=2),
     # same ensemble, the DAB (MPEG-1 Layer II, UEP table index 35) service selected: frames with a valid ISO 11172-3 CRC
     "multi_mp2_u8_25db": dict(kind="multi", n_frames=22, fmt="u8", snr=25.0, cfo=-2345.6, seed=21, tii=[(3, 9, 1.0, 0)], tii_mode=None, service=3),
+    # programme associated data: dynamic label segments (X-PAD applications 2/3) inside the data_stream_element of every AU
+    "c1_dls_u8_30db": dict(kind="config1", n_frames=40, fmt="u8", snr=30.0, cfo=100.0, seed=3, tii=[], tii_mode=None, service=0,
+                           dls=["Hello B200 - now playing: Test Tone One", "Second label", "x"]),
 }
 
 
@@ -29,6 +32,8 @@ def build_case(spec):
     if spec["kind"] == "config1":
         ens = synth.config1_ensemble(seed=1000 + spec["seed"])
         ens.tii = [synth.TiiTx(m, s, a, delay=d) for m, s, a, d in spec["tii"]]
+        if spec.get("dls"):
+            ens.subchannels[0].dls = list(spec["dls"])
     else:
         seed = spec["seed"]
         subs = [synth.SubChannel(1, 0, "dabplus", 96, ("EEP", 3, "A"), seed=seed),

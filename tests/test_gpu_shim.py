@@ -93,3 +93,38 @@ def test_dropin_mp2_service_against_reference():
     ref_sum = 2048.0 * 2048.0 * 28.0 ** 2
     assert all(0.8 * ref_sum < e["sum"] < 1.25 * ref_sum and e["inband"] > 0.98 * e["sum"] for e in sig)
     assert np.median([e["sum"] for e in nul]) < 0.05 * ref_sum
+
+
+def test_dropin_dynamic_label_against_reference():
+    """X-PAD dynamic label through the drop-in: the same data groups (prefix + characters + CRC), in the same order and at the
+    same place relative to the audio callbacks as the reference core delivers them"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("c1_dls_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "d.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12"])
+
+    def seq(events, sha=lambda e: e["sha1"]):
+        out = []
+        for e in events:
+            if e["ev"] == "audio":
+                out.append(("au", sha(e)))
+            elif e["ev"] == "dl":
+                assert e["id"] == 0 and e["len"] == len(e["data"]) // 2
+                out.append(("dl", e["data"]))
+        return out
+    mine = seq(ev, lambda e: hashlib.sha1(bytes.fromhex(e["data"])).hexdigest())
+    ref = seq(g["events"])
+    assert sum(1 for k, _ in mine if k == "dl") >= 30
+    # common stretch: from the first AU both delivered to the end of the shorter log
+    i0 = mine.index(ref[0]) if ref[0] in mine else None
+    j0 = 0
+    if i0 is None:
+        j0 = ref.index(mine[0]); i0 = 0
+    n = min(len(mine) - i0, len(ref) - j0)
+    assert n >= 80 and mine[i0:i0 + n] == ref[j0:j0 + n]
+    from abracadabra_b200 import pipeline
+    msgs = pipeline.dynamic_label_text([bytes.fromhex(d) for k, d in mine if k == "dl"])
+    assert set(g["spec"]["dls"]) <= set(msgs)

@@ -127,3 +127,41 @@ def test_scan_uff_files(tmp_path):
         ("5A", "174928", "E11001", "SCAN 5A", "21", "1")]
     assert float(rows[0][10]) == 0.0 and abs(float(rows[1][10]) + 6.0) < 0.3 and float(rows[2][10]) == 0.0
     assert all(abs(float(r[6]) - 30) < 3 for r in rows) and all(r[5] == "1" for r in rows)
+
+
+def test_xpad_dynamic_label_and_data_groups():
+    """pad.h against the modulator's X-PAD stream and against the reference core's dynamic-label callbacks (golden fixture)."""
+    import golden_cases as gc
+    g = gc.load_golden("c1_dls_u8_30db")
+    ref_dl = [bytes.fromhex(e["data"]) for e in g["events"] if e["ev"] == "dl"]
+    assert len(ref_dl) >= 30 and all(e["len"] == len(d) for e, d in zip([e for e in g["events"] if e["ev"] == "dl"], ref_dl))
+    # transmitted stream -> decoder: every group comes out once, in order, CRC intact
+    sc = synth.SubChannel(3, 0, "dabplus", 96, ("EEP", 3, "A"), seed=1003, dls=list(g["spec"]["dls"]),
+                          xpad_dg=[bytes(range(7, 60)), b"\x55" * 130])
+    for dg in range(len(sc.xpad_dg)):                       # MSC data groups end with their CRC-16
+        body = np.frombuffer(sc.xpad_dg[dg], np.uint8)
+        crc = int(synth.crc16_np(body[None, :])[0])
+        sc.xpad_dg[dg] = sc.xpad_dg[dg] + bytes([crc >> 8, crc & 0xFF])
+    _, aus = synth.dabplus_superframes(sc, 40, np.random.default_rng(5))
+    dec = pipeline.PadDecoder()
+    assert all(dec.feed(a) for a in aus)
+    sent = sc._pad_sent
+    n = len(dec.out)
+    assert n >= 20 and [(0 if k == "dl" else 12, d) for k, d in sent[:n]] == dec.out
+    assert {k for k, _ in dec.out} == {0, 12}
+    msgs = pipeline.dynamic_label_text([d for k, d in dec.out if k == 0])
+    assert msgs[:3] == list(g["spec"]["dls"])
+    # a corrupted group is dropped, the stream recovers
+    dec2 = pipeline.PadDecoder()
+    bad = bytearray(aus[0]); bad[6] ^= 0x40
+    for a in [bytes(bad)] + aus[1:]:
+        dec2.feed(a)
+    assert dec2.out == dec.out[1:]
+    assert not pipeline.PadDecoder().feed(b"\x21" + bytes(40))          # first element is not a DSE: no PAD
+    # the reference reports exactly the transmitted dynamic-label groups (from the point where it starts delivering audio)
+    sc3 = synth.SubChannel(3, 0, "dabplus", 96, ("EEP", 3, "A"), seed=1003, dls=list(g["spec"]["dls"]))
+    synth.dabplus_superframes(sc3, 40, np.random.default_rng(5))
+    tx = [d for _, d in sc3._pad_sent]
+    k0 = tx.index(ref_dl[0])
+    assert tx[k0:k0 + len(ref_dl)] == ref_dl
+    dec.close(); dec2.close()
