@@ -81,7 +81,7 @@ struct dabsdr_s {
     // statistics for NID_PERIODIC
     int period = -1;
     int64_t next_periodic = 0;
-    uint32_t fib_err = 0, crc_ok = 0, crc_err = 0, audio_bytes = 0, rs_unc = 0, rs_bit = 0, rs_bytes = 0;
+    uint32_t fib_err = 0, crc_ok = 0, crc_err = 0, audio_bytes = 0, pad_bytes = 0, rs_unc = 0, rs_bit = 0, rs_bytes = 0;
     float last_cfo = 0.f, last_snr = 0.f;
     // TII
     bool tii_on = false; int tii_mode = 1;
@@ -162,7 +162,7 @@ void reset_rx(dabsdr_s* h)
     h->db.reset();
     h->dec[0] = Decoder(); h->dec[1] = Decoder();
     h->have = 0; h->abs_pos = 0; h->last_frame_abs = -1; h->frame_no = -1;
-    h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->rs_unc = h->rs_bit = h->rs_bytes = 0;
+    h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->pad_bytes = h->rs_unc = h->rs_bit = h->rs_bytes = 0;
     h->tii_fold.clear(); h->tii_norm.clear(); h->tii_sign.clear();
     std::fill(h->tii_spectrum.begin(), h->tii_spectrum.end(), 0.f);
     h->next_periodic = h->period >= 0 ? ((int64_t)DAB_T_FRAME << h->period) : 0;
@@ -338,7 +338,8 @@ void deliver_xpad_dg(dabsdr_s* h, dabsdrDecoderId_t did, Decoder& d, int app, co
     if (fig::Component* c = find_component(h, d.sid, d.scids, &s))
         for (auto& u : c->user_apps) if (u.data_len >= 1 && (u.data[0] & 0x1F) == app) ua_type = u.type;
     dabsdrDataGroupCBData_t c;
-    c.id = did; c.SCId = d.scids; c.userAppType = ua_type; c.dgLen = (uint16_t)n; c.pDgData = p;
+    c.id = did; c.SCId = 0xFFFF;                              // the reference reports SCId 0xFFFF for X-PAD applications
+    c.userAppType = ua_type; c.dgLen = (uint16_t)n; c.pDgData = p;
     h->dg_cb(&c, h->dg_ctx);
 }
 
@@ -444,6 +445,7 @@ void process_window(dabsdr_s* h)
                     // programme associated data of this AU: complete dynamic-label groups go out right after the audio callback
                     const uint8_t* padb; int padn;
                     if (au.crc_ok && pad::dabplus_pad(r.frames[i] + au.offset, au.length, &padb, &padn)) {
+                        if (sc_dec[i] == 0) h->pad_bytes += (uint32_t)padn;
                         const dabsdrDecoderId_t did = (dabsdrDecoderId_t)sc_dec[i];
                         d.xpad.feed(padb, padn,
                             [&](const uint8_t* p, int n) {
@@ -490,9 +492,10 @@ void send_periodic(dabsdr_s* h)
     p.fibErrorCntr = (uint16_t)std::min<uint32_t>(h->fib_err, 65535);
     p.mscCrcOkCntr = (uint8_t)std::min<uint32_t>(h->crc_ok, 255); p.mscCrcErrorCntr = (uint8_t)std::min<uint32_t>(h->crc_err, 255);
     p.audioServiceBytes = (uint16_t)std::min<uint32_t>(h->audio_bytes, 65535);
+    p.padBytes = (uint16_t)std::min<uint32_t>(h->pad_bytes, 65535);       // bytes of the data_stream_elements that carry the PAD
     p.rsUncorrectableCntr = (uint16_t)std::min<uint32_t>(h->rs_unc, 65535); p.rsBitErrors = (uint16_t)std::min<uint32_t>(h->rs_bit, 65535);
     p.rsBytes = (uint16_t)std::min<uint32_t>(h->rs_bytes, 65535);
-    h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->rs_unc = h->rs_bit = 0;
+    h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->pad_bytes = h->rs_unc = h->rs_bit = 0;
     notify(h, DABSDR_NID_PERIODIC, DABSDR_NSTAT_SUCCESS, &p, sizeof p);
 }
 

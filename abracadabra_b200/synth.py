@@ -51,6 +51,7 @@ class Service:
     sid: int
     label: str
     subchid: int
+    user_apps: Optional[List[Tuple[int, bytes]]] = None   # FIG 0/13: (user application type, user application data)
 
 
 @dataclass
@@ -441,6 +442,13 @@ def fig0_2_entry(ens: EnsembleConfig, sv: Service) -> bytes:
     return bytes([sv.sid >> 8, sv.sid & 0xFF, 0x01, (0 << 6) | ascty, (sc.subchid << 2) | 0x02])
 
 
+def fig0_13_entry(sv: Service) -> bytes:
+    b = bytes([sv.sid >> 8, sv.sid & 0xFF, (0 << 4) | len(sv.user_apps)])
+    for ua_type, data in sv.user_apps:
+        b += bytes([(ua_type >> 3) & 0xFF, ((ua_type & 7) << 5) | len(data)]) + data
+    return b
+
+
 def fig0_9(ens: EnsembleConfig) -> bytes:
     return _fig(0, bytes([0x09, ens.lto & 0x3F, ens.ecc, 0x01]))
 
@@ -482,13 +490,17 @@ class FicBuilder:
         self.e01 = [fig0_1_entry(s) for s in ens.subchannels]
         self.e02 = [fig0_2_entry(ens, sv) for sv in ens.services]
         self.labels = [fig1(0, ens.eid, ens.label)] + [fig1(1, sv.sid, sv.label) for sv in ens.services]
-        self.i01 = self.i02 = self.ilab = 0
+        self.e13 = [fig0_13_entry(sv) for sv in ens.services if sv.user_apps]
+        self.i01 = self.i02 = self.ilab = self.i13 = 0
 
     def cif_fibs(self, cif_count: int) -> bytes:
         """Three FIBs (96 bytes) for one CIF."""
         f00 = fig0_0(self.ens, cif_count)
-        f01, self.i01 = _pack_rotating(self.e01, 0x01, 30 - len(f00), self.i01)
-        fib0 = make_fib(f00 + f01)
+        f13 = b""
+        if self.e13 and cif_count % 2 == 0:
+            f13, self.i13 = _pack_rotating(self.e13, 0x0D, 14, self.i13)
+        f01, self.i01 = _pack_rotating(self.e01, 0x01, 30 - len(f00) - len(f13), self.i01)
+        fib0 = make_fib(f00 + f13 + f01)
         f02, self.i02 = _pack_rotating(self.e02, 0x02, 30, self.i02)
         fib1 = make_fib(f02)
         lab = self.labels[self.ilab % len(self.labels)]

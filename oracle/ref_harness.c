@@ -51,6 +51,7 @@ typedef struct ev_s {
     int payload_len;
     uint32_t sids[64]; int nsids;                     /* SERVICE_LIST shadow (accessor only valid inside the callback) */
     uint32_t sc_sid; int sc_n, sc_addr0, sc_scids0;   /* SERVICE_COMPONENT_LIST shadow */
+    uint8_t xpad_apps[8]; int n_xpad_apps;            /* USER_APP_LIST shadow: X-PAD application types */
 } ev_t;
 
 static pthread_mutex_t g_mx = PTHREAD_MUTEX_INITIALIZER;
@@ -184,8 +185,10 @@ static void dg_cb(dabsdrDataGroupCBData_t *p, void *ctx)
     (void)ctx;
     if (!g_log) return;
     pthread_mutex_lock(&g_logmx);
-    fprintf(g_log, "{\"ev\":\"dg\",\"pos\":%llu,\"id\":%d,\"scid\":%u,\"uatype\":%u,\"len\":%u}\n",
+    fprintf(g_log, "{\"ev\":\"dg\",\"pos\":%llu,\"id\":%d,\"scid\":%u,\"uatype\":%u,\"len\":%u,\"data\":\"",
             (unsigned long long)g_pos, (int)p->id, p->SCId, p->userAppType, p->dgLen);
+    log_hex(g_log, p->pDgData, p->dgLen);
+    fprintf(g_log, "\"}\n");
     pthread_mutex_unlock(&g_logmx);
 }
 
@@ -219,6 +222,9 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
         int n = p->len < sizeof e->payload ? p->len : (int)sizeof e->payload;
         /* TUNE / RESET: the caller dereferences pData as a 32-bit value whatever `len` says (src/radiocontrol.cpp:2261, :2437) */
         if ((p->nid == DABSDR_NID_TUNE || p->nid == DABSDR_NID_RESET) && n < 4) n = 4;
+        /* same for the selection / stop structures (src/radiocontrol.cpp:2364-2372, :2378-2386) */
+        if ((p->nid == DABSDR_NID_SERVICE_SELECTION || p->nid == DABSDR_NID_SERVICE_STOP) && n < (int)sizeof(dabsdrNtfServiceSelection_t))
+            n = (int)sizeof(dabsdrNtfServiceSelection_t);
         memcpy(e->payload, p->pData, n);
         e->payload_len = n;
     }
@@ -259,6 +265,22 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
             }
             fprintf(g_log, "]}\n");
             break; }
+        case DABSDR_NID_USER_APP_LIST: {
+            const dabsdrNtfUserAppList_t *l = p->pData;
+            fprintf(g_log, "{\"ev\":\"ua_list\",\"pos\":%llu,\"status\":%d,\"sid\":%u,\"scids\":%u,\"n\":%u,\"items\":[", (unsigned long long)g_pos,
+                    (int)p->status, l->SId, l->SCIdS, l->numUserApps);
+            e->n_xpad_apps = 0;
+            for (int i = 0; i < l->numUserApps; i++) {
+                dabsdrUserAppListItem_t it; memset(&it, 0, sizeof it);
+                l->getUserAppListItem(g_h, i, &it);
+                fprintf(g_log, "%s{\"type\":%u,\"len\":%u,\"data\":\"", i ? "," : "", it.type, it.dataLen);
+                log_hex(g_log, it.data, it.dataLen);
+                fprintf(g_log, "\"}");
+                /* X-PAD user application: first data byte = CA flags + X-PAD application type (reference: src/radiocontrol.cpp:1546-1560) */
+                if (it.dataLen >= 2 && e->n_xpad_apps < 8) e->xpad_apps[e->n_xpad_apps++] = it.data[0] & 0x1F;
+            }
+            fprintf(g_log, "]}\n");
+            break; }
         case DABSDR_NID_TII: {
             const dabsdrNtfTii_t *t = p->pData;
             float spec[400]; memset(spec, 0, sizeof spec);
@@ -282,6 +304,7 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
 
 /* ------------------------------------------------------------------ main-thread protocol (mirrors RadioControl) */
 static uint32_t g_freq = 227360;
+static int g_xpad_apps;                 /* ask for the user application list and start the X-PAD applications */
 static int g_want_service_idx = -1;     /* index into the service list, -1 = none */
 static int g_want_second_idx = -1;
 static uint32_t g_want_sid;
@@ -328,8 +351,12 @@ static void log_notification(const ev_t *e)
                 pp->fibErrorCntr, pp->mscCrcOkCntr, pp->mscCrcErrorCntr, pp->audioServiceBytes, pp->padBytes,
                 pp->rsUncorrectableCntr, pp->rsBitErrors, pp->rsBytes);
         break; }
-    case DABSDR_NID_SERVICE_LIST: case DABSDR_NID_SERVICE_COMPONENT_LIST: case DABSDR_NID_TII:
+    case DABSDR_NID_SERVICE_LIST: case DABSDR_NID_SERVICE_COMPONENT_LIST: case DABSDR_NID_TII: case DABSDR_NID_USER_APP_LIST:
         break;                      /* logged with their accessor data in notif_cb */
+    case DABSDR_NID_XPAD_APP_START_STOP: {
+        const dabsdrNtfXpadAppStartStop_t *x = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"xpad_app\",\"pos\":%llu,\"status\":%d,\"app\":%u,\"start\":%d}\n", (unsigned long long)e->pos, e->status, x->appType, x->start);
+        break; }
     default:
         fprintf(f, "{\"ev\":\"other\",\"pos\":%llu,\"nid\":%d,\"status\":%d,\"len\":%d}\n", (unsigned long long)e->pos, e->kind, e->status, e->payload_len);
         break;
@@ -380,6 +407,15 @@ static void handle_event(ev_t *e)
             } else { g_retry_sid = e->sc_sid; g_retry_ticks = 2; }
         }
         break; }
+    case DABSDR_NID_SERVICE_SELECTION: {
+        /* reference: after a successful audio selection RadioControl asks for the user applications of the component
+         * (src/radiocontrol.cpp:1530-1545) and starts the X-PAD ones (:612) */
+        const dabsdrNtfServiceSelection_t *s = (const void *)e->payload;
+        if (g_xpad_apps && e->status == 0 && s->id == DABSDR_ID_AUDIO_PRIMARY) dabsdrRequest_GetUserAppList(g_h, s->SId, s->SCIdS);
+        break; }
+    case DABSDR_NID_USER_APP_LIST:
+        for (int i = 0; i < e->n_xpad_apps; i++) dabsdrRequest_XPadAppStart(g_h, e->xpad_apps[i], 1, DABSDR_ID_AUDIO_PRIMARY);
+        break;
     case DABSDR_NID_PERIODIC: {
         if (e->payload_len < 0) break;
         const dabsdrNtfPeriodic_t *pp = (const void *)e->payload;
@@ -407,6 +443,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--tail-frames") && i + 1 < argc) g_tail_samples = 196608ull * atoi(argv[++i]);
         else if (!strcmp(argv[i], "--no-au-data")) g_log_au_data = 0;
         else if (!strcmp(argv[i], "--free-run")) g_free_run = 1;
+        else if (!strcmp(argv[i], "--xpad-apps")) g_xpad_apps = 1;
     }
     int fd = open(path, O_RDONLY);
     if (fd < 0) { perror(path); return 1; }
@@ -416,6 +453,7 @@ int main(int argc, char **argv)
     if (g_file == MAP_FAILED) { perror("mmap"); return 1; }
     g_nsamples = g_file_bytes / (g_fmt == 0 ? 2 : g_fmt == 1 ? 4 : 8);
     if (strcmp(argv[3], "-")) { g_log = fopen(argv[3], "w"); if (!g_log) { perror(argv[3]); return 1; } }
+    if (g_log && getenv("HARNESS_LINEBUF")) setvbuf(g_log, NULL, _IOLBF, 0);      /* debugging aid: keep the log if the core crashes */
 
     dabsdrVersion_t v; dabsdrGetVersion(&v);
     if (dabsdrInit(&g_h) != 0) { fprintf(stderr, "dabsdrInit failed\n"); return 1; }

@@ -25,7 +25,22 @@ CASES = {
     # programme associated data: dynamic label segments (X-PAD applications 2/3) inside the data_stream_element of every AU
     "c1_dls_u8_30db": dict(kind="config1", n_frames=40, fmt="u8", snr=30.0, cfo=100.0, seed=3, tii=[], tii_mode=None, service=0,
                            dls=["Hello B200 - now playing: Test Tone One", "Second label", "x"]),
+    # MOT-style MSC data groups in the X-PAD (length indicator + applications 12/13), announced by FIG 0/13 as SlideShow (type 2)
+    "c1_mot_u8_30db": dict(kind="config1", n_frames=40, fmt="u8", snr=30.0, cfo=100.0, seed=4, tii=[], tii_mode=None, service=0,
+                           dls=["MOT test"], xpad_dg=3, xpad_apps=True),
 }
+
+
+def mot_data_groups(n, seed=9):
+    """n MSC data groups with CRC: header (CRC + segment flags, type 4, continuity k), segment number k, 40 random bytes"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        body = bytes([0x64, (k << 4) & 0xF0, 0x80, k & 0xFF, 0x00, 40]) + rng.integers(0, 256, 40, dtype=np.uint8).tobytes()
+        crc = int(synth.crc16_np(np.frombuffer(body, np.uint8)[None, :])[0])
+        out.append(body + bytes([crc >> 8, crc & 0xFF]))
+    return out
 
 
 def build_case(spec):
@@ -34,6 +49,9 @@ def build_case(spec):
         ens.tii = [synth.TiiTx(m, s, a, delay=d) for m, s, a, d in spec["tii"]]
         if spec.get("dls"):
             ens.subchannels[0].dls = list(spec["dls"])
+        if spec.get("xpad_dg"):
+            ens.subchannels[0].xpad_dg = mot_data_groups(spec["xpad_dg"])
+            ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]       # SlideShow over X-PAD application 12, DSCTy 60 (MOT)
     else:
         seed = spec["seed"]
         subs = [synth.SubChannel(1, 0, "dabplus", 96, ("EEP", 3, "A"), seed=seed),

@@ -128,3 +128,34 @@ def test_dropin_dynamic_label_against_reference():
     from abracadabra_b200 import pipeline
     msgs = pipeline.dynamic_label_text([bytes.fromhex(d) for k, d in mine if k == "dl"])
     assert set(g["spec"]["dls"]) <= set(msgs)
+
+
+def test_dropin_xpad_data_groups_against_reference():
+    """MSC data groups in the X-PAD (SlideShow announced by FIG 0/13): user application list, XPadAppStart answer and the data
+    group callbacks equal the reference's (group bytes incl. CRC, user application type 2, SCId 0xFFFF)"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("c1_mot_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "m.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12", "--xpad-apps"])
+
+    def one(events, kind):
+        return [e for e in events if e["ev"] == kind]
+    me, rf = one(ev, "ua_list")[0], one(g["events"], "ua_list")[0]
+    assert {k: me[k] for k in ("status", "sid", "scids", "n", "items")} == {k: rf[k] for k in ("status", "sid", "scids", "n", "items")}
+    me, rf = one(ev, "xpad_app")[0], one(g["events"], "xpad_app")[0]
+    assert (me["status"], me["app"], me["start"]) == (rf["status"], rf["app"], rf["start"]) == (0, 12, 1)
+    assert one(ev, "selection")[0]["sid"] == one(g["events"], "selection")[0]["sid"] == 0x1001
+    mine = [(e["id"], e["scid"], e["uatype"], e["len"], e["data"]) for e in one(ev, "dg")]
+    ref = [(e["id"], e["scid"], e["uatype"], e["len"], e["data"]) for e in one(g["events"], "dg")]
+    assert len(mine) >= 12 and len(ref) >= 12
+    sent = [d.hex() for d in gc.mot_data_groups(g["spec"]["xpad_dg"])]
+    assert all(m[:4] == (0, 0xFFFF, 2, 48) and m[4] in sent for m in mine), [m[:4] for m in mine[:4]]
+    # same cyclic sequence: align on the first group the reference delivered
+    i0 = next(i for i, m in enumerate(mine) if m == ref[0])
+    n = min(len(mine) - i0, len(ref))
+    assert n >= 12 and mine[i0:i0 + n] == ref[:n]
+    # the dynamic label keeps flowing next to the data groups
+    assert [e["data"] for e in one(ev, "dl")][:3] == [e["data"] for e in one(g["events"], "dl")][:3] or len(one(ev, "dl")) >= 5

@@ -129,3 +129,16 @@ def test_reference_structures_in_fixture():
     assert sl["n"] == 1 and sl["items"][0]["sid"] == 0x1001
     sc = [e for e in g["events"] if e["ev"] == "sc_list"][0]["items"][0]
     assert (sc["subchid"], sc["addr"], sc["size"], sc["prot"], sc["ascty"], sc["bitrate"], sc["ps"]) == (3, 0, 72, 8, 63, 96, 2)
+
+
+def test_reference_pad_fixtures():
+    """What the reference core reports for programme associated data (pins abracadabra_b200/csrc/pad.h, see also
+    tests/test_rawfile_scanner.py::test_xpad_dynamic_label_and_data_groups)"""
+    g = gc.load_golden("c1_mot_u8_30db")
+    dg = [e for e in g["events"] if e["ev"] == "dg"]
+    sent = [d.hex() for d in gc.mot_data_groups(g["spec"]["xpad_dg"])]
+    assert len(dg) >= 12 and all(e["id"] == 0 and e["scid"] == 0xFFFF and e["uatype"] == 2 and e["data"] in sent for e in dg)
+    ua = [e for e in g["events"] if e["ev"] == "ua_list"][0]
+    assert ua["items"] == [{"type": 2, "len": 2, "data": "0c3c"}]
+    per = [e for e in gc.load_golden("c1_dls_u8_30db")["events"] if e["ev"] == "periodic" and e.get("crcOk")]
+    assert per and all(e["padBytes"] == 16 * e["crcOk"] for e in per)        # 16 = bytes of the PAD data_stream_element per AU
