@@ -104,21 +104,28 @@ struct b200dab_ctx {
 
     // optional per-kernel timing (CUDA events on `stream`), enabled by b200dab_set_profiling
     bool profile = false;
+    // The events of the last PROF_RING calls are kept, so a caller can time K calls back to back and read the events afterwards
+    // (reading them costs ~0.1 ms of host time per call, which does not belong inside a timed region).
+    static constexpr int PROF_RING = 8;
     struct ProfEv { const char* name; cudaEvent_t a, b; };
-    std::vector<ProfEv> prof;
-    size_t prof_used = 0;
+    std::vector<ProfEv> prof_sets[PROF_RING];
+    size_t prof_counts[PROF_RING] = {};
+    int prof_slot = 0;
+    void prof_next() { prof_slot = (prof_slot + 1) % PROF_RING; prof_counts[prof_slot] = 0; }
     void prof_begin(const char* name)
     {
         if (!profile) return;
-        if (prof_used == prof.size()) { ProfEv e; e.name = name; cudaEventCreate(&e.a); cudaEventCreate(&e.b); prof.push_back(e); }
-        prof[prof_used].name = name;
-        cudaEventRecord(prof[prof_used].a, stream);
+        std::vector<ProfEv>& prof = prof_sets[prof_slot];
+        size_t& used = prof_counts[prof_slot];
+        if (used == prof.size()) { ProfEv e; e.name = name; cudaEventCreate(&e.a); cudaEventCreate(&e.b); prof.push_back(e); }
+        prof[used].name = name;
+        cudaEventRecord(prof[used].a, stream);
     }
     void prof_end()
     {
         if (!profile) return;
-        cudaEventRecord(prof[prof_used].b, stream);
-        prof_used++;
+        cudaEventRecord(prof_sets[prof_slot][prof_counts[prof_slot]].b, stream);
+        prof_counts[prof_slot]++;
     }
 
     void set_error(const char* what, cudaError_t e)
@@ -641,7 +648,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    for (auto& e : ctx->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -675,17 +682,24 @@ int b200dab_set_profiling(b200dab_ctx* ctx, int on)
 // per-kernel device times of the last b200dab_decode (CUDA events on the context stream); names are ';'-separated
 int b200dab_get_kernel_times(b200dab_ctx* ctx, char* names, int names_cap, float* ms, int max_n)
 {
-    if (!ctx) return -1;
+    return b200dab_get_kernel_times_back(ctx, 0, names, names_cap, ms, max_n);
+}
+
+int b200dab_get_kernel_times_back(b200dab_ctx* ctx, int back, char* names, int names_cap, float* ms, int max_n)
+{
+    if (!ctx || back < 0 || back >= b200dab_ctx::PROF_RING) return -1;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    const int slot = (ctx->prof_slot - back + 2 * b200dab_ctx::PROF_RING) % b200dab_ctx::PROF_RING;
+    const std::vector<b200dab_ctx::ProfEv>& prof = ctx->prof_sets[slot];
     int n = 0;
     std::string all;
-    for (size_t i = 0; i < ctx->prof_used && n < max_n; i++, n++) {
+    for (size_t i = 0; i < ctx->prof_counts[slot] && n < max_n; i++, n++) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, ctx->prof[i].a, ctx->prof[i].b) != cudaSuccess) t = -1.f;
+        if (cudaEventElapsedTime(&t, prof[i].a, prof[i].b) != cudaSuccess) t = -1.f;
         if (ms) ms[n] = t;
         if (!all.empty()) all += ";";
-        all += ctx->prof[i].name;
+        all += prof[i].name;
     }
     if (names && names_cap > 0) { strncpy(names, all.c_str(), (size_t)names_cap - 1); names[names_cap - 1] = 0; }
     return n;
@@ -735,7 +749,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     cudaSetDevice(ctx->device);
     memset(res, 0, sizeof *res);
     ctx->launches = 0;
-    ctx->prof_used = 0;
+    ctx->prof_next();
     ctx->t_trace0 = now_ms();
     ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
     const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
@@ -1037,7 +1051,7 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     CKC(cudaMemcpyAsync(ctx->d_groups.p, groups.data(), groups.size() * sizeof(VitGroup), cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->d_vin.p, vin.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, zero_prbs.data(), 512 * 4, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->prof_used = 0;
+    ctx->prof_next();
     CKC(ctx->d_meet.ensure((size_t)ng * VIT_MEET_WORDS * sizeof(unsigned short)));
     ctx->prof_begin("k_viterbi(stage)");
     k_viterbi<<<ng * 4, 32, ctx->vit_dsmem, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),

@@ -107,6 +107,7 @@ def lib():
         L.b200dab_decode.argtypes = [vp, vp, u64, i32, i32, ct.POINTER(SubCh), i32, ct.c_uint32, ct.POINTER(Result)]
         L.b200dab_set_profiling.argtypes = [vp, i32]
         L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
+        L.b200dab_get_kernel_times_back.argtypes = [vp, i32, ct.c_char_p, i32, vp, i32]
         L.b200dab_stage_coarse.argtypes = [vp, vp, u64, i32, vp, vp, vp, ct.POINTER(i32), i32]
         L.b200dab_stage_fine.argtypes = [vp, vp, u64, i32, vp, i32, vp, vp, vp]
         L.b200dab_stage_demod.argtypes = [vp, vp, u64, i32, vp, vp, i32, vp]
@@ -121,7 +122,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -289,11 +290,12 @@ class Receiver:
     def set_profiling(self, on: bool) -> None:
         lib().b200dab_set_profiling(self._h, int(on))
 
-    def kernel_times(self):
-        """[(kernel name, ms)] of the last decode (needs set_profiling(True) before it)."""
+    def kernel_times(self, back: int = 0):
+        """[(kernel name, ms)] of the last decode, or of the decode `back` calls ago (the last 8 are kept); needs
+        set_profiling(True) before them."""
         names = ct.create_string_buffer(32768)
         ms = np.zeros(1024, np.float32)
-        n = lib().b200dab_get_kernel_times(self._h, names, 32768, ms.ctypes.data, 1024)
+        n = lib().b200dab_get_kernel_times_back(self._h, back, names, 32768, ms.ctypes.data, 1024)
         nm = names.value.decode().split(";") if n > 0 else []
         tot = {}
         for k, v in zip(nm, ms[:n].tolist()):      # a kernel may be launched several times per decode (chunked front end)

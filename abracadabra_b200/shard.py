@@ -61,3 +61,25 @@ def run_sharded(units: Sequence[Any], fn: Callable[[Any], Any], rank: int, world
     dist.all_gather_object(gathered, mine)
     flat = sorted((x for part in gathered for x in part), key=lambda x: x[0])
     return [r for _, r in flat]
+
+
+def bind_to_gpu(device: int) -> list:
+    """Pin the calling process to the CPU cores NVML reports as local to `device` (same NUMA node / PCIe root), so that pinned
+    host buffers are allocated next to the GPU and launches / host reads do not cross the socket interconnect.  One process per
+    GPU is the deployment unit of this path; without this, an 8-rank run loses ~20 % per rank to remote-NUMA latency.
+    Returns the CPU list (empty if NVML is unavailable: then nothing is changed)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < n_cpu]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []

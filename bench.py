@@ -228,6 +228,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
+    from abracadabra_b200 import shard
+    affinity0 = os.sched_getaffinity(0)
+    cpus = shard.bind_to_gpu(dev)                 # before any pinned allocation: NUMA-local host buffers and launch threads
+    config["cpu_affinity"] = f"{len(cpus)} cores local to the GPU (NVML)" if cpus else "unchanged"
 
     raw, res, n_frames = make_recording(args.seconds, rank)
     n_samples = raw.size // 2
@@ -251,6 +255,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    per_rank = []          # per-rank ms per step of every timed run (device-resident, sequential host), for the scaling picture
+
     def timed(fn, k, collect):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -260,16 +266,20 @@ def main():
         last = None
         for _ in range(k):
             last = fn()
-            if collect:                      # per-kernel CUDA-event times of this step (device-resident run only)
-                for nm, ms in rx.kernel_times():
-                    ktimes.setdefault(nm, []).append(ms)
         e1.record(stream)
         e1.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         ms = e0.elapsed_time(e1)
+        if collect:                          # per-kernel CUDA-event times of the timed steps, read back after the timed region
+            for back in range(min(k, 8)):
+                for nm, v in rx.kernel_times(back):
+                    ktimes.setdefault(nm, []).append(v)
         barrier()
         if dist is not None:
             t = torch.tensor([ms, wall], device=f"cuda:{dev}", dtype=torch.float64)
+            every = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(every, t)
+            per_rank.append([round(float(x[0]) / k, 4) for x in every])
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1])
         return ms, wall, ktimes, last
@@ -368,10 +378,11 @@ def main():
                     "api": "ReceiverPool(depth=2).map_raw: two receiver contexts per GPU, steps pipelined (upload of step k+1 under the back end of step k)",
                     "sequential_value": total_samples * args.steps / (ms_seq * 1e-3) / 1e6, "sequential_ms_per_step": ms_seq / args.steps},
             "gpu_launches": int(launches) * args.steps, "launches_per_step": int(launches), "clocks": clk,
-            "wall_ms_per_step": wall_dev / args.steps, "roofline": roof, "stages": stages,
+            "wall_ms_per_step": wall_dev / args.steps, "per_rank_ms_per_step": per_rank[0] if per_rank else None, "roofline": roof, "stages": stages,
             "check": {"frames": n_frames, "all_fib_crc_ok": ok_fib, "all_subchannels_equal_payload": ok_msc, "aus": n_aus, "aus_crc_ok": int(n_aus_ok),
                       "tii_ids": tii_ids}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, affinity0)            # the reference gets every host core again
         line["cpu_baseline"] = run_reference_cpu(raw, len(res.ens.services), args.cpu_sample_seconds, cores)
     if rank == 0:
         print(json.dumps(line))
