@@ -92,6 +92,7 @@ struct dabsdr_s {
     std::vector<dabsdrServiceListItem_t> snap_services;
     std::vector<dabsdrServiceCompListItem_t> snap_comps;
     std::vector<dabsdrUserAppListItem_t> snap_uas;
+    std::vector<uint8_t> pad_tmp;      // PAD of an MP2 frame, re-joined across the ScF-CRC
 };
 
 namespace {
@@ -421,6 +422,19 @@ void process_window(dabsdr_s* h)
                         dabsdrAudioCBData_t a;
                         a.id = (dabsdrDecoderId_t)sc_dec[i]; a.ASCTy = 0; a.header.raw = 0; a.auLen = (uint16_t)(hdr_ok ? pitch : 0); a.pAuData = fr;
                         h->audio_cb(&a, h->audio_ctx);
+                    }
+                    int scf = 0;
+                    if (hdr_ok && pad::mp2_pad(fr, pitch, h->pad_tmp, &scf)) {
+                        const dabsdrDecoderId_t did = (dabsdrDecoderId_t)sc_dec[i];
+                        const int used = d.xpad.feed(h->pad_tmp.data(), (int)h->pad_tmp.size(),
+                            [&](const uint8_t* p, int n) {
+                                if (!h->dl_cb) return;
+                                dabsdrDynamicLabelCBData_t c; c.id = did; c.len = (uint16_t)n; c.pData = p;
+                                h->dl_cb(&c, h->dl_ctx);
+                            },
+                            [&](int app, const uint8_t* p, int n) { deliver_xpad_dg(h, did, d, app, p, n); });
+                        // the reference counts X-PAD + F-PAD + ScF-CRC + 1 per frame (probed: 15 / 21 / 25 for 6 / 12 / 16 data bytes)
+                        if (sc_dec[i] == 0) h->pad_bytes += (uint32_t)(used + 2 + scf + 1);
                     }
                 }
             } else {

@@ -34,6 +34,26 @@ inline bool dabplus_pad(const uint8_t* au, int len, const uint8_t** out, int* n)
     return true;
 }
 
+// DAB (MPEG Layer II) audio frame -> PAD bytes: the frame ends with [X-PAD, reversed] [ScF-CRC] [F-PAD byte L-1, byte L]
+// (EN 300 401 sec. 7.4 / annex B.3).  The ScF-CRC is 2 bytes below 56 kbit/s per channel at 48 kHz and 4 bytes otherwise.
+// `tmp` receives the up to 196 bytes before the ScF-CRC followed by the F-PAD, i.e. the layout Decoder::feed expects.
+inline bool mp2_pad(const uint8_t* f, int len, std::vector<uint8_t>& tmp, int* scf_len = nullptr)
+{
+    if (len < 16 || f[0] != 0xFF || (f[1] & 0xF0) != 0xF0) return false;
+    static const int br1[15] = {0, 32, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 384};
+    const int id = (f[1] >> 3) & 1, br_idx = f[2] >> 4, nch = (f[3] >> 6) == 3 ? 1 : 2;
+    if (br_idx == 0 || br_idx == 15) return false;
+    const int scf = (id == 1 && br1[br_idx] / nch < 56) ? 2 : 4;
+    if (scf_len) *scf_len = scf;
+    const int avail = len - 2 - scf - 6;                         // keep clear of header + CRC
+    if (avail <= 0) return false;
+    const int nx = avail < 196 ? avail : 196;
+    tmp.resize((size_t)nx + 2);
+    memcpy(tmp.data(), f + len - 2 - scf - nx, (size_t)nx);
+    tmp[(size_t)nx] = f[len - 2]; tmp[(size_t)nx + 1] = f[len - 1];
+    return true;
+}
+
 static const int kXpadLen[8] = {4, 6, 8, 12, 16, 24, 32, 48};
 
 struct Decoder {
@@ -87,18 +107,19 @@ struct Decoder {
     }
 
     // pad: the PAD field of one audio frame in transmission order (X-PAD bytes reversed, then F-PAD byte L-1 and byte L)
+    // returns the number of X-PAD bytes in use (contents indicators + sub-fields)
     template <class DlFn, class DgFn>
-    void feed(const uint8_t* padb, int n, DlFn&& on_dl, DgFn&& on_dg)
+    int feed(const uint8_t* padb, int n, DlFn&& on_dl, DgFn&& on_dg)
     {
-        if (n < 2) return;
+        if (n < 2) return 0;
         const uint8_t f0 = padb[n - 2], f1 = padb[n - 1];
-        if ((f0 >> 6) != 0) return;                                       // F-PAD type 00 only
+        if ((f0 >> 6) != 0) return 0;                                     // F-PAD type 00 only
         const int ind = (f0 >> 4) & 3;
         const bool ci = (f1 >> 1) & 1;
         int nx = n - 2;
-        if (ind == 0 || nx <= 0) return;
-        if (ind == 1) { if (nx < 4) return; padb += nx - 4; nx = 4; }     // short X-PAD: the four bytes next to the F-PAD
-        else if (ind != 2) return;
+        if (ind == 0 || nx <= 0) return 0;
+        if (ind == 1) { if (nx < 4) return 0; padb += nx - 4; nx = 4; }   // short X-PAD: the four bytes next to the F-PAD
+        else if (ind != 2) return 0;
         x.resize((size_t)nx);
         for (int i = 0; i < nx; i++) x[(size_t)i] = padb[nx - 1 - i];
         int pos = 0;
@@ -126,6 +147,7 @@ struct Decoder {
             pos += s.len;
         }
         if (!subs.empty()) last = subs;
+        return pos;
     }
 };
 

@@ -412,6 +412,15 @@ def mp2_frames(sc: SubChannel, n: int, rng: np.random.Generator, valid_crc: bool
             crc = _mp2_crc(crc, v, 2)
             pos += 2
         frames[f, 4], frames[f, 5] = crc >> 8, crc & 0xFF
+    if sc.dls or sc.xpad_dg:
+        # PAD at the end of the frame: [X-PAD, reversed] [ScF-CRC: 4 bytes at >= 56 kbit/s per channel, else 2] [F-PAD]
+        xp = XPadStream(sc.dls, sc.xpad_dg)
+        scf = 4 if sc.bitrate // 2 >= 56 else 2
+        for f in range(n):
+            pad = xp.next_pad()
+            tail = pad[:-2] + bytes(scf) + pad[-2:]
+            frames[f, fb - len(tail):] = np.frombuffer(tail, np.uint8)
+        sc._pad_sent = xp.sent
     return frames
 
 

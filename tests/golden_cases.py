@@ -28,6 +28,9 @@ CASES = {
     # MOT-style MSC data groups in the X-PAD (length indicator + applications 12/13), announced by FIG 0/13 as SlideShow (type 2)
     "c1_mot_u8_30db": dict(kind="config1", n_frames=40, fmt="u8", snr=30.0, cfo=100.0, seed=4, tii=[], tii_mode=None, service=0,
                            dls=["MOT test"], xpad_dg=3, xpad_apps=True),
+    # DAB (MPEG Layer II) service with a dynamic label in the PAD at the end of every audio frame
+    "mp2_dls_u8_30db": dict(kind="mp2pad", n_frames=30, fmt="u8", snr=30.0, cfo=50.0, seed=2, tii=[], tii_mode=None, service=0,
+                            dls=["MP2 dynamic label text, long enough for two segments", "short"]),
 }
 
 
@@ -52,6 +55,9 @@ def build_case(spec):
         if spec.get("xpad_dg"):
             ens.subchannels[0].xpad_dg = mot_data_groups(spec["xpad_dg"])
             ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]       # SlideShow over X-PAD application 12, DSCTy 60 (MOT)
+    elif spec["kind"] == "mp2pad":
+        subs = [synth.SubChannel(9, 0, "mp2", 128, ("UEP", 35), seed=spec["seed"] + 3, dls=list(spec["dls"]))]
+        ens = synth.EnsembleConfig(eid=0x3003, label="B200 MP2PAD", subchannels=subs, services=[synth.Service(0x3003, "MP2 PAD", 9)])
     else:
         seed = spec["seed"]
         subs = [synth.SubChannel(1, 0, "dabplus", 96, ("EEP", 3, "A"), seed=seed),

@@ -159,3 +159,30 @@ def test_dropin_xpad_data_groups_against_reference():
     assert n >= 12 and mine[i0:i0 + n] == ref[:n]
     # the dynamic label keeps flowing next to the data groups
     assert [e["data"] for e in one(ev, "dl")][:3] == [e["data"] for e in one(g["events"], "dl")][:3] or len(one(ev, "dl")) >= 5
+
+
+def test_dropin_mp2_dynamic_label_against_reference():
+    """PAD at the end of DAB (MPEG Layer II) frames: same dynamic-label groups, same interleaving with the audio callbacks,
+    same padBytes statistic as the reference"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("mp2_dls_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "d.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12"])
+
+    def seq(events, sha):
+        return [("au", sha(e)) if e["ev"] == "audio" else ("dl", e["data"]) for e in events if e["ev"] in ("audio", "dl")]
+    mine = seq(ev, lambda e: hashlib.sha1(bytes.fromhex(e["data"])).hexdigest())
+    ref = seq(g["events"], lambda e: e["sha1"])
+    assert sum(1 for k, _ in ref if k == "dl") >= 40
+    # either side may start one or two frames earlier: align on the first audio frame both delivered
+    common = set(mine) & set(ref)
+    i0 = next(i for i, x in enumerate(mine) if x[0] == "au" and x in common)
+    j0 = ref.index(mine[i0])
+    n = min(len(mine) - i0, len(ref) - j0)
+    assert n >= 100 and mine[i0:i0 + n] == ref[j0:j0 + n]
+    per = [e for e in ev if e["ev"] == "periodic" and e.get("crcOk")]
+    assert per and all(e["padBytes"] == 21 * e["crcOk"] for e in per)
+    assert all(e["padBytes"] == 21 * e["crcOk"] for e in g["events"] if e["ev"] == "periodic" and e.get("crcOk"))

@@ -165,3 +165,14 @@ def test_xpad_dynamic_label_and_data_groups():
     k0 = tx.index(ref_dl[0])
     assert tx[k0:k0 + len(ref_dl)] == ref_dl
     dec.close(); dec2.close()
+    # DAB (MPEG Layer II) frames: PAD at the end of the frame, split by the ScF-CRC; pinned by the reference's log
+    g2 = gc.load_golden("mp2_dls_u8_30db")
+    _, res2 = gc.build_case(g2["spec"])
+    dec3 = pipeline.PadDecoder()
+    assert all(dec3.feed_mp2(bytes(fr)) for fr in res2.logical[9])
+    ref2 = [bytes.fromhex(e["data"]) for e in g2["events"] if e["ev"] == "dl"]
+    mine2 = [d for k, d in dec3.out if k == 0]
+    i0 = mine2.index(ref2[0])
+    assert len(ref2) >= 40 and mine2[i0:i0 + len(ref2)] == ref2
+    assert pipeline.dynamic_label_text(mine2)[:2] == list(g2["spec"]["dls"])
+    dec3.close()
