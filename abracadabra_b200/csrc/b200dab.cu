@@ -705,7 +705,7 @@ int b200dab_get_kernel_times_back(b200dab_ctx* ctx, int back, char* names, int n
     return n;
 }
 
-struct b200dab_pad { pad::Decoder d; std::vector<uint8_t> tmp; };
+struct b200dab_pad { pad::Decoder d; std::vector<uint8_t> tmp; packet::Assembler pk; };
 b200dab_pad* b200dab_pad_create(void) { return new b200dab_pad(); }
 void b200dab_pad_destroy(b200dab_pad* p) { delete p; }
 void b200dab_pad_reset(b200dab_pad* p) { if (p) p->d.reset(); }
@@ -714,6 +714,14 @@ int b200dab_pad_feed_au(b200dab_pad* p, const uint8_t* au, int len, b200dab_pad_
     const uint8_t* pb; int pn;
     if (!p || !au || !pad::dabplus_pad(au, len, &pb, &pn)) return 0;
     p->d.feed(pb, pn, [&](const uint8_t* d, int n) { if (cb) cb(user, 0, d, n); }, [&](int app, const uint8_t* d, int n) { if (cb) cb(user, app, d, n); });
+    return 1;
+}
+
+int b200dab_pad_feed_packets(b200dab_pad* p, int addr, const uint8_t* f, int len, b200dab_pad_cb cb, void* user)
+{
+    if (!p || !f) return 0;
+    if (p->pk.addr != addr) p->pk.reset(addr);
+    p->pk.frame(f, len, [&](const uint8_t* d, int n) { if (cb) cb(user, -1, d, n); });
     return 1;
 }
 

@@ -51,6 +51,18 @@ struct Decoder {               // one of the (up to two) audio decoder instances
     bool xpad_app[32] = {};    // X-PAD application types started with dabsdrRequest_XPadAppStart
 };
 
+constexpr int MAX_DATA_DEC = 4;
+struct DataDecoder {           // packet-mode service component started on DABSDR_ID_DATA
+    bool active = false;
+    uint32_t sid = 0;
+    uint8_t scids = 0;
+    int subch_id = -1;
+    uint16_t scid = 0;
+    uint16_t ua_type = 0xFFFF;
+    int64_t last_row = -1;
+    packet::Assembler as;
+};
+
 }  // namespace
 
 struct dabsdr_s {
@@ -72,6 +84,7 @@ struct dabsdr_s {
     int sync_level = 0;
     fig::Database db;
     Decoder dec[2];
+    DataDecoder data[MAX_DATA_DEC];
     std::vector<float> win;            // interleaved I,Q
     int64_t have = 0;                  // complex samples in win
     int64_t abs_pos = 0;               // absolute index of win[0]
@@ -162,6 +175,7 @@ void reset_rx(dabsdr_s* h)
 {
     h->db.reset();
     h->dec[0] = Decoder(); h->dec[1] = Decoder();
+    for (auto& d : h->data) d = DataDecoder();
     h->have = 0; h->abs_pos = 0; h->last_frame_abs = -1; h->frame_no = -1;
     h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->pad_bytes = h->rs_unc = h->rs_bit = h->rs_bytes = 0;
     h->tii_fold.clear(); h->tii_norm.clear(); h->tii_sign.clear();
@@ -286,7 +300,22 @@ bool handle_request(dabsdr_s* h, const Request& r)
         fig::Service* s = nullptr;
         fig::Component* c = find_component(h, r.a, (uint8_t)r.b, &s);
         if (!c) st = DABSDR_NSTAT_SERVICE_NOT_FOUND;
-        else if (r.c != DABSDR_ID_AUDIO_PRIMARY && r.c != DABSDR_ID_AUDIO_SECONDARY) st = DABSDR_NSTAT_SERVICE_NOT_SUPPORTED;   // data decoder: next row
+        else if (r.c == DABSDR_ID_DATA) {
+            // packet-mode data component (reference caller: src/radiocontrol.cpp:638); stream-mode data is not supported
+            DataDecoder* slot = nullptr;
+            for (auto& d : h->data) if (d.active && d.sid == r.a && d.scids == (uint8_t)r.b) slot = &d;
+            if (!slot) for (auto& d : h->data) if (!d.active) { slot = &d; break; }
+            if (c->tmid != 3 || !slot) st = DABSDR_NSTAT_SERVICE_NOT_SUPPORTED;
+            else if (c->subch_id < 0 || !h->db.subch[c->subch_id].valid || c->packet_addr < 0) st = DABSDR_NSTAT_SERVICE_NOT_READY;
+            else {
+                *slot = DataDecoder();
+                slot->active = true; slot->sid = r.a; slot->scids = (uint8_t)r.b; slot->subch_id = c->subch_id; slot->scid = c->scid;
+                slot->ua_type = c->user_apps.empty() ? 0xFFFF : c->user_apps[0].type;
+                slot->as.reset(c->packet_addr);
+                if (h->frame_no >= 0) slot->last_row = h->frame_no * 4 + 3;
+            }
+        }
+        else if (r.c != DABSDR_ID_AUDIO_PRIMARY && r.c != DABSDR_ID_AUDIO_SECONDARY) st = DABSDR_NSTAT_SERVICE_NOT_SUPPORTED;
         else if (c->tmid != 0) st = DABSDR_NSTAT_SERVICE_NOT_SUPPORTED;
         else if (c->subch_id < 0 || !h->db.subch[c->subch_id].valid) st = DABSDR_NSTAT_SERVICE_NOT_READY;
         else {
@@ -301,6 +330,7 @@ bool handle_request(dabsdr_s* h, const Request& r)
         dabsdrNtfServiceStop_t n;
         n.SId = r.a; n.SCIdS = (uint8_t)r.b; n.id = (dabsdrDecoderId_t)r.c;
         if (r.c == 0 || r.c == 1) h->dec[r.c].active = false;
+        else if (r.c == DABSDR_ID_DATA) for (auto& d : h->data) if (d.active && d.sid == r.a && d.scids == (uint8_t)r.b) d.active = false;
         notify(h, DABSDR_NID_SERVICE_STOP, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
         break; }
     case R_XPAD: {
@@ -347,14 +377,25 @@ void deliver_xpad_dg(dabsdr_s* h, dabsdrDecoderId_t did, Decoder& d, int app, co
 void process_window(dabsdr_s* h)
 {
     // sub-channels to decode: those of the active decoders (none -> FIC only)
-    b200dab_subch_t sc[2];
-    int n_sc = 0, sc_dec[2] = {-1, -1};
+    b200dab_subch_t sc[2 + MAX_DATA_DEC];
+    int n_sc = 0, sc_dec[2 + MAX_DATA_DEC];
+    for (int& x : sc_dec) x = -1;
     for (int k = 0; k < 2; k++)
         if (h->dec[k].active && h->db.subch[h->dec[k].subch_id].valid) {
             sc[n_sc] = h->db.subch[h->dec[k].subch_id].p;
             sc[n_sc].kind = h->dec[k].dabplus ? 1 : 0;
             sc_dec[n_sc++] = k;
         }
+    const int n_audio_sc = n_sc;
+    for (auto& d : h->data) {                                   // packet-mode sub-channels (several components may share one)
+        if (!d.active || !h->db.subch[d.subch_id].valid) continue;
+        bool have = false;
+        for (int i = n_audio_sc; i < n_sc; i++) if (sc[i].subch_id == d.subch_id) have = true;
+        if (have) continue;
+        sc[n_sc] = h->db.subch[d.subch_id].p;
+        sc[n_sc].kind = 0;
+        n_sc++;
+    }
     uint32_t flags = B200DAB_OPT_SYMSTAT | (h->tii_on ? B200DAB_OPT_TII : 0u) | (n_sc == 0 ? B200DAB_OPT_NO_MSC : 0u) |
                      (h->spectrum_on && h->spec_cb ? B200DAB_OPT_SPECTRUM : 0u);
     b200dab_result_t r;
@@ -405,8 +446,29 @@ void process_window(dabsdr_s* h)
     send_sync(h, any_fic || h->sync_level == DABSDR_SYNC_LEVEL_FIC ? DABSDR_SYNC_LEVEL_FIC : DABSDR_SYNC_LEVEL_ON_NULL);
 
     // ---- MSC: logical frame `row` of the window starts at CIF (row) = slot row/4, CIF row%4
-    if (r.frames && n_sc > 0) {
-        for (int i = 0; i < r.n_subch && i < n_sc; i++) {
+    if (r.frames && n_sc > n_audio_sc) {
+        auto abs_row = [&](int row) -> int64_t { const int s = row >> 2; return (s < r.n_slots && slot_no[s] >= 0) ? slot_no[s] * 4 + (row & 3) : -1; };
+        for (auto& d : h->data) {
+            if (!d.active) continue;
+            for (int i = n_audio_sc; i < r.n_subch && i < n_sc; i++) {
+                if (r.subch[i].subch_id != d.subch_id) continue;
+                const int rows = r.frame_rows[i], pitch = r.subch[i].bitrate * 3;
+                for (int row = 0; row < rows; row++) {
+                    const int64_t ar = abs_row(row);
+                    if (ar < 0 || ar <= d.last_row) continue;
+                    d.last_row = ar;
+                    d.as.frame(r.frames[i] + (size_t)row * pitch, pitch, [&](const uint8_t* p, int n) {
+                        if (!h->dg_cb) return;
+                        dabsdrDataGroupCBData_t c;
+                        c.id = DABSDR_ID_DATA; c.SCId = d.scid; c.userAppType = d.ua_type; c.dgLen = (uint16_t)n; c.pDgData = p;
+                        h->dg_cb(&c, h->dg_ctx);
+                    });
+                }
+            }
+        }
+    }
+    if (r.frames && n_audio_sc > 0) {
+        for (int i = 0; i < r.n_subch && i < n_audio_sc; i++) {
             Decoder& d = h->dec[sc_dec[i]];
             const int rows = r.frame_rows[i], pitch = r.subch[i].bitrate * 3;
             auto abs_row = [&](int row) -> int64_t { const int s = row >> 2; return (s < r.n_slots && slot_no[s] >= 0) ? slot_no[s] * 4 + (row & 3) : -1; };

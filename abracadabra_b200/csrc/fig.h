@@ -162,6 +162,7 @@ struct Database {
                     for (auto& e : s.comps)
                         if (e.tmid == nc.tmid && ((nc.tmid == 3 && e.scid == nc.scid) || (nc.tmid != 3 && e.subch_id == nc.subch_id))) {
                             found = true;
+                            if (nc.tmid == 3) nc.ascty_dscty = e.ascty_dscty;          // packet mode: the DSCTy comes from FIG 0/3
                             if (e.ascty_dscty != nc.ascty_dscty || e.ps != nc.ps) { e.ascty_dscty = nc.ascty_dscty; e.ps = nc.ps; e.ca = nc.ca; version++; }
                         }
                     if (!found) { if (nc.ps) nc.scids = 0; s.comps.push_back(nc); version++; }

@@ -152,3 +152,46 @@ struct Decoder {
 };
 
 }  // namespace pad
+
+// Packet mode (EN 300 401 sec. 5.3.2 / 5.3.3): a sub-channel is a sequence of packets of 24 / 48 / 72 / 96 bytes, each with a
+// 3-byte header (length, continuity index, first / last flags, 10-bit address, command flag, useful data length), a data field
+// and a CRC-16; the useful data of the packets of one address between a `first` and a `last` flag form one MSC data group.
+// The reference core hands the complete group (header .. CRC) to dabsdrDataGroupCBFunc_t with id = DABSDR_ID_DATA.
+namespace packet {
+
+struct Assembler {
+    int addr = -1;
+    std::vector<uint8_t> dg;
+    bool on = false;
+    int ci = -1;
+
+    void reset(int address) { addr = address; dg.clear(); on = false; ci = -1; }
+
+    // one logical frame of the sub-channel; on_dg(const uint8_t*, int) per complete data group
+    template <class Fn>
+    void frame(const uint8_t* f, int len, Fn&& on_dg)
+    {
+        int pos = 0;
+        while (pos + 24 <= len) {
+            const uint8_t* p = f + pos;
+            const int plen = 24 * ((p[0] >> 6) + 1);
+            if (pos + plen > len || !pad::crc_ok(p, (size_t)plen)) { pos += 24; continue; }     // damaged: resynchronise on the 24-byte grid
+            pos += plen;
+            const int a = ((p[0] & 3) << 8) | p[1];
+            if (a != addr) continue;                                                           // other component or padding (address 0)
+            const int cix = (p[0] >> 4) & 3, first = (p[0] >> 3) & 1, last = (p[0] >> 2) & 1, useful = p[2] & 0x7F;
+            if (useful > plen - 5) { on = false; continue; }
+            if (first) { dg.clear(); on = true; }
+            else if (!on || cix != ((ci + 1) & 3)) { on = false; ci = cix; continue; }           // a packet of this group was lost
+            ci = cix;
+            dg.insert(dg.end(), p + 3, p + 3 + useful);
+            if (last) {
+                const bool has_crc = !dg.empty() && (dg[0] & 0x40);
+                if (dg.size() >= 2 && (!has_crc || pad::crc_ok(dg.data(), dg.size()))) on_dg(dg.data(), (int)dg.size());
+                on = false;
+            }
+        }
+    }
+};
+
+}  // namespace packet

@@ -105,6 +105,7 @@ def lib():
         L.b200dab_pad_reset.argtypes = [vp]
         L.b200dab_pad_feed_au.argtypes = [vp, vp, i32, PAD_CB, vp]
         L.b200dab_pad_feed_mp2.argtypes = [vp, vp, i32, PAD_CB, vp]
+        L.b200dab_pad_feed_packets.argtypes = [vp, i32, vp, i32, PAD_CB, vp]
         L.b200dab_decode.argtypes = [vp, vp, u64, i32, i32, ct.POINTER(SubCh), i32, ct.c_uint32, ct.POINTER(Result)]
         L.b200dab_set_profiling.argtypes = [vp, i32]
         L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
@@ -123,7 +124,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -177,6 +178,11 @@ class PadDecoder:
     def feed_mp2(self, frame: bytes) -> bool:
         buf = (ct.c_uint8 * len(frame)).from_buffer_copy(frame)
         return bool(lib().b200dab_pad_feed_mp2(self._h, buf, len(frame), self._cb, None))
+
+    def feed_packets(self, addr: int, frame: bytes) -> bool:
+        """one logical frame of a packet-mode sub-channel; complete data groups of `addr` come out with kind -1"""
+        buf = (ct.c_uint8 * len(frame)).from_buffer_copy(frame)
+        return bool(lib().b200dab_pad_feed_packets(self._h, addr, buf, len(frame), self._cb, None))
 
     def close(self):
         if self._h:

@@ -22,12 +22,13 @@ from . import dabconst as C
 class SubChannel:
     subchid: int
     start_cu: int
-    kind: str                     # 'dabplus' | 'mp2' | 'data'
+    kind: str                     # 'dabplus' | 'mp2' | 'data' (random bytes) | 'packet' (packet mode, see packet_frames)
     bitrate: int                  # kbit/s
     prot: Tuple                   # ('EEP', level 1..4, 'A'|'B')  or ('UEP', table index 0..63)
     seed: int = 0
     dls: Optional[List[str]] = None       # dynamic label messages carried in the X-PAD of a DAB+ sub-channel (cycled)
     xpad_dg: Optional[List[bytes]] = None  # MSC data groups (incl. CRC) carried as X-PAD application 12/13 (MOT), cycled
+    packets: Optional[List[Tuple[int, List[bytes]]]] = None   # packet mode: [(packet address, [MSC data groups, cycled])]
 
     def profile(self):
         if self.prot[0] == "EEP":
@@ -47,11 +48,24 @@ class SubChannel:
 
 
 @dataclass
+class DataComponent:
+    """Secondary service component in packet mode (TMId 3): FIG 0/2 + 0/3 + 0/8 + 0/13"""
+    subchid: int
+    scid: int                     # 12-bit service component identifier
+    scids: int                    # identifier within the service (>= 1)
+    packet_addr: int              # 10 bit
+    dscty: int = 60               # 60 = MOT
+    dg_flag: int = 0              # 0 = MSC data groups are used
+    user_apps: Optional[List[Tuple[int, bytes]]] = None
+
+
+@dataclass
 class Service:
     sid: int
     label: str
     subchid: int
     user_apps: Optional[List[Tuple[int, bytes]]] = None   # FIG 0/13: (user application type, user application data)
+    data_comps: Optional[List[DataComponent]] = None
 
 
 @dataclass
@@ -424,6 +438,59 @@ def mp2_frames(sc: SubChannel, n: int, rng: np.random.Generator, valid_crc: bool
     return frames
 
 
+# ---------------------------------------------------------------------------- packet mode (EN 300 401 sec. 5.3.2, 5.3.3)
+PACKET_LEN = (24, 48, 72, 96)
+
+
+def make_packet(plen_code: int, ci: int, first: bool, last: bool, addr: int, data: bytes, command: int = 0) -> bytes:
+    n = PACKET_LEN[plen_code]
+    assert len(data) <= n - 5
+    hdr = bytes([(plen_code << 6) | ((ci & 3) << 4) | (first << 3) | (last << 2) | ((addr >> 8) & 3), addr & 0xFF,
+                 (command << 7) | len(data)])
+    body = hdr + data.ljust(n - 5, b"\x00")
+    crc = int(crc16_np(np.frombuffer(body, np.uint8)[None, :])[0])
+    return body + bytes([crc >> 8, crc & 0xFF])
+
+
+def packet_frames(sc: SubChannel, n: int, rng: np.random.Generator) -> np.ndarray:
+    """Logical frames of a packet-mode sub-channel: the data groups of every address are cut into packets of all four
+    lengths (cycling through a few frame layouts), interleaved address by address, with padding packets (address 0)."""
+    fb = sc.frame_bytes
+    layouts = [[0, 0, 1], [3], [2, 0], [1, 1], [0, 0, 0, 0]]            # packet length codes filling 96 bytes
+    assert fb % 96 == 0
+    state = []                                                         # per address: [addr, groups, next group, offset, ci]
+    for addr, groups in sc.packets or []:
+        state.append([addr, groups, 0, 0, 0])
+    sent = []
+    frames = np.zeros((n, fb), np.uint8)
+    turn = 0
+    for f in range(n):
+        out = b""
+        while len(out) < fb:
+            for code in layouts[(f + len(out) // 96) % len(layouts)]:
+                plen = PACKET_LEN[code]
+                if not state or (turn % 5) == 4:                       # padding packet
+                    out += make_packet(code, 0, True, True, 0, b"")
+                    turn += 1
+                    continue
+                st = state[turn % len(state)] if len(state) > 1 else state[0]
+                turn += 1
+                addr, groups, gi, off, ci = st
+                dg = groups[gi % len(groups)]
+                piece = dg[off:off + plen - 5]
+                first, last = off == 0, off + len(piece) >= len(dg)
+                out += make_packet(code, ci, first, last, addr, piece)
+                st[4] = (ci + 1) & 3
+                if last:
+                    sent.append((addr, dg))
+                    st[2], st[3] = gi + 1, 0
+                else:
+                    st[3] = off + len(piece)
+        frames[f] = np.frombuffer(out[:fb], np.uint8)
+    sc._packets_sent = sent
+    return frames
+
+
 # ============================================================================ FIC
 def _fig(type_: int, body: bytes) -> bytes:
     assert len(body) <= 29
@@ -448,7 +515,26 @@ def fig0_1_entry(sc: SubChannel) -> bytes:
 def fig0_2_entry(ens: EnsembleConfig, sv: Service) -> bytes:
     sc = next(s for s in ens.subchannels if s.subchid == sv.subchid)
     ascty = 63 if sc.kind == "dabplus" else 0
-    return bytes([sv.sid >> 8, sv.sid & 0xFF, 0x01, (0 << 6) | ascty, (sc.subchid << 2) | 0x02])
+    comps = bytes([(0 << 6) | ascty, (sc.subchid << 2) | 0x02])
+    for dc in sv.data_comps or []:
+        comps += bytes([(3 << 6) | (dc.scid >> 6), ((dc.scid & 0x3F) << 2)])          # TMId 3, secondary, no CA
+    return bytes([sv.sid >> 8, sv.sid & 0xFF, 1 + len(sv.data_comps or [])]) + comps
+
+
+def fig0_3_entry(dc: DataComponent) -> bytes:
+    return bytes([dc.scid >> 4, (dc.scid & 0xF) << 4, (dc.dg_flag << 7) | dc.dscty, (dc.subchid << 2) | (dc.packet_addr >> 8),
+                  dc.packet_addr & 0xFF])
+
+
+def fig0_8_entry(sv: Service, dc: DataComponent) -> bytes:
+    return bytes([sv.sid >> 8, sv.sid & 0xFF, dc.scids & 0x0F, 0x80 | (dc.scid >> 8), dc.scid & 0xFF])
+
+
+def fig0_13_entry_data(sv: Service, dc: DataComponent) -> bytes:
+    b = bytes([sv.sid >> 8, sv.sid & 0xFF, (dc.scids << 4) | len(dc.user_apps)])
+    for ua_type, data in dc.user_apps:
+        b += bytes([(ua_type >> 3) & 0xFF, ((ua_type & 7) << 5) | len(data)]) + data
+    return b
 
 
 def fig0_13_entry(sv: Service) -> bytes:
@@ -500,7 +586,10 @@ class FicBuilder:
         self.e02 = [fig0_2_entry(ens, sv) for sv in ens.services]
         self.labels = [fig1(0, ens.eid, ens.label)] + [fig1(1, sv.sid, sv.label) for sv in ens.services]
         self.e13 = [fig0_13_entry(sv) for sv in ens.services if sv.user_apps]
-        self.i01 = self.i02 = self.ilab = self.i13 = 0
+        self.e13 += [fig0_13_entry_data(sv, dc) for sv in ens.services for dc in (sv.data_comps or []) if dc.user_apps]
+        self.e03 = [fig0_3_entry(dc) for sv in ens.services for dc in (sv.data_comps or [])]
+        self.e08 = [fig0_8_entry(sv, dc) for sv in ens.services for dc in (sv.data_comps or [])]
+        self.i01 = self.i02 = self.ilab = self.i13 = self.i03 = self.i08 = 0
 
     def cif_fibs(self, cif_count: int) -> bytes:
         """Three FIBs (96 bytes) for one CIF."""
@@ -508,6 +597,10 @@ class FicBuilder:
         f13 = b""
         if self.e13 and cif_count % 2 == 0:
             f13, self.i13 = _pack_rotating(self.e13, 0x0D, 14, self.i13)
+        elif self.e03 and cif_count % 2 == 1:                       # packet-mode components: FIG 0/3 + FIG 0/8 on the odd CIFs
+            f03, self.i03 = _pack_rotating(self.e03, 0x03, 7, self.i03)
+            f08, self.i08 = _pack_rotating(self.e08, 0x08, 7, self.i08)
+            f13 = f03 + f08
         f01, self.i01 = _pack_rotating(self.e01, 0x01, 30 - len(f00) - len(f13), self.i01)
         fib0 = make_fib(f00 + f13 + f01)
         f02, self.i02 = _pack_rotating(self.e02, 0x02, 30, self.i02)
@@ -561,6 +654,8 @@ def build_cif_bits(ens: EnsembleConfig, n_cif: int, seed: int):
             sfs[sc.subchid] = sf
         elif sc.kind == "mp2":
             frames = mp2_frames(sc, n_cif, srng)
+        elif sc.kind == "packet":
+            frames = packet_frames(sc, n_cif, srng)
         else:
             frames = srng.integers(0, 256, (n_cif, sc.frame_bytes), dtype=np.uint8)
         logical[sc.subchid] = frames

@@ -146,6 +146,9 @@ B200DAB_API b200dab_pad *b200dab_pad_create(void);
 B200DAB_API void b200dab_pad_destroy(b200dab_pad *p);
 B200DAB_API void b200dab_pad_reset(b200dab_pad *p);
 B200DAB_API int b200dab_pad_feed_au(b200dab_pad *p, const uint8_t *au, int len, b200dab_pad_cb cb, void *user);   /* 1 = AU carried PAD */
+/* one logical frame of a packet-mode sub-channel (EN 300 401 sec. 5.3.2): complete MSC data groups of packet address `addr`
+ * are reported with kind -1 */
+B200DAB_API int b200dab_pad_feed_packets(b200dab_pad *p, int addr, const uint8_t *frame, int len, b200dab_pad_cb cb, void *user);
 B200DAB_API int b200dab_pad_feed_mp2(b200dab_pad *p, const uint8_t *frame, int len, b200dab_pad_cb cb, void *user); /* DAB (MPEG Layer II) frame */
 
 /* Whole hot path over one recording (or chunk): sync -> FFT -> DQPSK -> de-interleave -> Viterbi -> FIB CRC ->

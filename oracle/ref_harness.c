@@ -52,6 +52,7 @@ typedef struct ev_s {
     uint32_t sids[64]; int nsids;                     /* SERVICE_LIST shadow (accessor only valid inside the callback) */
     uint32_t sc_sid; int sc_n, sc_addr0, sc_scids0;   /* SERVICE_COMPONENT_LIST shadow */
     uint8_t xpad_apps[8]; int n_xpad_apps;            /* USER_APP_LIST shadow: X-PAD application types */
+    int n_pkt; int pkt_scids[8]; int pkt_addr[8];     /* packet-mode components of the SERVICE_COMPONENT_LIST */
 } ev_t;
 
 static pthread_mutex_t g_mx = PTHREAD_MUTEX_INITIALIZER;
@@ -256,11 +257,15 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
                 dabsdrServiceCompListItem_t it; memset(&it, 0, sizeof it);
                 l->getServiceComponentListItem(g_h, i, &it);
                 if (i == 0) { e->sc_addr0 = it.SubChAddr; e->sc_scids0 = it.SCIdS; }
+                if (it.TMId == 3 && e->n_pkt < 8) { e->pkt_scids[e->n_pkt] = it.SCIdS; e->pkt_addr[e->n_pkt] = it.packetData.packetAddress; e->n_pkt++; }
                 e->sc_sid = l->SId; e->sc_n = l->numServiceComponents;
                 fprintf(g_log, "%s{\"scids\":%u,\"subchid\":%u,\"addr\":%d,\"size\":%u,\"prot\":%u,\"uep_fec\":%u,\"ps\":%u,\"lang\":%u,\"ca\":%u,\"tmid\":%u,\"ascty\":%u,\"bitrate\":%u,\"numUA\":%u,",
                         i ? "," : "", it.SCIdS, it.SubChId, it.SubChAddr, it.SubChSize, it.protectionLevel, it.uepIdx, it.ps, it.lang,
                         it.CAflag, it.TMId, it.streamAudio.ASCTy, it.streamAudio.bitRate, it.numUserApps);
                 log_label(g_log, &it.label);
+                if (it.TMId == 3)
+                    fprintf(g_log, ",\"dscty\":%u,\"scid\":%u,\"dg\":%u,\"paddr\":%d", it.packetData.DSCTy, it.packetData.SCId, it.packetData.DGflag,
+                            it.packetData.packetAddress);
                 fprintf(g_log, "}");
             }
             fprintf(g_log, "]}\n");
@@ -304,6 +309,7 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
 
 /* ------------------------------------------------------------------ main-thread protocol (mirrors RadioControl) */
 static uint32_t g_freq = 227360;
+static int g_data_scids = -1, g_selected_data;   /* SCIdS of a packet-mode component to start on the data decoder */
 static int g_xpad_apps;                 /* ask for the user application list and start the X-PAD applications */
 static int g_want_service_idx = -1;     /* index into the service list, -1 = none */
 static int g_want_second_idx = -1;
@@ -406,6 +412,16 @@ static void handle_event(ev_t *e)
                 if (want1) g_selected = 1; else g_selected2 = 1;
             } else { g_retry_sid = e->sc_sid; g_retry_ticks = 2; }
         }
+        /* secondary packet-mode data component: started like RadioControl does (src/radiocontrol.cpp:638) once its packet address
+         * is known (re-request while it is negative, :1494) */
+        if (g_data_scids >= 0 && want1 && !g_selected_data) {
+            int found = 0;
+            for (int i = 0; i < e->n_pkt; i++) if (e->pkt_scids[i] == g_data_scids) {
+                found = 1;
+                if (e->pkt_addr[i] >= 0) { dabsdrRequest_ServiceSelection(g_h, e->sc_sid, (uint8_t)g_data_scids, DABSDR_ID_DATA); g_selected_data = 1; }
+            }
+            if (!g_selected_data && (found || e->n_pkt == 0)) { g_retry_sid = e->sc_sid; g_retry_ticks = 2; }
+        }
         break; }
     case DABSDR_NID_SERVICE_SELECTION: {
         /* reference: after a successful audio selection RadioControl asks for the user applications of the component
@@ -444,6 +460,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--no-au-data")) g_log_au_data = 0;
         else if (!strcmp(argv[i], "--free-run")) g_free_run = 1;
         else if (!strcmp(argv[i], "--xpad-apps")) g_xpad_apps = 1;
+        else if (!strcmp(argv[i], "--data-scids") && i + 1 < argc) g_data_scids = atoi(argv[++i]);
     }
     int fd = open(path, O_RDONLY);
     if (fd < 0) { perror(path); return 1; }

@@ -33,7 +33,8 @@ def main():
             path = Path(td) / f"{name}.{spec['fmt']}"
             raw.tofile(path)
             summ, ev = orc.run_ref(path, spec["fmt"], Path(td) / "log.jsonl", tii=spec.get("tii_mode"), service=spec.get("service"),
-                                   extra=["--xpad-apps"] if spec.get("xpad_apps") else ())
+                                   extra=(["--xpad-apps"] if spec.get("xpad_apps") else []) +
+                                         (["--data-scids", str(spec["data_scids"])] if spec.get("data_scids") is not None else []))
         out = {"spec": spec, "raw_sha1": hashlib.sha1(raw.tobytes()).hexdigest(), "summary": summ, "events": []}
         for e in ev:
             if e["ev"] == "audio":

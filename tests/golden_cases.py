@@ -31,6 +31,9 @@ CASES = {
     # DAB (MPEG Layer II) service with a dynamic label in the PAD at the end of every audio frame
     "mp2_dls_u8_30db": dict(kind="mp2pad", n_frames=30, fmt="u8", snr=30.0, cfo=50.0, seed=2, tii=[], tii_mode=None, service=0,
                             dls=["MP2 dynamic label text, long enough for two segments", "short"]),
+    # secondary packet-mode component (TMId 3, FIG 0/2 + 0/3 + 0/8 + 0/13) next to the audio: MSC data groups on the data decoder
+    "c1_packet_u8_30db": dict(kind="config1", n_frames=40, fmt="u8", snr=30.0, cfo=100.0, seed=5, tii=[], tii_mode=None, service=0,
+                              packet=dict(subchid=7, start_cu=80, scid=0x123, scids=1, addr=5, other_addr=9, n_dg=4), data_scids=1),
 }
 
 
@@ -52,6 +55,12 @@ def build_case(spec):
         ens.tii = [synth.TiiTx(m, s, a, delay=d) for m, s, a, d in spec["tii"]]
         if spec.get("dls"):
             ens.subchannels[0].dls = list(spec["dls"])
+        if spec.get("packet"):
+            pk = spec["packet"]
+            dgs = mot_data_groups(pk["n_dg"], seed=11)
+            ens.subchannels.append(synth.SubChannel(pk["subchid"], pk["start_cu"], "packet", 32, ("EEP", 3, "A"), seed=1,
+                                                    packets=[(pk["addr"], dgs), (pk["other_addr"], dgs[:2])]))
+            ens.services[0].data_comps = [synth.DataComponent(pk["subchid"], pk["scid"], pk["scids"], pk["addr"], user_apps=[(2, b"")])]
         if spec.get("xpad_dg"):
             ens.subchannels[0].xpad_dg = mot_data_groups(spec["xpad_dg"])
             ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]       # SlideShow over X-PAD application 12, DSCTy 60 (MOT)

@@ -186,3 +186,32 @@ def test_dropin_mp2_dynamic_label_against_reference():
     per = [e for e in ev if e["ev"] == "periodic" and e.get("crcOk")]
     assert per and all(e["padBytes"] == 21 * e["crcOk"] for e in per)
     assert all(e["padBytes"] == 21 * e["crcOk"] for e in g["events"] if e["ev"] == "periodic" and e.get("crcOk"))
+
+
+def test_dropin_packet_mode_data_service_against_reference():
+    """Secondary packet-mode component on DABSDR_ID_DATA: component list entry, selection answer and the MSC data groups
+    (id -1, SCId, user application type, bytes incl. CRC, order) equal the reference's; the audio keeps flowing"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("c1_packet_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "p.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12", "--data-scids", "1"])
+
+    def one(events, kind):
+        return [e for e in events if e["ev"] == kind]
+    me, rf = one(ev, "sc_list")[0], one(g["events"], "sc_list")[0]
+    assert me["n"] == rf["n"] == 2 and me["items"] == rf["items"]
+    sel_m = [(e["status"], e["sid"], e["scids"], e["id"]) for e in one(ev, "selection")]
+    sel_r = [(e["status"], e["sid"], e["scids"], e["id"]) for e in one(g["events"], "selection")]
+    assert sorted(sel_m) == sorted(sel_r) == [(0, 0x1001, 0, 0), (0, 0x1001, 1, -1)]
+    mine = [(e["id"], e["scid"], e["uatype"], e["len"], e["data"]) for e in one(ev, "dg")]
+    ref = [(e["id"], e["scid"], e["uatype"], e["len"], e["data"]) for e in one(g["events"], "dg")]
+    assert len(mine) >= 50 and len(ref) >= 50
+    common = set(mine) & set(ref)
+    i0 = next(i for i, x in enumerate(mine) if x in common)
+    j0 = ref.index(mine[i0])
+    n = min(len(mine) - i0, len(ref) - j0)
+    assert n >= 50 and mine[i0:i0 + n] == ref[j0:j0 + n]
+    assert len(one(ev, "audio")) >= 60

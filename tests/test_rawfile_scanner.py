@@ -176,3 +176,39 @@ def test_xpad_dynamic_label_and_data_groups():
     assert len(ref2) >= 40 and mine2[i0:i0 + len(ref2)] == ref2
     assert pipeline.dynamic_label_text(mine2)[:2] == list(g2["spec"]["dls"])
     dec3.close()
+
+
+def test_packet_mode_data_groups():
+    """Packet mode (csrc/pad.h packet::Assembler) against the modulator's packet stream and the reference core's data group
+    callbacks (tests/golden/c1_packet_u8_30db.json.gz)"""
+    import golden_cases as gc
+    g = gc.load_golden("c1_packet_u8_30db")
+    pk = g["spec"]["packet"]
+    _, res = gc.build_case(g["spec"])
+    sc = [s for s in res.ens.subchannels if s.kind == "packet"][0]
+    frames = res.logical[pk["subchid"]]
+    for addr in (pk["addr"], pk["other_addr"]):
+        dec = pipeline.PadDecoder()
+        for fr in frames:
+            dec.feed_packets(addr, bytes(fr))
+        sent = [d for a, d in sc._packets_sent if a == addr]
+        got = [d for k, d in dec.out]
+        assert len(got) >= 20 and all(k == -1 for k, _ in dec.out) and got == sent[:len(got)] and len(sent) - len(got) <= 1
+        dec.close()
+    ref = [e for e in g["events"] if e["ev"] == "dg"]
+    assert len(ref) >= 50 and all(e["id"] == -1 and e["scid"] == pk["scid"] and e["uatype"] == 2 for e in ref)
+    mine = [d.hex() for a, d in sc._packets_sent if a == pk["addr"]]
+    i0 = mine.index(ref[0]["data"])
+    assert [e["data"] for e in ref] == mine[i0:i0 + len(ref)]
+    # a damaged packet drops its data group only; the following groups come through
+    dec = pipeline.PadDecoder()
+    bad = frames.copy()
+    bad[3, 5] ^= 0x10
+    for fr in bad:
+        dec.feed_packets(pk["addr"], bytes(fr))
+    got = [d.hex() for k, d in dec.out]
+    assert len(mine) - 3 <= len(got) < len(mine) and set(got) <= set(mine)
+    dec.close()
+    # the component list of the reference shows the packet-mode component as the FIGs describe it
+    scl = [e for e in g["events"] if e["ev"] == "sc_list"][0]["items"]
+    assert scl[1]["tmid"] == 3 and scl[1]["scid"] == pk["scid"] and scl[1]["paddr"] == pk["addr"] and scl[1]["dscty"] == 60 and scl[1]["subchid"] == pk["subchid"]
