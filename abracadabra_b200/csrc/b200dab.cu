@@ -79,6 +79,7 @@ struct b200dab_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int launches = 0;
+    cudaEvent_t ev_msc = nullptr, ev_d2h = nullptr;   // ordering of the split device-to-host copy of the logical frames
     size_t vit_dsmem = 14 * 1024;  // extra dynamic shared memory per k_viterbi CTA: caps residency at 11 one-warp CTAs per SM, so the
                                    // shorter work items are dealt out as the long ones finish (tools/vit_residency.py sweeps this)
     // constant tables on the device
@@ -86,6 +87,14 @@ struct b200dab_ctx {
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
     DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out;
+    struct VitTables {              // device-resident job / group / step tables of one call site, kept between calls
+        bool valid = false;
+        std::vector<VitJob> jobs_in;
+        std::vector<uint32_t> stepinfo;
+        size_t n_groups = 0, words = 0;
+        int max_steps = 0;
+        DevBuf d_jobs, d_groups, d_stepinfo;
+    } vit_tables[2];
     DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
     DevBuf d_tmp_a, d_tmp_b, d_spec;
     HostBuf h_spec;
@@ -383,50 +392,60 @@ int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len
 // jobs_in: vin_off/dec_off are filled here; out_off, row0, ... by the caller.  Soft bits are read from d_soft.
 int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out)
 {
-    std::vector<VitJob> jobs = jobs_in;
-    std::vector<VitGroup> groups;
-    size_t words = 0;
-    int max_steps = 0;
-    for (size_t j = 0; j < jobs.size(); j++) {
-        const int ng = (jobs[j].n_rows + 31) / 32;
-        jobs[j].vin_off = (long long)words;
-        jobs[j].dec_off = (long long)words;
-        words += (size_t)ng * 32 * jobs[j].steps;
-        for (int g = 0; g < ng; g++) groups.push_back(VitGroup{(int)j, g});
-        max_steps = std::max(max_steps, jobs[j].steps);
+    const int st = jobs_in[0].kind == 0 ? 0 : 1;              // [0] FIC, [1] MSC: each call site owns its tables
+    VitTables& vt = vit_tables[st];
+    // The job / group / step tables only depend on the sub-channel organisation and the number of CIFs: when they equal those of
+    // the previous call (every window of a stream, every recording of one multiplex) what is already on the device is reused.
+    const bool same = vt.valid && vt.jobs_in.size() == jobs_in.size() && vt.stepinfo.size() == stepinfo.size() &&
+                      !memcmp(vt.jobs_in.data(), jobs_in.data(), jobs_in.size() * sizeof(VitJob)) &&
+                      !memcmp(vt.stepinfo.data(), stepinfo.data(), stepinfo.size() * 4);
+    if (!same) {
+        vt.valid = false;
+        std::vector<VitJob> jobs = jobs_in;
+        std::vector<VitGroup> groups;
+        size_t words = 0;
+        int max_steps = 0;
+        for (size_t j = 0; j < jobs.size(); j++) {
+            const int ng = (jobs[j].n_rows + 31) / 32;
+            jobs[j].vin_off = (long long)words;
+            jobs[j].dec_off = (long long)words;
+            words += (size_t)ng * 32 * jobs[j].steps;
+            for (int g = 0; g < ng; g++) groups.push_back(VitGroup{(int)j, g});
+            max_steps = std::max(max_steps, jobs[j].steps);
+        }
+        vt.n_groups = groups.size(); vt.words = words; vt.max_steps = max_steps;
+        if (groups.empty()) return 0;
+        std::stable_sort(groups.begin(), groups.end(), [&](const VitGroup& a, const VitGroup& b) { return jobs[a.job].steps > jobs[b.job].steps; });
+        // small tables go through pinned staging owned by the context (one set per call site), so no stream sync is needed here
+        CK(h_jobs[st].ensure(jobs.size() * sizeof(VitJob) + 16));
+        CK(h_groups[st].ensure(groups.size() * sizeof(VitGroup) + 16));
+        CK(h_stepinfo[st].ensure(stepinfo.size() * 4 + 16));
+        CK(vt.d_jobs.ensure(jobs.size() * sizeof(VitJob) + 16));
+        CK(vt.d_groups.ensure(groups.size() * sizeof(VitGroup) + 16));
+        CK(vt.d_stepinfo.ensure(stepinfo.size() * 4 + 16));
+        memcpy(h_jobs[st].p, jobs.data(), jobs.size() * sizeof(VitJob));
+        memcpy(h_groups[st].p, groups.data(), groups.size() * sizeof(VitGroup));
+        memcpy(h_stepinfo[st].p, stepinfo.data(), stepinfo.size() * 4);
+        if (fetch(vt.d_jobs.p, h_jobs[st].p, jobs.size() * sizeof(VitJob)) || fetch(vt.d_groups.p, h_groups[st].p, groups.size() * sizeof(VitGroup)) ||
+            fetch(vt.d_stepinfo.p, h_stepinfo[st].p, stepinfo.size() * 4)) { set_error("k_fetch launch failed"); return -1; }
+        vt.jobs_in = jobs_in; vt.stepinfo = stepinfo; vt.valid = true;
     }
-    if (groups.empty()) return 0;
-    std::stable_sort(groups.begin(), groups.end(), [&](const VitGroup& a, const VitGroup& b) { return jobs[a.job].steps > jobs[b.job].steps; });
-    CK(d_jobs.ensure(jobs.size() * sizeof(VitJob)));
-    CK(d_groups.ensure(groups.size() * sizeof(VitGroup)));
-    CK(d_stepinfo.ensure(stepinfo.size() * 4));
-    CK(d_vin.ensure(words * 4));
-    CK(d_dec.ensure(words * 8));
-    // small tables go through pinned staging owned by the context (one set per call site), so no stream sync is needed here
-    const int st = jobs[0].kind == 0 ? 0 : 1;
-    CK(h_jobs[st].ensure(jobs.size() * sizeof(VitJob) + 16));
-    CK(h_groups[st].ensure(groups.size() * sizeof(VitGroup) + 16));
-    CK(h_stepinfo[st].ensure(stepinfo.size() * 4 + 16));
-    CK(d_jobs.ensure(jobs.size() * sizeof(VitJob) + 16));
-    CK(d_groups.ensure(groups.size() * sizeof(VitGroup) + 16));
-    CK(d_stepinfo.ensure(stepinfo.size() * 4 + 16));
-    memcpy(h_jobs[st].p, jobs.data(), jobs.size() * sizeof(VitJob));
-    memcpy(h_groups[st].p, groups.data(), groups.size() * sizeof(VitGroup));
-    memcpy(h_stepinfo[st].p, stepinfo.data(), stepinfo.size() * 4);
-    if (fetch(d_jobs.p, h_jobs[st].p, jobs.size() * sizeof(VitJob)) || fetch(d_groups.p, h_groups[st].p, groups.size() * sizeof(VitGroup)) ||
-        fetch(d_stepinfo.p, h_stepinfo[st].p, stepinfo.size() * 4)) { set_error("k_fetch launch failed"); return -1; }
-    dim3 ggrid((unsigned)groups.size(), (unsigned)((max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
-    prof_begin(jobs[0].kind == 0 ? "k_gather(fic)" : "k_gather(msc)");
-    k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(), d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
+    if (vt.n_groups == 0) return 0;
+    const size_t n_groups = vt.n_groups;
+    CK(d_vin.ensure(vt.words * 4));
+    CK(d_dec.ensure(vt.words * 8));
+    CK(d_meet.ensure(n_groups * VIT_MEET_WORDS * sizeof(unsigned short)));
+    const VitJob* dj = vt.d_jobs.as<VitJob>();
+    const VitGroup* dg = vt.d_groups.as<VitGroup>();
+    dim3 ggrid((unsigned)n_groups, (unsigned)((vt.max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
+    prof_begin(st == 0 ? "k_gather(fic)" : "k_gather(msc)");
+    k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), dj, dg, vt.d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
-    CK(d_meet.ensure(groups.size() * VIT_MEET_WORDS * sizeof(unsigned short)));
-    prof_begin(jobs[0].kind == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
-    k_viterbi<<<(unsigned)groups.size() * 4, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(),
-                                                                   d_jobs.as<VitJob>(), d_groups.as<VitGroup>());
+    prof_begin(st == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
+    k_viterbi<<<(unsigned)n_groups * 4, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg);
     prof_end();
-    prof_begin(jobs[0].kind == 0 ? "k_vit_trace(fic)" : "k_vit_trace(msc)");
-    k_vit_trace<<<(unsigned)groups.size(), 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
-                                                         d_prbs_w.as<uint32_t>(), d_out);
+    prof_begin(st == 0 ? "k_vit_trace(fic)" : "k_vit_trace(msc)");
+    k_vit_trace<<<(unsigned)n_groups, 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out);
     prof_end();
     launches += 3;
     CK(cudaGetLastError());
@@ -640,13 +659,15 @@ void b200dab_destroy(b200dab_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
-                    &ctx->d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
+                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
                      &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
@@ -860,6 +881,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     }
     res->n_subch = (int)ctx->r_subch.size();
     res->subch = ctx->r_subch.data();
+    TRACE("sub-channels known");
     // ---- MSC
     std::vector<size_t> out_off;
     size_t msc_bytes = 0;
@@ -869,6 +891,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     int total_sf = 0, total_rows = 0;
     if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
         if (ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes)) return -1;
+        TRACE("msc submitted");
         for (size_t i = 0; i < ctx->r_subch.size(); i++) {
             if (ctx->r_subch[i].kind != 1) continue;
             DabPlusJob j;
@@ -877,9 +900,36 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             total_sf += j.max_sf; total_rows += n_rows;
             dpjobs.push_back(j); dp_subch.push_back((int)i);
         }
-        if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows)) return -1;
+        // The logical frames of the DAB (MP2) and data sub-channels are final once the trace kernel has run: their copy to the host
+        // goes to the copy stream and runs under the DAB+ kernels (fire code, RS, AU CRC); the DAB+ sub-channels follow on the
+        // main stream after the RS correction.  Adjacent sub-channels of the same class are copied in one piece.
         CKC(ctx->h_msc.ensure(msc_bytes + 64));
-        CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!ctx->copy_stream) CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        if (!ctx->ev_msc) { CKC(cudaEventCreateWithFlags(&ctx->ev_msc, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming)); }
+        auto copy_class = [&](bool dabplus_class, cudaStream_t st) -> int {
+            const size_t n = ctx->r_subch.size();
+            for (size_t i = 0; i < n;) {
+                if ((ctx->r_subch[i].kind == 1) != dabplus_class) { i++; continue; }
+                size_t j = i;
+                while (j + 1 < n && (ctx->r_subch[j + 1].kind == 1) == dabplus_class) j++;
+                const size_t a = out_off[i], b = (j + 1 < n) ? out_off[j + 1] : msc_bytes;
+                CKC(cudaMemcpyAsync((uint8_t*)ctx->h_msc.p + a, (const uint8_t*)ctx->d_msc_out.p + a, b - a, cudaMemcpyDeviceToHost, st));
+                i = j + 1;
+            }
+            return 0;
+        };
+        const bool split = !dpjobs.empty();
+        if (split) {
+            CKC(cudaEventRecord(ctx->ev_msc, ctx->stream));
+            CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_msc, 0));
+            if (copy_class(false, ctx->copy_stream)) return -1;
+            CKC(cudaEventRecord(ctx->ev_d2h, ctx->copy_stream));
+        }
+        if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows)) return -1;
+        if (split) {
+            if (copy_class(true, ctx->stream)) return -1;
+            CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));
+        } else CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (total_sf > 0) {
             CKC(ctx->h_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
             CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
@@ -938,6 +988,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         for (size_t i = 0; i < ctx->r_subch.size(); i++) { ctx->r_frames.push_back(ctx->h_msc.as<uint8_t>() + out_off[i]); ctx->r_rows.push_back(n_rows); }
         res->frames = ctx->r_frames.data(); res->frame_rows = ctx->r_rows.data();
         const SfInfo* sf = ctx->h_sf.as<SfInfo>();
+        ctx->r_aus.reserve((size_t)total_sf * 6);
         for (size_t k = 0; k < dpjobs.size(); k++) {
             const DabPlusJob& j = dpjobs[k];
             for (int m = 0; m < j.max_sf; m++) {
