@@ -43,7 +43,7 @@ __device__ __forceinline__ void fft_pass_d_scatter(const float2* __restrict__ wo
 
 // fdi_inv[p] = QPSK symbol index of the FFT output at logical position p of the digit-reversed result (0xffff = unused bin)
 template <int FMT>
-__global__ void __launch_bounds__(256, 2) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+__global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
                                                     const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_inv,
                                                     int8_t* __restrict__ soft, float* __restrict__ symstat)
 {
