@@ -173,19 +173,31 @@ __device__ __forceinline__ void fft_plan_init(FftPlan& pl, const float2* __restr
         pl.twC[k - 1] = __ldg(tw + (((t & 3) * k) << 6));
     }
 }
-// passes A, B, C only: the caller finishes with its own radix-4 pass over the quadruples at pD0 / pD1
-__device__ __forceinline__ void fft2048_planned_abc(float2* __restrict__ buf, const FftPlan& pl)
+// passes A, B, C only: the caller finishes with its own radix-4 pass over the quadruples at pD0 / pD1.
+// _regs variant: the thread already holds its eight pass-A inputs x[t + 256 r] (they are exactly the samples it loaded), so the
+// input never goes through shared memory; the caller guarantees that nobody still reads `buf` (a barrier since the last use).
+__device__ __forceinline__ void fft2048_planned_bc(float2* __restrict__ buf, const FftPlan& pl);
+__device__ __forceinline__ void fft2048_planned_abc_regs(float2* __restrict__ buf, const FftPlan& pl, float2 (&v)[8])
 {
-    float2 v[8];
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = buf[pl.pA + 288 * r];
     radix8(v);
 #pragma unroll
     for (int k = 1; k < 8; k++) v[k] = cmul(v[k], pl.twA[k - 1]);
 #pragma unroll
     for (int k = 0; k < 8; k++) buf[pl.pA + 288 * k] = v[k];
     __syncthreads();
+    fft2048_planned_bc(buf, pl);
+}
+__device__ __forceinline__ void fft2048_planned_abc(float2* __restrict__ buf, const FftPlan& pl)
+{
+    float2 v[8];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = buf[pl.pA + 288 * r];
+    fft2048_planned_abc_regs(buf, pl, v);
+}
+__device__ __forceinline__ void fft2048_planned_bc(float2* __restrict__ buf, const FftPlan& pl)
+{
+    float2 v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = buf[pl.pB + 36 * i];
     radix8(v);
@@ -273,6 +285,25 @@ __device__ __forceinline__ void store_symbol_rotor(float2* __restrict__ buf, int
         else if (FMT == B200DAB_FMT_S16) { short2 v = reinterpret_cast<const short2*>(r.v)[i]; x = make_float2((float)v.x, (float)v.y); }
         else x = reinterpret_cast<const float2*>(r.v)[i];
         buf[pA + 288 * i] = cmul(x, w);
+        w = cmul(w, step);
+    }
+}
+
+// same conversion + de-rotation, result kept in registers: v[i] = x[t + 256 i] (the pass-A inputs of this thread)
+template <int FMT>
+__device__ __forceinline__ void symbol_rotor_regs(float2 (&out)[8], const RawSym<FMT>& r, float base_cyc, float cpp, float2 step)
+{
+    float cyc = base_cyc + cpp * (float)threadIdx.x;
+    float ph = -6.283185307179586f * (cyc - rintf(cyc));
+    float2 w;
+    __sincosf(ph, &w.y, &w.x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float2 x;
+        if (FMT == B200DAB_FMT_U8) { uchar2 v = reinterpret_cast<const uchar2*>(r.v)[i]; x = make_float2((float)((int)v.x - 128), (float)((int)v.y - 128)); }
+        else if (FMT == B200DAB_FMT_S16) { short2 v = reinterpret_cast<const short2*>(r.v)[i]; x = make_float2((float)v.x, (float)v.y); }
+        else x = reinterpret_cast<const float2*>(r.v)[i];
+        out[i] = cmul(x, w);
         w = cmul(w, step);
     }
 }

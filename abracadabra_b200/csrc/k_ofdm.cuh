@@ -86,12 +86,15 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
     for (int l = l_ref; l <= l_end; l++) {
         double base = cyc_per * (double)((int64_t)DAB_T_SYM * l);
         base -= floor(base);
-        store_symbol_rotor<FMT>(work, plan.pA, rs, (float)base, cpp, step);
+        // the de-rotated samples x[t + 256 r] are this thread's own inputs of the first radix-8 pass: they stay in registers.
+        // `work` is free: its last readers (pass D of the previous symbol) are behind the barrier that ends fft_pass_d_scatter
+        float2 x[8];
+        symbol_rotor_regs<FMT>(x, rs, (float)base, cpp, step);
         if (l < l_end) {                                                             // in flight during the FFT
             const int64_t nx = fr.t_f + (int64_t)DAB_T_SYM * (l + 1);
             if (inside) fetch_symbol_fast<FMT>(rs, raw, nx); else fetch_symbol<FMT>(rs, raw, nsamp, nx);
         }
-        fft2048_planned_abc(work, plan);
+        fft2048_planned_abc_regs(work, plan, x);
         fft_pass_d_scatter(work, plan, cur, wp);
         if (l > l_ref) {
             // DQPSK against the previous symbol: thread handles QPSK symbols n = t + 256 j
