@@ -184,10 +184,51 @@ int b200dab_ctx::init_tables()
     CK(cudaMemcpy(d_tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     std::vector<int16_t> c_of_n(DAB_NCARR);
     dabtab::freq_deint(c_of_n.data());
-    // k_ofdm_demod scatters the spectrum straight into de-interleaved order: table[p] = QPSK symbol index n of the FFT output
-    // that lands at (logical) position p of the digit-reversed result, 0xffff for the 512 unused bins
-    std::vector<uint16_t> pos(DAB_NFFT, 0xffff);
-    for (int n = 0; n < DAB_NCARR; n++) pos[fft_pos(carrier_bin(c_of_n[n]))] = (uint16_t)n;
+    // k_ofdm_demod scatters the spectrum straight into de-interleaved order.  Where QPSK symbol n lives inside the 1536-entry
+    // spectrum buffer is free as long as it stays inside its group of 16 consecutive n (the DQPSK stage reads n = t + 256 j, so a
+    // half-warp reads one such group).  The slot inside the group is chosen so that the half-warp STORES of the last FFT pass are
+    // bank-conflict free as well: every n is an edge between its store group (half-warp, output index) and its read group, and a
+    // proper 16-colouring of that bipartite graph (Koenig: max degree 16) gives every node 16 distinct 8-byte banks.
+    //   table[p]        (p < 2048)  = address of the FFT output at logical position p of the digit-reversed result, 0xffff = unused bin
+    //   table[2048 + n] (n < 1536)  = address of QPSK symbol n
+    std::vector<int> n_of_p(DAB_NFFT, -1);
+    for (int n = 0; n < DAB_NCARR; n++) n_of_p[fft_pos(carrier_bin(c_of_n[n]))] = n;
+    const int NL = 128, NR = DAB_NCARR / 16;
+    std::vector<int> colour(DAB_NCARR, -1), left_of(DAB_NCARR, -1);
+    std::vector<std::vector<int>> at_l(NL, std::vector<int>(16, -1)), at_r(NR, std::vector<int>(16, -1));   // node x colour -> edge
+    for (int t = 0; t < 256; t++)
+        for (int h = 0; h < 2; h++)
+            for (int j = 0; j < 4; j++) {
+                const int n = n_of_p[4 * (t + 256 * h) + j];
+                if (n >= 0) left_of[n] = (t >> 4) * 8 + h * 4 + j;
+            }
+    for (int n = 0; n < DAB_NCARR; n++) {
+        const int u = left_of[n], v = n >> 4;
+        int a = 0, b = 0;
+        while (at_l[u][a] >= 0) a++;
+        while (at_r[v][b] >= 0) b++;
+        if (at_r[v][a] >= 0) {
+            // colour a is taken at v: walk the a/b alternating path that starts at v and swap the two colours along it
+            std::vector<int> path;
+            int node = v, side = 1, want = a;
+            for (;;) {
+                const int e = side ? at_r[node][want] : at_l[node][want];
+                if (e < 0) break;
+                path.push_back(e);
+                node = side ? left_of[e] : (e >> 4);
+                side ^= 1;
+                want = (want == a) ? b : a;
+            }
+            for (int e : path) { at_l[left_of[e]][colour[e]] = -1; at_r[e >> 4][colour[e]] = -1; }
+            for (int e : path) { colour[e] = (colour[e] == a) ? b : a; at_l[left_of[e]][colour[e]] = e; at_r[e >> 4][colour[e]] = e; }
+        }
+        colour[n] = a; at_l[u][a] = n; at_r[v][a] = n;
+    }
+    std::vector<uint16_t> pos(DAB_NFFT + DAB_NCARR, 0xffff);
+    for (int n = 0; n < DAB_NCARR; n++) pos[DAB_NFFT + n] = (uint16_t)(16 * (n >> 4) + colour[n]);
+    for (int q = 0; q < DAB_NFFT; q++) if (n_of_p[q] >= 0) pos[q] = pos[DAB_NFFT + n_of_p[q]];
+    for (int u = 0; u < NL; u++) for (int c = 0; c < 16; c++) for (int c2 = c + 1; c2 < 16; c2++)
+        if (at_l[u][c] >= 0 && at_l[u][c] == at_l[u][c2]) { set_error("de-interleaver colouring failed"); return -1; }
     CK(d_fdi_pos.ensure(pos.size() * 2));
     CK(cudaMemcpy(d_fdi_pos.p, pos.data(), pos.size() * 2, cudaMemcpyHostToDevice));
     std::vector<int8_t> prs(DAB_NCARR);

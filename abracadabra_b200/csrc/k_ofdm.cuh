@@ -41,7 +41,8 @@ __device__ __forceinline__ void fft_pass_d_scatter(const float2* __restrict__ wo
     __syncthreads();
 }
 
-// fdi_inv[p] = QPSK symbol index of the FFT output at logical position p of the digit-reversed result (0xffff = unused bin)
+// fdi_inv[p], p < 2048: address inside the spectrum buffer of the FFT output at logical position p of the digit-reversed result
+// (0xffff = unused bin); fdi_inv[2048 + n]: address of QPSK symbol n (a conflict-free slot inside its group of 16, see init_tables)
 template <int FMT>
 __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
                                                     const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_inv,
@@ -73,6 +74,9 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
         const uint2 p1 = __ldg(reinterpret_cast<const uint2*>(fdi_inv + 1024 + 4 * t));
         wp[0] = p0.x; wp[1] = p0.y; wp[2] = p1.x; wp[3] = p1.y;
     }
+    int rp[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) rp[j] = __ldg(fdi_inv + DAB_NFFT + t + 256 * j);
     float2 step;
     {
         double c256 = cyc_per * 256.0;
@@ -97,12 +101,12 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
         fft2048_planned_abc_regs(work, plan, x);
         fft_pass_d_scatter(work, plan, cur, wp);
         if (l > l_ref) {
-            // DQPSK against the previous symbol: thread handles QPSK symbols n = t + 256 j
+            // DQPSK against the previous symbol: thread handles QPSK symbols n = t + 256 j, stored at rp[j]
             float2 y[6];
             float sabs = 0.f, ssq = 0.f;
 #pragma unroll
             for (int j = 0; j < 6; j++) {
-                const float2 v = cmul_conj(cur[t + 256 * j], prev[t + 256 * j]);
+                const float2 v = cmul_conj(cur[rp[j]], prev[rp[j]]);
                 y[j] = v;
                 sabs += fabsf(v.x) + fabsf(v.y);
                 ssq += v.x * v.x + v.y * v.y;
