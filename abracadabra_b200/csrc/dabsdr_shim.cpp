@@ -171,6 +171,41 @@ void send_tii(dabsdr_s* h, const b200dab_tii_t* t)
     notify(h, DABSDR_NID_TII, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
 }
 
+// unsolicited notifications raised by the FIGs just parsed (SURVEY.md sec. 8 b; consumers src/radiocontrol.cpp:2323, :2441-2478)
+void send_fig_events(dabsdr_s* h)
+{
+    for (const fig::Database::Event& e : h->db.events) {
+        switch (e.kind) {
+        case fig::Database::Event::UA_UPDATE: {
+            dabsdrNtfUserAppUpdate_t n; memset(&n, 0, sizeof n);
+            n.SId = e.sid; n.SCIdS = e.scids;
+            notify(h, DABSDR_NID_USER_APP_UPDATE, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
+            break; }
+        case fig::Database::Event::PTY: {
+            dabsdrNtfPTy_t n; memset(&n, 0, sizeof n);
+            n.SId = e.sid;
+            if (fig::Service* s = h->db.find(e.sid)) { n.s = s->pty_s; n.d = s->pty_d; }
+            notify(h, DABSDR_NID_PTY, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
+            break; }
+        case fig::Database::Event::ASU: {
+            dabsdrNtfAnnouncementSupport_t n; memset(&n, 0, sizeof n);
+            n.SId = e.sid;
+            if (fig::Service* s = h->db.find(e.sid)) {
+                n.ASu = (uint16_t)(s->asu & 0xFFFE);                 // the alarm flag (b0) is implied and reported as 0 by the reference
+                n.numClusterIds = (uint8_t)std::min<size_t>(7, s->clusters.size()); memcpy(n.clusterIds, s->clusters.data(), n.numClusterIds);
+            }
+            notify(h, DABSDR_NID_ANNOUNCEMENT_SUPPORT, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
+            break; }
+        case fig::Database::Event::ASW: {
+            dabsdrNtfAnnouncementSwitching_t n; memset(&n, 0, sizeof n);         // the list ends with clusterId 0 (:1822)
+            for (int i = 0; i < e.n_asw && i < 7; i++) { n.asw[i].clusterId = e.asw[i].cluster; n.asw[i].subChId = e.asw[i].subch; n.asw[i].ASwFlags = e.asw[i].flags; }
+            notify(h, DABSDR_NID_ANNOUNCEMENT_SWITCHING, DABSDR_NSTAT_SUCCESS, &n, sizeof n);
+            break; }
+        }
+    }
+    h->db.events.clear();
+}
+
 void reset_rx(dabsdr_s* h)
 {
     h->db.reset();
@@ -290,7 +325,7 @@ bool handle_request(dabsdr_s* h, const Request& r)
         memset(&n, 0, sizeof n);
         n.SId = r.a;
         fig::Service* s = h->db.find(r.a);
-        if (s) { n.ASu = s->asu; n.numClusterIds = (uint8_t)std::min<size_t>(7, s->clusters.size()); memcpy(n.clusterIds, s->clusters.data(), n.numClusterIds); }
+        if (s) { n.ASu = (uint16_t)(s->asu & 0xFFFE); n.numClusterIds = (uint8_t)std::min<size_t>(7, s->clusters.size()); memcpy(n.clusterIds, s->clusters.data(), n.numClusterIds); }
         notify(h, DABSDR_NID_ANNOUNCEMENT_SUPPORT, s ? DABSDR_NSTAT_SUCCESS : DABSDR_NSTAT_SERVICE_NOT_FOUND, &n, sizeof n);
         break; }
     case R_SELECT: {
@@ -426,7 +461,7 @@ void process_window(dabsdr_s* h)
         // ---- a frame seen for the first time: FIC
         h->last_cfo = r.cfo_hz[s];
         for (int f = 0; f < 12; f++) {
-            if (r.fib_ok[(size_t)s * 12 + f]) { h->db.parse_fib(r.fibs + ((size_t)s * 12 + f) * 32); any_fic = true; }
+            if (r.fib_ok[(size_t)s * 12 + f]) { h->db.parse_fib(r.fibs + ((size_t)s * 12 + f) * 32); any_fic = true; send_fig_events(h); }
             else h->fib_err++;
         }
         if (r.spectrum && h->spectrum_on && h->spec_cb) {

@@ -56,6 +56,16 @@ struct Database {
     uint32_t date_hours_minutes = 0;    // FIG 0/10: MJD << 14 | LSI << 13 | hours << 6 | minutes
     uint16_t sec_msec = 0;
     uint64_t version = 0;               // bumps when something changed
+    // changes the caller is told about without asking (dabsdr.h: NID_USER_APP_UPDATE, NID_PTY, NID_ANNOUNCEMENT_SUPPORT,
+    // NID_ANNOUNCEMENT_SWITCHING); filled by parse_fib in FIG order, drained by the owner
+    struct Event {
+        enum Kind { UA_UPDATE, PTY, ASU, ASW } kind;
+        uint32_t sid = 0;
+        uint8_t scids = 0;
+        int n_asw = 0;
+        struct { uint8_t cluster, subch; uint16_t flags; } asw[8];
+    };
+    std::vector<Event> events;
 
     void reset() { *this = Database(); }
 
@@ -258,7 +268,12 @@ struct Database {
                     if (s) for (auto& c : s->comps) if (c.scids == scids) {
                         bool have = false;
                         for (auto& e : c.user_apps) if (e.type == ua.type) have = true;
-                        if (!have) { c.user_apps.push_back(ua); version++; }
+                        if (!have) {
+                            c.user_apps.push_back(ua); version++;
+                            bool queued = false;
+                            for (auto& e : events) if (e.kind == Event::UA_UPDATE && e.sid == sid && e.scids == scids) queued = true;
+                            if (!queued) { Event e; e.kind = Event::UA_UPDATE; e.sid = sid; e.scids = (uint8_t)scids; events.push_back(e); }
+                        }
                     }
                 }
             }
@@ -273,7 +288,10 @@ struct Database {
                 const uint8_t pty = d[q] & 0x1F;
                 q++;
                 if (cf) q++;
-                if (Service* s = find(sid)) { if (sd) s->pty_d = pty; else s->pty_s = pty; }
+                if (Service* s = find(sid)) {
+                    uint8_t& slot = sd ? s->pty_d : s->pty_s;
+                    if (slot != pty) { slot = pty; version++; Event e; e.kind = Event::PTY; e.sid = sid; events.push_back(e); }
+                }
                 k = q;
             }
             break;
@@ -282,10 +300,26 @@ struct Database {
                 const uint32_t sid = (uint32_t)((d[k] << 8) | d[k + 1]);
                 const uint16_t asu = (uint16_t)((d[k + 2] << 8) | d[k + 3]);
                 const int nc = d[k + 4] & 0x1F;
-                if (Service* s = find(sid)) { s->asu = asu; s->clusters.assign(d + k + 5, d + k + 5 + (k + 5 + nc <= len ? nc : 0)); }
+                if (Service* s = find(sid)) {
+                    std::vector<uint8_t> cl(d + k + 5, d + k + 5 + (k + 5 + nc <= len ? nc : 0));
+                    if (s->asu != asu || s->clusters != cl) {
+                        s->asu = asu; s->clusters = cl; version++;
+                        Event e; e.kind = Event::ASU; e.sid = sid; events.push_back(e);
+                    }
+                }
                 k += 5 + nc;
             }
             break;
+        case 19: {
+            // announcement switching: one notification per received FIG 0/19, as the reference core does
+            Event e; e.kind = Event::ASW;
+            while (k + 4 <= len) {
+                const int region = (d[k + 3] >> 6) & 1;
+                if (e.n_asw < 7) { e.asw[e.n_asw].cluster = d[k]; e.asw[e.n_asw].flags = (uint16_t)((d[k + 1] << 8) | d[k + 2]); e.asw[e.n_asw].subch = d[k + 3] & 0x3F; e.n_asw++; }
+                k += 4 + (region ? 1 : 0);
+            }
+            if (e.n_asw) events.push_back(e);
+            break; }
         default:
             break;
         }

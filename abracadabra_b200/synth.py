@@ -66,6 +66,8 @@ class Service:
     subchid: int
     user_apps: Optional[List[Tuple[int, bytes]]] = None   # FIG 0/13: (user application type, user application data)
     data_comps: Optional[List[DataComponent]] = None
+    pty: Optional[int] = None                              # FIG 0/17: programme type (international code)
+    asu: Optional[Tuple[int, List[int]]] = None            # FIG 0/18: (announcement support flags, cluster ids)
 
 
 @dataclass
@@ -87,6 +89,8 @@ class EnsembleConfig:
     services: List[Service] = field(default_factory=list)
     tii: List[TiiTx] = field(default_factory=list)
     tii_every_null: bool = False  # debugging: put TII in every null instead of every second one
+    # FIG 0/19 announcement switching: (first CIF, last CIF, cluster id, ASw flags, sub-channel id); flags 0 outside the interval
+    announcements: List[Tuple[int, int, int, int, int]] = field(default_factory=list)
     cif_count0: int = 0           # CIF counter of the first CIF (multiple of 4 keeps frames aligned)
 
     def check(self):
@@ -544,6 +548,19 @@ def fig0_13_entry(sv: Service) -> bytes:
     return b
 
 
+def fig0_17_entry(sv: Service) -> bytes:
+    return bytes([sv.sid >> 8, sv.sid & 0xFF, 0x00, sv.pty & 0x1F])          # static PTy, no language, no complementary code
+
+
+def fig0_18_entry(sv: Service) -> bytes:
+    asu, clusters = sv.asu
+    return bytes([sv.sid >> 8, sv.sid & 0xFF, asu >> 8, asu & 0xFF, len(clusters)]) + bytes(clusters)
+
+
+def fig0_19_entry(cluster: int, asw: int, subchid: int, new: int = 0) -> bytes:
+    return bytes([cluster, asw >> 8, asw & 0xFF, (new << 7) | (0 << 6) | (subchid & 0x3F)])
+
+
 def fig0_9(ens: EnsembleConfig) -> bytes:
     return _fig(0, bytes([0x09, ens.lto & 0x3F, ens.ecc, 0x01]))
 
@@ -589,7 +606,9 @@ class FicBuilder:
         self.e13 += [fig0_13_entry_data(sv, dc) for sv in ens.services for dc in (sv.data_comps or []) if dc.user_apps]
         self.e03 = [fig0_3_entry(dc) for sv in ens.services for dc in (sv.data_comps or [])]
         self.e08 = [fig0_8_entry(sv, dc) for sv in ens.services for dc in (sv.data_comps or [])]
-        self.i01 = self.i02 = self.ilab = self.i13 = self.i03 = self.i08 = 0
+        self.e17 = [fig0_17_entry(sv) for sv in ens.services if sv.pty is not None]
+        self.e18 = [fig0_18_entry(sv) for sv in ens.services if sv.asu is not None]
+        self.i01 = self.i02 = self.ilab = self.i13 = self.i03 = self.i08 = self.i17 = self.i18 = 0
 
     def cif_fibs(self, cif_count: int) -> bytes:
         """Three FIBs (96 bytes) for one CIF."""
@@ -604,7 +623,19 @@ class FicBuilder:
         f01, self.i01 = _pack_rotating(self.e01, 0x01, 30 - len(f00) - len(f13), self.i01)
         fib0 = make_fib(f00 + f13 + f01)
         f02, self.i02 = _pack_rotating(self.e02, 0x02, 30, self.i02)
-        fib1 = make_fib(f02)
+        extra = b""
+        if self.e17 and cif_count % 4 == 1:
+            f, self.i17 = _pack_rotating(self.e17, 0x11, 30 - len(f02), self.i17)
+            extra += f
+        if self.e18 and cif_count % 4 == 3:
+            f, self.i18 = _pack_rotating(self.e18, 0x12, 30 - len(f02) - len(extra), self.i18)
+            extra += f
+        if self.ens.announcements and cif_count % 2 == 0:
+            rel = cif_count - self.ens.cif_count0
+            e19 = [fig0_19_entry(cl, asw if a <= rel <= b else 0, sub) for a, b, cl, asw, sub in self.ens.announcements]
+            f, _ = _pack_rotating(e19, 0x13, 30 - len(f02) - len(extra), 0)
+            extra += f
+        fib1 = make_fib(f02 + extra)
         lab = self.labels[self.ilab % len(self.labels)]
         self.ilab += 1
         fib2 = make_fib(lab + fig0_9(self.ens))

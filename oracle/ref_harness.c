@@ -53,6 +53,7 @@ typedef struct ev_s {
     uint32_t sc_sid; int sc_n, sc_addr0, sc_scids0;   /* SERVICE_COMPONENT_LIST shadow */
     uint8_t xpad_apps[8]; int n_xpad_apps;            /* USER_APP_LIST shadow: X-PAD application types */
     int n_pkt; int pkt_scids[8]; int pkt_addr[8];     /* packet-mode components of the SERVICE_COMPONENT_LIST */
+    int raw_len;                                      /* `len` as the core reported it */
 } ev_t;
 
 static pthread_mutex_t g_mx = PTHREAD_MUTEX_INITIALIZER;
@@ -226,6 +227,12 @@ static void notif_cb(dabsdrNotificationCBData_t *p, void *ctx)
         /* same for the selection / stop structures (src/radiocontrol.cpp:2364-2372, :2378-2386) */
         if ((p->nid == DABSDR_NID_SERVICE_SELECTION || p->nid == DABSDR_NID_SERVICE_STOP) && n < (int)sizeof(dabsdrNtfServiceSelection_t))
             n = (int)sizeof(dabsdrNtfServiceSelection_t);
+        /* unsolicited notifications: the caller reads / copies the whole structure (src/radiocontrol.cpp:2325, :2457, :2469) */
+        if (p->nid == DABSDR_NID_USER_APP_UPDATE && n < (int)sizeof(dabsdrNtfUserAppUpdate_t)) n = (int)sizeof(dabsdrNtfUserAppUpdate_t);
+        if (p->nid == DABSDR_NID_ANNOUNCEMENT_SWITCHING && n < (int)sizeof(dabsdrNtfAnnouncementSwitching_t)) n = (int)sizeof(dabsdrNtfAnnouncementSwitching_t);
+        if (p->nid == DABSDR_NID_PTY && n < (int)sizeof(dabsdrNtfPTy_t)) n = (int)sizeof(dabsdrNtfPTy_t);
+        if (p->nid == DABSDR_NID_ANNOUNCEMENT_SUPPORT && n < (int)sizeof(dabsdrNtfAnnouncementSupport_t)) n = (int)sizeof(dabsdrNtfAnnouncementSupport_t);
+        e->raw_len = p->len;
         memcpy(e->payload, p->pData, n);
         e->payload_len = n;
     }
@@ -359,6 +366,29 @@ static void log_notification(const ev_t *e)
         break; }
     case DABSDR_NID_SERVICE_LIST: case DABSDR_NID_SERVICE_COMPONENT_LIST: case DABSDR_NID_TII: case DABSDR_NID_USER_APP_LIST:
         break;                      /* logged with their accessor data in notif_cb */
+    case DABSDR_NID_USER_APP_UPDATE: {
+        const dabsdrNtfUserAppUpdate_t *u = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"ua_update\",\"pos\":%llu,\"status\":%d,\"sid\":%u,\"scids\":%u}\n", (unsigned long long)e->pos, e->status, u->SId, u->SCIdS);
+        break; }
+    case DABSDR_NID_PTY: {
+        const dabsdrNtfPTy_t *t = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"pty\",\"pos\":%llu,\"status\":%d,\"sid\":%u,\"s\":%u,\"d\":%u}\n", (unsigned long long)e->pos, e->status, t->SId, t->s, t->d);
+        break; }
+    case DABSDR_NID_ANNOUNCEMENT_SWITCHING: {
+        const dabsdrNtfAnnouncementSwitching_t *a = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"asw\",\"pos\":%llu,\"status\":%d,\"len\":%d,\"asw\":[", (unsigned long long)e->pos, e->status, e->raw_len);
+        for (int i = 0; i < 8; i++) fprintf(f, "%s[%u,%u,%u]", i ? "," : "", a->asw[i].clusterId, a->asw[i].subChId, a->asw[i].ASwFlags);
+        fprintf(f, "]}\n");
+        break; }
+    case DABSDR_NID_RECONFIGURATION:
+        fprintf(f, "{\"ev\":\"reconfiguration\",\"pos\":%llu,\"status\":%d}\n", (unsigned long long)e->pos, e->status);
+        break;
+    case DABSDR_NID_ANNOUNCEMENT_SUPPORT: {
+        const dabsdrNtfAnnouncementSupport_t *a = (const void *)e->payload;
+        fprintf(f, "{\"ev\":\"asu\",\"pos\":%llu,\"status\":%d,\"len\":%d,\"sid\":%u,\"asu\":%u,\"n\":%u,\"clusters\":[", (unsigned long long)e->pos, e->status, e->raw_len, a->SId, a->ASu, a->numClusterIds);
+        for (int i = 0; i < a->numClusterIds && i < 7; i++) fprintf(f, "%s%u", i ? "," : "", a->clusterIds[i]);
+        fprintf(f, "]}\n");
+        break; }
     case DABSDR_NID_XPAD_APP_START_STOP: {
         const dabsdrNtfXpadAppStartStop_t *x = (const void *)e->payload;
         fprintf(f, "{\"ev\":\"xpad_app\",\"pos\":%llu,\"status\":%d,\"app\":%u,\"start\":%d}\n", (unsigned long long)e->pos, e->status, x->appType, x->start);

@@ -34,6 +34,10 @@ CASES = {
     # secondary packet-mode component (TMId 3, FIG 0/2 + 0/3 + 0/8 + 0/13) next to the audio: MSC data groups on the data decoder
     "c1_packet_u8_30db": dict(kind="config1", n_frames=40, fmt="u8", snr=30.0, cfo=100.0, seed=5, tii=[], tii_mode=None, service=0,
                               packet=dict(subchid=7, start_cu=80, scid=0x123, scids=1, addr=5, other_addr=9, n_dg=4), data_scids=1),
+    # service information the core reports without being asked: FIG 0/13 (user application update), 0/17 (programme type),
+    # 0/18 (announcement support), 0/19 (announcement switching: flags raised for CIFs 60..100)
+    "c1_ann_u8_30db": dict(kind="config1", n_frames=44, fmt="u8", snr=30.0, cfo=100.0, seed=6, tii=[], tii_mode=None, service=0,
+                           pty=10, asu=[0x0003, [5]], announcements=[[60, 100, 5, 0x0002, 3]], user_apps=True),
 }
 
 
@@ -55,6 +59,14 @@ def build_case(spec):
         ens.tii = [synth.TiiTx(m, s, a, delay=d) for m, s, a, d in spec["tii"]]
         if spec.get("dls"):
             ens.subchannels[0].dls = list(spec["dls"])
+        if spec.get("pty") is not None:
+            ens.services[0].pty = spec["pty"]
+        if spec.get("asu"):
+            ens.services[0].asu = (spec["asu"][0], list(spec["asu"][1]))
+        if spec.get("announcements"):
+            ens.announcements = [tuple(a) for a in spec["announcements"]]
+        if spec.get("user_apps"):
+            ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]
         if spec.get("packet"):
             pk = spec["packet"]
             dgs = mot_data_groups(pk["n_dg"], seed=11)

@@ -215,3 +215,41 @@ def test_dropin_packet_mode_data_service_against_reference():
     n = min(len(mine) - i0, len(ref) - j0)
     assert n >= 50 and mine[i0:i0 + n] == ref[j0:j0 + n]
     assert len(one(ev, "audio")) >= 60
+
+
+def test_dropin_unsolicited_service_information_against_reference():
+    """FIG 0/13, 0/17, 0/18, 0/19 -> NID_USER_APP_UPDATE, NID_PTY, NID_ANNOUNCEMENT_SUPPORT, NID_ANNOUNCEMENT_SWITCHING without a
+    request, with the payloads the reference core sends (one switching notification per received FIG 0/19, list ended by
+    clusterId 0, alarm flag of ASu masked)"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("c1_ann_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "a.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12"])
+
+    def one(events, kind):
+        return [e for e in events if e["ev"] == kind]
+    for kind, keys in (("ua_update", ("status", "sid", "scids")), ("pty", ("status", "sid", "s", "d")), ("asu", ("status", "sid", "asu", "n", "clusters"))):
+        me, rf = one(ev, kind), one(g["events"], kind)
+        assert len(me) == len(rf) == 1, kind
+        assert {k: me[0][k] for k in keys} == {k: rf[0][k] for k in keys}, kind
+    assert one(ev, "pty")[0]["s"] == 10 and one(ev, "asu")[0]["asu"] == 2 and one(ev, "asu")[0]["clusters"] == [5]
+    me = [tuple(e["asw"][0]) + tuple(e["asw"][1]) for e in one(ev, "asw")]
+    rf = [tuple(e["asw"][0]) + tuple(e["asw"][1]) for e in one(g["events"], "asw")]
+    assert all(x[3:] == (0, 0, 0) for x in me + rf)                       # terminator entry
+    assert abs(len(me) - len(rf)) <= 4 and len(me) >= 80
+
+    def runs(seq):
+        out = []
+        for x in seq:
+            if not out or out[-1][0] != x:
+                out.append([x, 0])
+            out[-1][1] += 1
+        return out
+    rm, rr = runs([x[:3] for x in me]), runs([x[:3] for x in rf])
+    assert [x for x, _ in rm] == [x for x, _ in rr] == [(5, 3, 0), (5, 3, 2), (5, 3, 0)]
+    assert rm[1][1] == rr[1][1]                                            # the announcement lasts the same number of notifications
+    # service list carries the programme type once FIG 0/17 is in
+    assert one(ev, "service_list")[0]["items"] == one(g["events"], "service_list")[0]["items"]
