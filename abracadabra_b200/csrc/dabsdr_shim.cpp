@@ -174,8 +174,10 @@ void send_tii(dabsdr_s* h, const b200dab_tii_t* t)
 // unsolicited notifications raised by the FIGs just parsed (SURVEY.md sec. 8 b; consumers src/radiocontrol.cpp:2323, :2441-2478)
 void send_fig_events(dabsdr_s* h)
 {
+    bool new_eid = false;
     for (const fig::Database::Event& e : h->db.events) {
         switch (e.kind) {
+        case fig::Database::Event::NEW_EID: new_eid = true; break;
         case fig::Database::Event::UA_UPDATE: {
             dabsdrNtfUserAppUpdate_t n; memset(&n, 0, sizeof n);
             n.SId = e.sid; n.SCIdS = e.scids;
@@ -204,6 +206,15 @@ void send_fig_events(dabsdr_s* h)
         }
     }
     h->db.events.clear();
+    if (new_eid) {
+        // the ensemble identifier changed while tuned: everything learnt so far belongs to the old multiplex.  The reference raises
+        // NID_RESET(NEW_EID) and keeps its decoders running; RadioControl answers by tuning again (src/radiocontrol.cpp:122-126)
+        fig::Database fresh;
+        for (int i = 0; i < 64; i++) fresh.subch[i] = h->db.subch[i];        // running decoders keep their sub-channels until FIG 0/1 says otherwise
+        h->db = fresh;
+        const int32_t flag = DABSDR_RESET_NEW_EID;
+        notify(h, DABSDR_NID_RESET, DABSDR_NSTAT_SUCCESS, &flag, sizeof flag);
+    }
 }
 
 void reset_rx(dabsdr_s* h)

@@ -59,7 +59,7 @@ struct Database {
     // changes the caller is told about without asking (dabsdr.h: NID_USER_APP_UPDATE, NID_PTY, NID_ANNOUNCEMENT_SUPPORT,
     // NID_ANNOUNCEMENT_SWITCHING); filled by parse_fib in FIG order, drained by the owner
     struct Event {
-        enum Kind { UA_UPDATE, PTY, ASU, ASW } kind;
+        enum Kind { UA_UPDATE, PTY, ASU, ASW, NEW_EID } kind;
         uint32_t sid = 0;
         uint8_t scids = 0;
         int n_asw = 0;
@@ -118,6 +118,7 @@ struct Database {
         case 0:
             if (len >= 5) {
                 const uint16_t e = (uint16_t)((d[1] << 8) | d[2]);
+                if (have_eid && e != eid) { Event ev; ev.kind = Event::NEW_EID; events.push_back(ev); }      // another ensemble on this frequency
                 if (!have_eid || e != eid) { eid = e; have_eid = true; version++; }
                 alarm = (d[3] >> 5) & 1;
                 cif_count = (d[3] & 0x1F) * 250 + d[4];

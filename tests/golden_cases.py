@@ -38,6 +38,8 @@ CASES = {
     # 0/18 (announcement support), 0/19 (announcement switching: flags raised for CIFs 60..100)
     "c1_ann_u8_30db": dict(kind="config1", n_frames=44, fmt="u8", snr=30.0, cfo=100.0, seed=6, tii=[], tii_mode=None, service=0,
                            pty=10, asu=[0x0003, [5]], announcements=[[60, 100, 5, 0x0002, 3]], user_apps=True),
+    # another ensemble takes over the frequency after 24 frames (same sub-channel organisation): NID_RESET(NEW_EID)
+    "two_ens_u8_30db": dict(kind="two", n_frames=24, n_frames_b=26, fmt="u8", snr=30.0, cfo=100.0, seed=7, tii=[], tii_mode=None, service=0),
 }
 
 
@@ -76,6 +78,20 @@ def build_case(spec):
         if spec.get("xpad_dg"):
             ens.subchannels[0].xpad_dg = mot_data_groups(spec["xpad_dg"])
             ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]       # SlideShow over X-PAD application 12, DSCTy 60 (MOT)
+    elif spec["kind"] == "two":
+        import numpy as np
+        a = synth.config1_ensemble(seed=1000 + spec["seed"])
+        b = synth.config1_ensemble(seed=2000 + spec["seed"])
+        b.eid, b.label, b.cif_count0 = 0x2222, "SECOND MUX", 100
+        b.services[0].sid, b.services[0].label = 0x2223, "OTHER SVC"
+        ca, ta = synth.modulate(a, spec["n_frames"], seed=spec["seed"])
+        cb, tb = synth.modulate(b, spec["n_frames_b"], seed=spec["seed"] + 1)
+        imp = synth.Impairments(snr_db=spec["snr"], cfo_hz=spec["cfo"], seed=spec["seed"])
+        raw = synth.quantize(synth.impair(np.concatenate([ca, cb]), imp, 150000), spec["fmt"], imp.rms)
+        res = synth.SynthResult(iq=None, n_frames=spec["n_frames"] + spec["n_frames_b"], fibs=np.concatenate([ta["fibs"], tb["fibs"]]),
+                                logical=ta["logical"], aus={3: ta["aus"][3] + tb["aus"][3]}, superframes=ta["superframes"], ens=a,
+                                frame0=imp.lead_in, cfo_hz=imp.cfo_hz)
+        return raw, res
     elif spec["kind"] == "mp2pad":
         subs = [synth.SubChannel(9, 0, "mp2", 128, ("UEP", 35), seed=spec["seed"] + 3, dls=list(spec["dls"]))]
         ens = synth.EnsembleConfig(eid=0x3003, label="B200 MP2PAD", subchannels=subs, services=[synth.Service(0x3003, "MP2 PAD", 9)])

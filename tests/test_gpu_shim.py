@@ -253,3 +253,29 @@ def test_dropin_unsolicited_service_information_against_reference():
     assert rm[1][1] == rr[1][1]                                            # the announcement lasts the same number of notifications
     # service list carries the programme type once FIG 0/17 is in
     assert one(ev, "service_list")[0]["items"] == one(g["events"], "service_list")[0]["items"]
+
+
+def test_dropin_new_ensemble_reset_against_reference():
+    """Another ensemble takes over the frequency mid-stream: NID_RESET(NEW_EID) at the same place as the reference raises it, audio
+    keeps flowing, and the access units outside the interleaver transition are the transmitted ones on both sides"""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("two_ens_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "t.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12"])
+    me = [e for e in ev if e["ev"] == "reset"]
+    rf = [e for e in g["events"] if e["ev"] == "reset"]
+    assert [e["flag"] for e in me] == [e["flag"] for e in rf] == [0, 1]
+    assert abs(me[1]["pos"] - rf[1]["pos"]) <= 4 * 196608 + 196608        # the drop-in works on 4-frame windows
+    truth = [hashlib.sha1(a).hexdigest() for a in res.aus[3]]
+    pos = {h: i for i, h in enumerate(truth)}
+    mine = [pos[h] for h in (hashlib.sha1(bytes.fromhex(e["data"])).hexdigest() for e in ev if e["ev"] == "audio" and e["len"] > 0) if h in pos]
+    ref = [pos[e["sha1"]] for e in g["events"] if e["ev"] == "audio" and e["sha1"] in pos]
+    assert mine == sorted(mine) and len(mine) >= len(ref) - 6 and len(ref) >= 75
+    # both ensembles' audio: units before the switch (ensemble A: indices < 72) and after it (ensemble B)
+    na = 3 * (g["spec"]["n_frames"] * 4 // 5)
+    assert any(i < na - 20 for i in mine) and any(i > na + 20 for i in mine)
+    # inside the stretch both delivered, nothing the reference has is missing here (start-up and end-of-file differ by a superframe)
+    assert {i for i in ref if min(mine) <= i <= max(mine)} <= set(mine)
