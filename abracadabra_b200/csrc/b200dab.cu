@@ -86,7 +86,7 @@ struct b200dab_ctx {
     DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin;
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
-    DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out;
+    DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out, d_aus, d_totals;
     struct VitTables {              // device-resident job / group / step tables of one call site, kept between calls
         bool valid = false;
         std::vector<VitJob> jobs_in;
@@ -596,8 +596,15 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     prof_begin("k_au_split+k_au_crc");
     k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
     k_au_crc<<<dim3((max_sf * 6 + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
+    // access-unit list and RS statistics in the layout of the result, put together on the device
+    const int nb = (total_sf + 255) / 256;
+    CK(d_aus.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + 64));
+    CK(d_totals.ensure(sizeof(DabPlusTotals) + (size_t)nb * 6 * sizeof(int)));
+    int* bsum = reinterpret_cast<int*>(d_totals.as<uint8_t>() + sizeof(DabPlusTotals));
+    k_au_count<<<nb, 256, 0, stream>>>(d_sf.as<SfInfo>(), total_sf, bsum);
+    k_au_write<<<nb, 256, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, d_sf.as<SfInfo>(), total_sf, bsum, d_aus.as<AuRecord>(), d_totals.as<DabPlusTotals>());
     prof_end();
-    launches += 5;
+    launches += 7;
     CK(cudaGetLastError());
     return 0;
 }
@@ -701,7 +708,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
-                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
@@ -937,7 +944,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             if (ctx->r_subch[i].kind != 1) continue;
             DabPlusJob j;
             j.frames_off = (long long)out_off[i]; j.n_rows = n_rows; j.pitch = ctx->r_subch[i].bitrate * 3; j.s = ctx->r_subch[i].bitrate / 8;
-            j.sf_off = total_sf; j.max_sf = n_rows / 5; j.flag_off = total_rows;
+            j.sf_off = total_sf; j.max_sf = n_rows / 5; j.flag_off = total_rows; j.subch_index = (int)i;
             total_sf += j.max_sf; total_rows += n_rows;
             dpjobs.push_back(j); dp_subch.push_back((int)i);
         }
@@ -972,8 +979,10 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));
         } else CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (total_sf > 0) {
-            CKC(ctx->h_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
-            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
+            static_assert(sizeof(AuRecord) == sizeof(b200dab_au_t), "AU record layout");
+            CKC(ctx->h_sf.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + sizeof(DabPlusTotals)));
+            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
     TRACE("msc+dab+ submitted");
@@ -1028,25 +1037,14 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     if (msc_bytes > 0) {
         for (size_t i = 0; i < ctx->r_subch.size(); i++) { ctx->r_frames.push_back(ctx->h_msc.as<uint8_t>() + out_off[i]); ctx->r_rows.push_back(n_rows); }
         res->frames = ctx->r_frames.data(); res->frame_rows = ctx->r_rows.data();
-        const SfInfo* sf = ctx->h_sf.as<SfInfo>();
-        ctx->r_aus.reserve((size_t)total_sf * 6);
-        for (size_t k = 0; k < dpjobs.size(); k++) {
-            const DabPlusJob& j = dpjobs[k];
-            for (int m = 0; m < j.max_sf; m++) {
-                const SfInfo& s = sf[j.sf_off + m];
-                if (!s.valid) continue;
-                res->superframes++;
-                res->rs_corrected += s.rs_corrected; res->rs_bit_errors += s.rs_bit_errors; res->rs_uncorrectable += s.rs_uncorrectable;
-                if (!s.firecode_ok) res->firecode_fail++;
-                for (int a = 0; a < s.n_aus; a++) {
-                    b200dab_au_t au;
-                    au.subch_index = dp_subch[k]; au.superframe = m; au.cif = s.row;
-                    au.offset = s.row * j.pitch + s.au_off[a]; au.length = s.au_len[a]; au.crc_ok = s.au_ok[a]; au.header = s.header;
-                    ctx->r_aus.push_back(au);
-                }
-            }
+        if (total_sf > 0) {
+            // the access-unit list and the RS totals were put together on the device (k_au_compact)
+            const DabPlusTotals* tot = ctx->h_sf.as<DabPlusTotals>();
+            res->superframes = tot->superframes; res->rs_corrected = tot->rs_corrected; res->rs_bit_errors = tot->rs_bit_errors;
+            res->rs_uncorrectable = tot->rs_uncorrectable; res->firecode_fail = tot->firecode_fail;
+            res->n_aus = tot->n_aus;
+            res->aus = reinterpret_cast<const b200dab_au_t*>(ctx->h_sf.as<uint8_t>() + sizeof(DabPlusTotals));
         }
-        res->n_aus = (int)ctx->r_aus.size(); res->aus = ctx->r_aus.data();
     }
     if (want_tii && n_win > 0) {
         static_assert(sizeof(TiiResult) == sizeof(b200dab_tii_t), "TII result layout");

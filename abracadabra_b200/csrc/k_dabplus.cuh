@@ -35,6 +35,7 @@ struct DabPlusJob {
     int sf_off;             // index of this job's first superframe slot in the per-superframe arrays
     int max_sf;             // slots reserved = n_rows / 5
     int flag_off;           // index into the per-row firecode flag array
+    int subch_index;        // index of the sub-channel in the caller's table (copied into the AU records)
 };
 struct SfInfo {             // per superframe slot
     int valid;              // 1 = slot used (inside the aligned run)
@@ -228,4 +229,75 @@ __global__ void __launch_bounds__(128) k_au_crc(const uint8_t* __restrict__ fram
     for (int i = 0; i < len; i++) crc = ((crc << 8) & 0xffffu) ^ tbl[((crc >> 8) ^ p[i]) & 0xff];
     crc = (~crc) & 0xffffu;
     info->au_ok[a] = crc == (uint32_t)((p[len] << 8) | p[len + 1]);
+}
+
+// Result records in the layout of the C ABI (b200dab_au_t: seven int32) and the totals the host used to add up from SfInfo.
+struct AuRecord { int subch_index, superframe, cif, offset, length, crc_ok, header; };
+struct DabPlusTotals { int n_aus, superframes, rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail, pad_[2]; };
+
+// Compaction in two small launches over all superframe slots in (job, superframe) order -- the order the host loop produced:
+// k_au_count: per CTA of 256 slots, the number of access units and the partial RS statistics;
+// k_au_write: prefix over the (<= a few dozen) CTA sums + scan inside the CTA, then every slot writes its records.
+__global__ void __launch_bounds__(256) k_au_count(const SfInfo* __restrict__ sf, int total_sf, int* __restrict__ block_sums)
+{
+    __shared__ int acc[6];
+    const int t = threadIdx.x, i = blockIdx.x * 256 + t;
+    if (t < 6) acc[t] = 0;
+    __syncthreads();
+    int v[6] = {0, 0, 0, 0, 0, 0};
+    if (i < total_sf && sf[i].valid) {
+        const SfInfo* p = sf + i;
+        v[0] = p->n_aus; v[1] = 1; v[2] = p->rs_corrected; v[3] = p->rs_bit_errors; v[4] = p->rs_uncorrectable; v[5] = p->firecode_ok ? 0 : 1;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        int x = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((t & 31) == 0 && x) atomicAdd(&acc[q], x);
+    }
+    __syncthreads();
+    if (t < 6) block_sums[blockIdx.x * 6 + t] = acc[t];
+}
+
+__global__ void __launch_bounds__(256) k_au_write(const DabPlusJob* __restrict__ jobs, int n_jobs, const SfInfo* __restrict__ sf, int total_sf,
+                                                  const int* __restrict__ block_sums, AuRecord* __restrict__ out, DabPlusTotals* __restrict__ totals)
+{
+    __shared__ int warp_tot[8];
+    __shared__ int job_off[65], job_pitch[64], job_sub[64];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, i = blockIdx.x * 256 + t;
+    if (n_jobs > 64) n_jobs = 64;
+    if (t < n_jobs) { job_off[t] = jobs[t].sf_off; job_pitch[t] = jobs[t].pitch; job_sub[t] = jobs[t].subch_index; }
+    if (t == n_jobs) job_off[t] = total_sf;
+    int base = 0;
+    for (int b = 0; b < (int)blockIdx.x; b++) base += block_sums[b * 6];
+    if (blockIdx.x == 0 && t == 0) {
+        DabPlusTotals r = {0, 0, 0, 0, 0, 0, {0, 0}};
+        for (int b = 0; b < (int)gridDim.x; b++) {
+            const int* q = block_sums + b * 6;
+            r.n_aus += q[0]; r.superframes += q[1]; r.rs_corrected += q[2]; r.rs_bit_errors += q[3]; r.rs_uncorrectable += q[4]; r.firecode_fail += q[5];
+        }
+        *totals = r;
+    }
+    SfInfo info;
+    int n = 0;
+    if (i < total_sf) { info = sf[i]; if (info.valid) n = info.n_aus; }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int pos = base + incl - n;
+    for (int w = 0; w < warp; w++) pos += warp_tot[w];
+    if (n > 0) {
+        int k = 0;
+        while (k + 1 < n_jobs && i >= job_off[k + 1]) k++;
+        const int m = i - job_off[k], pitch = job_pitch[k], sub = job_sub[k];
+        for (int a = 0; a < n; a++) {
+            AuRecord r;
+            r.subch_index = sub; r.superframe = m; r.cif = info.row;
+            r.offset = info.row * pitch + info.au_off[a]; r.length = info.au_len[a]; r.crc_ok = info.au_ok[a]; r.header = info.header;
+            out[pos + a] = r;
+        }
+    }
 }
