@@ -919,7 +919,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         ctx->r_subch.resize(B200DAB_MAX_SUBCH);
         std::vector<b200dab_subch_t> prev;
         int ns = 0;
-        for (int upto = std::min(n_slots, 24); ; upto = std::min(n_slots, upto * 2)) {
+        for (int upto = std::min(n_slots, 8); ; upto = std::min(n_slots, upto * 2)) {
             ns = parse_subch_impl(res->fibs, res->fib_ok, upto * 12, ctx->r_subch.data(), B200DAB_MAX_SUBCH);
             const bool same = (int)prev.size() == ns && (ns == 0 || !memcmp(prev.data(), ctx->r_subch.data(), (size_t)ns * sizeof(b200dab_subch_t)));
             if (upto >= n_slots || (same && ns > 0)) break;
