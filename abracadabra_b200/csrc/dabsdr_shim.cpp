@@ -244,7 +244,7 @@ fig::Component* find_component(dabsdr_s* h, uint32_t sid, uint8_t scids, fig::Se
 void fill_component(dabsdr_s* h, const fig::Component& c, dabsdrServiceCompListItem_t& o)
 {
     memset(&o, 0, sizeof o);
-    o.SCIdS = (uint8_t)(c.scids >= 0 ? c.scids : 0);
+    o.SCIdS = (uint8_t)(c.scids >= 0 ? c.scids : (c.ps ? 0 : 255));      // secondary component without FIG 0/8 yet: 255, like the reference
     o.SubChId = (uint8_t)(c.subch_id >= 0 ? c.subch_id : 0);
     o.SubChAddr = -1;
     o.ps = (uint8_t)(c.ps ? 2 : 0);            // raw bit mask, non-zero = primary
