@@ -91,6 +91,7 @@ class EnsembleConfig:
     tii_every_null: bool = False  # debugging: put TII in every null instead of every second one
     # FIG 0/19 announcement switching: (first CIF, last CIF, cluster id, ASw flags, sub-channel id); flags 0 outside the interval
     announcements: List[Tuple[int, int, int, int, int]] = field(default_factory=list)
+    utc: Optional[Tuple[int, int, int, int, int]] = None   # FIG 0/10 (long form): (MJD, hours, minutes, seconds, ms) at the first CIF
     cif_count0: int = 0           # CIF counter of the first CIF (multiple of 4 keeps frames aligned)
 
     def check(self):
@@ -561,6 +562,16 @@ def fig0_19_entry(cluster: int, asw: int, subchid: int, new: int = 0) -> bytes:
     return bytes([cluster, asw >> 8, asw & 0xFF, (new << 7) | (0 << 6) | (subchid & 0x3F)])
 
 
+def fig0_10(ens: EnsembleConfig, cif_rel: int) -> bytes:
+    mjd, h, m, sec, ms = ens.utc
+    t = ((h * 60 + m) * 60 + sec) * 1000 + ms + 24 * cif_rel                    # a CIF lasts 24 ms
+    mjd += t // 86400000
+    t %= 86400000
+    h, m, sec, ms = t // 3600000, (t // 60000) % 60, (t // 1000) % 60, t % 1000
+    v = (0 << 31) | (mjd << 14) | (0 << 13) | (0 << 12) | (1 << 11) | (h << 6) | m           # Rfu, MJD, LSI, Rfa, UTC flag = 1, hours, minutes
+    return _fig(0, bytes([0x0A, v >> 24, (v >> 16) & 0xFF, (v >> 8) & 0xFF, v & 0xFF, (sec << 2) | (ms >> 8), ms & 0xFF]))
+
+
 def fig0_9(ens: EnsembleConfig) -> bytes:
     return _fig(0, bytes([0x09, ens.lto & 0x3F, ens.ecc, 0x01]))
 
@@ -630,6 +641,10 @@ class FicBuilder:
         if self.e18 and cif_count % 4 == 3:
             f, self.i18 = _pack_rotating(self.e18, 0x12, 30 - len(f02) - len(extra), self.i18)
             extra += f
+        if self.ens.utc is not None and cif_count % 4 == 2:
+            f = fig0_10(self.ens, cif_count - self.ens.cif_count0)
+            if len(f02) + len(extra) + len(f) <= 30:
+                extra += f
         if self.ens.announcements and cif_count % 2 == 0:
             rel = cif_count - self.ens.cif_count0
             e19 = [fig0_19_entry(cl, asw if a <= rel <= b else 0, sub) for a, b, cl, asw, sub in self.ens.announcements]

@@ -37,7 +37,8 @@ CASES = {
     # service information the core reports without being asked: FIG 0/13 (user application update), 0/17 (programme type),
     # 0/18 (announcement support), 0/19 (announcement switching: flags raised for CIFs 60..100)
     "c1_ann_u8_30db": dict(kind="config1", n_frames=44, fmt="u8", snr=30.0, cfo=100.0, seed=6, tii=[], tii_mode=None, service=0,
-                           pty=10, asu=[0x0003, [5]], announcements=[[60, 100, 5, 0x0002, 3]], user_apps=True),
+                           pty=10, asu=[0x0003, [5]], announcements=[[60, 100, 5, 0x0002, 3]], user_apps=True,
+                           utc=[60600, 23, 59, 57, 100]),
     # another ensemble takes over the frequency after 24 frames (same sub-channel organisation): NID_RESET(NEW_EID)
     "two_ens_u8_30db": dict(kind="two", n_frames=24, n_frames_b=26, fmt="u8", snr=30.0, cfo=100.0, seed=7, tii=[], tii_mode=None, service=0),
 }
@@ -67,6 +68,8 @@ def build_case(spec):
             ens.services[0].asu = (spec["asu"][0], list(spec["asu"][1]))
         if spec.get("announcements"):
             ens.announcements = [tuple(a) for a in spec["announcements"]]
+        if spec.get("utc"):
+            ens.utc = tuple(spec["utc"])
         if spec.get("user_apps"):
             ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]
         if spec.get("packet"):

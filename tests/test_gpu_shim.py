@@ -254,6 +254,30 @@ def test_dropin_unsolicited_service_information_against_reference():
     # service list carries the programme type once FIG 0/17 is in
     assert one(ev, "service_list")[0]["items"] == one(g["events"], "service_list")[0]["items"]
 
+    # DAB time (FIG 0/10, long form) in the periodic notification: the last value received, packed as RadioControl unpacks it
+    # (src/dabtables.cpp:124-157); it crosses midnight inside this recording.  The drop-in works on 4-frame windows, so its
+    # value may be up to 4 frames (384 ms) newer than the reference's at the same stream position.
+    def ms_of(e):
+        d, sm = e["date"], e["secmsec"]
+        return ((((d >> 14) - 60600) * 24 + ((d >> 6) & 31)) * 60 + (d & 63)) * 60000 + (sm >> 10) * 1000 + (sm & 1023)
+    pm = [e for e in one(ev, "periodic") if not e.get("null") and e["date"]]
+    pr = [e for e in one(g["events"], "periodic") if not e.get("null") and e["date"]]
+    assert len(pm) >= 4 and len(pr) >= 4
+    t0 = ((23 * 60 + 59) * 60 + 57) * 1000 + 100
+    for e in pm + pr:
+        cif = (ms_of(e) - t0) / 24.0
+        assert cif == int(cif) and int(cif) % 4 == 2 and ((e["date"] >> 13) & 1) == 0       # a transmitted FIG 0/10, LSI clear
+    assert all(b - a == 768 for a, b in zip([ms_of(e) for e in pr], [ms_of(e) for e in pr][1:]))
+    # the reported time belongs to a frame the core had already consumed (`pos` = input position at the callback): the reference
+    # lags its input by less than a frame, the windowed drop-in by up to 12 frames
+    for e, lag in [(x, 12.5) for x in pm] + [(x, 1.5) for x in pr]:
+        frame_seen = (e["pos"] - 49152) / 196608.0
+        frame_of_time = ((ms_of(e) - t0) // 24) // 4
+        assert frame_seen - lag <= frame_of_time <= frame_seen + 0.5, (e["pos"], frame_of_time, frame_seen)
+    dm = [b - a for a, b in zip([ms_of(e) for e in pm], [ms_of(e) for e in pm][1:])]
+    assert all(d == 768 for d in dm[:-1]) and dm[-1] % 96 == 0, dm      # one per 8 frames; the last one comes with the end of the file
+    assert any((e["date"] >> 14) == 60601 for e in pm)                                     # past midnight
+
 
 def test_dropin_new_ensemble_reset_against_reference():
     """Another ensemble takes over the frequency mid-stream: NID_RESET(NEW_EID) at the same place as the reference raises it, audio
