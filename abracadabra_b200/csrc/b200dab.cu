@@ -296,7 +296,7 @@ int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, 
     else k_block_power<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
     prof_end();
     prof_begin("k_window_sum+k_candidates+k_sort_small");
-    k_window_sum<<<grid, 256, 0, stream>>>(d_P.as<float>(), nblk, d_S.as<float>());
+    k_window_sum<<<(unsigned)((nblk + 256 * WSUM_PER_THREAD - 1) / (256 * WSUM_PER_THREAD)), 256, 0, stream>>>(d_P.as<float>(), nblk, d_S.as<float>());
     k_candidates<<<grid, 256, 0, stream>>>(d_S.as<float>(), nblk, (int64_t)n, d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand);
     k_sort_small<<<1, 256, 0, stream>>>(d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand, d_cand.as<long long>());
     prof_end();
