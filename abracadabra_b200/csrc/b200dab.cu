@@ -176,12 +176,11 @@ struct b200dab_ctx {
 static size_t fmt_bytes(int fmt) { return fmt == B200DAB_FMT_U8 ? 2 : fmt == B200DAB_FMT_S16 ? 4 : 8; }
 #define FRONT_CHUNK_FRAMES 64     /* host uploads are pipelined in chunks of 64 transmission frames (25 MB of u8) */
 
-int b200dab_ctx::init_tables()
+// Spectrum-buffer layout of k_ofdm_demod (see the comment inside): out[p], p < 2048 = address of the FFT output at logical position p
+// of the digit-reversed result (0xffff = unused bin); out[2048 + n], n < 1536 = address of QPSK symbol n.  Returns 0, or -1 if the
+// colouring is not proper (cannot happen: Koenig).  Host-only, also exported for the tests (b200dab_spectrum_layout).
+static int build_spectrum_layout(std::vector<uint16_t>& pos)
 {
-    std::vector<float> tw(4096);
-    dabtab::twiddles(tw.data());
-    CK(d_tw.ensure(tw.size() * 4));
-    CK(cudaMemcpy(d_tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
     std::vector<int16_t> c_of_n(DAB_NCARR);
     dabtab::freq_deint(c_of_n.data());
     // k_ofdm_demod scatters the spectrum straight into de-interleaved order.  Where QPSK symbol n lives inside the 1536-entry
@@ -224,11 +223,24 @@ int b200dab_ctx::init_tables()
         }
         colour[n] = a; at_l[u][a] = n; at_r[v][a] = n;
     }
-    std::vector<uint16_t> pos(DAB_NFFT + DAB_NCARR, 0xffff);
+    pos.assign(DAB_NFFT + DAB_NCARR, 0xffff);
     for (int n = 0; n < DAB_NCARR; n++) pos[DAB_NFFT + n] = (uint16_t)(16 * (n >> 4) + colour[n]);
     for (int q = 0; q < DAB_NFFT; q++) if (n_of_p[q] >= 0) pos[q] = pos[DAB_NFFT + n_of_p[q]];
     for (int u = 0; u < NL; u++) for (int c = 0; c < 16; c++) for (int c2 = c + 1; c2 < 16; c2++)
-        if (at_l[u][c] >= 0 && at_l[u][c] == at_l[u][c2]) { set_error("de-interleaver colouring failed"); return -1; }
+        if (at_l[u][c] >= 0 && at_l[u][c] == at_l[u][c2]) return -1;
+    return 0;
+}
+
+int b200dab_ctx::init_tables()
+{
+    std::vector<float> tw(4096);
+    dabtab::twiddles(tw.data());
+    CK(d_tw.ensure(tw.size() * 4));
+    CK(cudaMemcpy(d_tw.p, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int16_t> c_of_n(DAB_NCARR);
+    dabtab::freq_deint(c_of_n.data());
+    std::vector<uint16_t> pos;
+    if (build_spectrum_layout(pos)) { set_error("de-interleaver colouring failed"); return -1; }
     CK(d_fdi_pos.ensure(pos.size() * 2));
     CK(cudaMemcpy(d_fdi_pos.p, pos.data(), pos.size() * 2, cudaMemcpyHostToDevice));
     std::vector<int8_t> prs(DAB_NCARR);
@@ -799,6 +811,14 @@ int b200dab_pad_feed_mp2(b200dab_pad* p, const uint8_t* f, int len, b200dab_pad_
     if (!p || !f || !pad::mp2_pad(f, len, p->tmp)) return 0;
     p->d.feed(p->tmp.data(), (int)p->tmp.size(), [&](const uint8_t* d, int n) { if (cb) cb(user, 0, d, n); }, [&](int app, const uint8_t* d, int n) { if (cb) cb(user, app, d, n); });
     return 1;
+}
+
+int b200dab_spectrum_layout(uint16_t* out, int n)
+{
+    std::vector<uint16_t> pos;
+    if (!out || n < DAB_NFFT + DAB_NCARR || build_spectrum_layout(pos)) return -1;
+    memcpy(out, pos.data(), pos.size() * sizeof(uint16_t));
+    return (int)pos.size();
 }
 
 int b200dab_parse_ensemble(const uint8_t* fibs, const uint8_t* fib_ok, int n_fibs, b200dab_ensemble_t* out)

@@ -99,6 +99,7 @@ def lib():
         L.b200dab_profile_eep.argtypes = [i32, i32, i32, ct.POINTER(SubCh)]
         L.b200dab_profile_uep.argtypes = [i32, ct.POINTER(SubCh)]
         L.b200dab_parse_subch.argtypes = [vp, vp, i32, ct.POINTER(SubCh), i32]
+        L.b200dab_spectrum_layout.argtypes = [vp, i32]
         L.b200dab_parse_ensemble.argtypes = [vp, vp, i32, ct.POINTER(EnsembleInfo)]
         L.b200dab_pad_create.restype = vp
         L.b200dab_pad_destroy.argtypes = [vp]
@@ -124,7 +125,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -160,6 +161,14 @@ def parse_subch(fibs: np.ndarray, fib_ok: Optional[np.ndarray] = None) -> List[S
     if n < 0:
         raise RuntimeError("parse_subch failed")
     return [out[i] for i in range(n)]
+
+
+def spectrum_layout() -> np.ndarray:
+    """[3584] uint16: slots of the OFDM kernel's spectrum buffer (see b200dab_spectrum_layout)"""
+    out = np.zeros(2048 + 1536, np.uint16)
+    if lib().b200dab_spectrum_layout(out.ctypes.data, out.size) != out.size:
+        raise RuntimeError("spectrum layout failed")
+    return out
 
 
 class PadDecoder:

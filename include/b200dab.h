@@ -117,6 +117,11 @@ B200DAB_API int b200dab_profile_uep(int table_index, b200dab_subch_t *out);
 /* parse FIBs (CRC-checked by the caller) into a sub-channel table: FIG 0/1 + FIG 0/2 (ASCTy 63 = DAB+) */
 B200DAB_API int b200dab_parse_subch(const uint8_t *fibs, const uint8_t *fib_ok, int n_fibs, b200dab_subch_t *out, int max_out);
 
+/* Shared-memory layout of the OFDM kernel's spectrum buffer (host-side table, exported for tests and tools): out[p], p < 2048, is
+ * the slot of the FFT output at position p of the digit-reversed result (0xffff = unused bin), out[2048 + n], n < 1536, the slot
+ * of QPSK symbol n.  n must be >= 3584; returns the number of entries or -1. */
+B200DAB_API int b200dab_spectrum_layout(uint16_t *out, int n);
+
 /* Ensemble / service summary out of decoded FIBs: the fields RadioControl receives in dabsdrNtfEnsemble_t and the service
  * list (dabsdr.h:169-318), for batch callers that do not go through the callback interface (band scan output). */
 typedef struct {

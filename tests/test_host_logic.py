@@ -115,3 +115,28 @@ def test_sample_clock_offset_and_multipath():
         assert np.all(np.abs(spacing - 196608 / (1 + ppm * 1e-6)) <= 3)
         assert np.array_equal(d["fibs"], res.fibs[:40])
         assert np.array_equal(d["frames"][0], res.logical[3][:d["frames"][0].shape[0]])
+
+
+def test_ofdm_spectrum_layout_is_conflict_free():
+    """The slot table of k_ofdm_demod's spectrum buffer: a permutation of the 1536 QPSK symbols that keeps every symbol inside its
+    group of 16 (so the DQPSK reads n = t + 256 j of a half-warp cover 16 distinct 8-byte banks) and gives the 16 lanes of every
+    half-warp store of the last FFT pass 16 distinct banks as well (proper edge colouring of the store-group x read-group graph)."""
+    from abracadabra_b200 import pipeline
+    tab = pipeline.spectrum_layout().astype(np.int64)
+    by_p, by_n = tab[:2048], tab[2048:]
+    assert sorted(by_n.tolist()) == list(range(1536))                       # bijection
+    assert np.array_equal(by_n >> 4, np.arange(1536) >> 4)                   # stays inside its read group
+    for g in range(96):
+        assert len(set((by_n[16 * g:16 * g + 16] & 15).tolist())) == 16      # read side: 16 banks per half-warp
+    used = by_p[by_p != 0xFFFF]
+    assert used.size == 1536 and sorted(used.tolist()) == list(range(1536))
+    # store side: thread t, quadruple h, output j writes position p = 4 (t + 256 h) + j; a half-warp is 16 consecutive t
+    worst = 0
+    for hw in range(16):
+        for h in range(2):
+            for j in range(4):
+                slots = [by_p[4 * (t + 256 * h) + j] for t in range(16 * hw, 16 * hw + 16)]
+                banks = [s & 15 for s in slots if s != 0xFFFF]
+                assert len(banks) == len(set(banks))
+                worst = max(worst, len(banks))
+    assert worst == 16
