@@ -161,6 +161,9 @@ struct b200dab_ctx {
     int fine(const void* d_iq, uint64_t n, int fmt, int n_cand);
     int prepare_slots(int max_slots, bool want_stat, bool want_tii);
     int demod(const void* d_iq, uint64_t n_visible, int fmt, int first, int count, bool want_stat, bool want_tii);
+    int tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int first, int count);
+    bool defer_tii_fold = false;   // single-range decode: the fold is launched after the FIC so that it runs while the host parses the FIGs
+    cudaEvent_t ev_fic = nullptr;
     int front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len, bool want_stat, bool want_tii, int max_slots);
     // front-end state across the ranges of one decode
     size_t fe_frames = 0; long long fe_t0 = 0, fe_last = 0; int fe_candidates = 0;
@@ -382,14 +385,24 @@ int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int first,
     else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
     prof_end();
     launches += 1;
-    if (want_tii) {
-        prof_begin("k_tii_fold");
-        if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
-        else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
-        else k_tii_fold<B200DAB_FMT_F32><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
-        prof_end();
-        launches += 1;
-    }
+    CK(cudaGetLastError());
+    if (want_tii && !defer_tii_fold) return tii_fold(d_iq, n_visible, fmt, first, count);
+    return 0;
+}
+
+// null-symbol spectra of frames [first, first + count), folded to the 384 TII bins
+int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int first, int count)
+{
+    if (count <= 0) return 0;
+    const FrameInfo* dfr = h_frames.as<FrameInfo>() + first;
+    const float2* tw = d_tw.as<float2>();
+    const int64_t n = (int64_t)n_visible;
+    prof_begin("k_tii_fold");
+    if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+    else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+    else k_tii_fold<B200DAB_FMT_F32><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+    prof_end();
+    launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
@@ -728,6 +741,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); }
+    if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
@@ -858,6 +872,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
     const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
     const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
+    bool deferred_tii = false;
     const int max_slots = (int)(n / DAB_T_FRAME) + 2;
     ctx->fe_frames = 0; ctx->fe_t0 = 0; ctx->fe_last = 0; ctx->fe_candidates = 0; ctx->fe_cir.clear();
     if (ctx->prepare_slots(max_slots, want_stat, want_tii)) return -1;
@@ -892,7 +907,11 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         if (trace) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[trace] front end done %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count()); }
     } else {
         if (ctx->upload_raw(iq, n, fmt, mem, &d_iq)) return -1;
-        if (ctx->front_end(d_iq, fmt, 0, n, want_stat, want_tii, max_slots)) return -1;
+        ctx->defer_tii_fold = want_tii;
+        const int rc = ctx->front_end(d_iq, fmt, 0, n, want_stat, want_tii, max_slots);
+        ctx->defer_tii_fold = false;
+        if (rc) return -1;
+        deferred_tii = want_tii;
     }
     TRACE("front end submitted");
     res->n_candidates = ctx->fe_candidates;
@@ -929,7 +948,12 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     CKC(cudaMemcpyAsync(ctx->h_fibs.p, ctx->d_fic_out.p, fib_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->h_fib_ok.p, ctx->d_fib_ok.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, ctx->stream));
     TRACE("fic submitted");
-    CKC(cudaStreamSynchronize(ctx->stream));
+    // The host only needs the FIBs to go on (FIG parse -> sub-channel organisation -> MSC jobs): it waits for the event behind
+    // their copy, not for the stream, and the TII fold is queued behind it so that the GPU has work during the parse.
+    if (!ctx->ev_fic) CKC(cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming));
+    CKC(cudaEventRecord(ctx->ev_fic, ctx->stream));
+    if (deferred_tii && ctx->tii_fold(d_iq, n, fmt, 0, n_frames)) return -1;
+    CKC(cudaEventSynchronize(ctx->ev_fic));
     TRACE("fic synced");
     res->fibs = ctx->h_fibs.as<uint8_t>(); res->fib_ok = ctx->h_fib_ok.as<uint8_t>();
     // ---- sub-channel organisation: given by the caller or discovered from FIG 0/1, 0/2
