@@ -347,13 +347,14 @@ int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
 }
 
 // ------------------------------------------------------------------------------------------------ OFDM demod
-// soft-bit / statistics / TII buffers for up to max_slots frames; cleared once so that lost frames read as erasures
+// soft-bit / statistics / TII buffers for up to max_slots frames
 int b200dab_ctx::prepare_slots(int max_slots, bool want_stat, bool want_tii)
 {
     CK(d_frames.ensure((size_t)max_slots * sizeof(FrameInfo)));
     CK(h_frames.ensure((size_t)max_slots * sizeof(FrameInfo)));
+    // Every frame that is found writes all of its soft bits; only the slots of LOST frames have to read as erasures, and those are
+    // cleared where the frames are chained (front_end) -- not the whole buffer (144 MB for 60 s) on every call.
     CK(d_soft.ensure((size_t)max_slots * DAB_FRAME_SOFT + 256));
-    CK(cudaMemsetAsync(d_soft.p, 0, (size_t)max_slots * DAB_FRAME_SOFT, stream));
     if (want_stat) {
         CK(d_symstat.ensure((size_t)max_slots * 150 * 4));
         CK(cudaMemsetAsync(d_symstat.p, 0, (size_t)max_slots * 150 * 4, stream));
@@ -445,6 +446,9 @@ int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len
         if (fe_frames == 0) fe_t0 = t_abs;
         const int slot = fe_frames == 0 ? 0 : hf[fe_frames - 1].slot + (int)((t_abs - fe_last + DAB_T_FRAME / 2) / DAB_T_FRAME);
         if (slot >= max_slots) break;
+        const int prev_slot = fe_frames == 0 ? -1 : hf[fe_frames - 1].slot;
+        if (slot > prev_slot + 1)                                                                    // lost frames in between: erasures
+            CK(cudaMemsetAsync(d_soft.as<int8_t>() + (size_t)(prev_slot + 1) * DAB_FRAME_SOFT, 0, (size_t)(slot - prev_slot - 1) * DAB_FRAME_SOFT, stream));
         FrameInfo fi;
         fi.t_f = t_abs; fi.cfo_hz = f[i].cfo_hz; fi.slot = slot;
         hf[fe_frames++] = fi;
