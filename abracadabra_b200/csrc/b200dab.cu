@@ -512,7 +512,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), dj, dg, vt.d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
     prof_begin(st == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
-    k_viterbi<<<(unsigned)n_groups * 4, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg);
+    k_viterbi<<<(unsigned)n_groups * 2, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg);
     prof_end();
     prof_begin(st == 0 ? "k_vit_trace(fic)" : "k_vit_trace(msc)");
     k_vit_trace<<<(unsigned)n_groups, 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out);
@@ -1207,7 +1207,7 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     ctx->prof_next();
     CKC(ctx->d_meet.ensure((size_t)ng * VIT_MEET_WORDS * sizeof(unsigned short)));
     ctx->prof_begin("k_viterbi(stage)");
-    k_viterbi<<<ng * 4, 32, ctx->vit_dsmem, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),
+    k_viterbi<<<ng * 2, 32, ctx->vit_dsmem, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),
                                                           ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>());
     ctx->prof_end();
     ctx->prof_begin("k_vit_trace(stage)");

@@ -7,10 +7,9 @@
 // Layout: codewords of one sub-channel (one per CIF) are handled in groups of 32, so every global access is a coalesced row:
 //   vin [group][step][32 codewords] uint32 : the 4 de-punctured int8 soft bits of that trellis step (0 = punctured)
 //   dec [group][step][32 codewords] uint2  : the 64 survivor decisions of that step (x: lane role 0, y: lane role 1)
-// Path metrics are int16, two states per 32-bit register, updated with packed 16x2 adds and VIMNMX.S16x2; VIMNMX delivers
-// both decision predicates of a register pair for free.  Each codeword is spread over TWO lanes (32 states each), and each
-// direction of the bidirectional recursion is its own one-warp CTA, so one recording yields ~4000 short work items that the
-// hardware deals to whichever SM sub-partition frees up first.
+// Path metrics are int16, two codewords per 32-bit register, updated with packed 16x2 adds and VIMNMX.S16x2; VIMNMX delivers
+// both decision predicates of a register pair for free.  A register holds the same state of TWO codewords, the 64 states of the
+// pair are spread over TWO lanes (32 registers each), and each direction of the bidirectional recursion is its own one-warp CTA.
 #pragma once
 #include "common.cuh"
 
@@ -98,244 +97,205 @@ __host__ __device__ constexpr int vit_parity7(int x) { return (x ^ (x >> 1) ^ (x
 __host__ __device__ constexpr int vit_cbit(int j, int q) { return vit_parity7((j << 1) & (q == 0 ? 0155 : q == 1 ? 0117 : 0123)); }
 __host__ __device__ constexpr int vit_kidx(int j) { return vit_cbit(j, 0) * 4 + vit_cbit(j, 1) * 2 + vit_cbit(j, 2); }
 
-// Two lanes per codeword.  Role 0 owns the butterflies whose index has bit 3 clear; role 1 owns the others but works in
-// COMPLEMENTED coordinates (physical state = logical state ^ 63, physical input = logical input ^ 1): the trellis is invariant
-// under that map, so both roles run the same code on physical butterflies 0..7, both keep the results whose next butterfly
-// index is < 8 and hand the rest to the partner with one SHFL.xor each, and a received state index is simply the complement
-// of the sender's.  Complementing the 7-bit window flips the code bits of the odd-weight polynomials (133, 171) and leaves
-// the even-weight one (145) alone: role 1 negates soft bits 0, 1 and 3.  The tie rules (include/b200dab_spec.h) are
-// invariant under the same map, which is what makes the two roles agree with the scalar formulation bit for bit.
+// One warp = one group of 32 codewords = 16 lane PAIRS; a pair works on TWO codewords at once, codeword p in the low and codeword
+// 16 + p in the high 16 bits of every register, so a packed add / VIMNMX.S16x2 serves both and -- unlike packing two states of
+// one codeword -- no register ever has to be taken apart again: where a survivor goes is pure register naming.
+// The 64 states are split over the two lanes of the pair by their LSB.  Role 0 owns the even states; role 1 owns the odd ones but
+// works in COMPLEMENTED coordinates (physical state = logical state ^ 63, physical input = logical input ^ 1): the trellis is
+// invariant under that map, so both roles run the same code on physical even states, and a state handed to the partner arrives as
+// the complement of the sender's index.  Complementing the 7-bit window flips the code bits of the odd-weight polynomials
+// (133, 171) and leaves the even-weight one (145) alone: role 1 negates soft bits 0, 1 and 3.  The tie rules
+// (include/b200dab_spec.h) are invariant under the same map, which makes the two roles agree with the scalar formulation bit for bit.
 //
-// forward registers : L[i] = (a[i], a[i+16]), H[i] = (a[i+32], a[i+48]), i = 0..7 (physical states)
-//   butterfly i: E[i] = (a'[2i], a'[2i+32]), O[i] = (a'[2i+1], a'[2i+33]); decision word bit (n & 15) + 16 (n >> 5) for
-//   physical new state n, 1 = survivor from physical predecessor (n >> 1) + 32
-// Decision bits are collected with predicated adds of a constant.  The ALU pipe (VIMNMX, PRMT, IADD3) is the busy one in this
-// kernel and issues one warp instruction per two cycles, the FMA pipe (IMAD) likewise: half of the bit-sets are therefore
-// written as a multiply-add by a register holding 1, which ptxas has to keep on the FMA pipe.
-__device__ __forceinline__ void vit_setbit_alu(uint32_t& d, bool p, uint32_t bit) { if (p) d |= bit; }
-__device__ __forceinline__ void vit_setbit_fma(uint32_t& d, bool p, uint32_t bit, uint32_t one)
+// registers: M[x] = metric of physical state 2x (x = 0..31) of both codewords.
+//   forward  butterfly j (0..15): predecessors 2j = M[j] and 2j+32 = M[j+16]; survivor of new state 4j stays (M'[2j]), the one of
+//            4j+1 belongs to the partner, where it is state 62-4j = M'[31-2j]: one SHFL.BFLY, no PRMT
+//   backward butterfly j: successors 4j = M[2j] and 4j+1 = the partner's M[31-2j]; results are states 2j = M'[j], 2j+32 = M'[j+16]
+// Branch metrics: beta_q = +-a0 +-a1 +-a2 +-a3 is one IDP.4A against a coefficient word that already holds the role's signs;
+// beta_(7-k) = -beta_k, and the negative of a packed pair is the negative of the 32-bit word, so four registers serve all eight
+// code-bit patterns (the sign goes into the add).
+// Decision bits are collected with predicated adds of a constant.  The ALU pipe (VIMNMX, LOP3, IADD3) and the FMA pipe (IMAD)
+// each issue one warp instruction per two cycles: half of the bit-sets are therefore written as a multiply-add by a register
+// holding 1, which ptxas has to keep on the FMA pipe.
+// max of two packed pairs with the decisions of both halves dropped straight into two decision words: bit BIT of dA is set when
+// the low half of b won, bit BIT of dB when the high half of b won.  TIE_A: a survives a tie (otherwise b does).  The predicates
+// never leave the PTX block (the CUDA intrinsic __vibmax_s16x2 hands them out as 0/1 integers, which ptxas re-materialises under
+// predicate pressure); max.s16x2 + setp.eq on the halves is the pattern ptxas folds into one VIMNMX.S16x2 with two predicates.
+template <int BIT, bool TIE_A>
+__device__ __forceinline__ uint32_t vit_max_dec(uint32_t a, uint32_t b, uint32_t& dA, uint32_t& dB, uint32_t one)
 {
-    if (p) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d) : "r"(one), "r"(bit));
+    uint32_t v;
+    if (TIE_A)          // predicate = (max == a) = a >= b; the bit is its negation
+        asm("{.reg .pred pu, pv; .reg .s16 rs0, rs1, rs2, rs3;\n\t"
+            "max.s16x2 %0, %3, %4;\n\t"
+            "mov.b32 {rs0, rs1}, %0;\n\t"
+            "mov.b32 {rs2, rs3}, %3;\n\t"
+            "setp.eq.s16 pv, rs0, rs2;\n\t"
+            "setp.eq.s16 pu, rs1, rs3;\n\t"
+            "@!pv or.b32 %1, %1, %5;\n\t"
+            "@!pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
+            : "=r"(v), "+r"(dA), "+r"(dB) : "r"(a), "r"(b), "n"(1u << BIT), "r"(one));
+    else                // operands swapped: predicate = (max == b) = b >= a = the bit itself
+        asm("{.reg .pred pu, pv; .reg .s16 rs0, rs1, rs2, rs3;\n\t"
+            "max.s16x2 %0, %4, %3;\n\t"
+            "mov.b32 {rs0, rs1}, %0;\n\t"
+            "mov.b32 {rs2, rs3}, %4;\n\t"
+            "setp.eq.s16 pv, rs0, rs2;\n\t"
+            "setp.eq.s16 pu, rs1, rs3;\n\t"
+            "@pv or.b32 %1, %1, %5;\n\t"
+            "@pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
+            : "=r"(v), "+r"(dA), "+r"(dB) : "r"(a), "r"(b), "n"(1u << BIT), "r"(one));
+    return v;
 }
 
-template <int I>
-__device__ __forceinline__ void vit_bfly(const uint32_t (&L)[8], const uint32_t (&H)[8], uint32_t (&E)[8], uint32_t (&O)[8],
-                                         const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
+// in0 + beta vs in1 - beta -> out0 (in0 survives a tie), in1 + beta vs in0 - beta -> out1 (in1 survives a tie); decision bits 2J
+// and 2J+1 of dA (low halves = codeword p) and dB (high halves = codeword 16 + p), 1 = in1 was taken.
+//   forward : in0/in1 = lower/upper predecessor, out0/out1 = even/odd new state (lower survives a tie for the even, upper for the odd)
+//   backward: in0/in1 = successor by input 0/1, out0/out1 = state 2J / 2J+32 (input 0 wins a tie below 32, input 1 above)
+template <int J>
+__device__ __forceinline__ void vit_bfly(uint32_t in0, uint32_t in1, uint32_t& out0, uint32_t& out1, const uint32_t (&BP)[4],
+                                         uint32_t (&dA)[4], uint32_t (&dB)[4], uint32_t one)
 {
-    uint32_t& dd = d[I & 3];              // four partial decision words: independent chains instead of one serial one
-    constexpr int k = vit_kidx(I);        // BP[k] = +beta, BP[7-k] = -beta
-    bool ph, pl;
-    const uint32_t t0 = L[I] + BP[k], t1 = H[I] + BP[7 - k];       // plain 32-bit adds: see the bias note in k_viterbi
-    E[I] = __vibmax_s16x2(t0, t1, &ph, &pl);          // even new state: the lower predecessor survives a tie
-    vit_setbit_alu(dd, !pl, 1u << (2 * I));
-    vit_setbit_fma(dd, !ph, 1u << (2 * I + 16), one);
-    const uint32_t u0 = L[I] + BP[7 - k], u1 = H[I] + BP[k];
-    O[I] = __vibmax_s16x2(u1, u0, &ph, &pl);          // odd new state: the upper predecessor survives a tie
-    vit_setbit_alu(dd, pl, 1u << (2 * I + 1));
-    vit_setbit_fma(dd, ph, 1u << (2 * I + 17), one);
+    constexpr int k = vit_kidx(2 * J);
+    constexpr bool neg = k >= 4;
+    constexpr int q = neg ? 7 - k : k;
+    const uint32_t t0 = neg ? in0 - BP[q] : in0 + BP[q], t1 = neg ? in1 + BP[q] : in1 - BP[q];     // plain 32-bit adds: see the bias note
+    out0 = vit_max_dec<2 * J, true>(t0, t1, dA[J & 3], dB[J & 3], one);
+    const uint32_t u0 = neg ? in0 + BP[q] : in0 - BP[q], u1 = neg ? in1 - BP[q] : in1 + BP[q];
+    out1 = vit_max_dec<2 * J + 1, false>(u0, u1, dA[J & 3], dB[J & 3], one);
 }
-template <int I> struct VitUnroll {
-    static __device__ __forceinline__ void run(const uint32_t (&L)[8], const uint32_t (&H)[8], uint32_t (&E)[8], uint32_t (&O)[8],
-                                               const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
+template <int J> struct VitFwd {
+    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&dA)[4],
+                                               uint32_t (&dB)[4], uint32_t one)
     {
-        VitUnroll<I - 1>::run(L, H, E, O, BP, d, one);
-        vit_bfly<I>(L, H, E, O, BP, d, one);
+        VitFwd<J - 1>::run(M, N, BP, dA, dB, one);
+        uint32_t e, o;
+        vit_bfly<J>(M[J], M[J + 16], e, o, BP, dA, dB, one);
+        N[2 * J] = e;
+        N[31 - 2 * J] = __shfl_xor_sync(0xffffffffu, o, 1);
     }
 };
-template <> struct VitUnroll<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[8], const uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8],
-                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t) {}
+template <> struct VitFwd<-1> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[4], uint32_t (&)[4], uint32_t) {}
 };
-
-// backward registers: A[i] = (b'[2i], b'[2i+32]), B[i] = (b'[2i+1], b'[2i+33]) (metrics of the NEXT trellis stage), outputs
-//   X[i] = (b[i], b[i+16]), Y[i] = (b[i+32], b[i+48]); decision word bit 2 (s & 7) + (s >> 5) + 16 ((s >> 4) & 1) for
-//   physical state s (the forward pattern again: ptxas turns other layouts into a slower P2R sequence), 1 = the best
-//   continuation takes physical input bit 1
-template <int I>
-__device__ __forceinline__ void vit_bfly_bwd(const uint32_t (&A)[8], const uint32_t (&B)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
-                                             const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
-{
-    uint32_t& dd = d[I & 3];
-    constexpr int k = vit_kidx(I);
-    bool ph, pl;
-    const uint32_t t0 = A[I] + BP[k], t1 = B[I] + BP[7 - k];         // states i, i+16: input 0 -> +beta; input 0 wins a tie
-    X[I] = __vibmax_s16x2(t0, t1, &ph, &pl);
-    vit_setbit_alu(dd, !pl, 1u << (2 * I));
-    vit_setbit_fma(dd, !ph, 1u << (2 * I + 16), one);
-    const uint32_t u0 = A[I] + BP[7 - k], u1 = B[I] + BP[k];         // states i+32, i+48: code bits flipped; input 1 wins a tie
-    Y[I] = __vibmax_s16x2(u1, u0, &ph, &pl);
-    vit_setbit_alu(dd, pl, 1u << (2 * I + 1));
-    vit_setbit_fma(dd, ph, 1u << (2 * I + 17), one);
-}
-template <int I> struct VitUnrollBwd {
-    static __device__ __forceinline__ void run(const uint32_t (&A)[8], const uint32_t (&B)[8], uint32_t (&X)[8], uint32_t (&Y)[8],
-                                               const uint32_t (&BP)[8], uint32_t (&d)[4], uint32_t one)
+template <int J> struct VitBwd {
+    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&dA)[4],
+                                               uint32_t (&dB)[4], uint32_t one)
     {
-        VitUnrollBwd<I - 1>::run(A, B, X, Y, BP, d, one);
-        vit_bfly_bwd<I>(A, B, X, Y, BP, d, one);
+        VitBwd<J - 1>::run(M, N, BP, dA, dB, one);
+        const uint32_t r = __shfl_xor_sync(0xffffffffu, M[31 - 2 * J], 1);
+        vit_bfly<J>(M[2 * J], r, N[J], N[J + 16], BP, dA, dB, one);
     }
 };
-template <> struct VitUnrollBwd<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[8], const uint32_t (&)[8], uint32_t (&)[8], uint32_t (&)[8],
-                                               const uint32_t (&)[8], uint32_t (&)[4], uint32_t) {}
+template <> struct VitBwd<-1> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[4], uint32_t (&)[4], uint32_t) {}
 };
-
-// sg = +1 (role 0) or -1 (role 1)
-__device__ __forceinline__ void vit_branch_metrics(uint32_t w, int sg, uint32_t (&BP)[8])
-{
-    const int a0 = (int8_t)(w), a1 = (int8_t)(w >> 8), a2 = (int8_t)(w >> 16), a3 = (int8_t)(w >> 24);
-    const int T = (a0 + a3) * sg, X1 = a1 * sg + a2, X2 = a1 * sg - a2;
-    // BP[k], k = c0*4 + c1*2 + c2 (1 = code bit 1 = negative contribution): low half  (1-2c0) T + x,
-    //                                                                      high half -(1-2c0) T + x  (state + 16 flips c0, c3)
-    const int xs[4] = {X1, X2, -X2, -X1};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        BP[q] = (uint32_t)((-T + xs[q]) * 65536 + (T + xs[q]));
-        BP[4 + q] = (uint32_t)((T + xs[q]) * 65536 + (-T + xs[q]));
-    }
-}
 
 #define VIT_BIAS 16384u
 #define VIT_PENV ((VIT_BIAS + VIT_START_PENALTY) * 65537u)
 #define VIT_MEET_WORDS (2 * 64 * 32)        /* unsigned shorts per group: [direction][state][codeword] */
+
+// one trellis step of a lane: branch metrics of both codewords from the ring, 16 butterflies M -> N, two decision words out
+template <bool BWD>
+__device__ __forceinline__ void vit_step(const uint32_t (&M)[32], uint32_t (&N)[32], uint32_t wA, uint32_t wB, const uint32_t (&C)[4],
+                                         uint32_t* dst, uint32_t one)
+{
+    uint32_t BP[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) BP[q] = (uint32_t)__dp4a((int)wA, (int)C[q], __dp4a((int)wB, (int)C[q], 0) << 16);
+    uint32_t dA[4] = {0, 0, 0, 0}, dB[4] = {0, 0, 0, 0};
+    if (BWD) VitBwd<15>::run(M, N, BP, dA, dB, one);
+    else VitFwd<15>::run(M, N, BP, dA, dB, one);
+    dst[0] = (dA[0] | dA[1]) | (dA[2] | dA[3]);
+    dst[32] = (dB[0] | dB[1]) | (dB[2] | dB[3]);
+}
 
 // Bidirectional decoding: the code is zero-terminated at BOTH ends, so one work item runs the trellis forward over steps
 // [0, m) from state 0 while another runs it backward over steps [m, T) from state 0; at stage m the state maximising
 // alpha + beta lies on the maximum-likelihood path (k_vit_trace picks it, traces back over [0, m) and forward over [m, T)).
 // Same path as one-directional Viterbi whenever the best path is unique; the tie rules are mirrored by the CPU checker.
 // Metrics carry a bias of 16384 so that both halves of a register stay non-negative and a packed add is one 32-bit add.
-// grid = 4 * n_groups one-warp CTAs (longest groups first): item = (group, which 16 codewords, direction)
+// grid = 2 * n_groups one-warp CTAs (longest groups first): item = (group, direction)
 __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec, unsigned short* __restrict__ meet,
                                                 const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups)
 {
     constexpr int PF = VIT_NORM_PERIOD;
+    static_assert(PF % 2 == 0, "the step loop is unrolled by two");
     __shared__ uint32_t ring[2][PF][32];
     const int item = blockIdx.x;
-    const VitGroup grp = groups[item >> 2];
+    const VitGroup grp = groups[item >> 1];
     const VitJob job = jobs[grp.job];
-    const int lane = threadIdx.x, role = lane & 1, dir = item & 1;
-    const int cw = ((item >> 1) & 1) * 16 + (lane >> 1);
-    const int sg = role ? -1 : 1;
+    const int lane = threadIdx.x, role = lane & 1, p = lane >> 1, dir = item & 1;
     const int steps = job.steps;
     const int m = ((steps >> 1) >> 5) << 5;                         // meeting stage, multiple of 32
-    const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + cw;
-    uint32_t* d = dec + (job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + cw) * 2 + role;
-    unsigned short* mt = meet + ((size_t)(item >> 2) * 2 + dir) * (64 * 32) + cw;
+    const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
+    uint32_t* d = dec + (job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + p) * 2 + role;     // codeword 16 + p: 32 words further on
+    unsigned short* mt = meet + ((size_t)(item >> 1) * 2 + dir) * (64 * 32) + p;
     const uint32_t flip = role ? 63u : 0u;
     const uint32_t one = job.steps > 0 ? 1u : 0u;                   // always 1, but not to the compiler: see vit_setbit_fma
+    // coefficient bytes (a0, a1, a2, a3) of beta_0..3 = T + X1, T + X2, T - X2, T - X1 with T = +-(a0 + a3), X1/X2 = +-a1 +/- a2
+    const uint32_t C[4] = {role ? 0xff01ffffu : 0x01010101u, role ? 0xffffffffu : 0x01ff0101u,
+                           role ? 0xff0101ffu : 0x0101ff01u, role ? 0xffff01ffu : 0x01ffff01u};
 
-    if (dir == 0) {
-        // ------------------------------------------------------------ forward over steps [0, m)
-        uint32_t L[8], H[8], E[8], O[8];
+    uint32_t M[32], N[32];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { L[j] = VIT_PENV; H[j] = VIT_PENV; }
-        if (role == 0) L[0] = ((VIT_BIAS + VIT_START_PENALTY) << 16) | VIT_BIAS;   // state 0 starts at 0, state 16 at the penalty
-        auto prefetch = [&](int buf, int t0) {
+    for (int j = 0; j < 32; j++) M[j] = VIT_PENV;
+    if (role == 0) M[0] = VIT_BIAS * 65537u;                        // both codewords start (forward) / end (backward) in state 0
+    auto prefetch = [&](int buf, int t_first, int t_step) {         // ring slot i holds step t_first + i * t_step
 #pragma unroll
-            for (int i = 0; i < PF; i++) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][i][lane]);
-                const uint32_t* src = in + (size_t)min(t0 + i, steps - 1) * 32;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        prefetch(0, 0);
-        int buf = 0;
-        for (int t0 = 0; t0 < m; t0 += PF, buf ^= 1) {
-            if (t0 + PF < m) { prefetch(buf ^ 1, t0 + PF); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            {   // re-reference all metrics to state 0 (keeps the int16 range; constants do not change any decision)
-                uint32_t c = (uint32_t)(((int)VIT_BIAS - (int)(L[0] & 0xffffu)) * 65537);
-                c = __shfl_sync(0xffffffffu, c, lane & ~1);
-#pragma unroll
-                for (int j = 0; j < 8; j++) { L[j] += c; H[j] += c; }
-            }
-            const int nst = min(PF, m - t0);
-#pragma unroll 2
-            for (int i = 0; i < nst; i++) {
-                uint32_t BP[8];
-                vit_branch_metrics(ring[buf][i][lane], sg, BP);
-                uint32_t dw[4] = {0, 0, 0, 0};
-                VitUnroll<7>::run(L, H, E, O, BP, dw, one);
-                d[(size_t)(t0 + i) * 64] = (dw[0] | dw[1]) | (dw[2] | dw[3]);
-                // E/O[0..3] stay (new states 0..7, 32..39); the partner's E/O[4..7] arrive complemented: its (8+2u+b, 40+2u+b)
-                // are my (55-2u-b, 23-2u-b)
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t re = __shfl_xor_sync(0xffffffffu, E[4 + u], 1), ro = __shfl_xor_sync(0xffffffffu, O[4 + u], 1);
-                    const int je = 7 - 2 * u, jo = 6 - 2 * u;           // received E -> odd slot, received O -> even slot
-                    const uint32_t own_o = O[je >> 1], own_e = E[jo >> 1];
-                    L[je] = __byte_perm(own_o, re, 0x7610); H[je] = __byte_perm(own_o, re, 0x5432);
-                    L[jo] = __byte_perm(own_e, ro, 0x7610); H[jo] = __byte_perm(own_e, ro, 0x5432);
-                }
-            }
+        for (int i = 0; i < PF; i++) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][i][lane]);
+            const uint32_t* src = in + (size_t)min(max(t_first + i * t_step, 0), steps - 1) * 32;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto renorm = [&]() {           // re-reference all metrics to state 0 (keeps the int16 range; constants do not change any decision)
+        const uint32_t c = __shfl_sync(0xffffffffu, VIT_BIAS * 65537u - M[0], lane & ~1);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            mt[((uint32_t)j ^ flip) * 32] = (unsigned short)(L[j] & 0xffffu);        mt[((uint32_t)(j + 16) ^ flip) * 32] = (unsigned short)(L[j] >> 16);
-            mt[((uint32_t)(j + 32) ^ flip) * 32] = (unsigned short)(H[j] & 0xffffu); mt[((uint32_t)(j + 48) ^ flip) * 32] = (unsigned short)(H[j] >> 16);
-        }
-    } else {
-        // ------------------------------------------------------------ backward over steps [m, T), T-1 first
-        uint32_t A[8], B[8], X[8], Y[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { A[j] = VIT_PENV; B[j] = VIT_PENV; }
-        if (role == 0) A[0] = ((VIT_BIAS + VIT_START_PENALTY) << 16) | VIT_BIAS;   // must end in state 0: A[0] = (b[0], b[32])
-        auto prefetch = [&](int buf, int t_hi) {                    // ring slot i holds step t_hi - i
-#pragma unroll
-            for (int i = 0; i < PF; i++) {
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][i][lane]);
-                const uint32_t* src = in + (size_t)max(t_hi - i, 0) * 32;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        prefetch(0, steps - 1);
-        int buf = 0;
-        for (int t_hi = steps - 1; t_hi >= m; t_hi -= PF, buf ^= 1) {
-            if (t_hi - PF >= m) { prefetch(buf ^ 1, t_hi - PF); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            {
-                uint32_t c = (uint32_t)(((int)VIT_BIAS - (int)(A[0] & 0xffffu)) * 65537);
-                c = __shfl_sync(0xffffffffu, c, lane & ~1);
-#pragma unroll
-                for (int j = 0; j < 8; j++) { A[j] += c; B[j] += c; }
-            }
-            const int nst = min(PF, t_hi - m + 1);
+        for (int j = 0; j < 32; j++) M[j] += c;
+    };
+    const int t_begin = dir == 0 ? 0 : steps - 1, t_step = dir == 0 ? 1 : -1, n_total = dir == 0 ? m : steps - m;
+    prefetch(0, t_begin, t_step);
+    int buf = 0;
+    for (int done = 0; done < n_total; done += PF, buf ^= 1) {
+        const int t0 = t_begin + done * t_step;
+        __syncwarp();                                               // everybody is through with the buffer that is refilled now
+        if (done + PF < n_total) { prefetch(buf ^ 1, t0 + PF * t_step, t_step); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                                               // a lane reads the words its neighbours fetched
+        renorm();
+        const int nst = min(PF, n_total - done);
+        if (dir == 0) {
 #pragma unroll 1
             for (int i = 0; i < nst; i++) {
-                uint32_t BP[8];
-                vit_branch_metrics(ring[buf][i][lane], sg, BP);
-                uint32_t dw[4] = {0, 0, 0, 0};
-                VitUnrollBwd<7>::run(A, B, X, Y, BP, dw, one);
-                d[(size_t)(t_hi - i) * 64] = (dw[0] | dw[1]) | (dw[2] | dw[3]);
-                // low halves (states 0..7, 32..39) stay; the partner's high halves (its 16+i, 48+i) are my 47-i, 15-i:
-                // its packed (Y[i].hi, X[i].hi) is my (b[15-i], b[47-i]) = A[(15-i)/2] for odd i, B[(14-i)/2] for even i
+                vit_step<false>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 + i) * 64, one);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t so = __byte_perm(Y[7 - 2 * j], X[7 - 2 * j], 0x7632), se = __byte_perm(Y[6 - 2 * j], X[6 - 2 * j], 0x7632);
-                    A[4 + j] = __shfl_xor_sync(0xffffffffu, so, 1);
-                    B[4 + j] = __shfl_xor_sync(0xffffffffu, se, 1);
-                }
+                for (int j = 0; j < 32; j++) M[j] = N[j];
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < nst; i++) {
+                vit_step<true>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 - i) * 64, one);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    A[j] = __byte_perm(X[2 * j], Y[2 * j], 0x5410);
-                    B[j] = __byte_perm(X[2 * j + 1], Y[2 * j + 1], 0x5410);
-                }
+                for (int j = 0; j < 32; j++) M[j] = N[j];
             }
         }
+    }
+    // metrics at the meeting stage: M[x] = physical state 2x
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            mt[((uint32_t)(2 * j) ^ flip) * 32] = (unsigned short)(A[j] & 0xffffu);     mt[((uint32_t)(2 * j + 32) ^ flip) * 32] = (unsigned short)(A[j] >> 16);
-            mt[((uint32_t)(2 * j + 1) ^ flip) * 32] = (unsigned short)(B[j] & 0xffffu); mt[((uint32_t)(2 * j + 33) ^ flip) * 32] = (unsigned short)(B[j] >> 16);
-        }
+    for (int j = 0; j < 32; j++) {
+        const uint32_t s = (uint32_t)(2 * j) ^ flip;
+        mt[s * 32] = (unsigned short)(M[j] & 0xffffu);
+        mt[s * 32 + 16] = (unsigned short)(M[j] >> 16);
     }
 }
 
 // Meeting state (maximum of alpha + beta, lowest state on ties), traceback over [0, m) (warp 0) and trace forward over
 // [m, n_info) (warp 1), energy-dispersal XOR on the way out.  grid = n_groups, 64 threads, one codeword per lane.
-// With w = x | (~brev(y)) << 32 of a decision pair, the bit of logical state n is bit (n&15 | (n>>1)&16 | (n&16)<<1) of w for a
-// forward step and bit ((s&7)<<1 | s>>5 | s&16 | (s&8)<<2) for a backward step (role 1 wrote complemented positions and values).
+// With w = x | (~brev(y)) << 32 of a decision pair (x: role 0, y: role 1), the bit of logical new state n is bit
+// ((n>>2)<<1 | n&1 | (n&2)<<4) of w for a forward step and the bit of logical state s is bit (s&30 | s>>5 | (s&1)<<5) for a
+// backward step (role 1 wrote complemented positions and values).
 // The state recursion is a dependent chain, so the 32 decision pairs of the next chunk are fetched while this one is traced.
 __device__ __forceinline__ void vit_load_chunk(uint2 (&b)[32], const uint2* d, int c)
 {
@@ -376,14 +336,14 @@ __global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec,
             for (int i = 31; i >= 0; i--) {
                 const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
                 word |= (s & 1u) << (31 - i);
-                const uint32_t idx = (s & 15u) | ((s >> 1) & 16u) | ((s & 16u) << 1);
+                const uint32_t idx = ((s >> 2) << 1) | (s & 1u) | ((s & 2u) << 4);
                 s = (s >> 1) | (((uint32_t)(w >> idx) & 1u) << 5);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
-                const uint32_t idx = ((s & 7u) << 1) | (s >> 5) | (s & 16u) | ((s & 8u) << 2);
+                const uint32_t idx = (s & 30u) | (s >> 5) | ((s & 1u) << 5);
                 const uint32_t bit = (uint32_t)(w >> idx) & 1u;
                 word |= bit << (31 - i);
                 s = ((s << 1) | bit) & 63u;
