@@ -786,6 +786,11 @@ int b200dab_get_kernel_times(b200dab_ctx* ctx, char* names, int names_cap, float
 
 int b200dab_get_kernel_times_back(b200dab_ctx* ctx, int back, char* names, int names_cap, float* ms, int max_n)
 {
+    return b200dab_get_kernel_timeline(ctx, back, names, names_cap, nullptr, ms, max_n);
+}
+
+int b200dab_get_kernel_timeline(b200dab_ctx* ctx, int back, char* names, int names_cap, float* start_ms, float* ms, int max_n)
+{
     if (!ctx || back < 0 || back >= b200dab_ctx::PROF_RING) return -1;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -797,6 +802,7 @@ int b200dab_get_kernel_times_back(b200dab_ctx* ctx, int back, char* names, int n
         float t = 0.f;
         if (cudaEventElapsedTime(&t, prof[i].a, prof[i].b) != cudaSuccess) t = -1.f;
         if (ms) ms[n] = t;
+        if (start_ms && cudaEventElapsedTime(&start_ms[n], prof[0].a, prof[i].a) != cudaSuccess) start_ms[n] = -1.f;
         if (!all.empty()) all += ";";
         all += prof[i].name;
     }

@@ -114,81 +114,55 @@ __host__ __device__ constexpr int vit_kidx(int j) { return vit_cbit(j, 0) * 4 + 
 // Branch metrics: beta_q = +-a0 +-a1 +-a2 +-a3 is one IDP.4A against a coefficient word that already holds the role's signs;
 // beta_(7-k) = -beta_k, and the negative of a packed pair is the negative of the 32-bit word, so four registers serve all eight
 // code-bit patterns (the sign goes into the add).
-// Decision bits are collected with predicated adds of a constant.  The ALU pipe (VIMNMX, LOP3, IADD3) and the FMA pipe (IMAD)
-// each issue one warp instruction per two cycles: half of the bit-sets are therefore written as a multiply-add by a register
-// holding 1, which ptxas has to keep on the FMA pipe.
-// max of two packed pairs with the decisions of both halves dropped straight into two decision words: bit BIT of dA is set when
-// the low half of b won, bit BIT of dB when the high half of b won.  TIE_A: a survives a tie (otherwise b does).  The predicates
-// never leave the PTX block (the CUDA intrinsic __vibmax_s16x2 hands them out as 0/1 integers, which ptxas re-materialises under
-// predicate pressure); max.s16x2 + setp.eq on the halves is the pattern ptxas folds into one VIMNMX.S16x2 with two predicates.
-template <int BIT, bool TIE_A>
-__device__ __forceinline__ uint32_t vit_max_dec(uint32_t a, uint32_t b, uint32_t& dA, uint32_t& dB, uint32_t one)
-{
-    uint32_t v;
-    if (TIE_A)          // predicate = (max == a) = a >= b; the bit is its negation
-        asm("{.reg .pred pu, pv; .reg .s16 rs0, rs1, rs2, rs3;\n\t"
-            "max.s16x2 %0, %3, %4;\n\t"
-            "mov.b32 {rs0, rs1}, %0;\n\t"
-            "mov.b32 {rs2, rs3}, %3;\n\t"
-            "setp.eq.s16 pv, rs0, rs2;\n\t"
-            "setp.eq.s16 pu, rs1, rs3;\n\t"
-            "@!pv or.b32 %1, %1, %5;\n\t"
-            "@!pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
-            : "=r"(v), "+r"(dA), "+r"(dB) : "r"(a), "r"(b), "n"(1u << BIT), "r"(one));
-    else                // operands swapped: predicate = (max == b) = b >= a = the bit itself
-        asm("{.reg .pred pu, pv; .reg .s16 rs0, rs1, rs2, rs3;\n\t"
-            "max.s16x2 %0, %4, %3;\n\t"
-            "mov.b32 {rs0, rs1}, %0;\n\t"
-            "mov.b32 {rs2, rs3}, %4;\n\t"
-            "setp.eq.s16 pv, rs0, rs2;\n\t"
-            "setp.eq.s16 pu, rs1, rs3;\n\t"
-            "@pv or.b32 %1, %1, %5;\n\t"
-            "@pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
-            : "=r"(v), "+r"(dA), "+r"(dB) : "r"(a), "r"(b), "n"(1u << BIT), "r"(one));
-    return v;
-}
-
-// in0 + beta vs in1 - beta -> out0 (in0 survives a tie), in1 + beta vs in0 - beta -> out1 (in1 survives a tie); decision bits 2J
-// and 2J+1 of dA (low halves = codeword p) and dB (high halves = codeword 16 + p), 1 = in1 was taken.
-//   forward : in0/in1 = lower/upper predecessor, out0/out1 = even/odd new state (lower survives a tie for the even, upper for the odd)
-//   backward: in0/in1 = successor by input 0/1, out0/out1 = state 2J / 2J+32 (input 0 wins a tie below 32, input 1 above)
+// Decision bits without predicates.  VIMNMX.S16x2 can hand out its two comparison results as predicates, but there are only seven
+// predicate registers and the predicates arrive ~13 cycles after issue, so a lone warp spent more than half of its time waiting
+// for them (ncu, stall "wait" on every first predicated consumer).  Instead: winner - loser-candidate + 0x7fff per half is
+// >= 0x8000 exactly when the OTHER candidate won (both halves >= 0, no borrow between them), i.e. one IADD3 puts the two
+// decisions into bits 15 and 31; PRMT with sign replication turns the four decision bits of a butterfly into four bytes of
+// 0x00 / 0xff, and one LOP3 bit-select drops them into bit J & 7 of the four bytes of an accumulator.  Same instruction count as
+// two predicated bit-sets per maximum, no predicate anywhere, and every instruction is free to move.
+//   accumulator J >> 3: byte 0 = out0 decisions of codeword p, byte 1 = out1 of p, byte 2 = out0 of 16 + p, byte 3 = out1 of 16 + p
+//   out0: bit = in1 taken.  out1: bit = in0 taken (complemented once per step with a constant).
 template <int J>
-__device__ __forceinline__ void vit_bfly(uint32_t in0, uint32_t in1, uint32_t& out0, uint32_t& out1, const uint32_t (&BP)[4],
-                                         uint32_t (&dA)[4], uint32_t (&dB)[4], uint32_t one)
+__device__ __forceinline__ void vit_bfly(uint32_t in0, uint32_t in1, uint32_t& out0, uint32_t& out1, const uint32_t (&BP)[4], uint32_t (&acc)[2])
 {
     constexpr int k = vit_kidx(2 * J);
     constexpr bool neg = k >= 4;
     constexpr int q = neg ? 7 - k : k;
     const uint32_t t0 = neg ? in0 - BP[q] : in0 + BP[q], t1 = neg ? in1 + BP[q] : in1 - BP[q];     // plain 32-bit adds: see the bias note
-    out0 = vit_max_dec<2 * J, true>(t0, t1, dA[J & 3], dB[J & 3], one);
+    out0 = __vmaxs2(t0, t1);                             // in0 survives a tie: the bit says t1 > t0
+    const uint32_t z0 = out0 - t0 + 0x7fff7fffu;
     const uint32_t u0 = neg ? in0 + BP[q] : in0 - BP[q], u1 = neg ? in1 - BP[q] : in1 + BP[q];
-    out1 = vit_max_dec<2 * J + 1, false>(u0, u1, dA[J & 3], dB[J & 3], one);
+    out1 = __vmaxs2(u0, u1);                             // in1 survives a tie: the bit says u0 > u1
+    const uint32_t z1 = out1 - u1 + 0x7fff7fffu;
+    uint32_t w;                                          // bytes (z0.1, z1.1, z0.3, z1.3), each replaced by eight copies of its MSB
+    asm("prmt.b32 %0, %1, %2, 0xfbd9;" : "=r"(w) : "r"(z0), "r"(z1));
+    constexpr uint32_t m = 0x01010101u << (J & 7);
+    acc[J >> 3] = (acc[J >> 3] & ~m) | (w & m);          // one LOP3
 }
 template <int J> struct VitFwd {
-    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&dA)[4],
-                                               uint32_t (&dB)[4], uint32_t one)
+    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&acc)[2])
     {
-        VitFwd<J - 1>::run(M, N, BP, dA, dB, one);
+        VitFwd<J - 1>::run(M, N, BP, acc);
         uint32_t e, o;
-        vit_bfly<J>(M[J], M[J + 16], e, o, BP, dA, dB, one);
+        vit_bfly<J>(M[J], M[J + 16], e, o, BP, acc);
         N[2 * J] = e;
         N[31 - 2 * J] = __shfl_xor_sync(0xffffffffu, o, 1);
     }
 };
 template <> struct VitFwd<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[4], uint32_t (&)[4], uint32_t) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[2]) {}
 };
 template <int J> struct VitBwd {
-    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&dA)[4],
-                                               uint32_t (&dB)[4], uint32_t one)
+    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&acc)[2])
     {
-        VitBwd<J - 1>::run(M, N, BP, dA, dB, one);
+        VitBwd<J - 1>::run(M, N, BP, acc);
         const uint32_t r = __shfl_xor_sync(0xffffffffu, M[31 - 2 * J], 1);
-        vit_bfly<J>(M[2 * J], r, N[J], N[J + 16], BP, dA, dB, one);
+        vit_bfly<J>(M[2 * J], r, N[J], N[J + 16], BP, acc);
     }
 };
 template <> struct VitBwd<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[4], uint32_t (&)[4], uint32_t) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[2]) {}
 };
 
 #define VIT_BIAS 16384u
@@ -198,16 +172,17 @@ template <> struct VitBwd<-1> {
 // one trellis step of a lane: branch metrics of both codewords from the ring, 16 butterflies M -> N, two decision words out
 template <bool BWD>
 __device__ __forceinline__ void vit_step(const uint32_t (&M)[32], uint32_t (&N)[32], uint32_t wA, uint32_t wB, const uint32_t (&C)[4],
-                                         uint32_t* dst, uint32_t one)
+                                         uint32_t* dst)
 {
     uint32_t BP[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) BP[q] = (uint32_t)__dp4a((int)wA, (int)C[q], __dp4a((int)wB, (int)C[q], 0) << 16);
-    uint32_t dA[4] = {0, 0, 0, 0}, dB[4] = {0, 0, 0, 0};
-    if (BWD) VitBwd<15>::run(M, N, BP, dA, dB, one);
-    else VitFwd<15>::run(M, N, BP, dA, dB, one);
-    dst[0] = (dA[0] | dA[1]) | (dA[2] | dA[3]);
-    dst[32] = (dB[0] | dB[1]) | (dB[2] | dB[3]);
+    uint32_t acc[2] = {0, 0};
+    if (BWD) VitBwd<15>::run(M, N, BP, acc);
+    else VitFwd<15>::run(M, N, BP, acc);
+    // codeword p: bytes 0, 1 of both accumulators; codeword 16 + p: bytes 2, 3; the out1 bytes are complemented (1 = in1 was taken)
+    dst[0] = __byte_perm(acc[0], acc[1], 0x5410) ^ 0xff00ff00u;
+    dst[32] = __byte_perm(acc[0], acc[1], 0x7632) ^ 0xff00ff00u;
 }
 
 // Bidirectional decoding: the code is zero-terminated at BOTH ends, so one work item runs the trellis forward over steps
@@ -232,7 +207,6 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
     uint32_t* d = dec + (job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + p) * 2 + role;     // codeword 16 + p: 32 words further on
     unsigned short* mt = meet + ((size_t)(item >> 1) * 2 + dir) * (64 * 32) + p;
     const uint32_t flip = role ? 63u : 0u;
-    const uint32_t one = job.steps > 0 ? 1u : 0u;                   // always 1, but not to the compiler: see vit_setbit_fma
     // coefficient bytes (a0, a1, a2, a3) of beta_0..3 = T + X1, T + X2, T - X2, T - X1 with T = +-(a0 + a3), X1/X2 = +-a1 +/- a2
     const uint32_t C[4] = {role ? 0xff01ffffu : 0x01010101u, role ? 0xffffffffu : 0x01ff0101u,
                            role ? 0xff0101ffu : 0x0101ff01u, role ? 0xffff01ffu : 0x01ffff01u};
@@ -266,17 +240,26 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
         __syncwarp();                                               // a lane reads the words its neighbours fetched
         renorm();
         const int nst = min(PF, n_total - done);
+        int i = 0;
         if (dir == 0) {
 #pragma unroll 1
-            for (int i = 0; i < nst; i++) {
-                vit_step<false>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 + i) * 64, one);
+            for (; i + 1 < nst; i += 2) {           // two steps per iteration: M -> N -> M, no register copies
+                vit_step<false>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 + i) * 64);
+                vit_step<false>(N, M, ring[buf][i + 1][p], ring[buf][i + 1][16 + p], C, d + (size_t)(t0 + i + 1) * 64);
+            }
+            if (i < nst) {
+                vit_step<false>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 + i) * 64);
 #pragma unroll
                 for (int j = 0; j < 32; j++) M[j] = N[j];
             }
         } else {
 #pragma unroll 1
-            for (int i = 0; i < nst; i++) {
-                vit_step<true>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 - i) * 64, one);
+            for (; i + 1 < nst; i += 2) {
+                vit_step<true>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 - i) * 64);
+                vit_step<true>(N, M, ring[buf][i + 1][p], ring[buf][i + 1][16 + p], C, d + (size_t)(t0 - i - 1) * 64);
+            }
+            if (i < nst) {
+                vit_step<true>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 - i) * 64);
 #pragma unroll
                 for (int j = 0; j < 32; j++) M[j] = N[j];
             }
@@ -293,9 +276,11 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
 
 // Meeting state (maximum of alpha + beta, lowest state on ties), traceback over [0, m) (warp 0) and trace forward over
 // [m, n_info) (warp 1), energy-dispersal XOR on the way out.  grid = n_groups, 64 threads, one codeword per lane.
-// With w = x | (~brev(y)) << 32 of a decision pair (x: role 0, y: role 1), the bit of logical new state n is bit
-// ((n>>2)<<1 | n&1 | (n&2)<<4) of w for a forward step and the bit of logical state s is bit (s&30 | s>>5 | (s&1)<<5) for a
-// backward step (role 1 wrote complemented positions and values).
+// A role's decision word holds the decision of butterfly J (0..15) for its first / second output at bit 16 (J >> 3) + (J & 7) and
+// 8 bits above.  Role 0 works on logical states: forward, new state n (n & 2 clear) is output n & 1 of butterfly n >> 2; backward,
+// state s (s & 1 clear) is output s >> 5 of butterfly (s >> 1) & 15.  Role 1 holds the complemented states with complemented
+// decisions, and the complement of (J, output) is (15 - J, 1 - output) = bit position 31 - pos: with w = x | (~brev(y)) << 32 of
+// a decision pair (x: role 0, y: role 1) both roles are read with the same index formula.
 // The state recursion is a dependent chain, so the 32 decision pairs of the next chunk are fetched while this one is traced.
 __device__ __forceinline__ void vit_load_chunk(uint2 (&b)[32], const uint2* d, int c)
 {
@@ -336,14 +321,14 @@ __global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec,
             for (int i = 31; i >= 0; i--) {
                 const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
                 word |= (s & 1u) << (31 - i);
-                const uint32_t idx = ((s >> 2) << 1) | (s & 1u) | ((s & 2u) << 4);
+                const uint32_t idx = ((s >> 5) << 4) | ((s & 1u) << 3) | ((s >> 2) & 7u) | ((s & 2u) << 4);
                 s = (s >> 1) | (((uint32_t)(w >> idx) & 1u) << 5);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
-                const uint32_t idx = (s & 30u) | (s >> 5) | ((s & 1u) << 5);
+                const uint32_t idx = (((s >> 4) & 1u) << 4) | ((s >> 5) << 3) | ((s >> 1) & 7u) | ((s & 1u) << 5);
                 const uint32_t bit = (uint32_t)(w >> idx) & 1u;
                 word |= bit << (31 - i);
                 s = ((s << 1) | bit) & 63u;

@@ -111,6 +111,7 @@ def lib():
         L.b200dab_set_profiling.argtypes = [vp, i32]
         L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
         L.b200dab_get_kernel_times_back.argtypes = [vp, i32, ct.c_char_p, i32, vp, i32]
+        L.b200dab_get_kernel_timeline.argtypes = [vp, i32, ct.c_char_p, i32, vp, vp, i32]
         L.b200dab_stage_coarse.argtypes = [vp, vp, u64, i32, vp, vp, vp, ct.POINTER(i32), i32]
         L.b200dab_stage_fine.argtypes = [vp, vp, u64, i32, vp, i32, vp, vp, vp]
         L.b200dab_stage_demod.argtypes = [vp, vp, u64, i32, vp, vp, i32, vp]
@@ -125,7 +126,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_get_kernel_timeline", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -321,6 +322,15 @@ class Receiver:
         for k, v in zip(nm, ms[:n].tolist()):      # a kernel may be launched several times per decode (chunked front end)
             tot[k] = tot.get(k, 0.0) + v
         return list(tot.items())
+
+    def kernel_timeline(self, back: int = 0):
+        """[(kernel name, start ms after the first kernel of that decode, duration ms)] in launch order."""
+        names = ct.create_string_buffer(32768)
+        ms = np.zeros(1024, np.float32)
+        st = np.zeros(1024, np.float32)
+        n = lib().b200dab_get_kernel_timeline(self._h, back, names, 32768, st.ctypes.data, ms.ctypes.data, 1024)
+        nm = names.value.decode().split(";") if n > 0 else []
+        return [(k, float(a), float(b)) for k, a, b in zip(nm, st[:n], ms[:n])]
 
     # ------------------------------------------------------------------ whole path
     def decode_raw(self, ptr: int, n_samples: int, fmt: str, on_device: bool, subch: Optional[Sequence[SubCh]] = None,

@@ -367,7 +367,7 @@ def main():
         if "viterbi(msc)" in dom["kernel"]:
             acs = trellis_steps * 64.0
             roof["issue"] = {"acs_per_s": acs / (dom["ms"] * 1e-3), "trellis_steps": trellis_steps,
-                             "warp_instr_per_step_per_16cw": 142, "est_issue_slots_used": round(trellis_steps / 16 * 142 / (dom["ms"] * 1e-3)
+                             "warp_instr_per_step_per_32cw": 209, "est_issue_slots_used": round(trellis_steps / 32 * 209 / (dom["ms"] * 1e-3)
                              / (148 * 4 * (clk.get("sm_mhz") or 1500) * 1e6), 4)}
 
     line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

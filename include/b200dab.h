@@ -166,6 +166,8 @@ B200DAB_API int b200dab_set_profiling(b200dab_ctx *ctx, int on);
 B200DAB_API int b200dab_get_kernel_times(b200dab_ctx *ctx, char *names, int names_cap, float *ms, int max_n);
 /* same for the call `back` calls ago (0 = last; the events of the last 8 calls are kept) */
 B200DAB_API int b200dab_get_kernel_times_back(b200dab_ctx *ctx, int back, char *names, int names_cap, float *ms, int max_n);
+/* same, plus where each kernel started on the stream (ms after the first kernel of that call): shows the gaps between kernels */
+B200DAB_API int b200dab_get_kernel_timeline(b200dab_ctx *ctx, int back, char *names, int names_cap, float *start_ms, float *ms, int max_n);
 
 /* ---- stage entry points (host buffers in, host buffers out): the kernels of the path one by one, for parity tests
  *      against oracle/ and for profiling.  They launch exactly the kernels b200dab_decode launches. */
