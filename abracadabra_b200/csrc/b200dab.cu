@@ -80,6 +80,7 @@ struct b200dab_ctx {
     std::string err;
     int launches = 0;
     cudaEvent_t ev_msc = nullptr, ev_d2h = nullptr;   // ordering of the split device-to-host copy of the logical frames
+    cudaEvent_t ev_rs = nullptr, ev_tii = nullptr;    // behind k_rs_decode (DAB+ frames final) / behind k_tii_detect
     size_t vit_dsmem = 14 * 1024;  // extra dynamic shared memory per k_viterbi CTA: caps residency at 11 one-warp CTAs per SM, so the
                                    // shorter work items are dealt out as the long ones finish (tools/vit_residency.py sweeps this)
     // constant tables on the device
@@ -622,6 +623,7 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     prof_begin("k_rs_decode");
     k_rs_decode<<<dim3((max_cw + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<GfTables>());
     prof_end();
+    if (ev_rs) CK(cudaEventRecord(ev_rs, stream));        // the logical frames are final from here on: the caller starts their copy
     prof_begin("k_au_split+k_au_crc");
     k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
     k_au_crc<<<dim3((max_sf * 6 + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
@@ -744,7 +746,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
                      &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
-    if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); }
+    if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); cudaEventDestroy(ctx->ev_rs); cudaEventDestroy(ctx->ev_tii); }
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -984,62 +986,13 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     res->n_subch = (int)ctx->r_subch.size();
     res->subch = ctx->r_subch.data();
     TRACE("sub-channels known");
-    // ---- MSC
-    std::vector<size_t> out_off;
-    size_t msc_bytes = 0;
-    const int n_rows = 4 * n_slots - (DAB_TDI_DEPTH - 1);
-    std::vector<DabPlusJob> dpjobs;
-    std::vector<int> dp_subch;
-    int total_sf = 0, total_rows = 0;
-    if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
-        if (ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes)) return -1;
-        TRACE("msc submitted");
-        for (size_t i = 0; i < ctx->r_subch.size(); i++) {
-            if (ctx->r_subch[i].kind != 1) continue;
-            DabPlusJob j;
-            j.frames_off = (long long)out_off[i]; j.n_rows = n_rows; j.pitch = ctx->r_subch[i].bitrate * 3; j.s = ctx->r_subch[i].bitrate / 8;
-            j.sf_off = total_sf; j.max_sf = n_rows / 5; j.flag_off = total_rows; j.subch_index = (int)i;
-            total_sf += j.max_sf; total_rows += n_rows;
-            dpjobs.push_back(j); dp_subch.push_back((int)i);
-        }
-        // The logical frames of the DAB (MP2) and data sub-channels are final once the trace kernel has run: their copy to the host
-        // goes to the copy stream and runs under the DAB+ kernels (fire code, RS, AU CRC); the DAB+ sub-channels follow on the
-        // main stream after the RS correction.  Adjacent sub-channels of the same class are copied in one piece.
-        CKC(ctx->h_msc.ensure(msc_bytes + 64));
-        if (!ctx->copy_stream) CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        if (!ctx->ev_msc) { CKC(cudaEventCreateWithFlags(&ctx->ev_msc, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming)); }
-        auto copy_class = [&](bool dabplus_class, cudaStream_t st) -> int {
-            const size_t n = ctx->r_subch.size();
-            for (size_t i = 0; i < n;) {
-                if ((ctx->r_subch[i].kind == 1) != dabplus_class) { i++; continue; }
-                size_t j = i;
-                while (j + 1 < n && (ctx->r_subch[j + 1].kind == 1) == dabplus_class) j++;
-                const size_t a = out_off[i], b = (j + 1 < n) ? out_off[j + 1] : msc_bytes;
-                CKC(cudaMemcpyAsync((uint8_t*)ctx->h_msc.p + a, (const uint8_t*)ctx->d_msc_out.p + a, b - a, cudaMemcpyDeviceToHost, st));
-                i = j + 1;
-            }
-            return 0;
-        };
-        const bool split = !dpjobs.empty();
-        if (split) {
-            CKC(cudaEventRecord(ctx->ev_msc, ctx->stream));
-            CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_msc, 0));
-            if (copy_class(false, ctx->copy_stream)) return -1;
-            CKC(cudaEventRecord(ctx->ev_d2h, ctx->copy_stream));
-        }
-        if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows)) return -1;
-        if (split) {
-            if (copy_class(true, ctx->stream)) return -1;
-            CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));
-        } else CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (total_sf > 0) {
-            static_assert(sizeof(AuRecord) == sizeof(b200dab_au_t), "AU record layout");
-            CKC(ctx->h_sf.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + sizeof(DabPlusTotals)));
-            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, ctx->stream));
-            CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, ctx->stream));
-        }
+    // the copy stream carries every larger device-to-host copy, each behind the event of the kernel that finishes its source
+    if (!ctx->copy_stream) CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_msc) {
+        CKC(cudaEventCreateWithFlags(&ctx->ev_msc, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ctx->ev_rs, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_tii, cudaEventDisableTiming));
     }
-    TRACE("msc+dab+ submitted");
+    bool copies_pending = false;
     // ---- TII detection needs to know which nulls carry TII: CIF counter (FIG 0/0) = 0 mod 8
     int n_win = 0;
     if (want_tii) {
@@ -1073,16 +1026,78 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         ctx->launches += 1;
         CKC(cudaGetLastError());
         CKC(ctx->h_tii.ensure(wins.size() * sizeof(TiiResult)));
-        CKC(cudaMemcpyAsync(ctx->h_tii.p, ctx->d_tii.p, wins.size() * sizeof(TiiResult), cudaMemcpyDeviceToHost, ctx->stream));
         CKC(ctx->h_fold.ensure((size_t)n_slots * TII_SPECTRUM_BINS * 4));
         CKC(ctx->h_norm.ensure((size_t)n_slots * 4));
-        CKC(cudaMemcpyAsync(ctx->h_fold.p, ctx->d_fold.p, (size_t)n_slots * TII_SPECTRUM_BINS * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CKC(cudaMemcpyAsync(ctx->h_norm.p, ctx->d_norm.p, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CKC(cudaEventRecord(ctx->ev_tii, ctx->stream));
+        CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tii, 0));
+        CKC(cudaMemcpyAsync(ctx->h_tii.p, ctx->d_tii.p, wins.size() * sizeof(TiiResult), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CKC(cudaMemcpyAsync(ctx->h_fold.p, ctx->d_fold.p, (size_t)n_slots * TII_SPECTRUM_BINS * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CKC(cudaMemcpyAsync(ctx->h_norm.p, ctx->d_norm.p, (size_t)n_slots * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        copies_pending = true;
         res->tii_fold = ctx->h_fold.as<float>(); res->tii_norm = ctx->h_norm.as<float>(); res->tii_sign = ctx->r_sign.data();
     }
+    // ---- MSC
+    std::vector<size_t> out_off;
+    size_t msc_bytes = 0;
+    const int n_rows = 4 * n_slots - (DAB_TDI_DEPTH - 1);
+    std::vector<DabPlusJob> dpjobs;
+    std::vector<int> dp_subch;
+    int total_sf = 0, total_rows = 0;
+    if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
+        if (ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes)) return -1;
+        TRACE("msc submitted");
+        for (size_t i = 0; i < ctx->r_subch.size(); i++) {
+            if (ctx->r_subch[i].kind != 1) continue;
+            DabPlusJob j;
+            j.frames_off = (long long)out_off[i]; j.n_rows = n_rows; j.pitch = ctx->r_subch[i].bitrate * 3; j.s = ctx->r_subch[i].bitrate / 8;
+            j.sf_off = total_sf; j.max_sf = n_rows / 5; j.flag_off = total_rows; j.subch_index = (int)i;
+            total_sf += j.max_sf; total_rows += n_rows;
+            dpjobs.push_back(j); dp_subch.push_back((int)i);
+        }
+        // The logical frames of the DAB (MP2) and data sub-channels are final once the trace kernel has run: their copy to the host
+        // goes to the copy stream and runs under the DAB+ kernels (fire code, RS); the DAB+ sub-channels follow on the copy stream
+        // as soon as the RS correction is through, under the access-unit kernels.  Adjacent sub-channels of the same class are
+        // copied in one piece.
+        CKC(ctx->h_msc.ensure(msc_bytes + 64));
+        auto copy_class = [&](bool dabplus_class, cudaStream_t st) -> int {
+            const size_t n = ctx->r_subch.size();
+            for (size_t i = 0; i < n;) {
+                if ((ctx->r_subch[i].kind == 1) != dabplus_class) { i++; continue; }
+                size_t j = i;
+                while (j + 1 < n && (ctx->r_subch[j + 1].kind == 1) == dabplus_class) j++;
+                const size_t a = out_off[i], b = (j + 1 < n) ? out_off[j + 1] : msc_bytes;
+                CKC(cudaMemcpyAsync((uint8_t*)ctx->h_msc.p + a, (const uint8_t*)ctx->d_msc_out.p + a, b - a, cudaMemcpyDeviceToHost, st));
+                i = j + 1;
+            }
+            return 0;
+        };
+        const bool split = !dpjobs.empty();
+        if (split) {
+            CKC(cudaEventRecord(ctx->ev_msc, ctx->stream));
+            CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_msc, 0));
+            if (copy_class(false, ctx->copy_stream)) return -1;
+            copies_pending = true;
+        }
+        if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows)) return -1;
+        if (split) {
+            CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rs, 0));
+            if (copy_class(true, ctx->copy_stream)) return -1;
+        } else CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (total_sf > 0) {
+            static_assert(sizeof(AuRecord) == sizeof(b200dab_au_t), "AU record layout");
+            CKC(ctx->h_sf.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + sizeof(DabPlusTotals)));
+            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    TRACE("msc+dab+ submitted");
     if (want_stat) {
         CKC(ctx->h_symstat.ensure((size_t)n_slots * 150 * 4));
         CKC(cudaMemcpyAsync(ctx->h_symstat.p, ctx->d_symstat.p, (size_t)n_slots * 150 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (copies_pending) {
+        CKC(cudaEventRecord(ctx->ev_d2h, ctx->copy_stream));
+        CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h, 0));
     }
     TRACE("all submitted");
     CKC(cudaStreamSynchronize(ctx->stream));
