@@ -73,6 +73,8 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 static const bool g_trace = getenv("B200DAB_TRACE") != nullptr;
 #define TRACE(msg) do { if (g_trace) fprintf(stderr, "[trace] %-28s %.3f ms\n", msg, now_ms() - ctx->t_trace0); } while (0)
 
+#define EARLY_FIC_FRAMES 16      /* frames of the early FIC slice: the first two prefixes (8, 16) of the sub-channel discovery */
+
 struct b200dab_ctx {
     int device = 0;
     double t_trace0 = 0;
@@ -95,12 +97,22 @@ struct b200dab_ctx {
         size_t n_groups = 0, words = 0;
         int max_steps = 0;
         DevBuf d_jobs, d_groups, d_stepinfo;
-    } vit_tables[2];
+        DevBuf d_vin, d_dec, d_meet;   // work buffers of the set: the FIC chain runs on its own stream next to the MSC chain
+    } vit_tables[3];                   // [0] FIC, [1] MSC, [2] FIC of the first frames only (early sub-channel discovery)
+    int vit_set = -1;                  // table set forced by the caller (-1: by job kind)
+    cudaStream_t cur = nullptr;        // stream the helpers below launch on (nullptr: `stream`)
+    cudaStream_t S() const { return cur ? cur : stream; }
+    cudaStream_t fic_stream = nullptr;
+    cudaEvent_t ev_early_demod = nullptr, ev_early_fic = nullptr, ev_demod = nullptr, ev_fic_stream = nullptr;
+    DevBuf d_fic_out_early, d_fib_ok_early;
+    HostBuf h_fibs_early, h_fib_ok_early;
+    int early_frames = 0;              // > 0: front_end splits its first demodulation launch and starts the early FIC slice
+    bool early_launched = false;
     DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
     DevBuf d_tmp_a, d_tmp_b, d_spec;
     HostBuf h_spec;
     HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
-    HostBuf h_jobs[2], h_groups[2], h_stepinfo[2], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
+    HostBuf h_jobs[3], h_groups[3], h_stepinfo[3], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
     std::vector<int32_t> r_sign;
     std::vector<std::pair<b200dab_subch_t, std::vector<uint32_t>>> stepinfo_cache;   // de-puncturing tables by protection profile
     // result storage
@@ -129,12 +141,12 @@ struct b200dab_ctx {
         size_t& used = prof_counts[prof_slot];
         if (used == prof.size()) { ProfEv e; e.name = name; cudaEventCreate(&e.a); cudaEventCreate(&e.b); prof.push_back(e); }
         prof[used].name = name;
-        cudaEventRecord(prof[used].a, stream);
+        cudaEventRecord(prof[used].a, S());
     }
     void prof_end()
     {
         if (!profile) return;
-        cudaEventRecord(prof_sets[prof_slot][prof_counts[prof_slot]].b, stream);
+        cudaEventRecord(prof_sets[prof_slot][prof_counts[prof_slot]].b, S());
         prof_counts[prof_slot]++;
     }
 
@@ -151,7 +163,7 @@ struct b200dab_ctx {
         const size_t nw = (bytes + 3) / 4;
         if (!nw) return 0;
         const unsigned grid = (unsigned)std::min<size_t>(64, (nw + 255) / 256);
-        k_fetch<<<grid, 256, 0, stream>>>(reinterpret_cast<uint32_t*>(d_dst), reinterpret_cast<const uint32_t*>(h_pinned), nw);
+        k_fetch<<<grid, 256, 0, S()>>>(reinterpret_cast<uint32_t*>(d_dst), reinterpret_cast<const uint32_t*>(h_pinned), nw);
         launches += 1;
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
@@ -172,7 +184,8 @@ struct b200dab_ctx {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
     int run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out);
-    int fic(int n_slots);
+    int fic(int n_slots, bool early = false);
+    int early_fic();
     int msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std::vector<size_t>& out_off, size_t* total);
     int dabplus(uint8_t* d_frames, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows);
 };
@@ -409,6 +422,26 @@ int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int fir
     return 0;
 }
 
+// FIC of the first `early_frames` frames on the FIC stream, behind their demodulation: FIG 0/1 and 0/2 repeat every few frames, so
+// the sub-channel organisation is known (and the MSC chain can be queued) while the rest of the recording is still demodulated.
+int b200dab_ctx::early_fic()
+{
+    const int k = early_frames;
+    CK(cudaEventRecord(ev_early_demod, stream));
+    CK(cudaStreamWaitEvent(fic_stream, ev_early_demod, 0));
+    cur = fic_stream;
+    const int rc = fic(k, true);
+    cur = nullptr;
+    if (rc) return -1;
+    CK(h_fibs_early.ensure((size_t)k * 12 * 32));
+    CK(h_fib_ok_early.ensure((size_t)k * 12));
+    CK(cudaMemcpyAsync(h_fibs_early.p, d_fic_out_early.p, (size_t)k * 12 * 32, cudaMemcpyDeviceToHost, fic_stream));
+    CK(cudaMemcpyAsync(h_fib_ok_early.p, d_fib_ok_early.p, (size_t)k * 12, cudaMemcpyDeviceToHost, fic_stream));
+    CK(cudaEventRecord(ev_early_fic, fic_stream));
+    early_launched = true;
+    return 0;
+}
+
 // Front end over the sample range [off, off + len) of the device buffer: coarse sync, fine sync, host-side chaining with the
 // frames found so far, OFDM demodulation of the new frames.  Ranges must come in ascending order and overlap by more than
 // one frame so that a frame cut by a range boundary is found whole in the next range.
@@ -456,14 +489,21 @@ int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len
         fe_cir.push_back(f[i].cir_ratio);
         fe_last = t_abs;
     }
-    return demod(d_iq, off + len, fmt, first_new, (int)fe_frames - first_new, want_stat, want_tii);
+    const int count = (int)fe_frames - first_new;
+    if (early_frames > 0 && !early_launched && first_new == 0 && count > early_frames && hf[early_frames - 1].slot == early_frames - 1) {
+        // the first frames on their own (no lost frame among them), the early FIC slice behind them, then the rest
+        if (demod(d_iq, off + len, fmt, 0, early_frames, want_stat, want_tii) || early_fic()) return -1;
+        return demod(d_iq, off + len, fmt, early_frames, count - early_frames, want_stat, want_tii);
+    }
+    return demod(d_iq, off + len, fmt, first_new, count, want_stat, want_tii);
 }
 
 // ------------------------------------------------------------------------------------------------ Viterbi (gather + ACS + traceback)
 // jobs_in: vin_off/dec_off are filled here; out_off, row0, ... by the caller.  Soft bits are read from d_soft.
 int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out)
 {
-    const int st = jobs_in[0].kind == 0 ? 0 : 1;              // [0] FIC, [1] MSC: each call site owns its tables
+    const int st = vit_set >= 0 ? vit_set : (jobs_in[0].kind == 0 ? 0 : 1);   // each call site owns its tables and work buffers
+    cudaStream_t stream = S();
     VitTables& vt = vit_tables[st];
     // The job / group / step tables only depend on the sub-channel organisation and the number of CIFs: when they equal those of
     // the previous call (every window of a stream, every recording of one multiplex) what is already on the device is reused.
@@ -503,19 +543,20 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     }
     if (vt.n_groups == 0) return 0;
     const size_t n_groups = vt.n_groups;
+    DevBuf &d_vin = vt.d_vin, &d_dec = vt.d_dec, &d_meet = vt.d_meet;
     CK(d_vin.ensure(vt.words * 4));
     CK(d_dec.ensure(vt.words * 8));
     CK(d_meet.ensure(n_groups * VIT_MEET_WORDS * sizeof(unsigned short)));
     const VitJob* dj = vt.d_jobs.as<VitJob>();
     const VitGroup* dg = vt.d_groups.as<VitGroup>();
     dim3 ggrid((unsigned)n_groups, (unsigned)((vt.max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
-    prof_begin(st == 0 ? "k_gather(fic)" : "k_gather(msc)");
+    prof_begin(st == 0 ? "k_gather(fic)" : st == 2 ? "k_gather(early fic)" : "k_gather(msc)");
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), dj, dg, vt.d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
-    prof_begin(st == 0 ? "k_viterbi(fic)" : "k_viterbi(msc)");
+    prof_begin(st == 0 ? "k_viterbi(fic)" : st == 2 ? "k_viterbi(early fic)" : "k_viterbi(msc)");
     k_viterbi<<<(unsigned)n_groups * 2, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg);
     prof_end();
-    prof_begin(st == 0 ? "k_vit_trace(fic)" : "k_vit_trace(msc)");
+    prof_begin(st == 0 ? "k_vit_trace(fic)" : st == 2 ? "k_vit_trace(early fic)" : "k_vit_trace(msc)");
     k_vit_trace<<<(unsigned)n_groups, 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out);
     prof_end();
     launches += 3;
@@ -541,8 +582,11 @@ static VitJob make_job(const b200dab_subch_t& sc, int kind, int n_rows, int max_
     return j;
 }
 
-int b200dab_ctx::fic(int n_slots)
+int b200dab_ctx::fic(int n_slots, bool early)
 {
+    cudaStream_t stream = S();
+    DevBuf& d_fic_out = early ? d_fic_out_early : this->d_fic_out;
+    DevBuf& d_fib_ok = early ? d_fib_ok_early : this->d_fib_ok;
     b200dab_subch_t ficp;
     memset(&ficp, 0, sizeof ficp);
     ficp.bitrate = 32; ficp.n_seg = 2; ficp.seg_len[0] = 21; ficp.seg_pi[0] = 16; ficp.seg_len[1] = 3; ficp.seg_pi[1] = 15;
@@ -552,9 +596,12 @@ int b200dab_ctx::fic(int n_slots)
     std::vector<VitJob> jobs(1, make_job(ficp, 0, n_rows, n_rows - 1, 0, 0));
     CK(d_fic_out.ensure((size_t)(n_rows + 32) * 96));
     CK(d_fib_ok.ensure((size_t)n_rows * 3 + 64));
-    if (run_viterbi(jobs, si, d_fic_out.as<uint8_t>())) return -1;
+    vit_set = early ? 2 : -1;
+    const int rc = run_viterbi(jobs, si, d_fic_out.as<uint8_t>());
+    vit_set = -1;
+    if (rc) return -1;
     const int n_fib = n_rows * 3;
-    prof_begin("k_fib_crc");
+    prof_begin(early ? "k_fib_crc(early)" : "k_fib_crc");
     k_fib_crc<<<(n_fib + 255) / 256, 256, 0, stream>>>(d_fic_out.as<uint8_t>(), n_fib, d_fib_ok.as<uint8_t>());
     prof_end();
     launches += 1;
@@ -726,6 +773,13 @@ int b200dab_create(b200dab_ctx** out, int device)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
     if (const char* e = getenv("B200DAB_VIT_DSMEM")) ctx->vit_dsmem = (size_t)atoi(e);
     cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    // The FIC stream has priority: its few small CTAs are placed as soon as slots free up, ahead of the thousands of pending CTAs of
+    // the demodulation / MSC kernels they run next to.
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&ctx->fic_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -5; }
+    cudaEventCreateWithFlags(&ctx->ev_early_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_early_fic, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_fic_stream, cudaEventDisableTiming);
     if (ctx->init_tables()) { fprintf(stderr, "b200dab: %s\n", ctx->err.c_str()); cudaStreamDestroy(ctx->stream); delete ctx; return -6; }
     *out = ctx;
     return 0;
@@ -739,15 +793,16 @@ void b200dab_destroy(b200dab_ctx* ctx)
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
-                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
-                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
+                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); cudaEventDestroy(ctx->ev_rs); cudaEventDestroy(ctx->ev_tii); }
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
+    if (ctx->fic_stream) { cudaEventDestroy(ctx->ev_early_demod); cudaEventDestroy(ctx->ev_early_fic); cudaEventDestroy(ctx->ev_demod); cudaEventDestroy(ctx->ev_fic_stream); cudaStreamDestroy(ctx->fic_stream); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
@@ -887,6 +942,10 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     bool deferred_tii = false;
     const int max_slots = (int)(n / DAB_T_FRAME) + 2;
     ctx->fe_frames = 0; ctx->fe_t0 = 0; ctx->fe_last = 0; ctx->fe_candidates = 0; ctx->fe_cir.clear();
+    // early sub-channel discovery pays when the sub-channels have to be found and there is an MSC to decode behind a long front end
+    ctx->early_launched = false;
+    ctx->cur = nullptr;
+    ctx->early_frames = (!(subch_in && n_subch_in > 0) && !(flags & B200DAB_OPT_NO_MSC)) ? EARLY_FIC_FRAMES : 0;
     if (ctx->prepare_slots(max_slots, want_stat, want_tii)) return -1;
     // ---- front end: sync + OFDM demodulation.  A host buffer is uploaded in chunks on a second stream and each chunk is
     //      synchronised and demodulated while the next one is still crossing PCIe; a device buffer is done in one range.
@@ -952,34 +1011,55 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(cudaMemcpyAsync(ctx->h_spec.p, ctx->d_spec.p, (size_t)n_slots * 2 * DAB_NFFT * 4, cudaMemcpyDeviceToHost, ctx->stream));
         res->spectrum = ctx->h_spec.as<float>();
     }
-    // ---- FIC
-    if (ctx->fic(n_slots)) return -1;
+    // ---- FIC: its own stream behind the demodulation, so that it runs next to the MSC chain once the sub-channels are known
+    if (!ctx->ev_fic) CKC(cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming));
+    CKC(cudaEventRecord(ctx->ev_demod, ctx->stream));
+    CKC(cudaStreamWaitEvent(ctx->fic_stream, ctx->ev_demod, 0));
+    ctx->cur = ctx->fic_stream;
+    const int fic_rc = ctx->fic(n_slots);
+    ctx->cur = nullptr;
+    if (fic_rc) return -1;
     const size_t fib_bytes = (size_t)n_slots * 12 * 32;
     CKC(ctx->h_fibs.ensure(fib_bytes));
     CKC(ctx->h_fib_ok.ensure((size_t)n_slots * 12));
-    CKC(cudaMemcpyAsync(ctx->h_fibs.p, ctx->d_fic_out.p, fib_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CKC(cudaMemcpyAsync(ctx->h_fib_ok.p, ctx->d_fib_ok.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->h_fibs.p, ctx->d_fic_out.p, fib_bytes, cudaMemcpyDeviceToHost, ctx->fic_stream));
+    CKC(cudaMemcpyAsync(ctx->h_fib_ok.p, ctx->d_fib_ok.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, ctx->fic_stream));
+    CKC(cudaEventRecord(ctx->ev_fic, ctx->fic_stream));
     TRACE("fic submitted");
-    // The host only needs the FIBs to go on (FIG parse -> sub-channel organisation -> MSC jobs): it waits for the event behind
-    // their copy, not for the stream, and the TII fold is queued behind it so that the GPU has work during the parse.
-    if (!ctx->ev_fic) CKC(cudaEventCreateWithFlags(&ctx->ev_fic, cudaEventDisableTiming));
-    CKC(cudaEventRecord(ctx->ev_fic, ctx->stream));
     if (deferred_tii && ctx->tii_fold(d_iq, n, fmt, 0, n_frames)) return -1;
-    CKC(cudaEventSynchronize(ctx->ev_fic));
-    TRACE("fic synced");
     res->fibs = ctx->h_fibs.as<uint8_t>(); res->fib_ok = ctx->h_fib_ok.as<uint8_t>();
-    // ---- sub-channel organisation: given by the caller or discovered from FIG 0/1, 0/2
-    if (subch_in && n_subch_in > 0) ctx->r_subch.assign(subch_in, subch_in + n_subch_in);
-    else {
-        // FIG 0/1 and 0/2 repeat every few frames: parse growing prefixes of the FIC until the table stops changing
+    // ---- sub-channel organisation: given by the caller or discovered from FIG 0/1, 0/2, which repeat every few frames: growing
+    //      prefixes of the FIC (8, 16, 32, ... frames) are parsed until the table stops changing.  The first two prefixes come
+    //      from the early FIC slice, which is through long before the whole FIC is; only if they disagree the host waits for it.
+    bool fic_synced = false;
+    auto subch_from = [&](const uint8_t* fibs, const uint8_t* ok, int have_slots, bool may_wait, bool* stable) -> int {
         ctx->r_subch.resize(B200DAB_MAX_SUBCH);
         std::vector<b200dab_subch_t> prev;
         int ns = 0;
-        for (int upto = std::min(n_slots, 8); ; upto = std::min(n_slots, upto * 2)) {
-            ns = parse_subch_impl(res->fibs, res->fib_ok, upto * 12, ctx->r_subch.data(), B200DAB_MAX_SUBCH);
+        *stable = false;
+        for (int upto = std::min(have_slots, 8); ; upto = std::min(have_slots, upto * 2)) {
+            ns = parse_subch_impl(fibs, ok, upto * 12, ctx->r_subch.data(), B200DAB_MAX_SUBCH);
             const bool same = (int)prev.size() == ns && (ns == 0 || !memcmp(prev.data(), ctx->r_subch.data(), (size_t)ns * sizeof(b200dab_subch_t)));
-            if (upto >= n_slots || (same && ns > 0)) break;
+            if (same && ns > 0) { *stable = true; break; }
+            if (upto >= have_slots) { *stable = may_wait; break; }       // the whole FIC has been looked at: that is the answer
             prev.assign(ctx->r_subch.begin(), ctx->r_subch.begin() + ns);
+        }
+        return ns;
+    };
+    if (subch_in && n_subch_in > 0) ctx->r_subch.assign(subch_in, subch_in + n_subch_in);
+    else {
+        bool stable = false;
+        int ns = 0;
+        if (ctx->early_launched) {
+            CKC(cudaEventSynchronize(ctx->ev_early_fic));
+            TRACE("early fic synced");
+            ns = subch_from(ctx->h_fibs_early.as<uint8_t>(), ctx->h_fib_ok_early.as<uint8_t>(), ctx->early_frames, false, &stable);
+        }
+        if (!stable) {
+            CKC(cudaEventSynchronize(ctx->ev_fic));
+            fic_synced = true;
+            TRACE("fic synced");
+            ns = subch_from(res->fibs, res->fib_ok, n_slots, true, &stable);
         }
         ctx->r_subch.resize(ns);
     }
@@ -993,8 +1073,15 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         CKC(cudaEventCreateWithFlags(&ctx->ev_rs, cudaEventDisableTiming)); CKC(cudaEventCreateWithFlags(&ctx->ev_tii, cudaEventDisableTiming));
     }
     bool copies_pending = false;
-    // ---- TII detection needs to know which nulls carry TII: CIF counter (FIG 0/0) = 0 mod 8
     int n_win = 0;
+    std::vector<size_t> out_off;
+    size_t msc_bytes = 0;
+    const int n_rows = 4 * n_slots - (DAB_TDI_DEPTH - 1);
+    std::vector<DabPlusJob> dpjobs;
+    std::vector<int> dp_subch;
+    int total_sf = 0, total_rows = 0;
+    auto tii_block = [&]() -> int {
+    // ---- TII detection needs to know which nulls carry TII: CIF counter (FIG 0/0) = 0 mod 8
     if (want_tii) {
         ctx->r_sign.assign(n_slots, 0);
         std::vector<int32_t>& sign = ctx->r_sign;
@@ -1021,14 +1108,14 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         memcpy(ctx->h_sign.p, sign.data(), (size_t)n_slots * 4);
         memcpy(ctx->h_windows.p, wins.data(), wins.size() * sizeof(int2));
         if (ctx->fetch(ctx->d_sign.p, ctx->h_sign.p, (size_t)n_slots * 4) || ctx->fetch(ctx->d_windows.p, ctx->h_windows.p, wins.size() * sizeof(int2))) return -1;
-        k_tii_detect<<<n_win, 384, 0, ctx->stream>>>(ctx->d_fold.as<float>(), ctx->d_norm.as<float>(), ctx->d_sign.as<int>(), ctx->d_windows.as<int2>(),
+        k_tii_detect<<<n_win, 384, 0, ctx->S()>>>(ctx->d_fold.as<float>(), ctx->d_norm.as<float>(), ctx->d_sign.as<int>(), ctx->d_windows.as<int2>(),
                                                      6.0f, ctx->d_tii.as<TiiResult>());
         ctx->launches += 1;
         CKC(cudaGetLastError());
         CKC(ctx->h_tii.ensure(wins.size() * sizeof(TiiResult)));
         CKC(ctx->h_fold.ensure((size_t)n_slots * TII_SPECTRUM_BINS * 4));
         CKC(ctx->h_norm.ensure((size_t)n_slots * 4));
-        CKC(cudaEventRecord(ctx->ev_tii, ctx->stream));
+        CKC(cudaEventRecord(ctx->ev_tii, ctx->S()));
         CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tii, 0));
         CKC(cudaMemcpyAsync(ctx->h_tii.p, ctx->d_tii.p, wins.size() * sizeof(TiiResult), cudaMemcpyDeviceToHost, ctx->copy_stream));
         CKC(cudaMemcpyAsync(ctx->h_fold.p, ctx->d_fold.p, (size_t)n_slots * TII_SPECTRUM_BINS * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -1036,13 +1123,9 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         copies_pending = true;
         res->tii_fold = ctx->h_fold.as<float>(); res->tii_norm = ctx->h_norm.as<float>(); res->tii_sign = ctx->r_sign.data();
     }
-    // ---- MSC
-    std::vector<size_t> out_off;
-    size_t msc_bytes = 0;
-    const int n_rows = 4 * n_slots - (DAB_TDI_DEPTH - 1);
-    std::vector<DabPlusJob> dpjobs;
-    std::vector<int> dp_subch;
-    int total_sf = 0, total_rows = 0;
+    return 0;
+    };
+    auto msc_block = [&]() -> int {
     if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
         if (ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes)) return -1;
         TRACE("msc submitted");
@@ -1091,6 +1174,18 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         }
     }
     TRACE("msc+dab+ submitted");
+    return 0;
+    };
+    // ---- MSC chain on the main stream; the FIC chain is still running (or already through) on its own
+    if (msc_block()) return -1;
+    // ---- everything below needs the whole FIC on the host
+    if (!fic_synced) { CKC(cudaEventSynchronize(ctx->ev_fic)); TRACE("fic synced"); }
+    ctx->cur = ctx->fic_stream;
+    const int tii_rc = tii_block();
+    ctx->cur = nullptr;
+    if (tii_rc) return -1;
+    CKC(cudaEventRecord(ctx->ev_fic_stream, ctx->fic_stream));
+    CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_fic_stream, 0));
     if (want_stat) {
         CKC(ctx->h_symstat.ensure((size_t)n_slots * 150 * 4));
         CKC(cudaMemcpyAsync(ctx->h_symstat.p, ctx->d_symstat.p, (size_t)n_slots * 150 * 4, cudaMemcpyDeviceToHost, ctx->stream));
