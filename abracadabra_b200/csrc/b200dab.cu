@@ -103,7 +103,7 @@ struct b200dab_ctx {
     cudaStream_t cur = nullptr;        // stream the helpers below launch on (nullptr: `stream`)
     cudaStream_t S() const { return cur ? cur : stream; }
     cudaStream_t fic_stream = nullptr;
-    cudaEvent_t ev_early_demod = nullptr, ev_early_fic = nullptr, ev_demod = nullptr, ev_fic_stream = nullptr;
+    cudaEvent_t ev_early_demod = nullptr, ev_early_done = nullptr, ev_early_fic = nullptr, ev_demod = nullptr, ev_fic_stream = nullptr;
     DevBuf d_fic_out_early, d_fib_ok_early;
     HostBuf h_fibs_early, h_fib_ok_early;
     int early_frames = 0;              // > 0: front_end splits its first demodulation launch and starts the early FIC slice
@@ -185,7 +185,7 @@ struct b200dab_ctx {
     std::vector<cudaEvent_t> copy_events;
     int run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out);
     int fic(int n_slots, bool early = false);
-    int early_fic();
+    int early_fic(const void* d_iq, uint64_t n_visible, int fmt, bool want_stat, bool want_tii);
     int msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std::vector<size_t>& out_off, size_t* total);
     int dabplus(uint8_t* d_frames, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows);
 };
@@ -394,6 +394,7 @@ int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int first,
     const float2* tw = d_tw.as<float2>();
     const uint16_t* fp = d_fdi_pos.as<uint16_t>();
     const int64_t n = (int64_t)n_visible;
+    cudaStream_t stream = S();
     prof_begin("k_ofdm_demod");
     if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
     else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
@@ -401,7 +402,13 @@ int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int first,
     prof_end();
     launches += 1;
     CK(cudaGetLastError());
-    if (want_tii && !defer_tii_fold) return tii_fold(d_iq, n_visible, fmt, first, count);
+    if (want_tii && !defer_tii_fold) {                    // the fold only reads the samples: it stays on the main stream
+        cudaStream_t keep = cur;
+        cur = nullptr;
+        const int rc = tii_fold(d_iq, n_visible, fmt, first, count);
+        cur = keep;
+        return rc;
+    }
     return 0;
 }
 
@@ -412,6 +419,7 @@ int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int fir
     const FrameInfo* dfr = h_frames.as<FrameInfo>() + first;
     const float2* tw = d_tw.as<float2>();
     const int64_t n = (int64_t)n_visible;
+    cudaStream_t stream = S();
     prof_begin("k_tii_fold");
     if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
     else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
@@ -424,15 +432,21 @@ int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int fir
 
 // FIC of the first `early_frames` frames on the FIC stream, behind their demodulation: FIG 0/1 and 0/2 repeat every few frames, so
 // the sub-channel organisation is known (and the MSC chain can be queued) while the rest of the recording is still demodulated.
-int b200dab_ctx::early_fic()
+int b200dab_ctx::early_fic(const void* d_iq, uint64_t n_visible, int fmt, bool want_stat, bool want_tii)
 {
     const int k = early_frames;
-    CK(cudaEventRecord(ev_early_demod, stream));
+    // The first frames are demodulated on the FIC stream as well, next to the rest of the recording on the main stream (64 CTAs on
+    // their own would leave the GPU idle for the length of a demodulation CTA).  The FIC stream joins the main stream here (buffers
+    // cleared at the start of the call) and the main stream waits for these frames before anything reads the soft bits.
+    // (ev_early_demod was recorded on the main stream before the rest of the recording was queued there)
     CK(cudaStreamWaitEvent(fic_stream, ev_early_demod, 0));
     cur = fic_stream;
-    const int rc = fic(k, true);
+    int rc = demod(d_iq, n_visible, fmt, 0, k, want_stat, want_tii);
+    if (!rc) rc = cudaEventRecord(ev_early_done, fic_stream) == cudaSuccess ? 0 : -1;
+    if (!rc) rc = fic(k, true);
     cur = nullptr;
     if (rc) return -1;
+    CK(cudaStreamWaitEvent(stream, ev_early_done, 0));
     CK(h_fibs_early.ensure((size_t)k * 12 * 32));
     CK(h_fib_ok_early.ensure((size_t)k * 12));
     CK(cudaMemcpyAsync(h_fibs_early.p, d_fic_out_early.p, (size_t)k * 12 * 32, cudaMemcpyDeviceToHost, fic_stream));
@@ -492,8 +506,9 @@ int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len
     const int count = (int)fe_frames - first_new;
     if (early_frames > 0 && !early_launched && first_new == 0 && count > early_frames && hf[early_frames - 1].slot == early_frames - 1) {
         // the first frames on their own (no lost frame among them), the early FIC slice behind them, then the rest
-        if (demod(d_iq, off + len, fmt, 0, early_frames, want_stat, want_tii) || early_fic()) return -1;
-        return demod(d_iq, off + len, fmt, early_frames, count - early_frames, want_stat, want_tii);
+        CK(cudaEventRecord(ev_early_demod, stream));
+        if (demod(d_iq, off + len, fmt, early_frames, count - early_frames, want_stat, want_tii)) return -1;
+        return early_fic(d_iq, off + len, fmt, want_stat, want_tii);
     }
     return demod(d_iq, off + len, fmt, first_new, count, want_stat, want_tii);
 }
@@ -779,6 +794,7 @@ int b200dab_create(b200dab_ctx** out, int device)
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     if (cudaStreamCreateWithPriority(&ctx->fic_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -5; }
     cudaEventCreateWithFlags(&ctx->ev_early_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_early_fic, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_early_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_fic_stream, cudaEventDisableTiming);
     if (ctx->init_tables()) { fprintf(stderr, "b200dab: %s\n", ctx->err.c_str()); cudaStreamDestroy(ctx->stream); delete ctx; return -6; }
     *out = ctx;
@@ -802,7 +818,7 @@ void b200dab_destroy(b200dab_ctx* ctx)
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); cudaEventDestroy(ctx->ev_rs); cudaEventDestroy(ctx->ev_tii); }
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
-    if (ctx->fic_stream) { cudaEventDestroy(ctx->ev_early_demod); cudaEventDestroy(ctx->ev_early_fic); cudaEventDestroy(ctx->ev_demod); cudaEventDestroy(ctx->ev_fic_stream); cudaStreamDestroy(ctx->fic_stream); }
+    if (ctx->fic_stream) { cudaEventDestroy(ctx->ev_early_demod); cudaEventDestroy(ctx->ev_early_done); cudaEventDestroy(ctx->ev_early_fic); cudaEventDestroy(ctx->ev_demod); cudaEventDestroy(ctx->ev_fic_stream); cudaStreamDestroy(ctx->fic_stream); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
@@ -1016,7 +1032,9 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     CKC(cudaEventRecord(ctx->ev_demod, ctx->stream));
     CKC(cudaStreamWaitEvent(ctx->fic_stream, ctx->ev_demod, 0));
     ctx->cur = ctx->fic_stream;
-    const int fic_rc = ctx->fic(n_slots);
+    int fic_rc = 0;
+    if (deferred_tii) fic_rc = ctx->tii_fold(d_iq, n, fmt, 0, n_frames);     // under the MSC gather instead of in front of it
+    if (!fic_rc) fic_rc = ctx->fic(n_slots);
     ctx->cur = nullptr;
     if (fic_rc) return -1;
     const size_t fib_bytes = (size_t)n_slots * 12 * 32;
@@ -1026,7 +1044,6 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     CKC(cudaMemcpyAsync(ctx->h_fib_ok.p, ctx->d_fib_ok.p, (size_t)n_slots * 12, cudaMemcpyDeviceToHost, ctx->fic_stream));
     CKC(cudaEventRecord(ctx->ev_fic, ctx->fic_stream));
     TRACE("fic submitted");
-    if (deferred_tii && ctx->tii_fold(d_iq, n, fmt, 0, n_frames)) return -1;
     res->fibs = ctx->h_fibs.as<uint8_t>(); res->fib_ok = ctx->h_fib_ok.as<uint8_t>();
     // ---- sub-channel organisation: given by the caller or discovered from FIG 0/1, 0/2, which repeat every few frames: growing
     //      prefixes of the FIC (8, 16, 32, ... frames) are parsed until the table stops changing.  The first two prefixes come
