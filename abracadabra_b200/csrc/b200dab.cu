@@ -678,17 +678,23 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     int max_rows = 0, max_sf = 0, max_cw = 0;
     for (auto& j : jobs) { max_rows = std::max(max_rows, j.n_rows); max_sf = std::max(max_sf, j.max_sf); max_cw = std::max(max_cw, j.max_sf * j.s); }
     const unsigned nj = (unsigned)jobs.size();
-    prof_begin("k_firecode_scan+k_sf_align");
+    prof_begin("k_firecode_scan");
     k_firecode_scan<<<dim3((max_rows + 255) / 256, nj), 256, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>());
-    k_sf_align<<<nj, 32, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>());
+    prof_end();
+    prof_begin("k_sf_align");
+    k_sf_align<<<nj, SF_ALIGN_THREADS, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>());
     prof_end();
     prof_begin("k_rs_decode");
     k_rs_decode<<<dim3((max_cw + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<GfTables>());
     prof_end();
     if (ev_rs) CK(cudaEventRecord(ev_rs, stream));        // the logical frames are final from here on: the caller starts their copy
-    prof_begin("k_au_split+k_au_crc");
+    prof_begin("k_au_split");
     k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
+    prof_end();
+    prof_begin("k_au_crc");
     k_au_crc<<<dim3((max_sf * 6 + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
+    prof_end();
+    prof_begin("k_au_count+k_au_write");
     // access-unit list and RS statistics in the layout of the result, put together on the device
     const int nb = (total_sf + 255) / 256;
     CK(d_aus.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + 64));

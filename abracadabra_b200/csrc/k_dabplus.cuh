@@ -59,24 +59,38 @@ __global__ void __launch_bounds__(256) k_firecode_scan(const uint8_t* __restrict
     flags[job.flag_off + r] = (fc == (uint16_t)((f[0] << 8) | f[1])) && ((f[0] | f[1] | f[2]) != 0);
 }
 
-// one warp per job: pick the residue (row mod 5) with most firecode hits; mark the superframe slots
-__global__ void __launch_bounds__(32) k_sf_align(const DabPlusJob* __restrict__ jobs, const uint8_t* __restrict__ flags,
-                                                 SfInfo* __restrict__ sf, int* __restrict__ residue_out)
+// one CTA per job: pick the residue (row mod 5) with most firecode hits; mark the superframe slots
+#define SF_ALIGN_THREADS 256
+__global__ void __launch_bounds__(SF_ALIGN_THREADS) k_sf_align(const DabPlusJob* __restrict__ jobs, const uint8_t* __restrict__ flags,
+                                                               SfInfo* __restrict__ sf, int* __restrict__ residue_out)
 {
+    __shared__ int part[SF_ALIGN_THREADS / 32][5];
+    __shared__ int s_best;
     const DabPlusJob job = jobs[blockIdx.x];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x;
     int cnt[5] = {0, 0, 0, 0, 0};
-    for (int r = lane; r < job.n_rows; r += 32)
+    for (int r = tid; r < job.n_rows; r += SF_ALIGN_THREADS)
         if (flags[job.flag_off + r]) cnt[r % 5]++;
 #pragma unroll
-    for (int k = 0; k < 5; k++)
+    for (int k = 0; k < 5; k++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
-    int best = -1, bc = 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) if (cnt[k] > bc) { bc = cnt[k]; best = k; }
-    if (lane == 0) residue_out[blockIdx.x] = best;
-    for (int m = lane; m < job.max_sf; m += 32) {
+        if ((tid & 31) == 0) part[tid >> 5][k] = cnt[k];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = -1, bc = 0;
+        for (int k = 0; k < 5; k++) {
+            int c = 0;
+            for (int w = 0; w < SF_ALIGN_THREADS / 32; w++) c += part[w][k];
+            if (c > bc) { bc = c; best = k; }
+        }
+        s_best = best;
+        residue_out[blockIdx.x] = best;
+    }
+    __syncthreads();
+    const int best = s_best;
+    for (int m = tid; m < job.max_sf; m += SF_ALIGN_THREADS) {
         SfInfo* o = sf + job.sf_off + m;
         const int row = best + 5 * m;
         o->valid = (best >= 0 && row + 5 <= job.n_rows) ? 1 : 0;
@@ -96,7 +110,25 @@ __global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames,
                                                    SfInfo* __restrict__ sf, const GfTables* __restrict__ gf_g)
 {
     __shared__ GfTables gf;
+    __shared__ uint8_t gen[12];                 // g(x) = prod_{i < 10} (x - alpha^i) = x^10 + gen[9] x^9 + ... + gen[0]
+    __shared__ uint32_t fb[256][3];             // fb[t] = t * (gen[0..3] | gen[4..7] | gen[8..9]): what t * g(x) adds to the remainder
     for (int i = threadIdx.x; i < (int)sizeof(GfTables); i += blockDim.x) reinterpret_cast<uint8_t*>(&gf)[i] = reinterpret_cast<const uint8_t*>(gf_g)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t g[12] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};           // g = 1, then times (x + alpha^i)
+        for (int i = 0; i < 10; i++) {
+            const uint8_t a = gf.exp[i];
+            for (int j = i + 1; j > 0; j--) g[j] = g[j - 1] ^ gf_mul(gf, g[j], a);
+            g[0] = gf_mul(gf, g[0], a);
+        }
+        for (int j = 0; j < 12; j++) gen[j] = j < 10 ? g[j] : 0;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        uint32_t w[3] = {0, 0, 0};
+        for (int j = 0; j < 10; j++) w[j >> 2] |= (uint32_t)gf_mul(gf, (uint8_t)t, gen[j]) << (8 * (j & 3));
+        fb[t][0] = w[0]; fb[t][1] = w[1]; fb[t][2] = w[2];
+    }
     __syncthreads();
     const DabPlusJob job = jobs[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,22 +138,34 @@ __global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames,
     if (!info->valid) return;
     uint8_t* base = frames + job.frames_off + (size_t)info->row * job.pitch;
     const int s = job.s, n = 120, nroots = 10;
-    uint8_t S[10];
-    uint32_t nz = 0;
-#pragma unroll
-    for (int i = 0; i < nroots; i++) S[i] = 0;
+    // Remainder of the received word modulo g(x), Horner style: R <- R x + c - t g(x) with t the coefficient that leaves at the top.
+    // The ten remainder bytes live in three words and t g(x) is one table row, so a received byte costs three shared-memory loads
+    // instead of the twenty of ten separate syndrome recursions.  R = 0 <=> all syndromes are 0 (the common case); otherwise the
+    // syndromes are R evaluated at alpha^i, since g(alpha^i) = 0.
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
     for (int k = 0; k < n; k++) {
-        const uint8_t c = base[j + s * k];
+        const uint32_t c = base[j + s * k];
+        const uint32_t t = (w2 >> 8) & 0xffu;
+        w2 = ((w2 << 8) | (w1 >> 24)) & 0xffffu;
+        w1 = (w1 << 8) | (w0 >> 24);
+        w0 = (w0 << 8) | c;
+        w0 ^= fb[t][0]; w1 ^= fb[t][1]; w2 ^= fb[t][2];
+    }
+    if (!(w0 | w1 | w2)) return;
+    uint8_t S[10];
+    {
+        uint8_t r[10];
 #pragma unroll
+        for (int q = 0; q < 10; q++) r[q] = (uint8_t)((q < 4 ? w0 : q < 8 ? w1 : w2) >> (8 * (q & 3)));
         for (int i = 0; i < nroots; i++) {
-            uint8_t v = S[i];
-            v = v ? gf.exp[gf.log[v] + i] : 0;            // * alpha^i
-            S[i] = v ^ c;
+            uint8_t v = 0;
+            for (int q = 9; q >= 0; q--) {
+                v = v ? gf.exp[gf.log[v] + i] : 0;            // * alpha^i
+                v ^= r[q];
+            }
+            S[i] = v;
         }
     }
-#pragma unroll
-    for (int i = 0; i < nroots; i++) nz |= S[i];
-    if (!nz) return;
     // Berlekamp-Massey
     uint8_t Lm[12], B[12], T[12];
 #pragma unroll
@@ -209,14 +253,23 @@ __global__ void __launch_bounds__(64) k_au_split(const uint8_t* __restrict__ fra
 // one thread per (superframe, access unit): table-driven CRC-16 (0x1021, init 0xFFFF, inverted) over the AU payload
 __global__ void __launch_bounds__(128) k_au_crc(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs, SfInfo* __restrict__ sf)
 {
-    __shared__ uint16_t tbl[256];
+    // slicing by four: tbl[k][v] = CRC state after byte v followed by k zero bytes, so four message bytes are folded in with four
+    // independent look-ups instead of a chain of four
+    __shared__ uint16_t tbl[4][256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         uint32_t c = (uint32_t)i << 8;
 #pragma unroll
         for (int b = 0; b < 8; b++) c = (c & 0x8000u) ? ((c << 1) ^ 0x1021u) & 0xffffu : (c << 1) & 0xffffu;
-        tbl[i] = (uint16_t)c;
+        tbl[0][i] = (uint16_t)c;
     }
     __syncthreads();
+    for (int k = 1; k < 4; k++) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            const uint32_t c = tbl[k - 1][i];
+            tbl[k][i] = (uint16_t)(((c << 8) & 0xffffu) ^ tbl[0][c >> 8]);
+        }
+        __syncthreads();
+    }
     const DabPlusJob job = jobs[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int m = idx / 6, a = idx - 6 * m;
@@ -226,7 +279,10 @@ __global__ void __launch_bounds__(128) k_au_crc(const uint8_t* __restrict__ fram
     const uint8_t* p = frames + job.frames_off + (size_t)info->row * job.pitch + info->au_off[a];
     const int len = info->au_len[a];
     uint32_t crc = 0xFFFF;
-    for (int i = 0; i < len; i++) crc = ((crc << 8) & 0xffffu) ^ tbl[((crc >> 8) ^ p[i]) & 0xff];
+    int i = 0;
+    for (; i + 4 <= len; i += 4)
+        crc = (uint32_t)tbl[3][((crc >> 8) ^ p[i]) & 0xff] ^ tbl[2][(crc ^ p[i + 1]) & 0xff] ^ tbl[1][p[i + 2]] ^ tbl[0][p[i + 3]];
+    for (; i < len; i++) crc = ((crc << 8) & 0xffffu) ^ tbl[0][((crc >> 8) ^ p[i]) & 0xff];
     crc = (~crc) & 0xffffu;
     info->au_ok[a] = crc == (uint32_t)((p[len] << 8) | p[len + 1]);
 }
