@@ -153,6 +153,9 @@ def algorithmic_bytes(name: str, n_frames: int, subch, n_samples: int) -> float:
         return n_frames * (76 * 2048 * 2 + 4 * 2048 * 2 + 75 * 3072) * 1.0   # u8 IQ of every useful part (+1 reference symbol per run) + soft bits
     if name == "k_tii_fold":
         return n_frames * (2 * 2048 * 2 + 384 * 4) * 1.0
+    if name.endswith("(early fic)") or name == "k_fib_crc(early)":      # the same FIC kernels on the first 16 frames only
+        base = name.replace("(early fic)", "(fic)")
+        return algorithmic_bytes(base, min(n_frames, 16), subch, n_samples) if base != name else 0.0
     if name == "k_gather(fic)":
         return n_cif * (2304 + 774 * 4) * 1.0
     if name == "k_viterbi(fic)":
@@ -191,7 +194,7 @@ def main():
 
     workload = f"{args.seconds:.0f} s synthetic full ensemble (FIC + 12 sub-channels, 854 CU: 8 DAB+ EEP, 4 MP2 UEP), u8 IQ @ 2.048 Msps, one recording per GPU"
     config = {"workload": workload, "recording_bytes": None, "l2_policy": "input (245.76 MB for 60 s) larger than the 126 MB L2; re-read from HBM every step",
-              "format": "u8", "tii": True, "subchannel_discovery": "FIG 0/1 + 0/2 parsed from the decoded FIC inside the step"}
+              "format": "u8", "tii": True, "subchannel_discovery": "FIG 0/1 + 0/2 parsed from the decoded FIC inside the step (first from the FIC of the first 16 frames, decoded under the demodulation of the rest; the whole FIC is decoded next to the MSC chain)"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
