@@ -916,6 +916,12 @@ int b200dab_pad_feed_mp2(b200dab_pad* p, const uint8_t* f, int len, b200dab_pad_
     return 1;
 }
 
+int b200dab_viterbi_decision_index(int state, int backward)
+{
+    if (state < 0 || state > 63) return -1;
+    return (int)(backward ? vit_dec_index_bwd((uint32_t)state) : vit_dec_index_fwd((uint32_t)state));
+}
+
 int b200dab_spectrum_layout(uint16_t* out, int n)
 {
     std::vector<uint16_t> pos;

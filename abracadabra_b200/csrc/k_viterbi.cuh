@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
 // decisions, and the complement of (J, output) is (15 - J, 1 - output) = bit position 31 - pos: with w = x | (~brev(y)) << 32 of
 // a decision pair (x: role 0, y: role 1) both roles are read with the same index formula.
 // The state recursion is a dependent chain, so the 32 decision pairs of the next chunk are fetched while this one is traced.
+__host__ __device__ __forceinline__ uint32_t vit_dec_index_fwd(uint32_t n) { return ((n >> 5) << 4) | ((n & 1u) << 3) | ((n >> 2) & 7u) | ((n & 2u) << 4); }
+__host__ __device__ __forceinline__ uint32_t vit_dec_index_bwd(uint32_t s) { return (((s >> 4) & 1u) << 4) | ((s >> 5) << 3) | ((s >> 1) & 7u) | ((s & 1u) << 5); }
 __device__ __forceinline__ void vit_load_chunk(uint2 (&b)[32], const uint2* d, int c)
 {
 #pragma unroll
@@ -321,14 +323,14 @@ __global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec,
             for (int i = 31; i >= 0; i--) {
                 const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
                 word |= (s & 1u) << (31 - i);
-                const uint32_t idx = ((s >> 5) << 4) | ((s & 1u) << 3) | ((s >> 2) & 7u) | ((s & 2u) << 4);
+                const uint32_t idx = vit_dec_index_fwd(s);
                 s = (s >> 1) | (((uint32_t)(w >> idx) & 1u) << 5);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
                 const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
-                const uint32_t idx = (((s >> 4) & 1u) << 4) | ((s >> 5) << 3) | ((s >> 1) & 7u) | ((s & 1u) << 5);
+                const uint32_t idx = vit_dec_index_bwd(s);
                 const uint32_t bit = (uint32_t)(w >> idx) & 1u;
                 word |= bit << (31 - i);
                 s = ((s << 1) | bit) & 63u;

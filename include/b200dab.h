@@ -122,6 +122,11 @@ B200DAB_API int b200dab_parse_subch(const uint8_t *fibs, const uint8_t *fib_ok, 
  * of QPSK symbol n.  n must be >= 3584; returns the number of entries or -1. */
 B200DAB_API int b200dab_spectrum_layout(uint16_t *out, int n);
 
+/* Bit of the 64-bit survivor word (role 0's word | ~bit-reverse(role 1's word) << 32) in which the Viterbi trace kernel finds the
+ * decision of `state` for a forward (backward = 0: state after the step) or backward (state before the step) trellis step; the
+ * index function of the kernel itself, exported for the layout test.  -1 for a state outside 0..63. */
+B200DAB_API int b200dab_viterbi_decision_index(int state, int backward);
+
 /* Ensemble / service summary out of decoded FIBs: the fields RadioControl receives in dabsdrNtfEnsemble_t and the service
  * list (dabsdr.h:169-318), for batch callers that do not go through the callback interface (band scan output). */
 typedef struct {

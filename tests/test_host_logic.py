@@ -140,3 +140,45 @@ def test_ofdm_spectrum_layout_is_conflict_free():
                 assert len(banks) == len(set(banks))
                 worst = max(worst, len(banks))
     assert worst == 16
+
+
+def test_viterbi_decision_word_layout():
+    """Bit layout of the survivor words k_viterbi writes and k_vit_trace reads (abracadabra_b200/csrc/k_viterbi.cuh): a lane of role r
+    puts the decision of butterfly J (0..15), output o (0/1), at bit 16 (J >> 3) + 8 o + (J & 7) of its word; role 1 works on
+    complemented states.  The trace kernel reads w = x | (~brev(y)) << 32 with one index formula per direction: check that the
+    formula (the kernel's own, through b200dab_viterbi_decision_index) finds, for every logical state, the bit its owner wrote, and
+    that the 64 positions are all different."""
+    import ctypes as ct
+    from abracadabra_b200 import pipeline
+    L = pipeline.lib()
+    L.b200dab_viterbi_decision_index.argtypes = [ct.c_int, ct.c_int]
+    L.b200dab_viterbi_decision_index.restype = ct.c_int
+    assert L.b200dab_viterbi_decision_index(64, 0) == -1
+
+    def pos(j, o):
+        return 16 * (j >> 3) + 8 * o + (j & 7)
+
+    def brev32(i):
+        return 31 - i
+
+    fwd, bwd = set(), set()
+    for n in range(64):
+        # forward step: new state n is computed by role (n >> 1) & 1; in that role's physical coordinates it is output p & 1 of butterfly p >> 2
+        role = (n >> 1) & 1
+        p = n ^ 63 if role else n
+        assert (p & 2) == 0
+        written = pos(p >> 2, p & 1)
+        in_w = 32 + brev32(written) if role else written           # role 1's word is bit-reversed into the upper half
+        idx = L.b200dab_viterbi_decision_index(n, 0)
+        assert idx == in_w == ((n >> 5) << 4) | ((n & 1) << 3) | ((n >> 2) & 7) | ((n & 2) << 4)
+        fwd.add(idx)
+        # backward step: state n is computed by role n & 1; physically it is output p >> 5 of butterfly (p >> 1) & 15
+        role = n & 1
+        p = n ^ 63 if role else n
+        assert (p & 1) == 0
+        written = pos((p >> 1) & 15, p >> 5)
+        in_w = 32 + brev32(written) if role else written
+        idx = L.b200dab_viterbi_decision_index(n, 1)
+        assert idx == in_w == (((n >> 4) & 1) << 4) | ((n >> 5) << 3) | ((n >> 1) & 7) | ((n & 1) << 5)
+        bwd.add(idx)
+    assert len(fwd) == 64 and len(bwd) == 64
