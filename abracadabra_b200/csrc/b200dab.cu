@@ -83,23 +83,40 @@ struct b200dab_ctx {
     int launches = 0;
     cudaEvent_t ev_msc = nullptr, ev_d2h = nullptr;   // ordering of the split device-to-host copy of the logical frames
     cudaEvent_t ev_rs = nullptr, ev_tii = nullptr;    // behind k_rs_decode (DAB+ frames final) / behind k_tii_detect
-    size_t vit_dsmem = 14 * 1024;  // extra dynamic shared memory per k_viterbi CTA: caps residency at 11 one-warp CTAs per SM, so the
-                                   // shorter work items are dealt out as the long ones finish (tools/vit_residency.py sweeps this)
+    int vit_ctas_per_sm = 3;       // persistent k_viterbi CTAs (four warps, one per sub-partition) per SM (tools/vit_split_sweep.py sweeps this)
+    int n_sm = 148;
+    DevBuf d_vit_counter;          // work queue heads of k_viterbi, one per table set + one for the stage entry point; zero between launches
+    unsigned vit_grid(size_t n_items) const { return (unsigned)std::min<size_t>((size_t)n_sm * vit_ctas_per_sm, (n_items + VIT_CTA_WARPS - 1) / VIT_CTA_WARPS); }
     // constant tables on the device
     DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin;
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
-    DevBuf d_jobs, d_groups, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out, d_aus, d_totals;
+    DevBuf d_jobs, d_groups, d_items, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out, d_aus, d_totals;
     struct VitTables {              // device-resident job / group / step tables of one call site, kept between calls
         bool valid = false;
         std::vector<VitJob> jobs_in;
         std::vector<uint32_t> stepinfo;
-        size_t n_groups = 0, words = 0;
-        int max_steps = 0;
-        DevBuf d_jobs, d_groups, d_stepinfo;
+        size_t n_groups = 0, n_items = 0, words = 0;
+        int max_steps = 0, vit4_min_steps = -1;
+        DevBuf d_jobs, d_groups, d_stepinfo, d_items;
         DevBuf d_vin, d_dec, d_meet;   // work buffers of the set: the FIC chain runs on its own stream next to the MSC chain
     } vit_tables[3];                   // [0] FIC, [1] MSC, [2] FIC of the first frames only (early sub-channel discovery)
     int vit_set = -1;                  // table set forced by the caller (-1: by job kind)
+    int vit4_min_steps = 0;            // codewords of at least this many trellis steps run in four-lane mode (k_viterbi.cuh); 0 = all
+    // work items of k_viterbi for `groups` (sorted), longest dependent instruction chain first
+    void build_items(const std::vector<VitJob>& jobs, const std::vector<VitGroup>& groups, std::vector<VitItem>& items) const
+    {
+        items.clear();
+        std::vector<std::pair<long long, VitItem>> tmp;
+        for (size_t g = 0; g < groups.size(); g++) {
+            const VitJob& j = jobs[groups[g].job];
+            // instructions per trellis step of one warp (tools/sass_loops.py): 185 (two lanes per codeword pair), 111 (four lanes)
+            if (j.mode4) for (int w = 0; w < 4; w++) tmp.push_back({(long long)j.steps * 111, VitItem{(int)g, 4 | w}});
+            else for (int w = 0; w < 2; w++) tmp.push_back({(long long)j.steps * 185, VitItem{(int)g, w}});
+        }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<long long, VitItem>& a, const std::pair<long long, VitItem>& b) { return a.first > b.first; });
+        for (auto& t : tmp) items.push_back(t.second);
+    }
     cudaStream_t cur = nullptr;        // stream the helpers below launch on (nullptr: `stream`)
     cudaStream_t S() const { return cur ? cur : stream; }
     cudaStream_t fic_stream = nullptr;
@@ -112,7 +129,7 @@ struct b200dab_ctx {
     DevBuf d_tmp_a, d_tmp_b, d_spec;
     HostBuf h_spec;
     HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
-    HostBuf h_jobs[3], h_groups[3], h_stepinfo[3], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
+    HostBuf h_jobs[3], h_groups[3], h_stepinfo[3], h_items[3], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
     std::vector<int32_t> r_sign;
     std::vector<std::pair<b200dab_subch_t, std::vector<uint32_t>>> stepinfo_cache;   // de-puncturing tables by protection profile
     // result storage
@@ -122,6 +139,10 @@ struct b200dab_ctx {
     std::vector<const uint8_t*> r_frames;
     std::vector<int32_t> r_rows;
     std::vector<b200dab_au_t> r_aus;
+    std::vector<b200dab_sf_t> r_sf;
+    std::vector<const uint8_t*> r_sf_flags;
+    std::vector<int32_t> r_sf_phase, forced_phase;
+    HostBuf h_sfinfo, h_flags, h_residue;
     std::vector<b200dab_tii_t> r_tii;
 
     // optional per-kernel timing (CUDA events on `stream`), enabled by b200dab_set_profiling
@@ -522,7 +543,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     VitTables& vt = vit_tables[st];
     // The job / group / step tables only depend on the sub-channel organisation and the number of CIFs: when they equal those of
     // the previous call (every window of a stream, every recording of one multiplex) what is already on the device is reused.
-    const bool same = vt.valid && vt.jobs_in.size() == jobs_in.size() && vt.stepinfo.size() == stepinfo.size() &&
+    const bool same = vt.valid && vt.vit4_min_steps == vit4_min_steps && vt.jobs_in.size() == jobs_in.size() && vt.stepinfo.size() == stepinfo.size() &&
                       !memcmp(vt.jobs_in.data(), jobs_in.data(), jobs_in.size() * sizeof(VitJob)) &&
                       !memcmp(vt.stepinfo.data(), stepinfo.data(), stepinfo.size() * 4);
     if (!same) {
@@ -533,6 +554,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
         int max_steps = 0;
         for (size_t j = 0; j < jobs.size(); j++) {
             const int ng = (jobs[j].n_rows + 31) / 32;
+            jobs[j].mode4 = (jobs[j].steps >= vit4_min_steps && jobs[j].steps % 2 == 0) ? 1 : 0;
             jobs[j].vin_off = (long long)words;
             jobs[j].dec_off = (long long)words;
             words += (size_t)ng * 32 * jobs[j].steps;
@@ -542,7 +564,14 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
         vt.n_groups = groups.size(); vt.words = words; vt.max_steps = max_steps;
         if (groups.empty()) return 0;
         std::stable_sort(groups.begin(), groups.end(), [&](const VitGroup& a, const VitGroup& b) { return jobs[a.job].steps > jobs[b.job].steps; });
+        std::vector<VitItem> items;
+        build_items(jobs, groups, items);
+        vt.n_items = items.size();
         // small tables go through pinned staging owned by the context (one set per call site), so no stream sync is needed here
+        CK(h_items[st].ensure(items.size() * sizeof(VitItem) + 16));
+        CK(vt.d_items.ensure(items.size() * sizeof(VitItem) + 16));
+        memcpy(h_items[st].p, items.data(), items.size() * sizeof(VitItem));
+        if (fetch(vt.d_items.p, h_items[st].p, items.size() * sizeof(VitItem))) { set_error("k_fetch launch failed"); return -1; }
         CK(h_jobs[st].ensure(jobs.size() * sizeof(VitJob) + 16));
         CK(h_groups[st].ensure(groups.size() * sizeof(VitGroup) + 16));
         CK(h_stepinfo[st].ensure(stepinfo.size() * 4 + 16));
@@ -554,7 +583,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
         memcpy(h_stepinfo[st].p, stepinfo.data(), stepinfo.size() * 4);
         if (fetch(vt.d_jobs.p, h_jobs[st].p, jobs.size() * sizeof(VitJob)) || fetch(vt.d_groups.p, h_groups[st].p, groups.size() * sizeof(VitGroup)) ||
             fetch(vt.d_stepinfo.p, h_stepinfo[st].p, stepinfo.size() * 4)) { set_error("k_fetch launch failed"); return -1; }
-        vt.jobs_in = jobs_in; vt.stepinfo = stepinfo; vt.valid = true;
+        vt.jobs_in = jobs_in; vt.stepinfo = stepinfo; vt.vit4_min_steps = vit4_min_steps; vt.valid = true;
     }
     if (vt.n_groups == 0) return 0;
     const size_t n_groups = vt.n_groups;
@@ -569,10 +598,11 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), dj, dg, vt.d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
     prof_begin(st == 0 ? "k_viterbi(fic)" : st == 2 ? "k_viterbi(early fic)" : "k_viterbi(msc)");
-    k_viterbi<<<(unsigned)n_groups * 2, 32, vit_dsmem, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg);
+    k_viterbi<<<vit_grid(vt.n_items), 32 * VIT_CTA_WARPS, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg, vt.d_items.as<VitItem>(),
+                                                                        (int)vt.n_items, d_vit_counter.as<int>() + st);
     prof_end();
     prof_begin(st == 0 ? "k_vit_trace(fic)" : st == 2 ? "k_vit_trace(early fic)" : "k_vit_trace(msc)");
-    k_vit_trace<<<(unsigned)n_groups, 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out);
+    k_vit_trace<<<(unsigned)n_groups, 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_vit_counter.as<int>() + st);
     prof_end();
     launches += 3;
     CK(cudaGetLastError());
@@ -792,8 +822,10 @@ int b200dab_create(b200dab_ctx** out, int device)
     b200dab_ctx* ctx = new b200dab_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
-    if (const char* e = getenv("B200DAB_VIT_DSMEM")) ctx->vit_dsmem = (size_t)atoi(e);
-    cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (const char* e = getenv("B200DAB_VIT_CTAS")) ctx->vit_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("B200DAB_VIT4_MIN_STEPS")) ctx->vit4_min_steps = atoi(e);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (ctx->d_vit_counter.ensure(64) != cudaSuccess || cudaMemset(ctx->d_vit_counter.p, 0, 64) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -5; }
     // The FIC stream has priority: its few small CTAs are placed as soon as slots free up, ahead of the thousands of pending CTAs of
     // the demodulation / MSC kernels they run next to.
     int prio_least = 0, prio_greatest = 0;
@@ -815,11 +847,11 @@ void b200dab_destroy(b200dab_ctx* ctx)
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
-                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->vit_tables[0].d_items, &ctx->vit_tables[1].d_items, &ctx->vit_tables[2].d_items, &ctx->d_items, &ctx->d_vit_counter, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
-                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows};
+                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_sfinfo, &ctx->h_flags, &ctx->h_residue};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); cudaEventDestroy(ctx->ev_rs); cudaEventDestroy(ctx->ev_tii); }
@@ -848,6 +880,13 @@ int b200dab_parse_subch(const uint8_t* fibs, const uint8_t* fib_ok, int n_fibs, 
 {
     if (!fibs || !out) return -1;
     return parse_subch_impl(fibs, fib_ok, n_fibs, out, max_out);
+}
+
+int b200dab_set_superframe_phase(b200dab_ctx* ctx, const int32_t* phase, int n)
+{
+    if (!ctx || n < 0 || (n > 0 && !phase)) return -1;
+    ctx->forced_phase.assign(phase, phase + n);
+    return 0;
 }
 
 int b200dab_set_profiling(b200dab_ctx* ctx, int on)
@@ -922,6 +961,19 @@ int b200dab_viterbi_decision_index(int state, int backward)
     return (int)(backward ? vit_dec_index_bwd((uint32_t)state) : vit_dec_index_fwd((uint32_t)state));
 }
 
+int b200dab_viterbi4_decision_index(int state, int backward)
+{
+    if (state < 0 || state > 63) return -1;
+    return (int)(backward ? vit4_dec_index_bwd((uint32_t)state) : vit4_dec_index_fwd((uint32_t)state));
+}
+
+int b200dab_set_viterbi_split(b200dab_ctx* ctx, int min_steps_four_lane)
+{
+    if (!ctx) return -1;
+    ctx->vit4_min_steps = min_steps_four_lane;
+    return 0;
+}
+
 int b200dab_spectrum_layout(uint16_t* out, int n)
 {
     std::vector<uint16_t> pos;
@@ -965,6 +1017,9 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     ctx->prof_next();
     ctx->t_trace0 = now_ms();
     ctx->r_aus.clear(); ctx->r_tii.clear(); ctx->r_subch.clear(); ctx->r_frames.clear(); ctx->r_rows.clear();
+    ctx->r_sf.clear(); ctx->r_sf_flags.clear(); ctx->r_sf_phase.clear();
+    const std::vector<int32_t> forced_phase = std::move(ctx->forced_phase);     // one-shot
+    ctx->forced_phase.clear();
     const bool want_stat = (flags & B200DAB_OPT_SYMSTAT) != 0;
     const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
     bool deferred_tii = false;
@@ -1163,6 +1218,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             DabPlusJob j;
             j.frames_off = (long long)out_off[i]; j.n_rows = n_rows; j.pitch = ctx->r_subch[i].bitrate * 3; j.s = ctx->r_subch[i].bitrate / 8;
             j.sf_off = total_sf; j.max_sf = n_rows / 5; j.flag_off = total_rows; j.subch_index = (int)i;
+            j.forced_phase = i < forced_phase.size() ? forced_phase[i] : -1; j.pad_ = 0;
             total_sf += j.max_sf; total_rows += n_rows;
             dpjobs.push_back(j); dp_subch.push_back((int)i);
         }
@@ -1200,6 +1256,12 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             CKC(ctx->h_sf.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + sizeof(DabPlusTotals)));
             CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, ctx->stream));
             CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(ctx->h_sfinfo.ensure((size_t)total_sf * sizeof(SfInfo)));
+            CKC(ctx->h_flags.ensure((size_t)total_rows + 64));
+            CKC(ctx->h_residue.ensure(dpjobs.size() * 4));
+            CKC(cudaMemcpyAsync(ctx->h_sfinfo.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(cudaMemcpyAsync(ctx->h_flags.p, ctx->d_flags.p, (size_t)total_rows, cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(cudaMemcpyAsync(ctx->h_residue.p, ctx->d_residue.p, dpjobs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
     TRACE("msc+dab+ submitted");
@@ -1237,6 +1299,22 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             res->rs_uncorrectable = tot->rs_uncorrectable; res->firecode_fail = tot->firecode_fail;
             res->n_aus = tot->n_aus;
             res->aus = reinterpret_cast<const b200dab_au_t*>(ctx->h_sf.as<uint8_t>() + sizeof(DabPlusTotals));
+            // the superframe layer in detail
+            ctx->r_sf_flags.assign(ctx->r_subch.size(), nullptr);
+            ctx->r_sf_phase.assign(ctx->r_subch.size(), -1);
+            const SfInfo* si = ctx->h_sfinfo.as<SfInfo>();
+            for (size_t k = 0; k < dpjobs.size(); k++) {
+                const DabPlusJob& j = dpjobs[k];
+                ctx->r_sf_flags[j.subch_index] = ctx->h_flags.as<uint8_t>() + j.flag_off;
+                ctx->r_sf_phase[j.subch_index] = ctx->h_residue.as<int32_t>()[k];
+                for (int m = 0; m < j.max_sf; m++) {
+                    const SfInfo& q = si[j.sf_off + m];
+                    if (!q.valid) continue;
+                    ctx->r_sf.push_back(b200dab_sf_t{j.subch_index, q.row, q.firecode_ok, q.rs_corrected, q.rs_bit_errors, q.rs_uncorrectable, q.n_aus, q.header});
+                }
+            }
+            res->n_sf = (int)ctx->r_sf.size(); res->sf = ctx->r_sf.data();
+            res->sf_flags = ctx->r_sf_flags.data(); res->sf_phase = ctx->r_sf_phase.data();
         }
     }
     if (want_tii && n_win > 0) {
@@ -1335,12 +1413,17 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     VitJob job;
     memset(&job, 0, sizeof job);
     job.n_rows = n_cw; job.steps = steps; job.n_info = steps - 6; job.out_pitch = job.n_info / 8;
+    job.mode4 = (steps >= ctx->vit4_min_steps && steps % 2 == 0) ? 1 : 0;
     std::vector<VitGroup> groups;
     for (int g = 0; g < ng; g++) groups.push_back(VitGroup{0, g});
+    std::vector<VitItem> items;
+    ctx->build_items(std::vector<VitJob>(1, job), groups, items);
     const size_t words = vin.size();
     std::vector<uint32_t> zero_prbs(512, 0);
     CKC(ctx->d_jobs.ensure(sizeof job));
     CKC(ctx->d_groups.ensure(groups.size() * sizeof(VitGroup)));
+    CKC(ctx->d_items.ensure(items.size() * sizeof(VitItem)));
+    CKC(cudaMemcpyAsync(ctx->d_items.p, items.data(), items.size() * sizeof(VitItem), cudaMemcpyHostToDevice, ctx->stream));
     CKC(ctx->d_vin.ensure(words * 4));
     CKC(ctx->d_dec.ensure(words * 8));
     CKC(ctx->d_tmp_a.ensure(512 * 4));
@@ -1352,12 +1435,13 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     ctx->prof_next();
     CKC(ctx->d_meet.ensure((size_t)ng * VIT_MEET_WORDS * sizeof(unsigned short)));
     ctx->prof_begin("k_viterbi(stage)");
-    k_viterbi<<<ng * 2, 32, ctx->vit_dsmem, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),
-                                                          ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>());
+    k_viterbi<<<ctx->vit_grid(items.size()), 32 * VIT_CTA_WARPS, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),
+                                                                                  ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(), ctx->d_items.as<VitItem>(),
+                                                                                  (int)items.size(), ctx->d_vit_counter.as<int>() + 3);
     ctx->prof_end();
     ctx->prof_begin("k_vit_trace(stage)");
     k_vit_trace<<<ng, 64, 0, ctx->stream>>>(ctx->d_dec.as<uint2>(), ctx->d_meet.as<unsigned short>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
-                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>());
+                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3);
     ctx->prof_end();
     ctx->launches += 2;
     CKC(cudaGetLastError());
@@ -1412,6 +1496,7 @@ int b200dab_stage_dabplus(b200dab_ctx* ctx, uint8_t* frames, int n_rows, int bit
     CKC(cudaMemcpyAsync(ctx->d_msc_out.p, frames, (size_t)n_rows * pitch, cudaMemcpyHostToDevice, ctx->stream));
     DabPlusJob j;
     j.frames_off = 0; j.n_rows = n_rows; j.pitch = pitch; j.s = bitrate / 8; j.sf_off = 0; j.max_sf = n_rows / 5; j.flag_off = 0;
+    j.subch_index = 0; j.forced_phase = -1; j.pad_ = 0;
     std::vector<DabPlusJob> jobs(1, j);
     if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), jobs, j.max_sf, n_rows)) return -1;
     std::vector<SfInfo> sf(j.max_sf);

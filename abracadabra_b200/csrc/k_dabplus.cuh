@@ -36,6 +36,8 @@ struct DabPlusJob {
     int max_sf;             // slots reserved = n_rows / 5
     int flag_off;           // index into the per-row firecode flag array
     int subch_index;        // index of the sub-channel in the caller's table (copied into the AU records)
+    int forced_phase;       // >= 0: superframes start at rows = forced_phase (mod 5), no vote (chunked decoding: the vote is global)
+    int pad_;
 };
 struct SfInfo {             // per superframe slot
     int valid;              // 1 = slot used (inside the aligned run)
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(SF_ALIGN_THREADS) k_sf_align(const DabPlusJob*
             for (int w = 0; w < SF_ALIGN_THREADS / 32; w++) c += part[w][k];
             if (c > bc) { bc = c; best = k; }
         }
+        if (job.forced_phase >= 0) best = job.forced_phase % 5;
         s_best = best;
         residue_out[blockIdx.x] = best;
     }

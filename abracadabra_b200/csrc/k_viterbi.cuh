@@ -28,7 +28,8 @@ struct VitJob {
     int stepinfo_off;      // index into the stepinfo table; entry [steps] is the sentinel (total punctured bits << 4)
     int out_pitch;         // bytes per decoded row = n_info / 8
     int kind;              // 0 FIC, 1 MSC
-    int pad_[2];
+    int mode4;             // 1: four-lane survivor-word layout (set by the host together with the work items)
+    int pad_;
 };
 struct VitGroup { int job; int g_in_job; };
 
@@ -123,49 +124,133 @@ __host__ __device__ constexpr int vit_kidx(int j) { return vit_cbit(j, 0) * 4 + 
 // two predicated bit-sets per maximum, no predicate anywhere, and every instruction is free to move.
 //   accumulator J >> 3: byte 0 = out0 decisions of codeword p, byte 1 = out1 of p, byte 2 = out0 of 16 + p, byte 3 = out1 of 16 + p
 //   out0: bit = in1 taken.  out1: bit = in0 taken (complemented once per step with a constant).
-template <int J>
-__device__ __forceinline__ void vit_bfly(uint32_t in0, uint32_t in1, uint32_t& out0, uint32_t& out1, const uint32_t (&BP)[4], uint32_t (&acc)[2])
+// K = code-bit pattern of the butterfly (vit_kidx of the state behind in0), BIT = bit of the four accumulator bytes it writes.
+// Branch metrics come as P[q] = c + beta_q and Q[q] = c - beta_q with c = VIT_C = 512 > max |beta|: both halves of both words are
+// non-negative, so (i) adding them is a plain 32-bit add with no borrow between the codewords and (ii) they are proper packed
+// operands for VIADDMNMX.S16x2 = max(a + b, c) per half, which does the second candidate's add and the maximum in ONE instruction.
+// Every candidate of a step carries the same extra c, which no decision sees; the renormalisation takes the drift out again.
+template <int K, int BIT>
+__device__ __forceinline__ void vit_bfly_k(uint32_t in0, uint32_t in1, uint32_t& out0, uint32_t& out1, const uint32_t (&P)[4], const uint32_t (&Q)[4], uint32_t& acc)
 {
-    constexpr int k = vit_kidx(2 * J);
+    constexpr int k = K;
     constexpr bool neg = k >= 4;
     constexpr int q = neg ? 7 - k : k;
-    const uint32_t t0 = neg ? in0 - BP[q] : in0 + BP[q], t1 = neg ? in1 + BP[q] : in1 - BP[q];     // plain 32-bit adds: see the bias note
-    out0 = __vmaxs2(t0, t1);                             // in0 survives a tie: the bit says t1 > t0
+    const uint32_t up = neg ? Q[q] : P[q], dn = neg ? P[q] : Q[q];     // in0 + beta / in1 - beta for the even successor, swapped for the odd one
+    const uint32_t t0 = in0 + up;                        // plain 32-bit add: see the bias note
+    out0 = __viaddmax_s16x2(in1, dn, t0);                // max(in1 - beta, t0); in0 survives a tie: the bit says t1 > t0
     const uint32_t z0 = out0 - t0 + 0x7fff7fffu;
-    const uint32_t u0 = neg ? in0 + BP[q] : in0 - BP[q], u1 = neg ? in1 - BP[q] : in1 + BP[q];
-    out1 = __vmaxs2(u0, u1);                             // in1 survives a tie: the bit says u0 > u1
+    const uint32_t u1 = in1 + up;
+    out1 = __viaddmax_s16x2(in0, dn, u1);                // max(in0 - beta, u1); in1 survives a tie: the bit says u0 > u1
     const uint32_t z1 = out1 - u1 + 0x7fff7fffu;
     uint32_t w;                                          // bytes (z0.1, z1.1, z0.3, z1.3), each replaced by eight copies of its MSB
     asm("prmt.b32 %0, %1, %2, 0xfbd9;" : "=r"(w) : "r"(z0), "r"(z1));
-    constexpr uint32_t m = 0x01010101u << (J & 7);
-    acc[J >> 3] = (acc[J >> 3] & ~m) | (w & m);          // one LOP3
+    constexpr uint32_t m = 0x01010101u << BIT;
+    acc = (acc & ~m) | (w & m);                          // one LOP3
+}
+#define VIT_C 512u
+// P[q], Q[q] of both codewords of a lane from their soft words (wA: low halves, wB: high halves) and the lane's coefficient words
+__device__ __forceinline__ void vit_branch(uint32_t wA, uint32_t wB, const uint32_t (&C)[4], uint32_t (&P)[4], uint32_t (&Q)[4])
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int hi = __dp4a((int)wB, (int)C[q], (int)VIT_C);
+        P[q] = (uint32_t)__dp4a((int)wA, (int)C[q], hi * 65536 + (int)VIT_C);
+        Q[q] = (2u * VIT_C) * 65537u - P[q];
+    }
+}
+template <int J>
+__device__ __forceinline__ void vit_bfly(uint32_t in0, uint32_t in1, uint32_t& out0, uint32_t& out1, const uint32_t (&P)[4], const uint32_t (&Q)[4], uint32_t (&acc)[2])
+{
+    vit_bfly_k<vit_kidx(2 * J), (J & 7)>(in0, in1, out0, out1, P, Q, acc[J >> 3]);
 }
 template <int J> struct VitFwd {
-    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&acc)[2])
+    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&P)[4], const uint32_t (&Q)[4], uint32_t (&acc)[2])
     {
-        VitFwd<J - 1>::run(M, N, BP, acc);
+        VitFwd<J - 1>::run(M, N, P, Q, acc);
         uint32_t e, o;
-        vit_bfly<J>(M[J], M[J + 16], e, o, BP, acc);
+        vit_bfly<J>(M[J], M[J + 16], e, o, P, Q, acc);
         N[2 * J] = e;
         N[31 - 2 * J] = __shfl_xor_sync(0xffffffffu, o, 1);
     }
 };
 template <> struct VitFwd<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[2]) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[2]) {}
 };
 template <int J> struct VitBwd {
-    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&BP)[4], uint32_t (&acc)[2])
+    static __device__ __forceinline__ void run(const uint32_t (&M)[32], uint32_t (&N)[32], const uint32_t (&P)[4], const uint32_t (&Q)[4], uint32_t (&acc)[2])
     {
-        VitBwd<J - 1>::run(M, N, BP, acc);
+        VitBwd<J - 1>::run(M, N, P, Q, acc);
         const uint32_t r = __shfl_xor_sync(0xffffffffu, M[31 - 2 * J], 1);
-        vit_bfly<J>(M[2 * J], r, N[J], N[J + 16], BP, acc);
+        vit_bfly<J>(M[2 * J], r, N[J], N[J + 16], P, Q, acc);
     }
 };
 template <> struct VitBwd<-1> {
-    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], uint32_t (&)[2]) {}
+    static __device__ __forceinline__ void run(const uint32_t (&)[32], uint32_t (&)[32], const uint32_t (&)[4], const uint32_t (&)[4], uint32_t (&)[2]) {}
 };
 
+// ------------------------------------------------------------------------------------------------ four-lane split
+// The same recursion with the 64 states of a codeword pair spread over FOUR lanes (16 registers each), 16 codewords per warp:
+// half the dependent instruction chain per trellis step (8 butterflies instead of 16), which is what bounds the launch for the
+// long sub-channels (a lone warp issues once per two cycles, so a chain of T steps costs T x instructions-per-step x 2 cycles
+// however idle the machine is).  tools/vit4_model.py is the scalar model of this layout and checks it against the plain recursion.
+//   lane a (0..3) of a quad owns the states with state & 3 == a; logical register r = state >> 2 lives in physical register
+//   r ^ X[a], X = {11, 0, 6, 13}.
+//   slot m (0..7): butterfly on physical registers m and m + 8.  Lanes 1, 2: in0 = state j, in1 = j + 32 and out0 / out1 are the
+//   even / odd successor; lanes 0, 3 (bit 3 of X set): in0 = j + 32, in1 = j, out0 / out1 = odd / even successor -- the same
+//   butterfly code with the same branch metric, and the tie rules fall on the right candidates in both cases.
+//   forward : out0 of every lane goes through ONE shuffle (lane a reads lane R1[a] = {2, 0, 1, 3}) into register 2m ^ 6,
+//             out1 through a second one (R2 = {0, 2, 3, 1}) into 2m ^ 13: no select on either side, register naming only.
+//   backward: the reverse flow -- in0 = register 2m ^ 6 of lane R1inv[a] = {1, 2, 0, 3}, in1 = register 2m ^ 13 of lane
+//             R2inv[a] = {0, 3, 1, 2}; results stay in registers m, m + 8.
+//   branch metrics: slot m has the code-bit pattern of state 4m; what the lane's own state bits and X[a] add is a sign per soft
+//   bit, folded into the IDP.4A coefficient words (lanes 0, 3: all four negated; lanes 1, 2: bits 1, 2 negated).
+// Survivor words: one 16-bit half per lane, codeword and step (bit m: out0 of slot m, bit 8 + m: out1, 1 = in1 taken); two
+// consecutive steps share a 32-bit word (even step in the low half):  dec32[((t / 2 * 2 + (a >> 1)) * 32 + codeword) * 2 + (a & 1)],
+// the same 8 bytes per codeword and step as the two-lane layout.
+#define VIT4_X0 11
+#define VIT4_C1 6
+#define VIT4_C2 13
+template <int M_> struct Vit4Fwd {
+    static __device__ __forceinline__ void run(const uint32_t (&M)[16], uint32_t (&N)[16], const uint32_t (&P)[4], const uint32_t (&Q)[4], uint32_t& acc, int s1, int s2)
+    {
+        Vit4Fwd<M_ - 1>::run(M, N, P, Q, acc, s1, s2);
+        uint32_t e, o;
+        vit_bfly_k<vit_kidx(4 * M_), M_>(M[M_], M[M_ + 8], e, o, P, Q, acc);
+        N[(2 * M_) ^ VIT4_C1] = __shfl_sync(0xffffffffu, e, s1);
+        N[(2 * M_) ^ VIT4_C2] = __shfl_sync(0xffffffffu, o, s2);
+    }
+};
+template <> struct Vit4Fwd<-1> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[16], uint32_t (&)[16], const uint32_t (&)[4], const uint32_t (&)[4], uint32_t&, int, int) {}
+};
+template <int M_> struct Vit4Bwd {
+    static __device__ __forceinline__ void run(const uint32_t (&M)[16], uint32_t (&N)[16], const uint32_t (&P)[4], const uint32_t (&Q)[4], uint32_t& acc, int s1, int s2)
+    {
+        Vit4Bwd<M_ - 1>::run(M, N, P, Q, acc, s1, s2);
+        const uint32_t i0 = __shfl_sync(0xffffffffu, M[(2 * M_) ^ VIT4_C1], s1);
+        const uint32_t i1 = __shfl_sync(0xffffffffu, M[(2 * M_) ^ VIT4_C2], s2);
+        vit_bfly_k<vit_kidx(4 * M_), M_>(i0, i1, N[M_], N[M_ + 8], P, Q, acc);
+    }
+};
+template <> struct Vit4Bwd<-1> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[16], uint32_t (&)[16], const uint32_t (&)[4], const uint32_t (&)[4], uint32_t&, int, int) {}
+};
+template <bool BWD>
+__device__ __forceinline__ uint32_t vit4_step(const uint32_t (&M)[16], uint32_t (&N)[16], uint32_t wA, uint32_t wB, const uint32_t (&C)[4], int s1, int s2)
+{
+    uint32_t P[4], Q[4];
+    vit_branch(wA, wB, C, P, Q);
+    uint32_t acc = 0;
+    if (BWD) Vit4Bwd<7>::run(M, N, P, Q, acc, s1, s2);
+    else Vit4Fwd<7>::run(M, N, P, Q, acc, s1, s2);
+    return acc;         // bytes: out0 of codeword p, out1 of p, out0 of 8 + p, out1 of 8 + p
+}
+
 #define VIT_BIAS 16384u
+// Metrics are re-referenced to state 0 every VIT_RENORM steps.  Range: state 0 = 16384 after it, the others within +-6096 of it
+// (6 steps x 1016), the penalised start states at 8192; a step adds 4..1020 (c +- beta), so after 8 steps every half lies in
+// [8224, 30640]: never negative, never beyond int16 -- what the packed adds and the signed packed maximum need.
+#define VIT_RENORM 8
 #define VIT_PENV ((VIT_BIAS + VIT_START_PENALTY) * 65537u)
 #define VIT_MEET_WORDS (2 * 64 * 32)        /* unsigned shorts per group: [direction][state][codeword] */
 
@@ -174,38 +259,36 @@ template <bool BWD>
 __device__ __forceinline__ void vit_step(const uint32_t (&M)[32], uint32_t (&N)[32], uint32_t wA, uint32_t wB, const uint32_t (&C)[4],
                                          uint32_t* dst)
 {
-    uint32_t BP[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) BP[q] = (uint32_t)__dp4a((int)wA, (int)C[q], __dp4a((int)wB, (int)C[q], 0) << 16);
+    uint32_t P[4], Q[4];
+    vit_branch(wA, wB, C, P, Q);
     uint32_t acc[2] = {0, 0};
-    if (BWD) VitBwd<15>::run(M, N, BP, acc);
-    else VitFwd<15>::run(M, N, BP, acc);
+    if (BWD) VitBwd<15>::run(M, N, P, Q, acc);
+    else VitFwd<15>::run(M, N, P, Q, acc);
     // codeword p: bytes 0, 1 of both accumulators; codeword 16 + p: bytes 2, 3; the out1 bytes are complemented (1 = in1 was taken)
     dst[0] = __byte_perm(acc[0], acc[1], 0x5410) ^ 0xff00ff00u;
     dst[32] = __byte_perm(acc[0], acc[1], 0x7632) ^ 0xff00ff00u;
 }
+
+// Work item of k_viterbi: one warp.  Two-lane mode: (group, direction) = 32 codewords; four-lane mode: (group, direction, half) =
+// 16 codewords.  The host sorts the items by the length of their dependent instruction chain, longest first.
+struct VitItem { int group; int what; };      // what: bit 0 direction, bit 1 half (four-lane), bit 2 four-lane mode
 
 // Bidirectional decoding: the code is zero-terminated at BOTH ends, so one work item runs the trellis forward over steps
 // [0, m) from state 0 while another runs it backward over steps [m, T) from state 0; at stage m the state maximising
 // alpha + beta lies on the maximum-likelihood path (k_vit_trace picks it, traces back over [0, m) and forward over [m, T)).
 // Same path as one-directional Viterbi whenever the best path is unique; the tie rules are mirrored by the CPU checker.
 // Metrics carry a bias of 16384 so that both halves of a register stay non-negative and a packed add is one 32-bit add.
-// grid = 2 * n_groups one-warp CTAs (longest groups first): item = (group, direction)
-__global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec, unsigned short* __restrict__ meet,
-                                                const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups)
+__device__ __forceinline__ void vit_run2(uint32_t (&ring)[2][VIT_NORM_PERIOD][32], const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec,
+                                         unsigned short* __restrict__ meet, const VitJob& job, int group, int g_in_job, int dir)
 {
     constexpr int PF = VIT_NORM_PERIOD;
     static_assert(PF % 2 == 0, "the step loop is unrolled by two");
-    __shared__ uint32_t ring[2][PF][32];
-    const int item = blockIdx.x;
-    const VitGroup grp = groups[item >> 1];
-    const VitJob job = jobs[grp.job];
-    const int lane = threadIdx.x, role = lane & 1, p = lane >> 1, dir = item & 1;
+    const int lane = threadIdx.x & 31, role = lane & 1, p = lane >> 1;
     const int steps = job.steps;
     const int m = ((steps >> 1) >> 5) << 5;                         // meeting stage, multiple of 32
-    const uint32_t* in = vin + job.vin_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
-    uint32_t* d = dec + (job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + p) * 2 + role;     // codeword 16 + p: 32 words further on
-    unsigned short* mt = meet + ((size_t)(item >> 1) * 2 + dir) * (64 * 32) + p;
+    const uint32_t* in = vin + job.vin_off + ((size_t)g_in_job * steps) * 32 + lane;
+    uint32_t* d = dec + (job.dec_off + ((size_t)g_in_job * steps) * 32 + p) * 2 + role;     // codeword 16 + p: 32 words further on
+    unsigned short* mt = meet + ((size_t)group * 2 + dir) * (64 * 32) + p;
     const uint32_t flip = role ? 63u : 0u;
     // coefficient bytes (a0, a1, a2, a3) of beta_0..3 = T + X1, T + X2, T - X2, T - X1 with T = +-(a0 + a3), X1/X2 = +-a1 +/- a2
     const uint32_t C[4] = {role ? 0xff01ffffu : 0x01010101u, role ? 0xffffffffu : 0x01ff0101u,
@@ -238,16 +321,17 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
         if (done + PF < n_total) { prefetch(buf ^ 1, t0 + PF * t_step, t_step); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();                                               // a lane reads the words its neighbours fetched
-        renorm();
         const int nst = min(PF, n_total - done);
         int i = 0;
         if (dir == 0) {
 #pragma unroll 1
             for (; i + 1 < nst; i += 2) {           // two steps per iteration: M -> N -> M, no register copies
+                if ((i & (VIT_RENORM - 1)) == 0) renorm();
                 vit_step<false>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 + i) * 64);
                 vit_step<false>(N, M, ring[buf][i + 1][p], ring[buf][i + 1][16 + p], C, d + (size_t)(t0 + i + 1) * 64);
             }
             if (i < nst) {
+                if ((i & (VIT_RENORM - 1)) == 0) renorm();
                 vit_step<false>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 + i) * 64);
 #pragma unroll
                 for (int j = 0; j < 32; j++) M[j] = N[j];
@@ -255,10 +339,12 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
         } else {
 #pragma unroll 1
             for (; i + 1 < nst; i += 2) {
+                if ((i & (VIT_RENORM - 1)) == 0) renorm();
                 vit_step<true>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 - i) * 64);
                 vit_step<true>(N, M, ring[buf][i + 1][p], ring[buf][i + 1][16 + p], C, d + (size_t)(t0 - i - 1) * 64);
             }
             if (i < nst) {
+                if ((i & (VIT_RENORM - 1)) == 0) renorm();
                 vit_step<true>(M, N, ring[buf][i][p], ring[buf][i][16 + p], C, d + (size_t)(t0 - i) * 64);
 #pragma unroll
                 for (int j = 0; j < 32; j++) M[j] = N[j];
@@ -274,6 +360,114 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
     }
 }
 
+// four-lane item: codewords 16 half + p (low register halves) and 16 half + 8 + p (high halves) of the group, p = lane >> 2.
+// The number of steps of either direction is even (steps and the meeting stage are), so steps always come in pairs.
+__device__ __forceinline__ void vit_run4(uint32_t (&ring)[2][VIT_NORM_PERIOD][32], const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec,
+                                         unsigned short* __restrict__ meet, const VitJob& job, int group, int g_in_job, int dir, int half)
+{
+    constexpr int PF = VIT_NORM_PERIOD;
+    const int lane = threadIdx.x & 31, a = lane & 3, p = lane >> 2, cw = 16 * half + p;
+    const int steps = job.steps;
+    const int m = ((steps >> 1) >> 5) << 5;
+    const uint32_t* in = vin + job.vin_off + ((size_t)g_in_job * steps) * 32 + 16 * half + (lane & 15);
+    // survivor word of step pair t2, lane a, codeword c: dec32[((2 t2 + (a >> 1)) * 32 + c) * 2 + (a & 1)]
+    uint32_t* d = dec + (job.dec_off + ((size_t)g_in_job * steps) * 32) * 2 + ((size_t)(a >> 1) * 32 + cw) * 2 + (a & 1);
+    unsigned short* mt = meet + ((size_t)group * 2 + dir) * (64 * 32) + cw;
+    const bool outer = (a == 0) || (a == 3);
+    const uint32_t C[4] = {outer ? 0xffffffffu : 0x01ffff01u, outer ? 0xff01ffffu : 0x0101ff01u,
+                           outer ? 0xffff01ffu : 0x01ff0101u, outer ? 0xff0101ffu : 0x01010101u};
+    const int quad = lane & ~3;
+    // shuffle sources: forward R1 = {2, 0, 1, 3}, R2 = {0, 2, 3, 1}; backward their inverses {1, 2, 0, 3}, {0, 3, 1, 2}
+    const int s1 = quad | (int)((dir == 0 ? 0x3102u : 0x3021u) >> (4 * a) & 3u);
+    const int s2 = quad | (int)((dir == 0 ? 0x1320u : 0x2130u) >> (4 * a) & 3u);
+
+    uint32_t M[16], N[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) M[j] = VIT_PENV;
+    if (a == 0) M[VIT4_X0] = VIT_BIAS * 65537u;                     // state 0: lane 0, logical register 0
+    auto prefetch = [&](int buf, int t_first, int t_step) {         // lanes 0..15 fetch the even ring slots, lanes 16..31 the odd ones
+#pragma unroll
+        for (int i = 0; i < PF / 2; i++) {
+            const int slot = 2 * i + (lane >> 4);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&ring[buf][slot][16 * half + (lane & 15)]);
+            const uint32_t* src = in + (size_t)min(max(t_first + slot * t_step, 0), steps - 1) * 32;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto renorm = [&]() {
+        const uint32_t c = __shfl_sync(0xffffffffu, VIT_BIAS * 65537u - M[VIT4_X0], quad);
+#pragma unroll
+        for (int j = 0; j < 16; j++) M[j] += c;
+    };
+    const int t_begin = dir == 0 ? 0 : steps - 1, t_step = dir == 0 ? 1 : -1, n_total = dir == 0 ? m : steps - m;
+    prefetch(0, t_begin, t_step);
+    int buf = 0;
+    for (int done = 0; done < n_total; done += PF, buf ^= 1) {
+        const int t0 = t_begin + done * t_step;
+        __syncwarp();
+        if (done + PF < n_total) { prefetch(buf ^ 1, t0 + PF * t_step, t_step); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const int nst = min(PF, n_total - done);
+        if (dir == 0) {
+#pragma unroll 1
+            for (int i = 0; i < nst; i += 2) {
+                if ((i & (VIT_RENORM - 1)) == 0) renorm();
+                const uint32_t e = vit4_step<false>(M, N, ring[buf][i][cw], ring[buf][i][cw + 8], C, s1, s2);
+                const uint32_t o = vit4_step<false>(N, M, ring[buf][i + 1][cw], ring[buf][i + 1][cw + 8], C, s1, s2);
+                uint32_t* dst = d + (size_t)(t0 + i) * 64;           // pair (t0 + i) / 2: 128 words per pair
+                dst[0] = __byte_perm(e, o, 0x5410) ^ 0xff00ff00u;
+                dst[16] = __byte_perm(e, o, 0x7632) ^ 0xff00ff00u;   // codeword + 8
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < nst; i += 2) {
+                if ((i & (VIT_RENORM - 1)) == 0) renorm();
+                const uint32_t o = vit4_step<true>(M, N, ring[buf][i][cw], ring[buf][i][cw + 8], C, s1, s2);          // odd step t0 - i
+                const uint32_t e = vit4_step<true>(N, M, ring[buf][i + 1][cw], ring[buf][i + 1][cw + 8], C, s1, s2);  // even step t0 - i - 1
+                uint32_t* dst = d + (size_t)(t0 - i - 1) * 64;
+                dst[0] = __byte_perm(e, o, 0x5410) ^ 0xff00ff00u;
+                dst[16] = __byte_perm(e, o, 0x7632) ^ 0xff00ff00u;
+            }
+        }
+    }
+    // metrics at the meeting stage: physical register j of lane a = logical register j ^ X[a] = state 4 (j ^ X[a]) + a
+    const uint32_t xa = (0xd60bu >> (4 * a)) & 15u;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t s = 4u * ((uint32_t)j ^ xa) + (uint32_t)a;
+        mt[s * 32] = (unsigned short)(M[j] & 0xffffu);
+        mt[s * 32 + 8] = (unsigned short)(M[j] >> 16);
+    }
+}
+
+// Persistent kernel: CTAs of four warps (one per SM sub-partition), a few CTAs per SM; every warp takes the next work item from
+// a global queue until it is empty.  The items are sorted by the length of their dependent instruction chain, longest first, so
+// the warps of every sub-partition stay busy until the short items at the end of the list run out (list scheduling); with
+// one-warp CTAs dealt by the hardware the sub-partitions of an SM ended up with 0.64-1.09 M instructions each (profiles/r01k).
+// `counter` is zero on entry; k_vit_trace, which always follows on the stream, clears it again.
+#define VIT_CTA_WARPS 4
+__global__ void __launch_bounds__(32 * VIT_CTA_WARPS) k_viterbi(const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec, unsigned short* __restrict__ meet,
+                                                                  const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
+                                                                  const VitItem* __restrict__ items, int n_items, int* __restrict__ counter)
+{
+    __shared__ uint32_t ring[VIT_CTA_WARPS][2][VIT_NORM_PERIOD][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_items) break;
+        const VitItem item = items[idx];
+        const VitGroup grp = groups[item.group];
+        const VitJob job = jobs[grp.job];
+        if (item.what & 4) vit_run4(ring[warp], vin, dec, meet, job, item.group, grp.g_in_job, item.what & 1, (item.what >> 1) & 1);
+        else vit_run2(ring[warp], vin, dec, meet, job, item.group, grp.g_in_job, item.what & 1);
+        __syncwarp();
+    }
+}
+
 // Meeting state (maximum of alpha + beta, lowest state on ties), traceback over [0, m) (warp 0) and trace forward over
 // [m, n_info) (warp 1), energy-dispersal XOR on the way out.  grid = n_groups, 64 threads, one codeword per lane.
 // A role's decision word holds the decision of butterfly J (0..15) for its first / second output at bit 16 (J >> 3) + (J & 7) and
@@ -284,24 +478,84 @@ __global__ void __launch_bounds__(32) k_viterbi(const uint32_t* __restrict__ vin
 // The state recursion is a dependent chain, so the 32 decision pairs of the next chunk are fetched while this one is traced.
 __host__ __device__ __forceinline__ uint32_t vit_dec_index_fwd(uint32_t n) { return ((n >> 5) << 4) | ((n & 1u) << 3) | ((n >> 2) & 7u) | ((n & 2u) << 4); }
 __host__ __device__ __forceinline__ uint32_t vit_dec_index_bwd(uint32_t s) { return (((s >> 4) & 1u) << 4) | ((s >> 5) << 3) | ((s >> 1) & 7u) | ((s & 1u) << 5); }
+// Four-lane layout: w = the four 16-bit halves of a step (lane a at bit 16 a).  The function gives bit index | invert << 6:
+// forward (state n after the step) -> MSB of the predecessor = bit ^ invert; backward (state s before the step) -> input bit.
+// Closed forms of the tables tools/vit4_model.py derives from the register maps: base[n & 7] ^ (n >> 3) and base[s & 3] ^ (s >> 2).
+__host__ __device__ __forceinline__ uint32_t vit4_dec_index_fwd(uint32_t n)
+{
+    const unsigned long long base = 0x757d2e261810434bull;                           // bytes 75, 67, 16, 24, 38, 46, 125, 117
+    return ((uint32_t)(base >> (8 * (n & 7u))) & 0x7fu) ^ (n >> 3);
+}
+__host__ __device__ __forceinline__ uint32_t vit4_dec_index_bwd(uint32_t s)
+{
+    const uint32_t base = 0x7d26104bu;                                               // bytes 75, 16, 38, 125
+    return ((base >> (8 * (s & 3u))) & 0x7fu) ^ (s >> 2);
+}
 __device__ __forceinline__ void vit_load_chunk(uint2 (&b)[32], const uint2* d, int c)
 {
 #pragma unroll
     for (int i = 0; i < 32; i++) b[i] = __ldcs(d + (size_t)(32 * c + i) * 32);
 }
+// the 64 survivor bits of step i (0..31) of a chunk, two-lane layout: role 0's word | ~bit-reverse(role 1's word) << 32
+__device__ __forceinline__ unsigned long long vit_word2(const uint2 (&b)[32], int i)
+{
+    return (unsigned long long)b[i].x | ((unsigned long long)(~__brev(b[i].y)) << 32);
+}
+// four-lane layout: b[2 k] = (lane 0, lane 1), b[2 k + 1] = (lane 2, lane 3) of step pair k; even step in the low halves
+__device__ __forceinline__ unsigned long long vit_word4(const uint2 (&b)[32], int i)
+{
+    const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
+    const uint2 lo = b[(i >> 1) * 2], hi = b[(i >> 1) * 2 + 1];
+    return (unsigned long long)__byte_perm(lo.x, lo.y, sel) | ((unsigned long long)__byte_perm(hi.x, hi.y, sel) << 32);
+}
+template <bool FOUR>
+__device__ __forceinline__ void vit_trace_run(const uint2* __restrict__ d, const VitJob& job, int dir, int m, uint32_t s, bool live,
+                                              uint32_t* __restrict__ orow, const uint32_t* __restrict__ prbs_w)
+{
+    const int c_first = dir == 0 ? m / 32 - 1 : m / 32, c_end = dir == 0 ? -1 : job.n_info / 32, c_step = dir == 0 ? -1 : 1;
+    uint2 cur[32], nxt[32];
+    if (c_first != c_end) vit_load_chunk(cur, d, c_first);
+    for (int c = c_first; c != c_end; c += c_step) {
+        const bool more = (c + c_step) != c_end;
+        if (more) vit_load_chunk(nxt, d, c + c_step);
+        uint32_t word = 0;
+        if (dir == 0) {
+            // traceback: s is the state after step 32 c + i
+#pragma unroll
+            for (int i = 31; i >= 0; i--) {
+                const unsigned long long w = FOUR ? vit_word4(cur, i) : vit_word2(cur, i);
+                word |= (s & 1u) << (31 - i);
+                const uint32_t idx = FOUR ? vit4_dec_index_fwd(s) : vit_dec_index_fwd(s);
+                s = (s >> 1) | ((((uint32_t)(w >> (idx & 63u)) ^ (idx >> 6)) & 1u) << 5);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                const unsigned long long w = FOUR ? vit_word4(cur, i) : vit_word2(cur, i);
+                const uint32_t idx = FOUR ? vit4_dec_index_bwd(s) : vit_dec_index_bwd(s);
+                const uint32_t bit = ((uint32_t)(w >> (idx & 63u)) ^ (idx >> 6)) & 1u;
+                word |= bit << (31 - i);
+                s = ((s << 1) | bit) & 63u;
+            }
+        }
+        if (live) orow[c] = __byte_perm(word, 0, 0x0123) ^ __ldg(prbs_w + c);
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) cur[i] = nxt[i];
+        }
+    }
+}
 __global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec, const unsigned short* __restrict__ meet,
                                                   const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
-                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out)
+                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out, int* __restrict__ vit_counter)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *vit_counter = 0;      // the work queue of the k_viterbi launch in front of this one
     const VitGroup grp = groups[blockIdx.x];
     const VitJob job = jobs[grp.job];
     const int lane = threadIdx.x & 31, dir = threadIdx.x >> 5;
     const int steps = job.steps;
     const int m = ((steps >> 1) >> 5) << 5;
     const uint2* d = dec + job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
-    const int c_first = dir == 0 ? m / 32 - 1 : m / 32, c_end = dir == 0 ? -1 : job.n_info / 32, c_step = dir == 0 ? -1 : 1;
-    uint2 cur[32], nxt[32];
-    if (c_first != c_end) vit_load_chunk(cur, d, c_first);
     const unsigned short* mt = meet + (size_t)blockIdx.x * VIT_MEET_WORDS + lane;
     uint32_t s = 0;
     int best = -1;
@@ -313,33 +567,6 @@ __global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec,
     const int row = grp.g_in_job * 32 + lane;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + job.out_off + (size_t)row * job.out_pitch);
     const bool live = row < job.n_rows;
-    for (int c = c_first; c != c_end; c += c_step) {
-        const bool more = (c + c_step) != c_end;
-        if (more) vit_load_chunk(nxt, d, c + c_step);
-        uint32_t word = 0;
-        if (dir == 0) {
-            // traceback: s is the state after step 32 c + i
-#pragma unroll
-            for (int i = 31; i >= 0; i--) {
-                const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
-                word |= (s & 1u) << (31 - i);
-                const uint32_t idx = vit_dec_index_fwd(s);
-                s = (s >> 1) | (((uint32_t)(w >> idx) & 1u) << 5);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const unsigned long long w = (unsigned long long)cur[i].x | ((unsigned long long)(~__brev(cur[i].y)) << 32);
-                const uint32_t idx = vit_dec_index_bwd(s);
-                const uint32_t bit = (uint32_t)(w >> idx) & 1u;
-                word |= bit << (31 - i);
-                s = ((s << 1) | bit) & 63u;
-            }
-        }
-        if (live) orow[c] = __byte_perm(word, 0, 0x0123) ^ __ldg(prbs_w + c);
-        if (more) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) cur[i] = nxt[i];
-        }
-    }
+    if (job.mode4) vit_trace_run<true>(d, job, dir, m, s, live, orow, prbs_w);
+    else vit_trace_run<false>(d, job, dir, m, s, live, orow, prbs_w);
 }

@@ -56,6 +56,11 @@ class EnsembleInfo(ct.Structure):
                 ("first_cif_count", ct.c_int32), ("n_services", ct.c_int32), ("services", ServiceInfo * 64)]
 
 
+class Sf(ct.Structure):
+    _fields_ = [("subch_index", ct.c_int32), ("row", ct.c_int32), ("firecode_ok", ct.c_int32), ("rs_corrected", ct.c_int32),
+                ("rs_bit_errors", ct.c_int32), ("rs_uncorrectable", ct.c_int32), ("n_aus", ct.c_int32), ("header", ct.c_int32)]
+
+
 class Result(ct.Structure):
     _fields_ = [("n_candidates", ct.c_int32), ("n_frames", ct.c_int32), ("n_slots", ct.c_int32),
                 ("t_f", ct.POINTER(ct.c_int64)), ("cfo_hz", ct.POINTER(ct.c_float)), ("cir_ratio", ct.POINTER(ct.c_float)),
@@ -68,7 +73,9 @@ class Result(ct.Structure):
                 ("n_tii", ct.c_int32), ("tii", ct.POINTER(Tii)),
                 ("symstat", ct.POINTER(ct.c_float)), ("snr_db", ct.c_float), ("gpu_launches", ct.c_int32),
                 ("tii_fold", ct.POINTER(ct.c_float)), ("tii_norm", ct.POINTER(ct.c_float)), ("tii_sign", ct.POINTER(ct.c_int32)),
-                ("spectrum", ct.POINTER(ct.c_float))]
+                ("spectrum", ct.POINTER(ct.c_float)),
+                ("n_sf", ct.c_int32), ("sf", ct.POINTER(Sf)), ("sf_flags", ct.POINTER(ct.POINTER(ct.c_uint8))),
+                ("sf_phase", ct.POINTER(ct.c_int32))]
 
 
 def build(verbose: bool = False) -> None:
@@ -109,6 +116,9 @@ def lib():
         L.b200dab_pad_feed_packets.argtypes = [vp, i32, vp, i32, PAD_CB, vp]
         L.b200dab_decode.argtypes = [vp, vp, u64, i32, i32, ct.POINTER(SubCh), i32, ct.c_uint32, ct.POINTER(Result)]
         L.b200dab_set_profiling.argtypes = [vp, i32]
+        L.b200dab_set_superframe_phase.argtypes = [vp, vp, i32]
+        L.b200dab_set_viterbi_split.argtypes = [vp, i32]
+        L.b200dab_viterbi4_decision_index.argtypes = [i32, i32]
         L.b200dab_get_kernel_times.argtypes = [vp, ct.c_char_p, i32, vp, i32]
         L.b200dab_get_kernel_times_back.argtypes = [vp, i32, ct.c_char_p, i32, vp, i32]
         L.b200dab_get_kernel_timeline.argtypes = [vp, i32, ct.c_char_p, i32, vp, vp, i32]
@@ -126,7 +136,7 @@ def lib():
 
 
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
-           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_get_kernel_timeline", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_viterbi_decision_index", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
+           "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_get_kernel_timeline", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_viterbi_decision_index", "b200dab_viterbi4_decision_index", "b200dab_set_viterbi_split", "b200dab_set_superframe_phase", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
@@ -273,6 +283,13 @@ class Decoded:
     tii: List[TiiWindow]
     snr_db: float
     gpu_launches: int
+    # DAB+ superframe layer and per-frame TII material (what a chunked decode is merged from, shard.decode_chunked)
+    sf: Optional[np.ndarray] = None          # [n_sf, 8] int32: subch_index, row, firecode_ok, rs_corrected, rs_bit_errors, rs_uncorrectable, n_aus, header
+    sf_flags: Optional[list] = None          # per sub-channel: uint8 [rows] fire-code hit before RS, or None
+    sf_phase: Optional[list] = None          # per sub-channel: row % 5 of the superframe starts, -1 = none
+    tii_fold: Optional[np.ndarray] = None    # [n_slots, 384]
+    tii_norm: Optional[np.ndarray] = None    # [n_slots]
+    tii_sign: Optional[np.ndarray] = None    # [n_slots]
 
 
 def _ptr(a):
@@ -311,6 +328,10 @@ class Receiver:
     def set_profiling(self, on: bool) -> None:
         lib().b200dab_set_profiling(self._h, int(on))
 
+    def set_viterbi_split(self, min_steps_four_lane: int) -> None:
+        """codewords of at least this many trellis steps use the four-lane kernel mode (0 = all, 1 << 30 = none)"""
+        lib().b200dab_set_viterbi_split(self._h, int(min_steps_four_lane))
+
     def kernel_times(self, back: int = 0):
         """[(kernel name, ms)] of the last decode, or of the decode `back` calls ago (the last 8 are kept); needs
         set_profiling(True) before them."""
@@ -345,8 +366,13 @@ class Receiver:
         return res
 
     def decode(self, raw, fmt: str, subch: Optional[Sequence[SubCh]] = None, tii: bool = False, symstat: bool = False,
-               no_msc: bool = False, n_samples: Optional[int] = None, on_device: bool = False) -> Decoded:
-        """raw: numpy array (host) or an integer device pointer with n_samples given."""
+               no_msc: bool = False, n_samples: Optional[int] = None, on_device: bool = False,
+               sf_phase: Optional[Sequence[int]] = None) -> Decoded:
+        """raw: numpy array (host) or an integer device pointer with n_samples given.  sf_phase: forced superframe alignment per
+        sub-channel (row % 5, -1 = vote) for this call (chunked decoding)."""
+        if sf_phase is not None:
+            ph = np.ascontiguousarray(sf_phase, np.int32)
+            lib().b200dab_set_superframe_phase(self._h, ph.ctypes.data, ph.size)
         if isinstance(raw, np.ndarray):
             raw = np.ascontiguousarray(raw)
             n_samples = raw.nbytes // FMT_BYTES[fmt]
@@ -377,8 +403,20 @@ class Receiver:
             t = r.tii[w]
             ids = [(int(t.main_id[i]), int(t.sub_id[i]), float(t.level[i])) for i in range(t.n_ids)]
             tiis.append(TiiWindow(ids, t.n_tii_frames, np.array(t.spectrum[:], dtype=np.float32), t.norm, t.noise))
-        return Decoded(r.n_candidates, r.n_frames, ns, t_f, cfo, cir, fibs, ok, scs, frames, aus, r.rs_corrected,
-                       r.rs_bit_errors, r.rs_uncorrectable, r.firecode_fail, r.superframes, tiis, r.snr_db, r.gpu_launches)
+        dec = Decoded(r.n_candidates, r.n_frames, ns, t_f, cfo, cir, fibs, ok, scs, frames, aus, r.rs_corrected,
+                      r.rs_bit_errors, r.rs_uncorrectable, r.firecode_fail, r.superframes, tiis, r.snr_db, r.gpu_launches)
+        if r.n_sf > 0 and r.sf:
+            dec.sf = np.ctypeslib.as_array(ct.cast(r.sf, ct.POINTER(ct.c_int32)), (r.n_sf, 8)).copy()
+        else:
+            dec.sf = np.zeros((0, 8), np.int32)
+        if r.sf_flags and r.frames:
+            dec.sf_flags = [np.ctypeslib.as_array(r.sf_flags[i], (r.frame_rows[i],)).copy() if r.sf_flags[i] else None for i in range(r.n_subch)]
+            dec.sf_phase = [int(r.sf_phase[i]) for i in range(r.n_subch)]
+        if tii and ns and r.tii_fold:
+            dec.tii_fold = np.ctypeslib.as_array(r.tii_fold, (ns, TII_BINS)).copy()
+            dec.tii_norm = np.ctypeslib.as_array(r.tii_norm, (ns,)).copy()
+            dec.tii_sign = np.ctypeslib.as_array(r.tii_sign, (ns,)).copy()
+        return dec
 
     # ------------------------------------------------------------------ stages (parity tests, profiling)
     def stage_coarse(self, raw: np.ndarray, fmt: str):

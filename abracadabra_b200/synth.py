@@ -827,6 +827,21 @@ def impair(x: np.ndarray, imp: Impairments, tail: int = 0) -> np.ndarray:
     return x
 
 
+def add_noise_staircase(x: np.ndarray, lead_in: int, snr_db_per_frame, seed: int = 5) -> np.ndarray:
+    """AWGN whose level changes from transmission frame to transmission frame (in place): frame f of a signal impaired with
+    snr_db=None gets SNR snr_db_per_frame[f]; lead-in and tail get the level of the nearest frame (BASELINE configs[4]: SNR sweep)."""
+    rng = np.random.default_rng(seed)
+    snr = np.asarray(snr_db_per_frame, float)
+    edges = [0] + [lead_in + (f + 1) * C.T_FRAME for f in range(len(snr) - 1)] + [x.size]
+    for f in range(len(snr)):
+        a, b = edges[f], min(edges[f + 1], x.size)
+        if a >= b:
+            continue
+        sg = np.float32(np.sqrt(0.5 * 10 ** (-snr[f] / 10)))
+        x[a:b] += (rng.standard_normal(2 * (b - a), dtype=np.float32) * sg).view(np.complex64)
+    return x
+
+
 def quantize(x: np.ndarray, fmt: str, rms: float) -> np.ndarray:
     """Complex baseband -> interleaved IQ in the raw-file formats RawFileInput reads
     (reference: src/input/rawfileinput.h:42-46, conversion rawfileinput.cpp:643-711), plus f32."""

@@ -76,6 +76,16 @@ typedef struct {
     float spectrum[TII_SPECTRUM_BINS];
 } b200dab_tii_t;
 
+/* per DAB+ superframe (five logical frames), in (sub-channel, row) order */
+typedef struct {
+    int32_t subch_index;
+    int32_t row;             /* logical frame (CIF row) the superframe starts at */
+    int32_t firecode_ok;     /* fire code of the header after RS correction */
+    int32_t rs_corrected, rs_bit_errors, rs_uncorrectable;   /* corrected bytes, corrected bits, uncorrectable codewords (of bitrate/8) */
+    int32_t n_aus;
+    int32_t header;
+} b200dab_sf_t;
+
 /* All pointers below refer to pinned host memory owned by the context; valid until the next decode/destroy. */
 typedef struct {
     int32_t n_candidates;            /* null-symbol candidates examined */
@@ -103,6 +113,11 @@ typedef struct {
     const float *tii_norm;           /* [n_slots] */
     const int32_t *tii_sign;         /* [n_slots] +1 TII null, -1 reference null, 0 unknown */
     const float *spectrum;           /* [n_slots][2][2048] linear power, FFT order: [0] PRS symbol, [1] null symbol (OPT_SPECTRUM) */
+    /* DAB+ superframe layer in detail (what the periodic statistics and a chunked decode are put together from) */
+    int32_t n_sf;
+    const b200dab_sf_t *sf;          /* [n_sf] every superframe of the aligned runs */
+    const uint8_t *const *sf_flags;  /* [n_subch] -> [frame_rows] 1 = fire code of that logical frame matches BEFORE RS (NULL: not DAB+) */
+    const int32_t *sf_phase;         /* [n_subch] row % 5 of the superframe starts (most fire-code hits, or forced); -1: none / not DAB+ */
 } b200dab_result_t;
 
 B200DAB_API int b200dab_version(void);
@@ -126,6 +141,13 @@ B200DAB_API int b200dab_spectrum_layout(uint16_t *out, int n);
  * decision of `state` for a forward (backward = 0: state after the step) or backward (state before the step) trellis step; the
  * index function of the kernel itself, exported for the layout test.  -1 for a state outside 0..63. */
 B200DAB_API int b200dab_viterbi_decision_index(int state, int backward);
+/* Same for the four-lane layout (long codewords): the four 16-bit halves of a step, lane a at bit 16 a.  Returns
+ * bit index | invert << 6: the decision is that bit of the word XOR invert.  tools/vit4_model.py derives the tables. */
+B200DAB_API int b200dab_viterbi4_decision_index(int state, int backward);
+/* Codewords of at least `min_steps_four_lane` trellis steps are decoded with four lanes per codeword pair (shorter dependent
+ * chains for the long sub-channels), shorter ones with two; 0 = four lanes for everything, a huge value = two lanes.  Both
+ * modes give identical bits (tests/test_gpu_parity.py). */
+B200DAB_API int b200dab_set_viterbi_split(b200dab_ctx *ctx, int min_steps_four_lane);
 
 /* Ensemble / service summary out of decoded FIBs: the fields RadioControl receives in dabsdrNtfEnsemble_t and the service
  * list (dabsdr.h:169-318), for batch callers that do not go through the callback interface (band scan output). */
@@ -165,6 +187,11 @@ B200DAB_API int b200dab_pad_feed_mp2(b200dab_pad *p, const uint8_t *frame, int l
  * [FIG 0/1 discovery] -> MSC Viterbi -> RS/AU -> TII.  iq: interleaved I,Q in `fmt`; mem says where it lives. */
 B200DAB_API int b200dab_decode(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, int mem,
                                const b200dab_subch_t *subch, int n_subch, uint32_t flags, b200dab_result_t *res);
+
+/* Superframe alignment of the NEXT b200dab_decode only: phase[i] >= 0 forces the superframes of sub-channel i (index into the
+ * sub-channel table of that decode) to start at rows = phase[i] (mod 5) instead of taking the residue with most fire-code hits
+ * of this call.  A recording decoded in time chunks votes over all chunks (abracadabra_b200/shard.py: decode_chunked). */
+B200DAB_API int b200dab_set_superframe_phase(b200dab_ctx *ctx, const int32_t *phase, int n);
 
 /* per-kernel device times (CUDA events on the context stream) of the last b200dab_decode; names ';'-separated */
 B200DAB_API int b200dab_set_profiling(b200dab_ctx *ctx, int on);

@@ -63,9 +63,15 @@ def test_viterbi_bit_exact(receiver, oracle):
         punct = rng.random(soft.shape) < 0.3
         soft[punct] = 0
         soft = np.clip(np.rint(soft), -127, 127).astype(np.int8)
-        got = receiver.stage_viterbi(soft)
-        for c in range(n_cw):
-            assert np.array_equal(got[c], oracle.viterbi(soft[c])), (steps, c)
+        soft[0, :40] = 0                                   # a run of ties right at the start
+        want = [oracle.viterbi(soft[c]) for c in range(n_cw)]
+        # both lane splits of k_viterbi (two lanes per codeword pair / four lanes for long codewords) give the checker's bits
+        for split in (1 << 30, 0):
+            receiver.set_viterbi_split(split)
+            got = receiver.stage_viterbi(soft)
+            for c in range(n_cw):
+                assert np.array_equal(got[c], want[c]), (steps, c, split)
+        receiver.set_viterbi_split(0)
 
 
 def test_fic_and_msc_bit_exact(receiver, oracle):

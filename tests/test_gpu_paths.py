@@ -171,3 +171,48 @@ def test_full_size_workload_properties():
     assert np.array_equal(d2.fibs, d.fibs) and np.array_equal(d2.t_f, d.t_f) and np.array_equal(d2.cfo_hz, d.cfo_hz)
     assert all(np.array_equal(a, b) for a, b in zip(d.frames, d2.frames))
     rx.close()
+
+
+def _same_decode(a, b):
+    assert a.n_frames == b.n_frames and a.n_slots == b.n_slots
+    assert np.array_equal(a.t_f, b.t_f) and np.array_equal(a.cfo_hz, b.cfo_hz) and np.array_equal(a.cir_ratio, b.cir_ratio)
+    assert np.array_equal(a.fibs, b.fibs) and np.array_equal(a.fib_ok, b.fib_ok)
+    assert len(a.subch) == len(b.subch) and all(bytes(x) == bytes(y) for x, y in zip(a.subch, b.subch))
+    for i, (x, y) in enumerate(zip(a.frames, b.frames)):
+        assert x.shape == y.shape and np.array_equal(x, y), f"logical frames of sub-channel {i}"
+    assert np.array_equal(a.sf, b.sf)
+    assert (a.superframes, a.rs_corrected, a.rs_bit_errors, a.rs_uncorrectable, a.firecode_fail) == \
+           (b.superframes, b.rs_corrected, b.rs_bit_errors, b.rs_uncorrectable, b.firecode_fail)
+    assert len(a.aus) == len(b.aus)
+    for x, y in zip(a.aus, b.aus):
+        assert (x.subch_index, x.superframe, x.cif, x.crc_ok, x.header, x.data) == (y.subch_index, y.superframe, y.cif, y.crc_ok, y.header, y.data)
+    assert len(a.tii) == len(b.tii)
+    for x, y in zip(a.tii, b.tii):
+        assert x.ids == y.ids and x.n_tii_frames == y.n_tii_frames and np.array_equal(x.spectrum, y.spectrum)
+
+
+def test_chunked_decode_equals_single_pass(receiver):
+    """BASELINE configs[4] at 1/30 of its length: a 120 s full-ensemble recording (s16 and f32) with linear CFO drift and an SNR
+    staircase 0 -> 20 dB, decoded in 2, 4 and 7 overlapping time chunks (shard.decode_chunked) -- frames, FIBs, logical frames of
+    all 12 sub-channels, superframes, RS statistics, access units and TII windows byte-identical to the single-pass decode."""
+    from abracadabra_b200 import shard
+    ens = synth.full_ensemble(seed=2300)
+    n_frames = 1250
+    clean, truth = synth.modulate(ens, n_frames, seed=23)
+    x = synth.impair(clean, synth.Impairments(snr_db=None, cfo_hz=-800.0, cfo_drift_hz_per_s=200.0 / 60.0, seed=4, lead_in=41000), tail=90000)
+    del clean
+    snr = np.floor(np.arange(n_frames) * 21.0 / n_frames)            # 0, 1, ... 20 dB, about 60 frames each
+    synth.add_noise_staircase(x, 41000, snr, seed=8)
+    for fmt, rms in (("s16", 6000.0), ("f32", 1.0)):
+        raw = synth.quantize(x, fmt, rms)
+        one = receiver.decode(raw, fmt, tii=True)
+        assert one.n_frames >= n_frames - 130                         # the first seconds at 0-1 dB may not synchronise
+        assert len(one.subch) == 12 and len(one.aus) > 5000
+        # the regimes of SURVEY App. B are all there: nothing at the bottom, clean at the top
+        late = [a for a in one.aus if a.cif > 4 * 900]
+        assert late and all(a.crc_ok for a in late)
+        for n_chunks in ((2, 4, 7) if fmt == "s16" else (4,)):
+            st = {}
+            got = shard.decode_chunked(raw, fmt, n_chunks, rx=receiver, tii=True, stats=st)
+            _same_decode(one, got)
+        del raw

@@ -182,3 +182,25 @@ def test_viterbi_decision_word_layout():
         assert idx == in_w == (((n >> 4) & 1) << 4) | ((n >> 5) << 3) | ((n >> 1) & 7) | ((n & 1) << 5)
         bwd.add(idx)
     assert len(fwd) == 64 and len(bwd) == 64
+
+
+def test_viterbi_four_lane_layout_matches_model():
+    """Four-lane mode of k_viterbi (long codewords): the scalar model of the lane split (tools/vit4_model.py: register maps, shuffle
+    sources, per-lane signs) reproduces the plain recursion of oracle/daboracle.c:orc_viterbi, metrics and decisions, and the
+    trace kernel's closed-form index function (through b200dab_viterbi4_decision_index) equals the tables the model derives."""
+    import ctypes as ct
+    import importlib.util
+    from pathlib import Path
+    from abracadabra_b200 import pipeline
+    spec = importlib.util.spec_from_file_location("vit4_model", Path(__file__).resolve().parent.parent / "tools" / "vit4_model.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()                                            # asserts inside
+    fwd, bwd = mod.build_luts()
+    L = pipeline.lib()
+    L.b200dab_viterbi4_decision_index.restype = ct.c_int
+    assert L.b200dab_viterbi4_decision_index(-1, 0) == -1
+    for s in range(64):
+        assert L.b200dab_viterbi4_decision_index(s, 0) == fwd[s]
+        assert L.b200dab_viterbi4_decision_index(s, 1) == bwd[s]
+    assert len({v & 63 for v in fwd}) == 64 and len({v & 63 for v in bwd}) == 64
