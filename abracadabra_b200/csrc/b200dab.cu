@@ -21,6 +21,7 @@
 #include "tables.h"
 #include "fig.h"
 #include "pad.h"
+#include "../../include/b200dab_snr_cal.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(#x, e_); return -1; } } while (0)
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->set_error(#x, e_); return -1; } } while (0)
@@ -754,8 +755,11 @@ static int parse_subch_impl(const uint8_t* fibs, const uint8_t* ok, int n_fibs, 
             if (len == 0 || i + 1 + len > 30) break;
             const uint8_t* d = p + i + 1;
             if (type == 0) {
-                const int ext = d[0] & 31, pd = (d[0] >> 5) & 1;
+                const int ext = d[0] & 31, pd = (d[0] >> 5) & 1, cn = d[0] >> 7;
                 int k = 1;
+                // C/N = 1 on the MCI extensions announces the NEXT multiplex configuration (EN 300 401 sec. 6.4, sent for up to 6 s
+                // ahead of a reconfiguration): it must not overwrite the organisation the MSC is decoded with now
+                if (cn && (ext == 1 || ext == 2)) { i += 1 + len; continue; }
                 if (ext == 1) {
                     while (k + 3 <= len) {
                         const int id = d[k] >> 2, start = ((d[k] & 3) << 8) | d[k + 1];
@@ -1271,6 +1275,22 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     if (msc_block()) return -1;
     // ---- everything below needs the whole FIC on the host
     if (!fic_synced) { CKC(cudaEventSynchronize(ctx->ev_fic)); TRACE("fic synced"); }
+    if (!(subch_in && n_subch_in > 0) && !(flags & B200DAB_OPT_NO_MSC)) {
+        // The table the MSC chain was queued with came from a prefix of the FIC (so that the GPU never waits for the host).  What
+        // counts is the organisation the WHOLE FIC of this call describes: a recording that starts in noise can show a stable but
+        // incomplete table in its first frames.  If the two differ (rare), the MSC chain runs again with the full table.
+        std::vector<b200dab_subch_t> full(B200DAB_MAX_SUBCH);
+        const int nf = parse_subch_impl(res->fibs, res->fib_ok, n_slots * 12, full.data(), B200DAB_MAX_SUBCH);
+        full.resize(nf);
+        const bool same = full.size() == ctx->r_subch.size() && (full.empty() || !memcmp(full.data(), ctx->r_subch.data(), full.size() * sizeof(b200dab_subch_t)));
+        if (!same) {
+            TRACE("sub-channel table revised from the whole FIC");
+            ctx->r_subch = full;
+            res->n_subch = (int)ctx->r_subch.size(); res->subch = ctx->r_subch.data();
+            dpjobs.clear(); dp_subch.clear(); total_sf = 0; total_rows = 0; msc_bytes = 0; out_off.clear();
+            if (msc_block()) return -1;
+        }
+    }
     ctx->cur = ctx->fic_stream;
     const int tii_rc = tii_block();
     ctx->cur = nullptr;
@@ -1334,7 +1354,8 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
                 if (mu > 0 && var > 0) { snr_acc += (double)mu * mu / var; cnt++; }
             }
         }
-        res->snr_db = cnt ? (float)(10.0 * log10(snr_acc / cnt)) : 0.f;
+        // decision-directed estimate, put on the scale of the reference's snr10 (include/b200dab_snr_cal.h: measured, not modelled)
+        res->snr_db = cnt ? b200dab_snr_calibrated((float)(10.0 * log10(snr_acc / cnt))) : 0.f;
     }
     res->gpu_launches = ctx->launches;
     TRACE("result assembled");
@@ -1533,6 +1554,26 @@ int b200dab_stage_tii_fold(b200dab_ctx* ctx, const float* nulls, int n, float* f
     ctx->launches += 1;
     CKC(cudaGetLastError());
     CKC(cudaMemcpyAsync(fold, ctx->d_fold.p, (size_t)n * TII_SPECTRUM_BINS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200dab_stage_spectrum(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, const int64_t* w0, int n_w, float* out)
+{
+    if (!ctx || !iq || !w0 || n_w <= 0 || !out || fmt < 0 || fmt > 2) return -1;
+    cudaSetDevice(ctx->device);
+    const void* d_iq;
+    if (ctx->upload_raw(iq, n, fmt, B200DAB_MEM_HOST, &d_iq)) return -1;
+    CKC(ctx->d_tmp_a.ensure((size_t)n_w * 8));
+    CKC(ctx->d_spec.ensure((size_t)n_w * DAB_NFFT * 4));
+    CKC(cudaMemcpyAsync(ctx->d_tmp_a.p, w0, (size_t)n_w * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const float2* tw = ctx->d_tw.as<float2>();
+    if (fmt == B200DAB_FMT_U8) k_spectrum_at<B200DAB_FMT_U8><<<n_w, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_tmp_a.as<long long>(), tw, ctx->d_spec.as<float>());
+    else if (fmt == B200DAB_FMT_S16) k_spectrum_at<B200DAB_FMT_S16><<<n_w, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_tmp_a.as<long long>(), tw, ctx->d_spec.as<float>());
+    else k_spectrum_at<B200DAB_FMT_F32><<<n_w, 256, 0, ctx->stream>>>(d_iq, (int64_t)n, ctx->d_tmp_a.as<long long>(), tw, ctx->d_spec.as<float>());
+    ctx->launches += 1;
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(out, ctx->d_spec.p, (size_t)n_w * DAB_NFFT * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -31,10 +31,10 @@
 
 namespace {
 
-constexpr int ADV_FRAMES = 4;                  // new frames per GPU pass (384 ms of signal)
+constexpr int ADV_FRAMES_MIN = 4;              // new frames per GPU pass of a live stream (384 ms of signal)
+constexpr int ADV_FRAMES_MAX = 64;             // ... of a source that delivers faster than real time (a file): the batch grows up to this
 constexpr int OVL_FRAMES = 6;                  // re-decoded overlap: 16 CIFs of interleaver memory + 5 CIFs of superframe
-constexpr int64_t WIN_SAMPLES = (int64_t)(ADV_FRAMES + OVL_FRAMES) * DAB_T_FRAME + 4096;
-constexpr int64_t ADV_SAMPLES = (int64_t)ADV_FRAMES * DAB_T_FRAME;
+constexpr int64_t WIN_SAMPLES_MAX = (int64_t)(ADV_FRAMES_MAX + OVL_FRAMES) * DAB_T_FRAME + 4096;
 
 enum ReqType { R_TUNE, R_ENSEMBLE, R_SERVICE_LIST, R_SERVICE_COMPS, R_USER_APPS, R_ANN_SUPPORT, R_SELECT, R_STOP, R_XPAD, R_PERIODIC, R_TII, R_SPECTRUM, R_EXIT };
 struct Request { ReqType type; uint32_t a = 0; uint32_t b = 0; int c = 0; };
@@ -47,6 +47,7 @@ struct Decoder {               // one of the (up to two) audio decoder instances
     bool dabplus = false;
     int64_t last_row = -1;     // absolute logical-frame number delivered last (MP2)
     int64_t last_sf_row = -1;  // absolute row of the last delivered superframe (DAB+)
+    int64_t last_stat_row = -1;// absolute row of the last superframe that went into the RS statistics
     pad::Decoder xpad;         // X-PAD state of this audio service
     bool xpad_app[32] = {};    // X-PAD application types started with dabsdrRequest_XPadAppStart
 };
@@ -86,6 +87,12 @@ struct dabsdr_s {
     Decoder dec[2];
     DataDecoder data[MAX_DATA_DEC];
     std::vector<float> win;            // interleaved I,Q
+    int adv_frames = ADV_FRAMES_MIN;   // new frames per pass: doubles while the input function delivers much faster than real time
+    int fast_pulls = 0;
+    int64_t win_samples() const { return (int64_t)(adv_frames + OVL_FRAMES) * DAB_T_FRAME + 4096; }
+    int64_t adv_samples() const { return (int64_t)adv_frames * DAB_T_FRAME; }
+    double t_pull0 = 0;                // wall clock when the pull of the current batch began
+    int64_t pulled0 = 0;               // samples in the window at that time
     int64_t have = 0;                  // complex samples in win
     int64_t abs_pos = 0;               // absolute index of win[0]
     int64_t last_frame_abs = -1;       // absolute t_f of the newest frame already accounted for
@@ -109,6 +116,13 @@ struct dabsdr_s {
 };
 
 namespace {
+
+double wall_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 void notify(dabsdr_s* h, dabsdrNotificationId_t nid, dabsdrNotificationStatus_t st, const void* data, uint16_t len)
 {
@@ -420,6 +434,8 @@ void deliver_xpad_dg(dabsdr_s* h, dabsdrDecoderId_t did, Decoder& d, int app, co
     h->dg_cb(&c, h->dg_ctx);
 }
 
+void send_periodic(dabsdr_s* h);
+
 void process_window(dabsdr_s* h)
 {
     // sub-channels to decode: those of the active decoders (none -> FIC only)
@@ -453,22 +469,36 @@ void process_window(dabsdr_s* h)
     h->last_snr = r.snr_db;
     // absolute frame numbers of the window's slots, counted from the newest frame already accounted for
     std::vector<int64_t> slot_no(r.n_slots, -1);
-    int64_t no = h->frame_no, last_abs = h->last_frame_abs;
-    const int64_t anchor_no = h->frame_no, anchor_tf = h->last_frame_abs;
-    bool any_fic = false;
-    for (int s = 0; s < r.n_slots; s++) {
-        if (r.t_f[s] < 0) continue;
-        const int64_t abs_tf = h->abs_pos + r.t_f[s];
-        int64_t n;
-        if (anchor_tf < 0) n = (last_abs < 0) ? 0 : no + (abs_tf - last_abs + DAB_T_FRAME / 2) / DAB_T_FRAME;
-        else {
-            const int64_t d = abs_tf - anchor_tf;
-            n = anchor_no + (d >= 0 ? (d + DAB_T_FRAME / 2) / DAB_T_FRAME : -((-d + DAB_T_FRAME / 2) / DAB_T_FRAME));
+    std::vector<int> fresh;                                     // slots holding a frame seen for the first time, in order
+    {
+        int64_t no = h->frame_no, last_abs = h->last_frame_abs;
+        const int64_t anchor_no = h->frame_no, anchor_tf = h->last_frame_abs;
+        for (int s = 0; s < r.n_slots; s++) {
+            if (r.t_f[s] < 0) continue;
+            const int64_t abs_tf = h->abs_pos + r.t_f[s];
+            int64_t n;
+            if (anchor_tf < 0) n = (last_abs < 0) ? 0 : no + (abs_tf - last_abs + DAB_T_FRAME / 2) / DAB_T_FRAME;
+            else {
+                const int64_t d = abs_tf - anchor_tf;
+                n = anchor_no + (d >= 0 ? (d + DAB_T_FRAME / 2) / DAB_T_FRAME : -((-d + DAB_T_FRAME / 2) / DAB_T_FRAME));
+            }
+            slot_no[s] = n;
+            if (n <= no && last_abs >= 0) continue;             // decoded already in an earlier window
+            no = n;
+            last_abs = abs_tf;
+            fresh.push_back(s);
         }
-        slot_no[s] = n;
-        if (n <= no && last_abs >= 0) continue;                 // decoded already in an earlier window
-        no = n;
-        last_abs = abs_tf;
+    }
+    // Results are handed out in the order and rhythm of a live stream whatever the size of the batch: ADV_FRAMES_MIN new frames at a
+    // time -- their FIC, then the logical frames / access units that are complete once those frames are in (row <= 4 (n + 1) - 16 for
+    // newest frame n: 15 CIFs of interleaver memory), TII every 40 frames, the periodic notification when its time has come.
+    for (size_t f0 = 0; f0 < fresh.size() || f0 == 0; f0 += ADV_FRAMES_MIN) {
+    const size_t f1 = std::min(fresh.size(), f0 + (size_t)ADV_FRAMES_MIN);
+    const bool last_part = f1 >= fresh.size();
+    bool any_fic = false;
+    for (size_t fi = f0; fi < f1; fi++) {
+        const int s = fresh[fi];
+        h->frame_no = slot_no[s]; h->last_frame_abs = h->abs_pos + r.t_f[s];
         // ---- a frame seen for the first time: FIC
         h->last_cfo = r.cfo_hz[s];
         for (int f = 0; f < 12; f++) {
@@ -476,7 +506,7 @@ void process_window(dabsdr_s* h)
             else h->fib_err++;
         }
         if (r.spectrum && h->spectrum_on && h->spec_cb) {
-            // like the reference: per frame one SIGNAL spectrum and one of the null symbol (TII when that null carries TII)
+            // like the reference: per frame one spectrum of the null symbol (TII when that null carries TII) and one SIGNAL spectrum
             const float* sp = r.spectrum + (size_t)s * 2 * DAB_NFFT;
             const bool tii_null = r.tii_sign && r.tii_sign[s] > 0;
             h->spec_cb(sp + DAB_NFFT, tii_null ? DABSDR_SPECT_TII : DABSDR_SPECT_NULL, h->spec_ctx);
@@ -488,8 +518,8 @@ void process_window(dabsdr_s* h)
             h->tii_sign.push_back(r.tii_sign[s]);
         }
     }
-    h->frame_no = no; h->last_frame_abs = last_abs;
     send_sync(h, any_fic || h->sync_level == DABSDR_SYNC_LEVEL_FIC ? DABSDR_SYNC_LEVEL_FIC : DABSDR_SYNC_LEVEL_ON_NULL);
+    const int64_t row_limit = last_part ? INT64_MAX : 4 * (h->frame_no + 1) - 16;
 
     // ---- MSC: logical frame `row` of the window starts at CIF (row) = slot row/4, CIF row%4
     if (r.frames && n_sc > n_audio_sc) {
@@ -502,6 +532,7 @@ void process_window(dabsdr_s* h)
                 for (int row = 0; row < rows; row++) {
                     const int64_t ar = abs_row(row);
                     if (ar < 0 || ar <= d.last_row) continue;
+                    if (ar > row_limit) break;
                     d.last_row = ar;
                     d.as.frame(r.frames[i] + (size_t)row * pitch, pitch, [&](const uint8_t* p, int n) {
                         if (!h->dg_cb) return;
@@ -522,6 +553,7 @@ void process_window(dabsdr_s* h)
                 for (int row = 0; row < rows; row++) {
                     const int64_t ar = abs_row(row);
                     if (ar < 0 || ar <= d.last_row) continue;
+                    if (ar > row_limit) break;
                     d.last_row = ar;
                     const uint8_t* fr = r.frames[i] + (size_t)row * pitch;
                     const bool hdr_ok = mp2::check_frame(fr, pitch) == 1;      // ISO 11172-3 CRC; a failing frame is delivered empty
@@ -551,11 +583,8 @@ void process_window(dabsdr_s* h)
                     const b200dab_au_t& au = r.aus[k];
                     if (au.subch_index != i) continue;
                     const int64_t ar = abs_row(au.cif);
-                    if (ar < 0 || ar <= d.last_sf_row) continue;
-                    if (ar > newest) {
-                        newest = ar;
-                        if (sc_dec[i] == 0) h->rs_bytes = (uint32_t)(120 * (r.subch[i].bitrate / 8));
-                    }
+                    if (ar < 0 || ar <= d.last_sf_row || ar + 4 > row_limit) continue;
+                    if (ar > newest) newest = ar;
                     if (sc_dec[i] == 0) { if (au.crc_ok) h->crc_ok++; else h->crc_err++; h->audio_bytes += au.length; }
                     if (h->audio_cb) {
                         dabsdrAudioCBData_t a;
@@ -579,13 +608,23 @@ void process_window(dabsdr_s* h)
                     }
                 }
                 d.last_sf_row = newest;
+                // RS statistics of the primary decoder, superframe by superframe, each counted once (dabsdr.h:159-165).  The reference
+                // counts rsBytes = 24 * (bitrate / 8) per superframe -- 288 at 96 kbit/s (golden c1_u8_40db: 1440 / 1728 / 2016 for
+                // 5 / 6 / 7 superframes per period) -- and starts with the second superframe it decodes; the application shows
+                // rsBitErrors * 0.125 / rsBytes (src/ensembleinfobackend.cpp:438-440).
+                if (sc_dec[i] == 0) {
+                    for (int k = 0; k < r.n_sf; k++) {
+                        const b200dab_sf_t& q = r.sf[k];
+                        if (q.subch_index != i) continue;
+                        const int64_t ar = abs_row(q.row);
+                        if (ar < 0 || ar <= d.last_stat_row || ar + 4 > row_limit) continue;
+                        if (d.last_stat_row >= 0) h->rs_bytes += (uint32_t)(24 * (r.subch[i].bitrate / 8));
+                        h->rs_bit += (uint32_t)q.rs_bit_errors;
+                        h->rs_unc += (uint32_t)q.rs_uncorrectable;
+                        d.last_stat_row = ar;
+                    }
+                }
             }
-        }
-        // RS statistics are per pass over the whole window: scale to the new share of it
-        if (sc_dec[0] == 0 || sc_dec[1] == 0) {
-            const double share = (double)ADV_FRAMES / (double)(ADV_FRAMES + OVL_FRAMES);
-            h->rs_bit += (uint32_t)llround(share * (double)r.rs_bit_errors);
-            h->rs_unc += (uint32_t)llround(share * (double)r.rs_uncorrectable);
         }
     }
 
@@ -601,6 +640,14 @@ void process_window(dabsdr_s* h)
         h->tii_norm.erase(h->tii_norm.begin(), h->tii_norm.begin() + TII_NOTIFY_FRAMES);
         h->tii_sign.erase(h->tii_sign.begin(), h->tii_sign.begin() + TII_NOTIFY_FRAMES);
     }
+    // the periodic notification at the feed position a live stream would have reached with these frames in
+    const int64_t feed = last_part ? h->abs_pos + h->have : h->last_frame_abs + DAB_T_FRAME + DAB_T_FRAME / 2;
+    while (h->period >= 0 && feed >= h->next_periodic) {
+        send_periodic(h);
+        h->next_periodic += (int64_t)DAB_T_FRAME << h->period;
+    }
+    if (last_part) break;
+    }   // parts of ADV_FRAMES_MIN new frames
 }
 
 void send_periodic(dabsdr_s* h)
@@ -617,7 +664,7 @@ void send_periodic(dabsdr_s* h)
     p.padBytes = (uint16_t)std::min<uint32_t>(h->pad_bytes, 65535);       // bytes of the data_stream_elements that carry the PAD
     p.rsUncorrectableCntr = (uint16_t)std::min<uint32_t>(h->rs_unc, 65535); p.rsBitErrors = (uint16_t)std::min<uint32_t>(h->rs_bit, 65535);
     p.rsBytes = (uint16_t)std::min<uint32_t>(h->rs_bytes, 65535);
-    h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->pad_bytes = h->rs_unc = h->rs_bit = 0;
+    h->fib_err = h->crc_ok = h->crc_err = h->audio_bytes = h->pad_bytes = h->rs_unc = h->rs_bit = h->rs_bytes = 0;
     notify(h, DABSDR_NID_PERIODIC, DABSDR_NSTAT_SUCCESS, &p, sizeof p);
 }
 
@@ -629,7 +676,7 @@ void* worker(void* arg)
         fprintf(stderr, "dabsdr(b200): no CUDA device -- this build has no CPU fallback\n");
         h->gpu = nullptr;
     }
-    h->win.resize((size_t)WIN_SAMPLES * 2);
+    h->win.resize((size_t)WIN_SAMPLES_MAX * 2);
     for (;;) {
         // requests are served between GPU passes; while untuned the worker sleeps on the mailbox
         {
@@ -648,20 +695,32 @@ void* worker(void* arg)
         // pull one chunk (blocks inside the input function = flow control); requests are looked at again after every chunk,
         // i.e. every 8 ms of signal, so a request/notification round trip costs less than one transmission frame
         {
-            const int64_t n = std::min<int64_t>(16384, WIN_SAMPLES - h->have);
+            if (h->t_pull0 == 0) { h->t_pull0 = wall_ms(); h->pulled0 = h->have; }
+            const int64_t n = std::min<int64_t>(16384, h->win_samples() - h->have);
             h->in(h->win.data() + 2 * h->have, (uint16_t)n);
             h->have += n;
         }
-        if (h->have < WIN_SAMPLES) continue;
+        if (h->have < h->win_samples()) continue;
+        // A live stream delivers one second of signal per second; a file (RawFileInput without pacing, a scanner replay) much faster.
+        // Latency only matters for the former, so the batch of new frames per GPU pass doubles (up to ADV_FRAMES_MAX) while the pull
+        // of a batch takes less than a quarter of its signal time, and falls back to ADV_FRAMES_MIN as soon as it does not.
+        {
+            const double took = wall_ms() - h->t_pull0, signal_ms = (double)(h->have - h->pulled0) * 1000.0 / DAB_FS;
+            h->t_pull0 = 0;
+            if (took < 0.25 * signal_ms) h->fast_pulls++; else { h->fast_pulls = 0; }
+        }
+        const int64_t adv = h->adv_samples();
         process_window(h);
-        if (h->period >= 0 && h->abs_pos + h->have >= h->next_periodic) {
+        while (h->period >= 0 && h->abs_pos + h->have >= h->next_periodic) {
             send_periodic(h);
             h->next_periodic += (int64_t)DAB_T_FRAME << h->period;
         }
-        // slide by ADV frames
-        memmove(h->win.data(), h->win.data() + 2 * ADV_SAMPLES, (size_t)(h->have - ADV_SAMPLES) * 2 * sizeof(float));
-        h->have -= ADV_SAMPLES;
-        h->abs_pos += ADV_SAMPLES;
+        // slide by the frames of this batch
+        memmove(h->win.data(), h->win.data() + 2 * adv, (size_t)(h->have - adv) * 2 * sizeof(float));
+        h->have -= adv;
+        h->abs_pos += adv;
+        if (h->fast_pulls >= 2 && h->adv_frames < ADV_FRAMES_MAX) h->adv_frames = std::min(ADV_FRAMES_MAX, h->adv_frames * 2);
+        else if (h->fast_pulls == 0) h->adv_frames = ADV_FRAMES_MIN;
     }
 }
 

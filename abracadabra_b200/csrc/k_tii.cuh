@@ -75,8 +75,15 @@ __global__ void __launch_bounds__(256) k_tii_fold_nulls(const float2* __restrict
 }
 
 // signal-spectrum callback material (dabsdr.h:393, consumer src/radiocontrol.cpp:2604-2609): per frame two 2048-bin linear power
-// spectra in natural FFT order, unnormalised |FFT|^2 of the raw samples like the reference's: [0] the PRS symbol (SIGNAL),
-// [1] the null symbol (NULL / TII).  One CTA per frame.
+// Where the reference takes the 2048 samples of its spectrum callbacks from (probed, tests/golden/c1_spectrum_u8_30db: every
+// callback equals |FFT|^2 of a block of RAW samples, sum ratio 1.00000): SIGNAL = the first 2048 samples of the 2552-sample block
+// it pulled last, which starts 7354..7674 samples after the frame start (it moves with the core's time tracking); NULL / TII = the
+// first 2048 samples of the 2656-sample block around the null symbol, starting 86..406 samples BEFORE the frame start.  The
+// offsets below put our windows in the middle of those ranges, relative to our own t_f (= frame start + 3136 - first-path shift).
+#define SPECTRUM_SIGNAL_OFFSET 4364
+#define SPECTRUM_NULL_OFFSET (-3386)
+// spectra in natural FFT order, unnormalised |FFT|^2 of the raw samples like the reference's: [0] SIGNAL, [1] NULL / TII.
+// One CTA per frame.
 template <int FMT>
 __global__ void __launch_bounds__(256) k_spectrum(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
                                                   const float2* __restrict__ tw, float* __restrict__ spec)
@@ -86,7 +93,7 @@ __global__ void __launch_bounds__(256) k_spectrum(const void* __restrict__ raw, 
     const FrameInfo fr = frames[blockIdx.x];
 #pragma unroll
     for (int which = 0; which < 2; which++) {
-        load_symbol<FMT>(buf, raw, nsamp, which == 0 ? fr.t_f : fr.t_f - DAB_T_SYM, 0.f, 0.f);
+        load_symbol<FMT>(buf, raw, nsamp, fr.t_f + (which == 0 ? SPECTRUM_SIGNAL_OFFSET : SPECTRUM_NULL_OFFSET), 0.f, 0.f);
         fft2048_smem(buf, tw);
         float* o = spec + ((size_t)fr.slot * 2 + which) * DAB_NFFT;
         for (int k = t; k < DAB_NFFT; k += 256) {
@@ -94,6 +101,21 @@ __global__ void __launch_bounds__(256) k_spectrum(const void* __restrict__ raw, 
             o[k] = v.x * v.x + v.y * v.y;
         }
         __syncthreads();
+    }
+}
+
+// |FFT|^2 of the 2048 raw samples starting at w0[blockIdx.x] (stage entry point: parity of the spectrum callback on given windows)
+template <int FMT>
+__global__ void __launch_bounds__(256) k_spectrum_at(const void* __restrict__ raw, int64_t nsamp, const long long* __restrict__ w0,
+                                                     const float2* __restrict__ tw, float* __restrict__ spec)
+{
+    __shared__ float2 buf[FFT_BUF_LEN];
+    load_symbol<FMT>(buf, raw, nsamp, w0[blockIdx.x], 0.f, 0.f);
+    fft2048_smem(buf, tw);
+    float* o = spec + (size_t)blockIdx.x * DAB_NFFT;
+    for (int k = threadIdx.x; k < DAB_NFFT; k += 256) {
+        const float2 v = buf[fft_phys(fft_pos(k))];
+        o[k] = v.x * v.x + v.y * v.y;
     }
 }
 
@@ -161,19 +183,19 @@ __global__ void __launch_bounds__(384) k_tii_detect(const float* __restrict__ fo
         s_binmax = bm;
     }
     __syncthreads();
-    const float thr = fmaxf(thr_k * s_noise, 0.05f * s_peak);
-    // comb search: thread (sub, main) tests whether all four blocks of the pattern are lit; hits go to a short list
+    // comb search: thread (sub, main) tests the four blocks of the pattern (rule: oracle/daboracle.c orc_tii_detect); hits go to a short list
+    const float thr_mean = fmaxf(thr_k * s_noise, 0.02f * s_peak), thr_lit = 0.5f * thr_k * s_noise;
     for (int i = t; i < 24 * 70; i += 384) {
         const int sub = i / 70, m = i - sub * 70;
         const unsigned pat = c_tii_pattern[m];
-        unsigned mask = 0; float mn = 1e30f, mx = 0.f; int cnt = 0;
+        float mn = 1e30f, mx = 0.f, sum = 0.f; int cnt = 0;
 #pragma unroll
         for (int b = 0; b < 8; b++) {
             const float v = pair[24 * b + sub];
-            if (v > thr) { mask |= 0x80u >> b; cnt++; }
-            if (pat & (0x80u >> b)) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
+            if (v > thr_lit) cnt++;
+            if (pat & (0x80u >> b)) { mn = fminf(mn, v); mx = fmaxf(mx, v); sum += v; }
         }
-        bool hit = (mask & pat) == pat;
+        bool hit = sum >= 4.f * thr_mean && mn > thr_lit;
         if (hit && cnt > 4) hit = mn >= 0.5f * mx;      // several transmitters share this sub id: keep consistent combs only
         if (hit) { const int k = atomicAdd(&s_count, 1); if (k < 64) hits[k] = (unsigned short)i; }
     }
@@ -189,8 +211,8 @@ __global__ void __launch_bounds__(384) k_tii_detect(const float* __restrict__ fo
             float sum = 0.f;
             for (int b = 0; b < 8; b++) if (pat & (0x80u >> b)) sum += pair[24 * b + sub];
             r->main_id[n] = (unsigned char)m; r->sub_id[n] = (unsigned char)sub;
-            // like the reference: mean of the transmitter's 8 bins relative to the strongest bin of the spectrum
-            r->level[n] = s_binmax > 0.f ? (sum / 8.f) / s_binmax : 0.f;
+            // like the reference: mean of the transmitter's 8 bins relative to the strongest carrier pair (half its sum)
+            r->level[n] = s_peak > 0.f ? (sum / 8.f) / (0.5f * s_peak) : 0.f;
             n++;
         }
         r->n_ids = n; r->n_tii_frames = s_ntii; r->norm = s_norm; r->noise = s_noise;

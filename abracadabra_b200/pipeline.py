@@ -129,6 +129,7 @@ def lib():
         L.b200dab_stage_fic.argtypes = [vp, vp, i32, vp, vp]
         L.b200dab_stage_msc.argtypes = [vp, vp, i32, ct.POINTER(SubCh), vp]
         L.b200dab_stage_dabplus.argtypes = [vp, vp, i32, i32, ct.POINTER(Au), ct.POINTER(i32), i32, vp]
+        L.b200dab_stage_spectrum.argtypes = [vp, vp, u64, i32, vp, i32, vp]
         L.b200dab_stage_tii_fold.argtypes = [vp, vp, i32, vp]
         L.b200dab_stage_tii_detect.argtypes = [vp, vp, vp, vp, i32, ct.c_float, ct.POINTER(Tii)]
         _lib = L
@@ -138,7 +139,7 @@ def lib():
 EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
            "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_get_kernel_timeline", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_viterbi_decision_index", "b200dab_viterbi4_decision_index", "b200dab_set_viterbi_split", "b200dab_set_superframe_phase", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
-           "b200dab_stage_dabplus", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
+           "b200dab_stage_dabplus", "b200dab_stage_spectrum", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]
 
 
 def subch_eep(subch_id: int, start_cu: int, bitrate: int, level: int, option: str, dabplus: bool) -> SubCh:
@@ -494,6 +495,15 @@ class Receiver:
                           bytes(flat[aus[i].offset:aus[i].offset + aus[i].length])) for i in range(n.value)]
         return out, dict(superframes=int(stats[0]), rs_corrected=int(stats[1]), rs_bit_errors=int(stats[2]),
                          rs_uncorrectable=int(stats[3]), firecode_fail=int(stats[4])), frames
+
+    def stage_spectrum(self, raw: np.ndarray, fmt: str, w0) -> np.ndarray:
+        """[len(w0), 2048] |FFT|^2 of the raw samples starting at every w0 (the spectrum callback's arithmetic)"""
+        n = raw.nbytes // FMT_BYTES[fmt]
+        w0 = np.ascontiguousarray(w0, np.int64)
+        out = np.zeros((w0.size, 2048), np.float32)
+        if lib().b200dab_stage_spectrum(self._h, raw.ctypes.data, n, FMT[fmt], w0.ctypes.data, w0.size, out.ctypes.data) != 0:
+            raise self._err("stage_spectrum")
+        return out
 
     def stage_tii_fold(self, nulls: np.ndarray) -> np.ndarray:
         nulls = np.ascontiguousarray(nulls, np.complex64).reshape(-1, 2048)

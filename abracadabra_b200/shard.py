@@ -95,8 +95,8 @@ def decode_chunked(iq, fmt: str, n_chunks: int, rx=None, device: int = 0, tii: b
 
     * frames are chained across chunks with the front end's own rule; a frame found in the overlap by two chunks has the same
       t_f and CFO in both (the sync kernels see the same block grid: chunk starts are multiples of 32768 samples);
-    * what a single pass decides globally is decided globally here too: the sub-channel table (FIG 0/1, 0/2 over growing
-      prefixes of the whole FIC) and the DAB+ superframe alignment (fire-code hits over all logical frames).  Every chunk is
+    * what a single pass decides globally is decided globally here too: the sub-channel table (FIG 0/1, 0/2 of the whole
+      FIC) and the DAB+ superframe alignment (fire-code hits over all logical frames).  Every chunk is
       decoded once with its own view; a chunk whose view differs from the global one (possible only where the signal is too
       noisy to decode anyway) is decoded a second time with the global table / alignment forced;
     * logical frames, superframes, access units and RS statistics are taken from exactly one chunk each (boundaries on
@@ -142,14 +142,8 @@ def decode_chunked(iq, fmt: str, n_chunks: int, rx=None, device: int = 0, tii: b
     for c, k, g in chain:
         fibs[g * 12:(g + 1) * 12] = every[c]["fibs"][k * 12:(k + 1) * 12]
         ok[g * 12:(g + 1) * 12] = every[c]["ok"][k * 12:(k + 1) * 12]
-    # ---- the global sub-channel table: growing prefixes of the FIC, as b200dab_decode does
-    table, prev, upto = [], None, min(n_slots, 8)
-    while n_slots:
-        table = pipeline.parse_subch(fibs[:upto * 12], ok[:upto * 12])
-        key = _subch_key(table)
-        if (prev == key and table) or upto >= n_slots:
-            break
-        prev, upto = key, min(n_slots, upto * 2)
+    # ---- the global sub-channel table: what the whole FIC describes (b200dab_decode's own rule)
+    table = pipeline.parse_subch(fibs, ok) if n_slots else []
     gkey = _subch_key(table)
     n_rows = max(4 * n_slots - 15, 0)
     # ---- the global superframe alignment per DAB+ sub-channel: fire-code hits of every logical frame, counted once

@@ -106,7 +106,8 @@ typedef struct {
     int32_t n_tii;
     const b200dab_tii_t *tii;        /* [n_tii] one per 40-frame window */
     const float *symstat;            /* [n_slots * 75 * 2] mean |soft|, mean soft^2 before scaling (OPT_SYMSTAT) */
-    float snr_db;                    /* decision-directed estimate over all frames (OPT_SYMSTAT) */
+    float snr_db;                    /* decision-directed estimate over all frames (OPT_SYMSTAT), on the scale of the reference's snr10
+                                      * (dabsdr.h:153; include/b200dab_snr_cal.h) */
     int32_t gpu_launches;            /* kernels launched by this call */
     /* per-frame TII material for streaming callers (OPT_TII): folded null spectra, reference magnitude, TII/reference sign */
     const float *tii_fold;           /* [n_slots][384] */
@@ -217,6 +218,10 @@ B200DAB_API int b200dab_stage_msc(b200dab_ctx *ctx, const int8_t *soft /* [n_fra
                                   const b200dab_subch_t *sc, uint8_t *frames /* [4*n_frames-15][24*bitrate/8] */);
 B200DAB_API int b200dab_stage_dabplus(b200dab_ctx *ctx, uint8_t *frames /* [n_rows][pitch], corrected in place */, int n_rows,
                                       int bitrate, b200dab_au_t *aus, int32_t *n_aus, int max_aus, int64_t *stats /* [5] */);
+/* the spectrum callback's arithmetic on given windows: out[i] = |FFT|^2 (2048 bins, FFT order, unnormalised) of the 2048 raw samples
+ * starting at sample w0[i] -- what dabsdrSpectrumCBFunc_t delivers (dabsdr.h:393; pinned by tests/golden/c1_spectrum_u8_30db) */
+B200DAB_API int b200dab_stage_spectrum(b200dab_ctx *ctx, const void *iq, uint64_t n_samples, int fmt, const int64_t *w0, int n_w,
+                                       float *out /* [n_w][2048] */);
 B200DAB_API int b200dab_stage_tii_fold(b200dab_ctx *ctx, const float *nulls /* [n][2048] complex64 */, int n, float *fold /* [n][384] */);
 B200DAB_API int b200dab_stage_tii_detect(b200dab_ctx *ctx, const float *fold /* [n][384] */, const float *norm /* [n] */,
                                          const int32_t *sign /* [n] */, int n, float thr_k, b200dab_tii_t *out);

@@ -195,11 +195,19 @@ static void dg_cb(dabsdrDataGroupCBData_t *p, void *ctx)
 }
 
 static uint64_t g_n_spec;
+static int g_spectrum_bins;            /* --spectrum-bins N: the first N spectrum callbacks are logged with all 2048 bins */
 static void spectrum_cb(const float *p, dabsdrSpectrum_t type, void *ctx)
 {
     (void)ctx;
     g_n_spec++;
     if (!g_log) return;
+    if ((int)g_n_spec <= g_spectrum_bins) {
+        pthread_mutex_lock(&g_logmx);
+        fprintf(g_log, "{\"ev\":\"spectrum_bins\",\"pos\":%llu,\"type\":%d,\"bins\":[", (unsigned long long)g_pos, (int)type);
+        for (int i = 0; i < 2048; i++) fprintf(g_log, "%s%.7g", i ? "," : "", (double)p[i]);
+        fprintf(g_log, "]}\n");
+        pthread_mutex_unlock(&g_logmx);
+    }
     /* 2048 linear-power bins in FFT order (src/radiocontrol.cpp:2604-2609, src/signalbackend.cpp:383-431) */
     double sum = 0, mx = 0; int arg = 0;
     for (int i = 0; i < 2048; i++) { sum += p[i]; if (p[i] > mx) { mx = p[i]; arg = i; } }
@@ -324,6 +332,7 @@ static uint32_t g_want_sid;
 static uint32_t g_sids[64]; static int g_nsids;
 static int g_need_ensemble, g_have_ensemble, g_selected, g_selected2, g_fic_sync;
 static uint32_t g_retry_sid; static int g_retry_ticks;
+static int g_list_retry_ticks;          /* empty service list: ask again one frame later (reference: src/radiocontrol.cpp:1427-1436, 100 ms timer) */
 static uint64_t g_fib_err, g_rs_bit, g_rs_unc, g_crc_ok, g_crc_err, g_n_periodic;
 
 /* logging happens inside the callback (exact callback order); handle_event only runs the RadioControl-like protocol */
@@ -406,6 +415,7 @@ static void handle_event(ev_t *e)
     case -1: /* tick, once per frame of signal */
         if (g_need_ensemble && g_fic_sync && !g_have_ensemble) dabsdrRequest_GetEnsemble(g_h);
         if (g_retry_ticks > 0 && --g_retry_ticks == 0) dabsdrRequest_GetServiceComponents(g_h, g_retry_sid);
+        if (g_list_retry_ticks > 0 && --g_list_retry_ticks == 0) dabsdrRequest_GetServiceList(g_h);
         break;
     case DABSDR_NID_SYNC_STATUS: {
         const dabsdrNtfSyncStatus_t *s = (const void *)e->payload;
@@ -425,6 +435,7 @@ static void handle_event(ev_t *e)
         }
         break; }
     case DABSDR_NID_SERVICE_LIST:
+        if (e->nsids == 0) { g_list_retry_ticks = 1; break; }
         g_nsids = e->nsids;
         for (int i = 0; i < e->nsids; i++) g_sids[i] = e->sids[i];
         /* reference: src/radiocontrol.cpp:1427-1468 -- one GetServiceComponents per service */
@@ -485,6 +496,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--second") && i + 1 < argc) g_want_second_idx = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--sid") && i + 1 < argc) g_want_sid = (uint32_t)strtoul(argv[++i], NULL, 16);
         else if (!strcmp(argv[i], "--spectrum")) spectrum = 1;
+        else if (!strcmp(argv[i], "--spectrum-bins") && i + 1 < argc) { spectrum = 1; g_spectrum_bins = atoi(argv[++i]); }
         else if (!strcmp(argv[i], "--freq") && i + 1 < argc) g_freq = (uint32_t)atoi(argv[++i]);
         else if (!strcmp(argv[i], "--tail-frames") && i + 1 < argc) g_tail_samples = 196608ull * atoi(argv[++i]);
         else if (!strcmp(argv[i], "--no-au-data")) g_log_au_data = 0;

@@ -34,12 +34,15 @@ def main():
             raw.tofile(path)
             summ, ev = orc.run_ref(path, spec["fmt"], Path(td) / "log.jsonl", tii=spec.get("tii_mode"), service=spec.get("service"),
                                    extra=(["--xpad-apps"] if spec.get("xpad_apps") else []) +
-                                         (["--data-scids", str(spec["data_scids"])] if spec.get("data_scids") is not None else []))
+                                         (["--data-scids", str(spec["data_scids"])] if spec.get("data_scids") is not None else []) +
+                                         (["--spectrum-bins", str(spec["spectrum_bins"])] if spec.get("spectrum_bins") else []))
         out = {"spec": spec, "raw_sha1": hashlib.sha1(raw.tobytes()).hexdigest(), "summary": summ, "events": []}
         for e in ev:
             if e["ev"] == "audio":
                 out["events"].append({"ev": "audio", "pos": e["pos"], "id": e["id"], "ascty": e["ascty"], "header": e["header"], "len": e["len"],
                                       "sha1": hashlib.sha1(bytes.fromhex(e["data"])).hexdigest()})
+            elif e["ev"] == "spectrum_bins":
+                out["events"].append({"ev": "spectrum_bins", "pos": e["pos"], "type": e["type"], "bins": [float("%.6g" % x) for x in e["bins"]]})
             elif e["ev"] == "tii":
                 e = dict(e)
                 e["spectrum"] = [round(float(x), 3) for x in e["spectrum"]]

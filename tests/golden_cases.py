@@ -39,6 +39,9 @@ CASES = {
     "c1_ann_u8_30db": dict(kind="config1", n_frames=44, fmt="u8", snr=30.0, cfo=100.0, seed=6, tii=[], tii_mode=None, service=0,
                            pty=10, asu=[0x0003, [5]], announcements=[[60, 100, 5, 0x0002, 3]], user_apps=True,
                            utc=[60600, 23, 59, 57, 100]),
+    # signal-spectrum callback (dabsdr.h:365-370, :428) with all 2048 bins of the first callbacks: 2 per frame, SIGNAL and NULL / TII
+    "c1_spectrum_u8_30db": dict(kind="config1", n_frames=14, fmt="u8", snr=30.0, cfo=0.0, seed=8, tii=[(12, 5, 1.0, 0)], tii_mode=1, service=None,
+                                spectrum_bins=14),
     # another ensemble takes over the frequency after 24 frames (same sub-channel organisation): NID_RESET(NEW_EID)
     "two_ens_u8_30db": dict(kind="two", n_frames=24, n_frames_b=26, fmt="u8", snr=30.0, cfo=100.0, seed=7, tii=[], tii_mode=None, service=0),
 }

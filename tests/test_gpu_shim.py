@@ -9,6 +9,7 @@ import pytest
 
 import golden_cases as gc
 import orc
+from abracadabra_b200 import pipeline
 
 pytestmark = pytest.mark.gpu
 
@@ -58,6 +59,19 @@ def test_dropin_against_reference_event_log():
     assert good and all(e["fibErr"] == 0 and e["rsUnc"] == 0 for e in good)
     ref_cfo = np.median([e["freqOffset"] for e in ref_ev if e["ev"] == "periodic" and "freqOffset" in e and e["level"] == 3][1:])
     assert abs(np.median([e["freqOffset"] for e in good]) - ref_cfo) <= 10          # units of 0.1 Hz
+    # a15, the counters of dabsdrNtfPeriodic_t as the reference produces them (dabsdr.h:151-166): per period of 8 frames (6.4 DAB+
+    # superframes) 18 or 21 access units with a good CRC, 436 audio bytes each, 288 RS bytes (= 24 x bitrate / 8) per superframe,
+    # nothing to correct at 40 dB; snr10 within 0.5 dB of the reference's
+    ref_per = [e for e in ref_ev if e["ev"] == "periodic" and e.get("level") == 3 and e["crcOk"] > 0]
+    my_per = [e for e in good if e["crcOk"] > 0]
+    assert len(my_per) >= 3 and {e["crcOk"] for e in my_per[1:]} <= {18, 21} and {e["crcOk"] for e in ref_per[1:]} <= {18, 21}
+    assert all(e["audioBytes"] == 436 * e["crcOk"] and e["crcErr"] == 0 for e in my_per)
+    assert all(e["rsBytes"] == 288 * e["crcOk"] // 3 for e in my_per[1:]) and all(e["rsBytes"] == 288 * e["crcOk"] // 3 for e in ref_per[1:])
+    assert my_per[0]["rsBytes"] in (288 * (my_per[0]["crcOk"] // 3 - 1), 288 * (my_per[0]["crcOk"] // 3))       # the first superframe is not counted
+    assert all(e["rsBitErr"] == 0 and e["rsUnc"] == 0 for e in my_per)
+    assert abs(np.mean([e["crcOk"] for e in my_per[1:]]) - np.mean([e["crcOk"] for e in ref_per[1:]])) < 1.0
+    ref_snr = np.median([e["snr10"] for e in ref_ev if e["ev"] == "periodic" and e.get("level") == 3][1:])
+    assert abs(np.median([e["snr10"] for e in good]) - ref_snr) <= 5, (np.median([e["snr10"] for e in good]), ref_snr)
     # TII: same ids as the reference, level within 0.3 dB
     tii = [e for e in ev if e["ev"] == "tii" and e["n"] > 0]
     rt = [e for e in ref_ev if e["ev"] == "tii" and e["n"] > 0]
@@ -303,3 +317,41 @@ def test_dropin_new_ensemble_reset_against_reference():
     assert any(i < na - 20 for i in mine) and any(i > na + 20 for i in mine)
     # inside the stretch both delivered, nothing the reference has is missing here (start-up and end-of-file differ by a superframe)
     assert {i for i in ref if min(mine) <= i <= max(mine)} <= set(mine)
+
+
+def test_spectrum_bins_against_reference_fixture():
+    """a14: the spectrum callback's arithmetic on the reference's own windows -- every bin of the fixture's SIGNAL / NULL / TII spectra
+    (2048 bins each, generated by libdabsdr 4.0.1) within 5e-3 of the maximum, total power within 1e-4 -- and the drop-in's own
+    callbacks: same number and types per frame, same total power (Parseval) and the same placement of the window in the frame
+    (SIGNAL across the second / third data symbol, NULL from just before the null symbol), so that the smoothed in-band shape agrees."""
+    g = gc.load_golden("c1_spectrum_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    sp = [e for e in g["events"] if e["ev"] == "spectrum_bins"][1:]
+    rx = pipeline.Receiver(0)
+    got = rx.stage_spectrum(raw, "u8", [e["pos"] - (2552 if e["type"] == 0 else 2656) for e in sp])
+    for e, mine in zip(sp, got):
+        b = np.array(e["bins"])
+        assert abs(mine.sum() / b.sum() - 1) < 1e-4
+        assert np.abs(mine / mine.max() - b / b.max()).max() < 5e-3, (e["type"], e["pos"])
+    rx.close()
+    harness = orc.REF_DIR / "shim_harness"
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "s.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", tii=1, harness=harness, extra=["--tail-frames", "12", "--spectrum-bins", "14"])
+    mine = [e for e in ev if e["ev"] == "spectrum_bins"]
+    assert len(mine) >= 12
+    ref_sig = np.mean([np.array(e["bins"]) for e in sp if e["type"] == 0], axis=0)
+    my_sig = np.mean([np.array(e["bins"]) for e in mine if e["type"] == 0], axis=0)
+    ref_nul = [np.array(e["bins"]).sum() for e in sp if e["type"] != 0]
+    my_nul = [np.array(e["bins"]).sum() for e in mine if e["type"] != 0]
+    assert abs(my_sig.sum() / ref_sig.sum() - 1) < 0.02
+    assert 0.5 < np.median(my_nul) / np.median(ref_nul) < 2.0                     # same place in the frame: same leak of the neighbouring symbol
+
+    def smooth(v):                                                               # 64-bin boxcar over the FFT-shifted spectrum
+        w = np.fft.fftshift(v)
+        return np.convolve(w, np.ones(64) / 64, mode="same")
+    a, b = smooth(my_sig), smooth(ref_sig)
+    band = slice(1024 - 700, 1024 + 700)
+    assert np.abs(a[band] / b[band] - 1).max() < 0.25
+    assert a[:150].max() < 0.02 * a[band].mean() and a[-150:].max() < 0.02 * a[band].mean()   # nothing outside the 1536 carriers
