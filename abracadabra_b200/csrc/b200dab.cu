@@ -867,6 +867,20 @@ void b200dab_destroy(b200dab_ctx* ctx)
     delete ctx;
 }
 
+void* b200dab_host_alloc(b200dab_ctx* ctx, size_t bytes)
+{
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+void b200dab_host_free(b200dab_ctx* ctx, void* p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
+}
+
 const char* b200dab_last_error(b200dab_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 void* b200dab_stream(b200dab_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 

@@ -17,6 +17,7 @@
 #include <condition_variable>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -33,6 +34,7 @@ namespace {
 
 constexpr int ADV_FRAMES_MIN = 4;              // new frames per GPU pass of a live stream (384 ms of signal)
 constexpr int ADV_FRAMES_MAX = 64;             // ... of a source that delivers faster than real time (a file): the batch grows up to this
+                                               // (B200DAB_DROPIN_MAX_BATCH in the environment lowers the limit; 4 = always behave as live)
 constexpr int OVL_FRAMES = 6;                  // re-decoded overlap: 16 CIFs of interleaver memory + 5 CIFs of superframe
 constexpr int64_t WIN_SAMPLES_MAX = (int64_t)(ADV_FRAMES_MAX + OVL_FRAMES) * DAB_T_FRAME + 4096;
 
@@ -48,6 +50,7 @@ struct Decoder {               // one of the (up to two) audio decoder instances
     int64_t last_row = -1;     // absolute logical-frame number delivered last (MP2)
     int64_t last_sf_row = -1;  // absolute row of the last delivered superframe (DAB+)
     int64_t last_stat_row = -1;// absolute row of the last superframe that went into the RS statistics
+    uint8_t mp2_drc = 0;       // DRC value for the NEXT MP2 frame: F-PAD of the frame before it (dabsdr.h:50 mp2DRC)
     pad::Decoder xpad;         // X-PAD state of this audio service
     bool xpad_app[32] = {};    // X-PAD application types started with dabsdrRequest_XPadAppStart
 };
@@ -86,9 +89,13 @@ struct dabsdr_s {
     fig::Database db;
     Decoder dec[2];
     DataDecoder data[MAX_DATA_DEC];
-    std::vector<float> win;            // interleaved I,Q
+    struct Win { float* p = nullptr; float* data() { return p; } } win;   // interleaved I,Q: pinned host memory (b200dab_host_alloc)
+    float* win_data = nullptr;
+    std::vector<float> win_fallback;
     int adv_frames = ADV_FRAMES_MIN;   // new frames per pass: doubles while the input function delivers much faster than real time
+    int adv_max = ADV_FRAMES_MAX;
     int fast_pulls = 0;
+    bool at_end = false;               // the source has run out (zero-filled chunks): batches stay small
     int64_t win_samples() const { return (int64_t)(adv_frames + OVL_FRAMES) * DAB_T_FRAME + 4096; }
     int64_t adv_samples() const { return (int64_t)adv_frames * DAB_T_FRAME; }
     double t_pull0 = 0;                // wall clock when the pull of the current batch began
@@ -192,6 +199,10 @@ void send_fig_events(dabsdr_s* h)
     for (const fig::Database::Event& e : h->db.events) {
         switch (e.kind) {
         case fig::Database::Event::NEW_EID: new_eid = true; break;
+        case fig::Database::Event::RECONFIGURATION:
+            // the caller clears its service list and asks for the new one (src/radiocontrol.cpp:178-190)
+            notify(h, DABSDR_NID_RECONFIGURATION, DABSDR_NSTAT_SUCCESS, nullptr, 0);
+            break;
         case fig::Database::Event::UA_UPDATE: {
             dabsdrNtfUserAppUpdate_t n; memset(&n, 0, sizeof n);
             n.SId = e.sid; n.SCIdS = e.scids;
@@ -560,9 +571,13 @@ void process_window(dabsdr_s* h)
                     if (sc_dec[i] == 0) { if (hdr_ok) h->crc_ok++; else h->crc_err++; h->audio_bytes += pitch; }
                     if (h->audio_cb) {
                         dabsdrAudioCBData_t a;
-                        a.id = (dabsdrDecoderId_t)sc_dec[i]; a.ASCTy = 0; a.header.raw = 0; a.auLen = (uint16_t)(hdr_ok ? pitch : 0); a.pAuData = fr;
+                        // header = dynamic range control of this frame, which travels in the F-PAD of the PREVIOUS frame: byte L >> 2
+                        // when bit 0 of byte L-1 is set ("byte L carries DRC data", EN 300 401 sec. 7.4.1), else 0 -- as the reference
+                        // reports it (golden multi_mp2_u8_25db; consumer src/audiodecoder.cpp:285-326: gain = 10^(mp2DRC / 80))
+                        a.id = (dabsdrDecoderId_t)sc_dec[i]; a.ASCTy = 0; a.header.raw = d.mp2_drc; a.auLen = (uint16_t)(hdr_ok ? pitch : 0); a.pAuData = fr;
                         h->audio_cb(&a, h->audio_ctx);
                     }
+                    d.mp2_drc = (hdr_ok && (fr[pitch - 2] & 1)) ? (uint8_t)(fr[pitch - 1] >> 2) : 0;
                     int scf = 0;
                     if (hdr_ok && pad::mp2_pad(fr, pitch, h->pad_tmp, &scf)) {
                         const dabsdrDecoderId_t did = (dabsdrDecoderId_t)sc_dec[i];
@@ -672,11 +687,6 @@ void* worker(void* arg)
 {
     dabsdr_s* h = (dabsdr_s*)arg;
     pthread_setname_np(pthread_self(), "dabsdr");
-    if (b200dab_create(&h->gpu, 0) != 0) {
-        fprintf(stderr, "dabsdr(b200): no CUDA device -- this build has no CPU fallback\n");
-        h->gpu = nullptr;
-    }
-    h->win.resize((size_t)WIN_SAMPLES_MAX * 2);
     for (;;) {
         // requests are served between GPU passes; while untuned the worker sleeps on the mailbox
         {
@@ -687,7 +697,7 @@ void* worker(void* arg)
                 h->q.pop_front();
                 lk.unlock();
                 const bool go = handle_request(h, r);
-                if (!go) { if (h->gpu) b200dab_destroy(h->gpu); h->gpu = nullptr; return nullptr; }
+                if (!go) { if (h->gpu) { if (h->win_fallback.empty()) b200dab_host_free(h->gpu, h->win_data); b200dab_destroy(h->gpu); } h->gpu = nullptr; h->win_data = nullptr; return nullptr; }
                 lk.lock();
             }
         }
@@ -697,8 +707,24 @@ void* worker(void* arg)
         {
             if (h->t_pull0 == 0) { h->t_pull0 = wall_ms(); h->pulled0 = h->have; }
             const int64_t n = std::min<int64_t>(16384, h->win_samples() - h->have);
-            h->in(h->win.data() + 2 * h->have, (uint16_t)n);
+            float* dst = h->win.data() + 2 * h->have;
+            h->in(dst, (uint16_t)n);
             h->have += n;
+            // A chunk of exact zeros is the end of the source (InputDevice zero-fills after flush(), src/input/inputdevice.cpp:95-108;
+            // a receiver never delivers 16384 exact zeros): what a large batch still holds is decoded now instead of waiting for it to fill.
+            bool zeros = dst[0] == 0.f && dst[1] == 0.f;
+            for (int64_t i = 0; zeros && i < 2 * n; i++) zeros = dst[i] == 0.f;
+            if (zeros && !h->at_end && h->adv_frames > ADV_FRAMES_MIN && h->have > (int64_t)(ADV_FRAMES_MIN + OVL_FRAMES) * DAB_T_FRAME + 4096) {
+                h->at_end = true;
+                h->t_pull0 = 0; h->fast_pulls = 0;
+                process_window(h);
+                const int64_t keep = (int64_t)OVL_FRAMES * DAB_T_FRAME + 4096, adv = h->have - keep;
+                memmove(h->win.data(), h->win.data() + 2 * adv, (size_t)keep * 2 * sizeof(float));
+                h->have = keep; h->abs_pos += adv;
+                h->adv_frames = ADV_FRAMES_MIN;
+                continue;
+            }
+            if (!zeros) h->at_end = false;
         }
         if (h->have < h->win_samples()) continue;
         // A live stream delivers one second of signal per second; a file (RawFileInput without pacing, a scanner replay) much faster.
@@ -719,7 +745,7 @@ void* worker(void* arg)
         memmove(h->win.data(), h->win.data() + 2 * adv, (size_t)(h->have - adv) * 2 * sizeof(float));
         h->have -= adv;
         h->abs_pos += adv;
-        if (h->fast_pulls >= 2 && h->adv_frames < ADV_FRAMES_MAX) h->adv_frames = std::min(ADV_FRAMES_MAX, h->adv_frames * 2);
+        if (h->fast_pulls >= 2 && !h->at_end && h->adv_frames < h->adv_max) h->adv_frames = std::min(h->adv_max, h->adv_frames * 2);
         else if (h->fast_pulls == 0) h->adv_frames = ADV_FRAMES_MIN;
     }
 }
@@ -740,12 +766,22 @@ DABSDR_API uint8_t dabsdrInit(dabsdrHandle_t* handle)
 {
     if (!handle) return 1;
     *handle = new dabsdr_s();
+    if (const char* e = getenv("B200DAB_DROPIN_MAX_BATCH")) (*handle)->adv_max = std::max(ADV_FRAMES_MIN, std::min(ADV_FRAMES_MAX, atoi(e)));
     return 0;
 }
 
 DABSDR_API void dabsdr(dabsdrHandle_t h)
 {
     if (!h || h->started) return;
+    // The CUDA context and the (pinned) sample window are set up here, once, before the worker starts: RadioControl calls dabsdr()
+    // at application start (src/radiocontrol.cpp:93), long before the first Tune.
+    if (!h->gpu && b200dab_create(&h->gpu, 0) != 0) {
+        fprintf(stderr, "dabsdr(b200): no CUDA device -- this build has no CPU fallback\n");
+        h->gpu = nullptr;
+    }
+    if (h->gpu && !h->win_data) h->win_data = (float*)b200dab_host_alloc(h->gpu, (size_t)WIN_SAMPLES_MAX * 2 * sizeof(float));
+    if (!h->win_data) { h->win_fallback.resize((size_t)WIN_SAMPLES_MAX * 2); h->win_data = h->win_fallback.data(); }
+    h->win.p = h->win_data;
     h->started = pthread_create(&h->thr, nullptr, worker, h) == 0;
 }
 

@@ -59,15 +59,38 @@ struct Database {
     // changes the caller is told about without asking (dabsdr.h: NID_USER_APP_UPDATE, NID_PTY, NID_ANNOUNCEMENT_SUPPORT,
     // NID_ANNOUNCEMENT_SWITCHING); filled by parse_fib in FIG order, drained by the owner
     struct Event {
-        enum Kind { UA_UPDATE, PTY, ASU, ASW, NEW_EID } kind;
+        enum Kind { UA_UPDATE, PTY, ASU, ASW, NEW_EID, RECONFIGURATION } kind;
         uint32_t sid = 0;
         uint8_t scids = 0;
         int n_asw = 0;
         struct { uint8_t cluster, subch; uint16_t flags; } asw[8];
     };
     std::vector<Event> events;
+    // Multiplex reconfiguration (EN 300 401 sec. 6.4, 6.5): while FIG 0/0 carries change flags, the MCI extensions sent with C/N = 1
+    // describe the NEXT configuration and are kept apart; one frame before the CIF counter reaches the announced occurrence the next
+    // configuration becomes the current one and the owner is told (DABSDR_NID_RECONFIGURATION, dabsdr.h:112).
+    SubCh next_subch[64];
+    std::vector<Service> next_services;
+    int change_flags = 0, occurrence = -1;
+    bool reconfigured = false;          // this announcement has been acted upon
 
     void reset() { *this = Database(); }
+
+    void apply_next_configuration()
+    {
+        // Sub-channel organisation: the announced one takes over at once, so the decoders of the running services keep their
+        // (possibly moved) sub-channels without a gap.  Service organisation: dropped and rebuilt from the FIGs of the new
+        // configuration, which arrive with C/N = 0 from the change on -- like the reference, whose first service list after a
+        // reconfiguration is empty and whose second one is complete (golden c1_reconf_u8_30db); RadioControl asks again until it is
+        // (src/radiocontrol.cpp:1427-1436).
+        bool any = false;
+        for (int i = 0; i < 64; i++) any = any || next_subch[i].valid;
+        if (any) for (int i = 0; i < 64; i++) subch[i] = next_subch[i];
+        services.clear();
+        next_services.clear();
+        for (auto& n : next_subch) n = SubCh();
+        version++;
+    }
 
     Service* find(uint32_t sid) { for (auto& s : services) if (s.sid == sid) return &s; return nullptr; }
     Service& get(uint32_t sid)
@@ -111,8 +134,22 @@ struct Database {
 
     void fig0(const uint8_t* d, int len)
     {
-        const int ext = d[0] & 31, pd = (d[0] >> 5) & 1, oe = (d[0] >> 6) & 1;
+        const int ext = d[0] & 31, pd = (d[0] >> 5) & 1, oe = (d[0] >> 6) & 1, cn = d[0] >> 7;
         if (oe && ext != 0) return;                        // other-ensemble information is not kept
+        if (cn && (ext == 1 || ext == 2 || ext == 3 || ext == 8)) {
+            // MCI of the next configuration: parsed with the same code into the tables kept for it
+            std::swap(services, next_services);
+            for (int i = 0; i < 64; i++) std::swap(subch[i], next_subch[i]);
+            uint8_t tmp[32];
+            memcpy(tmp, d, (size_t)len);
+            tmp[0] &= 0x7F;
+            const uint64_t v = version;
+            fig0(tmp, len);
+            version = v;
+            std::swap(services, next_services);
+            for (int i = 0; i < 64; i++) std::swap(subch[i], next_subch[i]);
+            return;
+        }
         int k = 1;
         switch (ext) {
         case 0:
@@ -122,6 +159,18 @@ struct Database {
                 if (!have_eid || e != eid) { eid = e; have_eid = true; version++; }
                 alarm = (d[3] >> 5) & 1;
                 cif_count = (d[3] & 0x1F) * 250 + d[4];
+                const int flags = d[3] >> 6;
+                if (flags && len >= 6) {
+                    if (!change_flags || occurrence != d[5]) reconfigured = false;
+                    change_flags = flags; occurrence = d[5];
+                    // the change takes effect with the frame that follows this one (a frame carries four CIF counts)
+                    const int ahead = ((occurrence - d[4]) % 250 + 250) % 250;
+                    if (!reconfigured && ahead <= 4) {
+                        reconfigured = true;
+                        apply_next_configuration();
+                        Event ev; ev.kind = Event::RECONFIGURATION; events.push_back(ev);
+                    }
+                } else if (!flags) { change_flags = 0; occurrence = -1; reconfigured = false; }
             }
             break;
         case 1:

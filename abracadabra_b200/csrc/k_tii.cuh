@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(256) k_tii_fold_nulls(const float2* __restrict
 // signal-spectrum callback material (dabsdr.h:393, consumer src/radiocontrol.cpp:2604-2609): per frame two 2048-bin linear power
 // Where the reference takes the 2048 samples of its spectrum callbacks from (probed, tests/golden/c1_spectrum_u8_30db: every
 // callback equals |FFT|^2 of a block of RAW samples, sum ratio 1.00000): SIGNAL = the first 2048 samples of the 2552-sample block
-// it pulled last, which starts 7354..7674 samples after the frame start (it moves with the core's time tracking); NULL / TII = the
-// first 2048 samples of the 2656-sample block around the null symbol, starting 86..406 samples BEFORE the frame start.  The
-// offsets below put our windows in the middle of those ranges, relative to our own t_f (= frame start + 3136 - first-path shift).
-#define SPECTRUM_SIGNAL_OFFSET 4364
-#define SPECTRUM_NULL_OFFSET (-3386)
+// it pulls for the third symbol of the frame, NULL / TII = the first 2048 samples of the 2656-sample block of the null symbol; with
+// its timing locked both blocks begin 4 samples ahead of the symbol (while it is still pulling in they sit up to 400 samples
+// earlier).  Relative to our t_f (FFT window of the PRS = frame start + 2656 + 504 - 24 for a single path):
+#define SPECTRUM_SIGNAL_OFFSET (2 * DAB_T_SYM - DAB_T_CP + 24 - 4)      /* frame start + 7756 */
+#define SPECTRUM_NULL_OFFSET (-(DAB_T_NULL + DAB_T_CP - 24) - 4)        /* frame start - 4 */
 // spectra in natural FFT order, unnormalised |FFT|^2 of the raw samples like the reference's: [0] SIGNAL, [1] NULL / TII.
 // One CTA per frame.
 template <int FMT>

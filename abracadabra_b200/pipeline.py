@@ -136,7 +136,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream",
+EXPORTS = ["b200dab_version", "b200dab_create", "b200dab_destroy", "b200dab_last_error", "b200dab_stream", "b200dab_host_alloc", "b200dab_host_free",
            "b200dab_set_profiling", "b200dab_get_kernel_times", "b200dab_get_kernel_times_back", "b200dab_get_kernel_timeline", "b200dab_profile_eep", "b200dab_profile_uep", "b200dab_parse_subch", "b200dab_parse_ensemble", "b200dab_spectrum_layout", "b200dab_viterbi_decision_index", "b200dab_viterbi4_decision_index", "b200dab_set_viterbi_split", "b200dab_set_superframe_phase", "b200dab_pad_create", "b200dab_pad_destroy", "b200dab_pad_reset", "b200dab_pad_feed_au", "b200dab_pad_feed_mp2", "b200dab_pad_feed_packets", "b200dab_decode", "b200dab_stage_coarse",
            "b200dab_stage_fine", "b200dab_stage_demod", "b200dab_stage_viterbi", "b200dab_stage_fic", "b200dab_stage_msc",
            "b200dab_stage_dabplus", "b200dab_stage_spectrum", "b200dab_stage_tii_fold", "b200dab_stage_tii_detect"]

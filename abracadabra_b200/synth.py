@@ -93,6 +93,10 @@ class EnsembleConfig:
     announcements: List[Tuple[int, int, int, int, int]] = field(default_factory=list)
     utc: Optional[Tuple[int, int, int, int, int]] = None   # FIG 0/10 (long form): (MJD, hours, minutes, seconds, ms) at the first CIF
     cif_count0: int = 0           # CIF counter of the first CIF (multiple of 4 keeps frames aligned)
+    # multiplex reconfiguration (EN 300 401 sec. 6.4): dict(at=CIF (relative to the first) from which the new configuration holds,
+    # lead=CIFs of advance notice, subchannels=[SubChannel added], services=[Service added]).  From at - lead on FIG 0/0 carries the
+    # change flags and the occurrence change, and the new configuration is sent with C/N = 1 next to the current one.
+    reconfig: Optional[dict] = None
 
     def check(self):
         used = np.zeros(864, dtype=int)
@@ -502,9 +506,12 @@ def _fig(type_: int, body: bytes) -> bytes:
     return bytes([(type_ << 5) | len(body)]) + body
 
 
-def fig0_0(ens: EnsembleConfig, cif_count: int) -> bytes:
+def fig0_0(ens: EnsembleConfig, cif_count: int, change: int = 0, occurrence: int = 0) -> bytes:
     hi, lo = (cif_count // 250) % 20, cif_count % 250
-    return _fig(0, bytes([0x00, ens.eid >> 8, ens.eid & 0xFF, hi & 0x1F, lo]))
+    body = [0x00, ens.eid >> 8, ens.eid & 0xFF, ((change & 3) << 6) | (hi & 0x1F), lo]
+    if change:
+        body.append(occurrence & 0xFF)
+    return _fig(0, bytes(body))
 
 
 def fig0_1_entry(sc: SubChannel) -> bytes:
@@ -518,7 +525,7 @@ def fig0_1_entry(sc: SubChannel) -> bytes:
 
 
 def fig0_2_entry(ens: EnsembleConfig, sv: Service) -> bytes:
-    sc = next(s for s in ens.subchannels if s.subchid == sv.subchid)
+    sc = next(s for s in list(ens.subchannels) + list((ens.reconfig or {}).get("subchannels", [])) if s.subchid == sv.subchid)
     ascty = 63 if sc.kind == "dabplus" else 0
     comps = bytes([(0 << 6) | ascty, (sc.subchid << 2) | 0x02])
     for dc in sv.data_comps or []:
@@ -613,6 +620,12 @@ class FicBuilder:
         self.e01 = [fig0_1_entry(s) for s in ens.subchannels]
         self.e02 = [fig0_2_entry(ens, sv) for sv in ens.services]
         self.labels = [fig1(0, ens.eid, ens.label)] + [fig1(1, sv.sid, sv.label) for sv in ens.services]
+        rc = ens.reconfig
+        if rc:
+            self.n01 = self.e01 + [fig0_1_entry(s) for s in rc["subchannels"]]         # the next configuration, complete
+            self.n02 = self.e02 + [fig0_2_entry(ens, sv) for sv in rc["services"]]
+            self.nlabels = self.labels + [fig1(1, sv.sid, sv.label) for sv in rc["services"]]
+            self.in01 = self.in02 = 0
         self.e13 = [fig0_13_entry(sv) for sv in ens.services if sv.user_apps]
         self.e13 += [fig0_13_entry_data(sv, dc) for sv in ens.services for dc in (sv.data_comps or []) if dc.user_apps]
         self.e03 = [fig0_3_entry(dc) for sv in ens.services for dc in (sv.data_comps or [])]
@@ -623,7 +636,19 @@ class FicBuilder:
 
     def cif_fibs(self, cif_count: int) -> bytes:
         """Three FIBs (96 bytes) for one CIF."""
-        f00 = fig0_0(self.ens, cif_count)
+        rc = self.ens.reconfig
+        rel = (cif_count - self.ens.cif_count0) % 5000
+        announce = bool(rc) and rc["at"] - rc["lead"] <= rel < rc["at"]
+        if rc and rel == rc["at"]:                                   # the new configuration is the current one from here on
+            self.e01, self.e02, self.labels = self.n01, self.n02, self.nlabels
+        f00 = fig0_0(self.ens, cif_count, 3 if announce else 0, (self.ens.cif_count0 + rc["at"]) % 250 if announce else 0)
+        if announce and rel % 2 == 1:
+            # every second CIF of the notice period carries the NEXT configuration (C/N = 1) instead of the rotating current one
+            f01, self.in01 = _pack_rotating(self.n01, 0x81, 30 - len(f00), self.in01)
+            f02, self.in02 = _pack_rotating(self.n02, 0x82, 30, self.in02)
+            lab = self.labels[self.ilab % len(self.labels)]
+            self.ilab += 1
+            return make_fib(f00 + f01) + make_fib(f02) + make_fib(lab + fig0_9(self.ens))
         f13 = b""
         if self.e13 and cif_count % 2 == 0:
             f13, self.i13 = _pack_rotating(self.e13, 0x0D, 14, self.i13)
@@ -689,7 +714,13 @@ def build_cif_bits(ens: EnsembleConfig, n_cif: int, seed: int):
     # ---- MSC
     msc_pre = rng.integers(0, 2, (n_cif, C.CIF_BITS), dtype=np.uint8)   # filler in unused CUs
     logical, aus, sfs = {}, {}, {}
-    for sc in ens.subchannels:
+    added = ens.reconfig["subchannels"] if ens.reconfig else []
+    n_cif_all = n_cif
+    for sc in list(ens.subchannels) + list(added):
+        r0 = ens.reconfig["at"] if sc in added else 0           # a sub-channel of the next configuration starts at the change
+        n_cif = max(n_cif_all - r0, 0)
+        if n_cif == 0:
+            continue
         srng = np.random.default_rng(sc.seed + 77)
         segs, size_cu, pad = sc.profile()
         if sc.kind == "dabplus":
@@ -709,7 +740,8 @@ def build_cif_bits(ens: EnsembleConfig, n_cif: int, seed: int):
         scr = bytes_to_bits(frames) ^ C.prbs_bits(nb)[None, :]
         enc = encode_protected(scr, segs, pad)
         assert enc.shape[1] == size_cu * 64, (enc.shape, size_cu)
-        msc_pre[:, sc.start_cu * 64:(sc.start_cu + size_cu) * 64] = enc
+        msc_pre[r0:, sc.start_cu * 64:(sc.start_cu + size_cu) * 64] = enc
+    n_cif = n_cif_all
     # ---- time interleaving: out[r][i] = in[r - D(i mod 16)][i]
     msc = np.zeros_like(msc_pre)
     for j, d in enumerate(C.TIME_DEINT_DELAY):

@@ -14,6 +14,7 @@
  */
 #ifndef B200DAB_H
 #define B200DAB_H
+#include <stddef.h>
 #include <stdint.h>
 #include "b200dab_spec.h"
 
@@ -125,7 +126,11 @@ B200DAB_API int b200dab_version(void);
 B200DAB_API int b200dab_create(b200dab_ctx **out, int device);
 B200DAB_API void b200dab_destroy(b200dab_ctx *ctx);
 B200DAB_API const char *b200dab_last_error(b200dab_ctx *ctx);
-B200DAB_API void *b200dab_stream(b200dab_ctx *ctx);                 /* cudaStream_t the context launches on */
+B200DAB_API void *b200dab_stream(b200dab_ctx *ctx);
+/* page-locked host memory for sample buffers handed to b200dab_decode with B200DAB_MEM_HOST: the upload then runs at the full PCIe
+ * rate and asynchronously (a pageable buffer is staged by the driver at a fraction of it) */
+B200DAB_API void *b200dab_host_alloc(b200dab_ctx *ctx, size_t bytes);
+B200DAB_API void b200dab_host_free(b200dab_ctx *ctx, void *p);                 /* cudaStream_t the context launches on */
 
 /* protection profile helpers (EN 300 401 tables 7/8 and 11.3.2); fill seg_len/seg_pi/size_cu/bitrate */
 B200DAB_API int b200dab_profile_eep(int bitrate, int level /*1..4*/, int option /*0=A,1=B*/, b200dab_subch_t *out);

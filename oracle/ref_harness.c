@@ -434,6 +434,11 @@ static void handle_event(ev_t *e)
             dabsdrRequest_GetServiceList(g_h);
         }
         break; }
+    case DABSDR_NID_RECONFIGURATION:
+        /* reference: src/radiocontrol.cpp:178-190 -- the service list is dropped and requested again */
+        g_nsids = 0;
+        dabsdrRequest_GetServiceList(g_h);
+        break;
     case DABSDR_NID_SERVICE_LIST:
         if (e->nsids == 0) { g_list_retry_ticks = 1; break; }
         g_nsids = e->nsids;

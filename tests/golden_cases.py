@@ -42,6 +42,10 @@ CASES = {
     # signal-spectrum callback (dabsdr.h:365-370, :428) with all 2048 bins of the first callbacks: 2 per frame, SIGNAL and NULL / TII
     "c1_spectrum_u8_30db": dict(kind="config1", n_frames=14, fmt="u8", snr=30.0, cfo=0.0, seed=8, tii=[(12, 5, 1.0, 0)], tii_mode=1, service=None,
                                 spectrum_bins=14),
+    # multiplex reconfiguration: from CIF 140 on a second sub-channel and service exist; announced 80 CIFs ahead through the FIG 0/0
+    # change flags + occurrence change and the next configuration sent with C/N = 1 (EN 300 401 sec. 6.4)
+    "c1_reconf_u8_30db": dict(kind="config1", n_frames=70, fmt="u8", snr=30.0, cfo=100.0, seed=31, tii=[], tii_mode=None, service=0,
+                              reconfig=dict(at=140, lead=80, subchid=9, start_cu=200, bitrate=64, sid=0x1234, label="ADDED SERVICE")),
     # another ensemble takes over the frequency after 24 frames (same sub-channel organisation): NID_RESET(NEW_EID)
     "two_ens_u8_30db": dict(kind="two", n_frames=24, n_frames_b=26, fmt="u8", snr=30.0, cfo=100.0, seed=7, tii=[], tii_mode=None, service=0),
 }
@@ -81,6 +85,11 @@ def build_case(spec):
             ens.subchannels.append(synth.SubChannel(pk["subchid"], pk["start_cu"], "packet", 32, ("EEP", 3, "A"), seed=1,
                                                     packets=[(pk["addr"], dgs), (pk["other_addr"], dgs[:2])]))
             ens.services[0].data_comps = [synth.DataComponent(pk["subchid"], pk["scid"], pk["scids"], pk["addr"], user_apps=[(2, b"")])]
+        if spec.get("reconfig"):
+            rc = spec["reconfig"]
+            ens.reconfig = dict(at=rc["at"], lead=rc["lead"],
+                                subchannels=[synth.SubChannel(rc["subchid"], rc["start_cu"], "dabplus", rc["bitrate"], ("EEP", 3, "A"), seed=3109)],
+                                services=[synth.Service(rc["sid"], rc["label"], rc["subchid"])])
         if spec.get("xpad_dg"):
             ens.subchannels[0].xpad_dg = mot_data_groups(spec["xpad_dg"])
             ens.services[0].user_apps = [(2, bytes([0x0C, 0x3C]))]       # SlideShow over X-PAD application 12, DSCTy 60 (MOT)

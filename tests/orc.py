@@ -244,7 +244,7 @@ def have_ref() -> bool:
     return (REF_DIR / "ref_harness").exists() and (REF_DIR / "libdabsdr.so.4.0.1").exists()
 
 
-def run_ref(path, fmt, log_path=None, tii=None, service=None, second=None, extra=(), harness=None, timeout=600):
+def run_ref(path, fmt, log_path=None, tii=None, service=None, second=None, extra=(), harness=None, timeout=600, env=None):
     """Run the harness (by default against the reference core).  Returns (summary dict, [events])."""
     exe = str(harness or (REF_DIR / "ref_harness"))
     cmd = [exe, str(path), fmt, str(log_path) if log_path else "-"]
@@ -255,7 +255,7 @@ def run_ref(path, fmt, log_path=None, tii=None, service=None, second=None, extra
     if second is not None:
         cmd += ["--second", str(second)]
     cmd += list(extra)
-    out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=timeout).stdout
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=timeout, env=env).stdout
     summary = json.loads(out.strip().splitlines()[-1])
     events = []
     if log_path and os.path.exists(log_path):

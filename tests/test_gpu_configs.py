@@ -112,8 +112,8 @@ def test_config3_fifty_recordings_vs_reference():
                 top = max(list(r.values()) + list(o.values()))
                 for k in set(r) ^ set(o):
                     assert k in sent and (r.get(k) or o.get(k)) < 0.1 * top / 0.9, (i, k, ref_ids, my_ids, txs)
-                common = [k for k in (m_s[:2] for m_s in ref_ids) if k in o]
-                assert [k for k in (m_s[:2] for m_s in my_ids) if k in r] == common          # same order
+                common = [k for k in (tuple(m_s[:2]) for m_s in ref_ids) if k in o]
+                assert [k for k in (tuple(m_s[:2]) for m_s in my_ids) if k in r] == common          # same order
             top = max(r.values()) if r else 1.0
             for k in set(r) & set(o):
                 (hi if r[k] >= 0.5 * top else lo).append(abs(20 * np.log10(o[k] / r[k])))

@@ -9,9 +9,15 @@ import pytest
 
 import golden_cases as gc
 import orc
-from abracadabra_b200 import pipeline
+from abracadabra_b200 import pipeline, synth
 
 pytestmark = pytest.mark.gpu
+
+# The event logs of the reference were recorded with the lock-stepped feed, which behaves like a live stream in signal time but
+# delivers as fast as a file: the drop-in is told to keep its live-stream batches (4 new frames per GPU pass) so that the place of
+# every notification in the stream can be compared; bench.py --impl dropin measures the adaptive batches.
+import os
+os.environ["B200DAB_DROPIN_MAX_BATCH"] = "4"
 
 
 def test_dropin_against_reference_event_log():
@@ -99,6 +105,11 @@ def test_dropin_mp2_service_against_reference():
     i0 = truth.index(sha[0])
     assert sha == truth[i0:i0 + len(sha)]
     assert set(sha) & {e["sha1"] for e in g["events"] if e["ev"] == "audio"}
+    # header byte = DRC data of the F-PAD of the frame before (dabsdr.h:50 mp2DRC): equal to the reference's for every common frame
+    ref_hdr = {e["sha1"]: e["header"] for e in g["events"] if e["ev"] == "audio"}
+    first_ref = next(e["sha1"] for e in g["events"] if e["ev"] == "audio")
+    common = [(e["header"], ref_hdr[h]) for e, h in zip(got[1:], sha[1:]) if h in ref_hdr and h != first_ref]
+    assert len(common) >= 25 and all(a == b for a, b in common) and any(b != 0 for _, b in common), common
     # signal-spectrum callback: two spectra per frame (null/TII + signal), Parseval-sized, energy inside the 1536 carriers
     sp = [e for e in ev if e["ev"] == "spectrum"]
     sig = [e for e in sp if e["type"] == 0]
@@ -355,3 +366,76 @@ def test_spectrum_bins_against_reference_fixture():
     band = slice(1024 - 700, 1024 + 700)
     assert np.abs(a[band] / b[band] - 1).max() < 0.25
     assert a[:150].max() < 0.02 * a[band].mean() and a[-150:].max() < 0.02 * a[band].mean()   # nothing outside the 1536 carriers
+
+
+def test_dropin_adaptive_batches_deliver_the_same_stream():
+    """A source faster than real time (a file): the drop-in lets its batch of new frames per GPU pass grow to 64, yet every callback
+    comes in the order of the stream -- the access units of a 20 s recording are the transmitted ones, contiguous, and contain
+    everything the reference core delivers for the same file; the periodic notifications keep their rhythm (18 / 21 AUs each)."""
+    harness = orc.REF_DIR / "shim_harness"
+    ens = synth.config1_ensemble(seed=41)
+    raw, res = synth.synthesize(ens, 208, "u8", synth.Impairments(snr_db=25.0, cfo_hz=-640.0, seed=41, lead_in=33000), seed=41, tail=100000)
+    env = {k: v for k, v in os.environ.items() if k != "B200DAB_DROPIN_MAX_BATCH"}
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "a.u8"
+        raw.tofile(p)
+        _, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", tii=1, service=0, harness=harness, extra=["--tail-frames", "12", "--free-run"], env=env)
+        _, rv = orc.run_ref(p, "u8", Path(td) / "ref.jsonl", tii=1, service=0, extra=["--tail-frames", "12"])
+    mine = [bytes.fromhex(e["data"]) for e in ev if e["ev"] == "audio" and e["len"] > 0]
+    ref = [bytes.fromhex(e["data"]) for e in rv if e["ev"] == "audio" and e["len"] > 0]
+    truth = res.aus[ens.subchannels[0].subchid]
+    i0 = truth.index(mine[0])
+    assert mine == truth[i0:i0 + len(mine)] and len(mine) >= 3 * 160
+    j0 = mine.index(ref[0])
+    k = min(len(ref), len(mine) - j0)
+    assert mine[j0:j0 + k] == ref[:k] and len(ref) - k <= 18
+    per = [e for e in ev if e["ev"] == "periodic" and not e.get("null") and e.get("level") == 3 and e["crcOk"] > 0]
+    assert len(per) >= 20 and {e["crcOk"] for e in per[1:-1]} <= {18, 21}
+    tii = [e for e in ev if e["ev"] == "tii" and e["n"] > 0]
+    assert len(tii) >= 4 and all([(m, s) for m, s, _ in t["ids"]] == [(12, 5)] for t in tii)
+
+
+def test_dropin_multiplex_reconfiguration_against_reference():
+    """a3 / NID_RECONFIGURATION (dabsdr.h:112; consumer src/radiocontrol.cpp:178-190, :2420): a second sub-channel and service join the
+    multiplex at CIF 140, announced 80 CIFs ahead (FIG 0/0 change flags + occurrence change, next configuration with C/N = 1).  The
+    drop-in raises the notification once, in the frame before the change like the reference; the service list asked for afterwards
+    ends up equal to the reference's (two services, labels included), the component lists too (the new sub-channel at CU 200, 48 CU,
+    64 kbit/s), and the running audio service does not lose an access unit."""
+    harness = orc.REF_DIR / "shim_harness"
+    g = gc.load_golden("c1_reconf_u8_30db")
+    raw, res = gc.build_case(g["spec"])
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "r.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, harness=harness, extra=["--tail-frames", "12"])
+    ref_ev = g["events"]
+    mine_rc = [e for e in ev if e["ev"] == "reconfiguration"]
+    ref_rc = [e for e in ref_ev if e["ev"] == "reconfiguration"]
+    assert len(mine_rc) == 1 and len(ref_rc) == 1 and mine_rc[0]["status"] == 0
+    # `pos` is the input position at the callback: the reference lags its input by less than a frame, the windowed drop-in by up to 12
+    assert 0 <= mine_rc[0]["pos"] - ref_rc[0]["pos"] <= 13 * 196608
+    def after(evs, kind, rc):
+        return [e for e in evs if e["ev"] == kind and e["pos"] >= rc["pos"]]
+    me, rf = after(ev, "service_list", mine_rc[0])[-1], after(ref_ev, "service_list", ref_rc[0])[-1]
+    assert me["n"] == rf["n"] == 2 and me["items"] == rf["items"]
+    before = [e for e in ev if e["ev"] == "service_list" and e["pos"] < mine_rc[0]["pos"]][-1]
+    assert before["n"] == 1
+    me_sc = {e["sid"]: e["items"] for e in after(ev, "sc_list", mine_rc[0])}
+    rf_sc = {e["sid"]: e["items"] for e in after(ref_ev, "sc_list", ref_rc[0])}
+    assert me_sc == rf_sc and me_sc[0x1234][0]["addr"] == 200 and me_sc[0x1234][0]["size"] == 48 and me_sc[0x1234][0]["bitrate"] == 64
+    # the selected service plays through the change
+    truth = res.aus[3]
+    got = [bytes.fromhex(e["data"]) for e in ev if e["ev"] == "audio"]
+    i0 = truth.index(got[0])
+    assert got == truth[i0:i0 + len(got)] and len(got) >= 3 * 40
+    # the batch path sees the same thing: before the change one sub-channel (the announcement is not mistaken for the current
+    # organisation), over the whole recording both
+    rx = pipeline.Receiver(0)
+    d = rx.decode(raw[:2 * (49152 + 30 * 196608)], "u8")
+    assert [s.subch_id for s in d.subch] == [3]
+    d = rx.decode(raw, "u8")
+    assert [s.subch_id for s in d.subch] == [3, 9]
+    assert np.array_equal(d.frames[0], res.logical[3][:d.frames[0].shape[0]])
+    new = res.logical[9]
+    assert np.array_equal(d.frames[1][140:140 + new.shape[0] - 15], new[:new.shape[0] - 15])      # rows of the new sub-channel from the change on
+    rx.close()

@@ -204,3 +204,23 @@ def test_viterbi_four_lane_layout_matches_model():
         assert L.b200dab_viterbi4_decision_index(s, 0) == fwd[s]
         assert L.b200dab_viterbi4_decision_index(s, 1) == bwd[s]
     assert len({v & 63 for v in fwd}) == 64 and len({v & 63 for v in bwd}) == 64
+
+
+def test_next_configuration_is_not_mistaken_for_the_current_one():
+    """Multiplex reconfiguration (EN 300 401 sec. 6.4): FIG 0/1 / 0/2 sent with C/N = 1 announce the NEXT configuration and must not
+    enter the sub-channel table the MSC is decoded with, nor the service list, before the change; after it both hold the new entries."""
+    ens = synth.config1_ensemble(seed=31)
+    ens.reconfig = dict(at=140, lead=80, subchannels=[synth.SubChannel(9, 200, "dabplus", 64, ("EEP", 3, "A"), seed=3109)],
+                        services=[synth.Service(0x1234, "ADDED SERVICE", 9)])
+    _, _, truth = synth.build_cif_bits(ens, 200, 5)
+    fibs = truth["fibs"].reshape(-1, 32)
+    announced = fibs[3 * 60:3 * 139]
+    assert any(f[0] == 0x06 and f[4] >> 6 == 3 for f in announced)                # FIG 0/0 with change flags + occurrence change
+    assert any((f[i] & 0xE0) == 0 and f[i + 1] == 0x81 for f in announced for i in range(0, 8) if f[i] != 0xFF)   # FIG 0/1 with C/N = 1
+    assert [s.subch_id for s in pipeline.parse_subch(fibs[:3 * 139])] == [3]
+    assert [s.subch_id for s in pipeline.parse_subch(fibs)] == [3, 9]
+    e = pipeline.parse_ensemble(fibs[:3 * 136])
+    assert [s["sid"] for s in e["services"]] == [0x1001]
+    e = pipeline.parse_ensemble(fibs)
+    assert sorted(s["sid"] for s in e["services"]) == [0x1001, 0x1234]
+    assert [s["label"].rstrip() for s in e["services"] if s["sid"] == 0x1234] == ["ADDED SERVICE"]
