@@ -224,3 +224,38 @@ def test_next_configuration_is_not_mistaken_for_the_current_one():
     e = pipeline.parse_ensemble(fibs)
     assert sorted(s["sid"] for s in e["services"]) == [0x1001, 0x1234]
     assert [s["label"].rstrip() for s in e["services"] if s["sid"] == 0x1234] == ["ADDED SERVICE"]
+
+
+def test_chunk_chaining_and_core_partition():
+    """Host logic of the time-chunked decode (shard.decode_chunked) and of the per-rank core slices (shard.bind_to_gpu)."""
+    from abracadabra_b200 import shard
+    T = shard.T_FRAME
+    # 3 chunks of one recording: frames every T samples from 5000 on, the overlaps found twice, one frame lost in chunk 1
+    t_all = [5000 + k * T for k in range(40)]
+    c0 = t_all[:16]
+    c1 = [t for t in t_all[10:30] if t != t_all[20]]
+    slots1 = {t: (t - c1[0] + T // 2) // T for t in c1}
+    a1 = [-1] * (max(slots1.values()) + 1)
+    for t, s in slots1.items():
+        a1[s] = t
+    c2 = t_all[25:40]
+    chain, slot0 = shard.chain_frames([c0, a1, c2])
+    assert slot0 == [0, 10, 25]
+    got = [g for _, _, g in chain]
+    assert got == [k for k in range(40) if k != 20]                      # every frame once, the lost one leaves a gap
+    assert [c for c, _, _ in chain] == [0] * 16 + [1] * 13 + [2] * 10    # a frame is taken from the first chunk that has it
+    # frame numbering that disagrees between a chunk and the recording is an error, not silently merged
+    bad = [c0, [t + 3 * T // 2 if i > 8 else t for i, t in enumerate(t_all[10:30])], c2]
+    with pytest.raises(RuntimeError):
+        shard.chain_frames(bad)
+    r = shard.chunk_recording(60 * 2048000, 4)
+    assert r[0][0] == 0 and r[-1][1] == 60 * 2048000 and all(a % shard.CHUNK_ALIGN == 0 for a, _ in r)
+    assert all(r[i][1] - r[i + 1][0] >= shard.CHUNK_OVERLAP_FRAMES * T for i in range(3))
+    # eight GPUs reporting the same 32 local cores get eight disjoint slices of four; two NUMA halves are split separately
+    same = [list(range(32))] * 8
+    parts = [shard.partition_cpus(same, g) for g in range(8)]
+    assert sorted(c for p in parts for c in p) == list(range(32)) and all(len(p) == 4 for p in parts)
+    numa = [list(range(0, 16))] * 4 + [list(range(16, 32))] * 4
+    parts = [shard.partition_cpus(numa, g) for g in range(8)]
+    assert parts[0] == [0, 1, 2, 3] and parts[4] == [16, 17, 18, 19] and sorted(c for p in parts for c in p) == list(range(32))
+    assert shard.partition_cpus([[0, 1]] * 4, 3) == [0, 1]                  # fewer cores than ranks: left alone

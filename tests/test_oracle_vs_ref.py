@@ -166,3 +166,36 @@ def test_spectrum_callback_is_power_spectrum_of_raw_blocks():
         # the orc FFT (the arithmetic the CUDA kernel mirrors) gives the same bins
         Q = np.abs(orc.fft2048(x[w0:w0 + 2048].astype(np.complex64))) ** 2
         assert np.abs(Q / Q.max() - P / P.max()).max() < 1e-5
+
+
+def test_uep_table_index_23_follows_the_standard():
+    """the UEP table inside the reference binary has PI2 = 7 for index 23 (80 kbit/s, level 1, 84 CU) where EN 300 401
+    table 8 -- and the arithmetic of the sizes -- say 17.  Decided by experiment and documented here: for a sub-channel coded per the
+    standard (PI 24 / 17 / 12 / 18) the reference core gets the first segment (192 bits: header and ISO CRC, so its crcOk counter is
+    happy) and then garbage from the first bit of the second segment on -- it really de-punctures with 7.  This path (csrc/tables.h)
+    follows the standard: the checker decodes the same file to the transmitted frames.  Index 23 is therefore the one place where
+    'identical to the reference' is deliberately not the bar."""
+    if not orc.have_ref():
+        pytest.skip("reference core not built (oracle/_ref)")
+    import tempfile
+    from pathlib import Path
+    from abracadabra_b200 import synth
+    sub = synth.SubChannel(5, 0, "mp2", 80, ("UEP", 23), seed=7)
+    assert sub.profile()[0][1] == (10, 17)
+    ens = synth.EnsembleConfig(eid=0x2323, label="UEP23", subchannels=[sub], services=[synth.Service(0x2323, "UEP 23 SVC", 5)])
+    raw, res = synth.synthesize(ens, 24, "u8", synth.Impairments(snr_db=30.0, cfo_hz=10.0, seed=2), seed=2, tail=150000)
+    with tempfile.TemporaryDirectory() as td:
+        p = Path(td) / "u.u8"
+        raw.tofile(p)
+        summ, ev = orc.run_ref(p, "u8", Path(td) / "log.jsonl", service=0, extra=["--tail-frames", "12"])
+    sc = [e for e in ev if e["ev"] == "sc_list"][0]["items"][0]
+    assert (sc["uep_fec"], sc["size"], sc["bitrate"]) == (23, 84, 80)
+    au = [np.frombuffer(bytes.fromhex(e["data"]), np.uint8) for e in ev if e["ev"] == "audio" and e["len"] > 0]
+    assert len(au) >= 40 and summ["crc_err"] == 0
+    truth = res.logical[5]
+    for a in au[3:12]:
+        f = next(f for f in truth if np.array_equal(f[:16], a[:16]))             # header + first segment are right ...
+        diff = np.nonzero(f != a)[0]
+        assert diff.size > 100 and diff[0] == 24                                  # ... the rest is not: it breaks at bit 192 = segment 2
+    o = orc.decode(raw, "u8", [orc.subch_struct(sub)])
+    assert np.array_equal(o["frames"][0], truth[:o["frames"][0].shape[0]])
