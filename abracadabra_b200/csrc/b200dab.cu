@@ -84,12 +84,17 @@ struct b200dab_ctx {
     int launches = 0;
     cudaEvent_t ev_msc = nullptr, ev_d2h = nullptr;   // ordering of the split device-to-host copy of the logical frames
     cudaEvent_t ev_rs = nullptr, ev_tii = nullptr;    // behind k_rs_decode (DAB+ frames final) / behind k_tii_detect
-    int vit_ctas_per_sm = 3;       // persistent k_viterbi CTAs (four warps, one per sub-partition) per SM (tools/vit_split_sweep.py sweeps this)
+    int vit_ctas_per_sm = 2;       // persistent k_viterbi CTAs (four warps, one per sub-partition) per SM (tools/vit_split_sweep.py sweeps this)
     int n_sm = 148;
     DevBuf d_vit_counter;          // work queue heads of k_viterbi, one per table set + one for the stage entry point; zero between launches
+    // Dynamic shared memory nobody uses, sized so that exactly vit_ctas_per_sm CTAs fit on an SM: the persistent CTAs are then spread
+    // evenly however the SMs drain from the kernel in front (without it the block scheduler may pile four of them on the SMs that
+    // are free first and leave others with one: the work queue evens out the items, not the issue slots).
+    bool vit_smem_cap = true;
+    size_t vit_dyn_smem() const { return vit_smem_cap ? (size_t)(227 * 1024 / vit_ctas_per_sm) - sizeof(uint32_t) * VIT_CTA_WARPS * 2 * VIT_NORM_PERIOD * 32 - 2048 : 0; }
     unsigned vit_grid(size_t n_items) const { return (unsigned)std::min<size_t>((size_t)n_sm * vit_ctas_per_sm, (n_items + VIT_CTA_WARPS - 1) / VIT_CTA_WARPS); }
     // constant tables on the device
-    DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin;
+    DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin, d_naus;   // d_gf: SfTables of k_sf_decode; d_naus: access units per superframe slot
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
     DevBuf d_jobs, d_groups, d_items, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out, d_aus, d_totals;
@@ -193,16 +198,19 @@ struct b200dab_ctx {
     // device-side stages (all asynchronous on `stream` unless noted)
     int upload_raw(const void* iq, uint64_t n, int fmt, int mem, const void** d_out);
     int coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, int* max_cand_out);
-    int fine(const void* d_iq, uint64_t n, int fmt, int n_cand);
+    int fine(const void* d_iq, uint64_t n, int fmt, int grid, int max_cand, long long range_off, int chain_range_idx, int max_slots);
     int prepare_slots(int max_slots, bool want_stat, bool want_tii);
-    int demod(const void* d_iq, uint64_t n_visible, int fmt, int first, int count, bool want_stat, bool want_tii);
-    int tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int first, int count);
+    int demod(const void* d_iq, uint64_t n_visible, int fmt, int range_idx, int skip, int limit, int bound, bool want_stat, bool want_tii);
+    int tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int range_idx, int skip, int limit, int bound);
+    DevBuf d_chain, d_frame_cir;       // ChainState + per-frame CIR ratio, written by the last CTA of k_fine_sync
+    HostBuf h_chain, h_frame_cir;
+    cudaEvent_t ev_chain = nullptr, ev_frames = nullptr;
+    int fe_ranges = 0;                 // front-end ranges queued in this call
     bool defer_tii_fold = false;   // single-range decode: the fold is launched after the FIC so that it runs while the host parses the FIGs
     cudaEvent_t ev_fic = nullptr;
     int front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len, bool want_stat, bool want_tii, int max_slots);
     // front-end state across the ranges of one decode
-    size_t fe_frames = 0; long long fe_t0 = 0, fe_last = 0; int fe_candidates = 0;
-    std::vector<float> fe_cir;
+    size_t fe_frames = 0; int fe_candidates = 0;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
     int run_viterbi(const std::vector<VitJob>& jobs_in, const std::vector<uint32_t>& stepinfo, uint8_t* d_out);
@@ -305,10 +313,34 @@ int b200dab_ctx::init_tables()
     dabtab::prbs_words(pw.data(), 512);
     CK(d_prbs_w.ensure(pw.size() * 4));
     CK(cudaMemcpy(d_prbs_w.p, pw.data(), pw.size() * 4, cudaMemcpyHostToDevice));
-    GfTables gf;
-    dabtab::gf_tables(gf.exp, gf.log);
-    CK(d_gf.ensure(sizeof gf));
-    CK(cudaMemcpy(d_gf.p, &gf, sizeof gf, cudaMemcpyHostToDevice));
+    {   // tables of k_sf_decode: GF(2^8), t * g(x) of the RS(120,110) generator, CRC-16 slicing by four
+        static SfTables tb;
+        dabtab::gf_tables(tb.gf.exp, tb.gf.log);
+        auto mul = [&](uint8_t a, uint8_t b) -> uint8_t { return (a && b) ? tb.gf.exp[tb.gf.log[a] + tb.gf.log[b]] : 0; };
+        uint8_t g[12] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};           // g = 1, then times (x + alpha^i), i = 0..9
+        for (int i = 0; i < 10; i++) {
+            const uint8_t a = tb.gf.exp[i];
+            for (int j = i + 1; j > 0; j--) g[j] = g[j - 1] ^ mul(g[j], a);
+            g[0] = mul(g[0], a);
+        }
+        for (int t = 0; t < 256; t++) {
+            uint32_t w[3] = {0, 0, 0};
+            for (int j = 0; j < 10; j++) w[j >> 2] |= (uint32_t)mul((uint8_t)t, g[j]) << (8 * (j & 3));
+            tb.fb[t][0] = w[0]; tb.fb[t][1] = w[1]; tb.fb[t][2] = w[2];
+        }
+        for (int i = 0; i < 256; i++) {
+            uint32_t c = (uint32_t)i << 8;
+            for (int b = 0; b < 8; b++) c = (c & 0x8000u) ? ((c << 1) ^ 0x1021u) & 0xffffu : (c << 1) & 0xffffu;
+            tb.crc[0][i] = (uint16_t)c;
+        }
+        for (int k = 1; k < 4; k++)
+            for (int i = 0; i < 256; i++) {
+                const uint32_t c = tb.crc[k - 1][i];
+                tb.crc[k][i] = (uint16_t)(((c << 8) & 0xffffu) ^ tb.crc[0][c >> 8]);
+            }
+        CK(d_gf.ensure(sizeof tb));
+        CK(cudaMemcpy(d_gf.p, &tb, sizeof tb, cudaMemcpyHostToDevice));
+    }
     uint8_t pat[70];
     dabtab::tii_patterns(pat);
     CK(cudaMemcpyToSymbol(c_tii_pattern, pat, 70));
@@ -327,6 +359,7 @@ int b200dab_ctx::upload_raw(const void* iq, uint64_t n, int fmt, int mem, const 
 }
 
 // ------------------------------------------------------------------------------------------------ coarse sync
+// block powers, then one launch for window sums, candidate test and the sorted candidate list (d_cand, d_ncand)
 int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, int* max_cand_out)
 {
     const int64_t nblk = (int64_t)(n / SYNC_BLK);
@@ -334,48 +367,58 @@ int b200dab_ctx::coarse(const void* d_iq, uint64_t n, int fmt, int* n_cand_out, 
     *max_cand_out = max_cand;
     if (n_cand_out) *n_cand_out = 0;
     if (nblk <= 0) return 0;
+    const unsigned tiles = (unsigned)((nblk + CO_TILE - 1) / CO_TILE);
     CK(d_P.ensure((size_t)nblk * 4));
     CK(d_S.ensure((size_t)nblk * 4));
-    CK(d_cand_raw.ensure((size_t)max_cand * 8));
+    CK(d_cand_raw.ensure((size_t)tiles * (CO_CAP * 8 + 4)));
     CK(d_cand.ensure((size_t)max_cand * 8));
-    CK(d_ncand.ensure(4));
-    CK(cudaMemsetAsync(d_ncand.p, 0, 4, stream));
-    const unsigned grid = (unsigned)((nblk + 255) / 256);
+    CK(d_ncand.ensure(16));                                   // [0] candidates, [1] ticket of k_coarse, [2] ticket of k_fine_sync
+    CK(cudaMemsetAsync(d_ncand.p, 0, 16, stream));
+    long long* tile_list = d_cand_raw.as<long long>();
+    int* tile_cnt = reinterpret_cast<int*>(tile_list + (size_t)tiles * CO_CAP);
+    int* nc = d_ncand.as<int>();
+    const unsigned pgrid = (unsigned)((nblk + 255) / 256);
     prof_begin("k_block_power");
-    if (fmt == B200DAB_FMT_U8) k_block_power<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
-    else if (fmt == B200DAB_FMT_S16) k_block_power<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
-    else k_block_power<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    if (fmt == B200DAB_FMT_U8) k_block_power<B200DAB_FMT_U8><<<pgrid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    else if (fmt == B200DAB_FMT_S16) k_block_power<B200DAB_FMT_S16><<<pgrid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
+    else k_block_power<B200DAB_FMT_F32><<<pgrid, 256, 0, stream>>>(d_iq, nblk, d_P.as<float>());
     prof_end();
-    prof_begin("k_window_sum+k_candidates+k_sort_small");
-    k_window_sum<<<(unsigned)((nblk + 256 * WSUM_PER_THREAD - 1) / (256 * WSUM_PER_THREAD)), 256, 0, stream>>>(d_P.as<float>(), nblk, d_S.as<float>());
-    k_candidates<<<grid, 256, 0, stream>>>(d_S.as<float>(), nblk, (int64_t)n, d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand);
-    k_sort_small<<<1, 256, 0, stream>>>(d_cand_raw.as<long long>(), d_ncand.as<int>(), max_cand, d_cand.as<long long>());
+    prof_begin("k_coarse");
+    k_coarse<<<tiles, 256, 0, stream>>>(d_P.as<float>(), nblk, (int64_t)n, d_S.as<float>(), tile_list, tile_cnt, nc + 1, d_cand.as<long long>(), nc, max_cand);
     prof_end();
-    launches += 4;
+    launches += 1;
+    launches += 1;
     CK(cudaGetLastError());
     if (n_cand_out) {                     // stage entry point: the caller wants the count now
-        int nc = 0;
-        CK(cudaMemcpyAsync(&nc, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
+        int c = 0;
+        CK(cudaMemcpyAsync(&c, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        if (nc > max_cand) nc = max_cand;
-        *n_cand_out = nc;
+        if (c > max_cand) c = max_cand;
+        *n_cand_out = c;
     }
     return 0;
 }
 
-int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
+// Fine synchronisation of the candidates in d_cand (grid CTAs take them in turn); with chain_range >= 0 the last CTA chains the
+// frames on the device (d_chain, d_frames, d_frame_cir), range_off = first sample of the range inside the recording.
+int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int grid, int max_cand, long long range_off, int chain_range_idx, int max_slots)
 {
-    if (n_cand <= 0) return 0;
-    CK(d_fine.ensure((size_t)n_cand * sizeof(FineOut)));
+    if (grid <= 0) return 0;
+    CK(d_fine.ensure((size_t)max_cand * sizeof(FineOut)));
     const float2* tw = d_tw.as<float2>();
     const int8_t* prs = d_prs_q.as<int8_t>();
+    ChainState* ch = chain_range_idx >= 0 ? d_chain.as<ChainState>() : nullptr;
+    int* nc = d_ncand.as<int>();
     prof_begin("k_fine_sync");
     if (fmt == B200DAB_FMT_U8)
-        k_fine_sync<B200DAB_FMT_U8><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>());
+        k_fine_sync<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), nc, max_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>(),
+                                                              range_off, chain_range_idx, max_slots, ch, d_frames.as<FrameInfo>(), d_frame_cir.as<float>(), nc + 2);
     else if (fmt == B200DAB_FMT_S16)
-        k_fine_sync<B200DAB_FMT_S16><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>());
+        k_fine_sync<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), nc, max_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>(),
+                                                               range_off, chain_range_idx, max_slots, ch, d_frames.as<FrameInfo>(), d_frame_cir.as<float>(), nc + 2);
     else
-        k_fine_sync<B200DAB_FMT_F32><<<n_cand, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), d_ncand.as<int>(), n_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>());
+        k_fine_sync<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, (int64_t)n, d_cand.as<long long>(), nc, max_cand, tw, prs, d_cls_bin.as<uint16_t>(), d_fine.as<FineOut>(),
+                                                               range_off, chain_range_idx, max_slots, ch, d_frames.as<FrameInfo>(), d_frame_cir.as<float>(), nc + 2);
     prof_end();
     launches += 1;
     CK(cudaGetLastError());
@@ -383,13 +426,18 @@ int b200dab_ctx::fine(const void* d_iq, uint64_t n, int fmt, int n_cand)
 }
 
 // ------------------------------------------------------------------------------------------------ OFDM demod
-// soft-bit / statistics / TII buffers for up to max_slots frames
+// soft-bit / statistics / TII buffers for up to max_slots frames; the frame chain of the call starts empty
 int b200dab_ctx::prepare_slots(int max_slots, bool want_stat, bool want_tii)
 {
-    CK(d_frames.ensure((size_t)max_slots * sizeof(FrameInfo)));
-    CK(h_frames.ensure((size_t)max_slots * sizeof(FrameInfo)));
+    CK(d_frames.ensure((size_t)(max_slots + 1) * sizeof(FrameInfo)));
+    CK(d_frame_cir.ensure((size_t)(max_slots + 1) * 4));
+    CK(h_frames.ensure((size_t)(max_slots + 1) * sizeof(FrameInfo)));
+    CK(h_frame_cir.ensure((size_t)(max_slots + 1) * 4));
+    CK(h_chain.ensure(sizeof(ChainState)));
+    CK(d_chain.ensure(sizeof(ChainState)));
+    CK(cudaMemsetAsync(d_chain.p, 0, 32, stream));            // counters; range_first[] is written before it is read
     // Every frame that is found writes all of its soft bits; only the slots of LOST frames have to read as erasures, and those are
-    // cleared where the frames are chained (front_end) -- not the whole buffer (144 MB for 60 s) on every call.
+    // cleared by the demodulation CTAs of the frame behind the gap -- not the whole buffer (144 MB for 60 s) on every call.
     CK(d_soft.ensure((size_t)max_slots * DAB_FRAME_SOFT + 256));
     if (want_stat) {
         CK(d_symstat.ensure((size_t)max_slots * 150 * 4));
@@ -404,48 +452,50 @@ int b200dab_ctx::prepare_slots(int max_slots, bool want_stat, bool want_tii)
     return 0;
 }
 
-// OFDM demodulation (and TII fold) of frames [first, first + count) of h_frames; n_visible = samples valid in d_iq
-int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int first, int count, bool want_stat, bool want_tii)
+// OFDM demodulation (and TII fold) of the frames of range `range_idx` of the device-side chain (< 0: all frames), leaving out `skip`
+// frames at the front and taking at most `limit`; `bound` = upper bound of the number of frames (grid size); n_visible = samples
+// valid in d_iq
+int b200dab_ctx::demod(const void* d_iq, uint64_t n_visible, int fmt, int range_idx, int skip, int limit, int bound, bool want_stat, bool want_tii)
 {
-    if (count <= 0) return 0;
-    // The kernels read the (16-byte) frame descriptors straight from pinned host memory (unified addressing): an H2D copy
-    // here would queue on the copy engine behind the bulk IQ upload and serialise the whole front end with it.
-    const FrameInfo* dfr = h_frames.as<FrameInfo>() + first;
+    if (bound <= 0) return 0;
+    const FrameInfo* dfr = d_frames.as<FrameInfo>();
+    const ChainState* ch = d_chain.as<ChainState>();
     float* st = want_stat ? d_symstat.as<float>() : nullptr;
-    const unsigned grid = (unsigned)count * OFDM_GROUPS;
+    const unsigned grid = (unsigned)bound * OFDM_GROUPS;
     const float2* tw = d_tw.as<float2>();
     const uint16_t* fp = d_fdi_pos.as<uint16_t>();
     const int64_t n = (int64_t)n_visible;
     cudaStream_t stream = S();
     prof_begin("k_ofdm_demod");
-    if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
-    else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
-    else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, n, dfr, tw, fp, d_soft.as<int8_t>(), st);
+    if (fmt == B200DAB_FMT_U8) k_ofdm_demod<B200DAB_FMT_U8><<<grid, 256, 0, stream>>>(d_iq, n, dfr, ch, range_idx, skip, limit, tw, fp, d_soft.as<int8_t>(), st);
+    else if (fmt == B200DAB_FMT_S16) k_ofdm_demod<B200DAB_FMT_S16><<<grid, 256, 0, stream>>>(d_iq, n, dfr, ch, range_idx, skip, limit, tw, fp, d_soft.as<int8_t>(), st);
+    else k_ofdm_demod<B200DAB_FMT_F32><<<grid, 256, 0, stream>>>(d_iq, n, dfr, ch, range_idx, skip, limit, tw, fp, d_soft.as<int8_t>(), st);
     prof_end();
     launches += 1;
     CK(cudaGetLastError());
     if (want_tii && !defer_tii_fold) {                    // the fold only reads the samples: it stays on the main stream
         cudaStream_t keep = cur;
         cur = nullptr;
-        const int rc = tii_fold(d_iq, n_visible, fmt, first, count);
+        const int rc = tii_fold(d_iq, n_visible, fmt, range_idx, skip, limit, bound);
         cur = keep;
         return rc;
     }
     return 0;
 }
 
-// null-symbol spectra of frames [first, first + count), folded to the 384 TII bins
-int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int first, int count)
+// null-symbol spectra of the same selection of frames, folded to the 384 TII bins
+int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int range_idx, int skip, int limit, int bound)
 {
-    if (count <= 0) return 0;
-    const FrameInfo* dfr = h_frames.as<FrameInfo>() + first;
+    if (bound <= 0) return 0;
+    const FrameInfo* dfr = d_frames.as<FrameInfo>();
+    const ChainState* ch = d_chain.as<ChainState>();
     const float2* tw = d_tw.as<float2>();
     const int64_t n = (int64_t)n_visible;
     cudaStream_t stream = S();
     prof_begin("k_tii_fold");
-    if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
-    else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
-    else k_tii_fold<B200DAB_FMT_F32><<<count, 256, 0, stream>>>(d_iq, n, dfr, tw, d_fold.as<float>(), d_norm.as<float>());
+    if (fmt == B200DAB_FMT_U8) k_tii_fold<B200DAB_FMT_U8><<<bound, 256, 0, stream>>>(d_iq, n, dfr, ch, range_idx, skip, limit, tw, d_fold.as<float>(), d_norm.as<float>());
+    else if (fmt == B200DAB_FMT_S16) k_tii_fold<B200DAB_FMT_S16><<<bound, 256, 0, stream>>>(d_iq, n, dfr, ch, range_idx, skip, limit, tw, d_fold.as<float>(), d_norm.as<float>());
+    else k_tii_fold<B200DAB_FMT_F32><<<bound, 256, 0, stream>>>(d_iq, n, dfr, ch, range_idx, skip, limit, tw, d_fold.as<float>(), d_norm.as<float>());
     prof_end();
     launches += 1;
     CK(cudaGetLastError());
@@ -454,16 +504,18 @@ int b200dab_ctx::tii_fold(const void* d_iq, uint64_t n_visible, int fmt, int fir
 
 // FIC of the first `early_frames` frames on the FIC stream, behind their demodulation: FIG 0/1 and 0/2 repeat every few frames, so
 // the sub-channel organisation is known (and the MSC chain can be queued) while the rest of the recording is still demodulated.
+// Queued blindly (the frame list is still on the device): whether the slice is usable -- more than early_frames frames, none of the
+// first ones lost -- is decided by the host when it has the list; an unusable slice is simply ignored.
 int b200dab_ctx::early_fic(const void* d_iq, uint64_t n_visible, int fmt, bool want_stat, bool want_tii)
 {
     const int k = early_frames;
     // The first frames are demodulated on the FIC stream as well, next to the rest of the recording on the main stream (64 CTAs on
     // their own would leave the GPU idle for the length of a demodulation CTA).  The FIC stream joins the main stream here (buffers
-    // cleared at the start of the call) and the main stream waits for these frames before anything reads the soft bits.
+    // cleared at the start of the call, frames chained) and the main stream waits for these frames before anything reads the soft bits.
     // (ev_early_demod was recorded on the main stream before the rest of the recording was queued there)
     CK(cudaStreamWaitEvent(fic_stream, ev_early_demod, 0));
     cur = fic_stream;
-    int rc = demod(d_iq, n_visible, fmt, 0, k, want_stat, want_tii);
+    int rc = demod(d_iq, n_visible, fmt, 0, 0, k, k, want_stat, want_tii);
     if (!rc) rc = cudaEventRecord(ev_early_done, fic_stream) == cudaSuccess ? 0 : -1;
     if (!rc) rc = fic(k, true);
     cur = nullptr;
@@ -478,61 +530,31 @@ int b200dab_ctx::early_fic(const void* d_iq, uint64_t n_visible, int fmt, bool w
     return 0;
 }
 
-// Front end over the sample range [off, off + len) of the device buffer: coarse sync, fine sync, host-side chaining with the
-// frames found so far, OFDM demodulation of the new frames.  Ranges must come in ascending order and overlap by more than
-// one frame so that a frame cut by a range boundary is found whole in the next range.
+// Front end over the sample range [off, off + len) of the device buffer: coarse sync, fine sync + chaining with the frames found so
+// far (on the device), OFDM demodulation of the new frames -- queued without a host round trip; the host reads the frame list once,
+// behind the last range.  Ranges must come in ascending order and overlap by more than one frame so that a frame cut by a range
+// boundary is found whole in the next range.
 int b200dab_ctx::front_end(const void* d_iq, int fmt, uint64_t off, uint64_t len, bool want_stat, bool want_tii, int max_slots)
 {
     const uint8_t* base = reinterpret_cast<const uint8_t*>(d_iq) + off * fmt_bytes(fmt);
-    int n_cand = 0, max_cand = 0;
+    const int range_idx = fe_ranges;
+    if (range_idx >= CHAIN_MAX_RANGES) { set_error("too many front-end ranges in one call"); return -1; }
+    int max_cand = 0;
     if (coarse(base, len, fmt, nullptr, &max_cand)) return -1;
     if (max_cand <= 0) return 0;
-    // fine sync is launched for an upper bound of candidates (CTAs beyond the device-side count exit at once), so the
-    // candidate count and the results come back with a single synchronisation
-    int bound = std::min(max_cand, 2 * (int)(len / DAB_T_FRAME) + 64);
-    for (int pass = 0; pass < 2; pass++) {
-        if (fine(base, len, fmt, bound)) return -1;
-        CK(h_fine.ensure((size_t)bound * sizeof(FineOut) + 16));
-        CK(h_misc.ensure(64));
-        CK(cudaMemcpyAsync(h_misc.p, d_ncand.p, 4, cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(h_fine.p, d_fine.p, (size_t)bound * sizeof(FineOut), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        if (g_trace) fprintf(stderr, "[trace] %-28s %.3f ms\n", "fine synced", now_ms() - t_trace0);
-        n_cand = std::min(*h_misc.as<int>(), max_cand);
-        if (n_cand <= bound) break;
-        bound = n_cand;                   // rare: far more candidates than frames (noise-like input); run again on all of them
-    }
-    fe_candidates += n_cand;
-    if (n_cand <= 0) return 0;
-    const FineOut* f = h_fine.as<FineOut>();
-    FrameInfo* hf = h_frames.as<FrameInfo>();
-    const int first_new = (int)fe_frames;
-    for (int i = 0; i < n_cand; i++) {
-        if (!(f[i].cir_ratio >= SYNC_CIR_MIN)) continue;
-        const long long t_abs = f[i].t_f + (long long)off;
-        if (fe_frames > 0 && t_abs - fe_last < (long long)(DAB_T_FRAME * 9 / 10)) continue;       // seen already / too close
-        // slot numbers advance by the rounded distance to the previous frame (not to the first one), so a sample-clock
-        // offset that accumulates to more than half a frame over a long recording cannot shift the CIF numbering
-        if (fe_frames == 0) fe_t0 = t_abs;
-        const int slot = fe_frames == 0 ? 0 : hf[fe_frames - 1].slot + (int)((t_abs - fe_last + DAB_T_FRAME / 2) / DAB_T_FRAME);
-        if (slot >= max_slots) break;
-        const int prev_slot = fe_frames == 0 ? -1 : hf[fe_frames - 1].slot;
-        if (slot > prev_slot + 1)                                                                    // lost frames in between: erasures
-            CK(cudaMemsetAsync(d_soft.as<int8_t>() + (size_t)(prev_slot + 1) * DAB_FRAME_SOFT, 0, (size_t)(slot - prev_slot - 1) * DAB_FRAME_SOFT, stream));
-        FrameInfo fi;
-        fi.t_f = t_abs; fi.cfo_hz = f[i].cfo_hz; fi.slot = slot;
-        hf[fe_frames++] = fi;
-        fe_cir.push_back(f[i].cir_ratio);
-        fe_last = t_abs;
-    }
-    const int count = (int)fe_frames - first_new;
-    if (early_frames > 0 && !early_launched && first_new == 0 && count > early_frames && hf[early_frames - 1].slot == early_frames - 1) {
-        // the first frames on their own (no lost frame among them), the early FIC slice behind them, then the rest
+    // one CTA per candidate up to twice the frames the range can hold; more candidates than that (noise-like input) are taken in turn
+    const int bound_frames = (int)(len / DAB_T_FRAME) + 2;
+    const int grid = std::min(max_cand, 2 * bound_frames + 64);
+    if (fine(base, len, fmt, grid, max_cand, (long long)off, range_idx, max_slots)) return -1;
+    fe_ranges++;
+    CK(cudaEventRecord(ev_chain, stream));                // the frame list of everything up to this range is final here
+    if (early_frames > 0 && !early_launched && range_idx == 0 && bound_frames > early_frames + 2) {
+        // the first frames on their own, the early FIC slice behind them, then the rest
         CK(cudaEventRecord(ev_early_demod, stream));
-        if (demod(d_iq, off + len, fmt, early_frames, count - early_frames, want_stat, want_tii)) return -1;
+        if (demod(d_iq, off + len, fmt, range_idx, early_frames, 1 << 30, bound_frames, want_stat, want_tii)) return -1;
         return early_fic(d_iq, off + len, fmt, want_stat, want_tii);
     }
-    return demod(d_iq, off + len, fmt, first_new, count, want_stat, want_tii);
+    return demod(d_iq, off + len, fmt, range_idx, 0, 1 << 30, bound_frames, want_stat, want_tii);
 }
 
 // ------------------------------------------------------------------------------------------------ Viterbi (gather + ACS + traceback)
@@ -599,7 +621,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), dj, dg, vt.d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
     prof_begin(st == 0 ? "k_viterbi(fic)" : st == 2 ? "k_viterbi(early fic)" : "k_viterbi(msc)");
-    k_viterbi<<<vit_grid(vt.n_items), 32 * VIT_CTA_WARPS, 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg, vt.d_items.as<VitItem>(),
+    k_viterbi<<<vit_grid(vt.n_items), 32 * VIT_CTA_WARPS, vit_dyn_smem(), stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg, vt.d_items.as<VitItem>(),
                                                                         (int)vt.n_items, d_vit_counter.as<int>() + st);
     prof_end();
     prof_begin(st == 0 ? "k_vit_trace(fic)" : st == 2 ? "k_vit_trace(early fic)" : "k_vit_trace(msc)");
@@ -706,35 +728,26 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     CK(h_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob) + 16));
     memcpy(h_dpjobs.p, jobs.data(), jobs.size() * sizeof(DabPlusJob));
     if (fetch(d_dpjobs.p, h_dpjobs.p, jobs.size() * sizeof(DabPlusJob))) { set_error("k_fetch launch failed"); return -1; }
-    int max_rows = 0, max_sf = 0, max_cw = 0;
-    for (auto& j : jobs) { max_rows = std::max(max_rows, j.n_rows); max_sf = std::max(max_sf, j.max_sf); max_cw = std::max(max_cw, j.max_sf * j.s); }
+    int max_sf = 0;
+    for (auto& j : jobs) { max_sf = std::max(max_sf, j.max_sf); if (j.s > 24 || j.s < 1 || j.pitch != 24 * j.s) { set_error("DAB+ sub-channel bitrate out of range"); return -1; } }
     const unsigned nj = (unsigned)jobs.size();
-    prof_begin("k_firecode_scan");
-    k_firecode_scan<<<dim3((max_rows + 255) / 256, nj), 256, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>());
+    CK(d_aus.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + 64));
+    CK(d_totals.ensure(sizeof(DabPlusTotals)));
+    CK(d_naus.ensure((size_t)total_sf * 4 + 64));
+    prof_begin("k_fire_align");
+    k_fire_align<<<nj, FIRE_THREADS, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>(), d_totals.as<DabPlusTotals>());
     prof_end();
-    prof_begin("k_sf_align");
-    k_sf_align<<<nj, SF_ALIGN_THREADS, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>());
-    prof_end();
-    prof_begin("k_rs_decode");
-    k_rs_decode<<<dim3((max_cw + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<GfTables>());
+    // RS correction, fire code, access-unit table and access-unit CRCs of a superframe by one warp, in one launch
+    prof_begin("k_sf_decode");
+    k_sf_decode<<<dim3((max_sf + SF_PER_CTA - 1) / SF_PER_CTA, nj), 32 * SF_PER_CTA, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<SfTables>(),
+                                                                                              d_naus.as<int>(), d_totals.as<DabPlusTotals>());
     prof_end();
     if (ev_rs) CK(cudaEventRecord(ev_rs, stream));        // the logical frames are final from here on: the caller starts their copy
-    prof_begin("k_au_split");
-    k_au_split<<<dim3((max_sf + 63) / 64, nj), 64, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
-    prof_end();
-    prof_begin("k_au_crc");
-    k_au_crc<<<dim3((max_sf * 6 + 127) / 128, nj), 128, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>());
-    prof_end();
-    prof_begin("k_au_count+k_au_write");
     // access-unit list and RS statistics in the layout of the result, put together on the device
-    const int nb = (total_sf + 255) / 256;
-    CK(d_aus.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + 64));
-    CK(d_totals.ensure(sizeof(DabPlusTotals) + (size_t)nb * 6 * sizeof(int)));
-    int* bsum = reinterpret_cast<int*>(d_totals.as<uint8_t>() + sizeof(DabPlusTotals));
-    k_au_count<<<nb, 256, 0, stream>>>(d_sf.as<SfInfo>(), total_sf, bsum);
-    k_au_write<<<nb, 256, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, d_sf.as<SfInfo>(), total_sf, bsum, d_aus.as<AuRecord>(), d_totals.as<DabPlusTotals>());
+    prof_begin("k_au_list");
+    k_au_list<<<(total_sf + 255) / 256, 256, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, d_sf.as<SfInfo>(), d_naus.as<int>(), total_sf, d_aus.as<AuRecord>(), d_totals.as<DabPlusTotals>());
     prof_end();
-    launches += 7;
+    launches += 3;
     CK(cudaGetLastError());
     return 0;
 }
@@ -827,6 +840,8 @@ int b200dab_create(b200dab_ctx** out, int device)
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
     if (const char* e = getenv("B200DAB_VIT_CTAS")) ctx->vit_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("B200DAB_VIT_SMEMCAP")) ctx->vit_smem_cap = atoi(e) != 0;
+    cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (const char* e = getenv("B200DAB_VIT4_MIN_STEPS")) ctx->vit4_min_steps = atoi(e);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (ctx->d_vit_counter.ensure(64) != cudaSuccess || cudaMemset(ctx->d_vit_counter.p, 0, 64) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -5; }
@@ -837,6 +852,7 @@ int b200dab_create(b200dab_ctx** out, int device)
     if (cudaStreamCreateWithPriority(&ctx->fic_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return -5; }
     cudaEventCreateWithFlags(&ctx->ev_early_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_early_fic, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_early_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_frames, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_fic_stream, cudaEventDisableTiming);
     if (ctx->init_tables()) { fprintf(stderr, "b200dab: %s\n", ctx->err.c_str()); cudaStreamDestroy(ctx->stream); delete ctx; return -6; }
     *out = ctx;
@@ -848,13 +864,13 @@ void b200dab_destroy(b200dab_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
-                    &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
+    DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_naus, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
+                    &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_chain, &ctx->d_frame_cir, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
                     &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->vit_tables[0].d_items, &ctx->vit_tables[1].d_items, &ctx->vit_tables[2].d_items, &ctx->d_items, &ctx->d_vit_counter, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
+    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_chain, &ctx->h_frame_cir, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
                      &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_sfinfo, &ctx->h_flags, &ctx->h_residue};
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
@@ -1042,7 +1058,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     const bool want_tii = (flags & B200DAB_OPT_TII) != 0;
     bool deferred_tii = false;
     const int max_slots = (int)(n / DAB_T_FRAME) + 2;
-    ctx->fe_frames = 0; ctx->fe_t0 = 0; ctx->fe_last = 0; ctx->fe_candidates = 0; ctx->fe_cir.clear();
+    ctx->fe_frames = 0; ctx->fe_candidates = 0; ctx->fe_ranges = 0;
     // early sub-channel discovery pays when the sub-channels have to be found and there is an MSC to decode behind a long front end
     ctx->early_launched = false;
     ctx->cur = nullptr;
@@ -1086,20 +1102,37 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         deferred_tii = want_tii;
     }
     TRACE("front end submitted");
+    // ---- the frame list was put together on the device (last CTA of every k_fine_sync launch): it comes back on the copy stream,
+    //      behind the last chaining step, while the GPU is busy with the demodulation that was queued behind it
+    if (!ctx->copy_stream) CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (ctx->fe_ranges > 0) {
+        CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chain, 0));
+        CKC(cudaMemcpyAsync(ctx->h_chain.p, ctx->d_chain.p, 32, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CKC(cudaMemcpyAsync(ctx->h_frames.p, ctx->d_frames.p, (size_t)max_slots * sizeof(FrameInfo), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CKC(cudaMemcpyAsync(ctx->h_frame_cir.p, ctx->d_frame_cir.p, (size_t)max_slots * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CKC(cudaEventRecord(ctx->ev_frames, ctx->copy_stream));
+        CKC(cudaEventSynchronize(ctx->ev_frames));
+        TRACE("frame list on the host");
+        const ChainState* cs = ctx->h_chain.as<ChainState>();
+        ctx->fe_frames = (size_t)std::min(cs->n_frames, max_slots);
+        ctx->fe_candidates = cs->n_candidates;
+    }
     res->n_candidates = ctx->fe_candidates;
     const int n_frames = (int)ctx->fe_frames;
     const FrameInfo* frames = ctx->h_frames.as<FrameInfo>();
     const int n_slots = n_frames ? frames[n_frames - 1].slot + 1 : 0;
     res->n_frames = n_frames; res->n_slots = n_slots;
     ctx->r_tf.assign(n_slots, -1); ctx->r_cfo.assign(n_slots, 0.f); ctx->r_cir.assign(n_slots, 0.f);
-    for (int i = 0; i < n_frames; i++) { ctx->r_tf[frames[i].slot] = frames[i].t_f; ctx->r_cfo[frames[i].slot] = frames[i].cfo_hz; ctx->r_cir[frames[i].slot] = ctx->fe_cir[i]; }
+    for (int i = 0; i < n_frames; i++) { ctx->r_tf[frames[i].slot] = frames[i].t_f; ctx->r_cfo[frames[i].slot] = frames[i].cfo_hz; ctx->r_cir[frames[i].slot] = ctx->h_frame_cir.as<float>()[i]; }
     res->t_f = ctx->r_tf.data(); res->cfo_hz = ctx->r_cfo.data(); res->cir_ratio = ctx->r_cir.data();
+    // the early FIC slice was queued blindly: it is usable if its frames exist and none of them was lost
+    if (ctx->early_launched && !(n_frames > ctx->early_frames && frames[ctx->early_frames - 1].slot == ctx->early_frames - 1)) ctx->early_launched = false;
     if (n_frames == 0) { res->gpu_launches = ctx->launches; return 0; }
     if (flags & B200DAB_OPT_SPECTRUM) {
         CKC(ctx->d_spec.ensure((size_t)n_slots * 2 * DAB_NFFT * 4));
         CKC(ctx->h_spec.ensure((size_t)n_slots * 2 * DAB_NFFT * 4));
         CKC(cudaMemsetAsync(ctx->d_spec.p, 0, (size_t)n_slots * 2 * DAB_NFFT * 4, ctx->stream));
-        const FrameInfo* dfr = ctx->h_frames.as<FrameInfo>();
+        const FrameInfo* dfr = ctx->d_frames.as<FrameInfo>();
         const float2* tw = ctx->d_tw.as<float2>();
         const int64_t nn = (int64_t)n;
         ctx->prof_begin("k_spectrum");
@@ -1118,7 +1151,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     CKC(cudaStreamWaitEvent(ctx->fic_stream, ctx->ev_demod, 0));
     ctx->cur = ctx->fic_stream;
     int fic_rc = 0;
-    if (deferred_tii) fic_rc = ctx->tii_fold(d_iq, n, fmt, 0, n_frames);     // under the MSC gather instead of in front of it
+    if (deferred_tii) fic_rc = ctx->tii_fold(d_iq, n, fmt, -1, 0, 1 << 30, n_frames);     // under the MSC gather instead of in front of it
     if (!fic_rc) fic_rc = ctx->fic(n_slots);
     ctx->cur = nullptr;
     if (fic_rc) return -1;
@@ -1401,11 +1434,12 @@ int b200dab_stage_fine(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, co
     const void* d_iq;
     if (ctx->upload_raw(iq, n, fmt, B200DAB_MEM_HOST, &d_iq)) return -1;
     CKC(ctx->d_cand.ensure((size_t)n_cand * 8));
-    CKC(ctx->d_ncand.ensure(4));
+    CKC(ctx->d_ncand.ensure(16));
     CKC(cudaMemcpyAsync(ctx->d_cand.p, cand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemsetAsync(ctx->d_ncand.p, 0, 16, ctx->stream));
     CKC(cudaMemcpyAsync(ctx->d_ncand.p, &n_cand, 4, cudaMemcpyHostToDevice, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
-    if (ctx->fine(d_iq, n, fmt, n_cand)) return -1;
+    if (ctx->fine(d_iq, n, fmt, n_cand, n_cand, 0, -1, 0)) return -1;
     std::vector<FineOut> f(n_cand);
     CKC(cudaMemcpyAsync(f.data(), ctx->d_fine.p, (size_t)n_cand * sizeof(FineOut), cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
@@ -1426,7 +1460,11 @@ int b200dab_stage_demod(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, c
     if (ctx->prepare_slots(n_frames, false, false)) return -1;
     FrameInfo* fr = ctx->h_frames.as<FrameInfo>();
     for (int i = 0; i < n_frames; i++) { fr[i].t_f = t_f[i]; fr[i].cfo_hz = cfo[i]; fr[i].slot = i; }
-    if (ctx->demod(d_iq, n, fmt, 0, n_frames, false, false)) return -1;
+    ChainState* cs = ctx->h_chain.as<ChainState>();
+    cs->n_frames = n_frames; cs->n_candidates = 0; cs->last_t = 0;
+    CKC(cudaMemcpyAsync(ctx->d_frames.p, fr, (size_t)n_frames * sizeof(FrameInfo), cudaMemcpyHostToDevice, ctx->stream));
+    CKC(cudaMemcpyAsync(ctx->d_chain.p, cs, 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->demod(d_iq, n, fmt, -1, 0, 1 << 30, n_frames, false, false)) return -1;
     CKC(cudaMemcpyAsync(soft, ctx->d_soft.p, (size_t)n_frames * DAB_FRAME_SOFT, cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -42,6 +42,31 @@ __device__ __forceinline__ float2 rot_mq(float2 a, int q)
     switch (q & 3) { case 0: return a; case 1: return make_float2(a.y, -a.x); case 2: return make_float2(-a.x, -a.y); default: return make_float2(-a.y, a.x); }
 }
 
+// ------------------------------------------------------------------------------------------------ frame list (device-resident)
+struct FrameInfo {
+    long long t_f;     // FFT window start of symbol 0 (PRS)
+    float cfo_hz;
+    int slot;          // frame slot in the soft-bit buffer (gaps = lost frames)
+};
+// Frames chained on the device (k_fine_sync, last CTA): what the host used to do between the fine synchronisation and the OFDM
+// demodulation, so that no host round trip sits in the middle of the front end.  One state per decode call, ranges in ascending order.
+#define CHAIN_MAX_RANGES 2048
+struct ChainState {
+    int n_frames;                 // frames chained so far (all ranges of this call)
+    int n_candidates;             // candidates looked at so far
+    long long last_t;             // FFT window start (absolute) of the last chained frame
+    int range_first[CHAIN_MAX_RANGES + 1];   // frames [range_first[c], range_first[c + 1]) were found in range c
+};
+// frames [first, end) a launch works on: range_idx >= 0: the frames found in that range, < 0: all frames; then `skip` frames are
+// left out at the front and at most `limit` frames (counted from the unskipped start) are taken
+__device__ __forceinline__ void chain_range(const ChainState* __restrict__ chain, int range_idx, int skip, int limit, int& first, int& end)
+{
+    int a = 0, b = chain->n_frames;
+    if (range_idx >= 0) { a = chain->range_first[range_idx]; b = chain->range_first[range_idx + 1]; }
+    end = (limit < b - a) ? a + limit : b;
+    first = a + skip;
+}
+
 // ------------------------------------------------------------------------------------------------ reductions (256-thread CTAs)
 __device__ __forceinline__ float warp_sum(float v)
 {

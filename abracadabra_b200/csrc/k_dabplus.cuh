@@ -49,30 +49,59 @@ struct SfInfo {             // per superframe slot
     int header;             // superframe byte 2
 };
 
-// firecode over bytes 2..10 of every logical frame (pre-RS, like the reference, which needs it to find alignment)
-__global__ void __launch_bounds__(256) k_firecode_scan(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
-                                                       uint8_t* __restrict__ flags)
+// Result records in the layout of the C ABI (b200dab_au_t: seven int32) and the totals the host used to add up from SfInfo.
+struct AuRecord { int subch_index, superframe, cif, offset, length, crc_ok, header; };
+struct DabPlusTotals { int n_aus, superframes, rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail, pad_[2]; };
+
+// ---- GF(2^8) / 0x11D
+struct GfTables { uint8_t exp[512]; uint8_t log[256]; };
+__device__ __forceinline__ uint8_t gf_mul(const GfTables& g, uint8_t a, uint8_t b) { return (a && b) ? g.exp[g.log[a] + g.log[b]] : 0; }
+__device__ __forceinline__ uint8_t gf_inv(const GfTables& g, uint8_t a) { return g.exp[255 - g.log[a]]; }
+
+// Constant tables of the superframe kernel, built once on the host (b200dab_ctx::init_tables) and copied to shared memory per CTA:
+//   fb[t]  = t * g(x), g(x) = prod_{i < 10} (x - alpha^i): what coefficient t leaving at the top adds to the remainder (3 words = 10 bytes)
+//   crc[k][v] = CRC-16 (0x1021) state after byte v followed by k zero bytes (slicing by four)
+struct SfTables {
+    uint32_t fb[256][3];
+    uint16_t crc[4][256];
+    GfTables gf;
+};
+
+// fire code of one logical frame: CRC-16 (0x782F, init 0) over bytes 2..10 against bytes 0..1; an all-zero header never counts
+__device__ __forceinline__ int firecode_ok(const uint8_t* f)
 {
-    const DabPlusJob job = jobs[blockIdx.y];
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= job.n_rows) return;
-    const uint8_t* f = frames + job.frames_off + (size_t)r * job.pitch;
-    uint16_t fc = crc16_ccitt_dev(f + 2, 9, 0, 0x782F);
-    flags[job.flag_off + r] = (fc == (uint16_t)((f[0] << 8) | f[1])) && ((f[0] | f[1] | f[2]) != 0);
+    const uint16_t fc = crc16_ccitt_dev(f + 2, 9, 0, 0x782F);
+    return (fc == (uint16_t)((f[0] << 8) | f[1])) && ((f[0] | f[1] | f[2]) != 0);
 }
 
-// one CTA per job: pick the residue (row mod 5) with most firecode hits; mark the superframe slots
-#define SF_ALIGN_THREADS 256
-__global__ void __launch_bounds__(SF_ALIGN_THREADS) k_sf_align(const DabPlusJob* __restrict__ jobs, const uint8_t* __restrict__ flags,
-                                                               SfInfo* __restrict__ sf, int* __restrict__ residue_out)
+// One CTA per DAB+ sub-channel: fire code over bytes 2..10 of every logical frame (pre-RS, like the reference, which needs it to
+// find the alignment), the residue (row mod 5) with most hits, and the superframe slots that follow from it.  (Was two launches:
+// a scan with a thread per row and a vote with a CTA per sub-channel; the tail of a step is latency-bound, every launch counts.)
+#define FIRE_THREADS 1024
+__global__ void __launch_bounds__(FIRE_THREADS) k_fire_align(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
+                                                             uint8_t* __restrict__ flags, SfInfo* __restrict__ sf, int* __restrict__ residue_out,
+                                                             DabPlusTotals* __restrict__ totals)
 {
-    __shared__ int part[SF_ALIGN_THREADS / 32][5];
+    __shared__ int part[FIRE_THREADS / 32][5];
+    if (blockIdx.x == 0 && threadIdx.x < (int)(sizeof(DabPlusTotals) / 4)) reinterpret_cast<int*>(totals)[threadIdx.x] = 0;   // k_sf_decode / k_au_list add to it
     __shared__ int s_best;
     const DabPlusJob job = jobs[blockIdx.x];
     const int tid = threadIdx.x;
     int cnt[5] = {0, 0, 0, 0, 0};
-    for (int r = tid; r < job.n_rows; r += SF_ALIGN_THREADS)
-        if (flags[job.flag_off + r]) cnt[r % 5]++;
+    for (int r = tid; r < job.n_rows; r += FIRE_THREADS) {
+        // the first 12 bytes of the row in two loads (rows are 8-byte aligned: the pitch is a multiple of 24)
+        const uint8_t* f = frames + job.frames_off + (size_t)r * job.pitch;
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(f));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(f + 8));
+        uint8_t h[12];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { h[i] = (uint8_t)(a.x >> (8 * i)); h[4 + i] = (uint8_t)(a.y >> (8 * i)); h[8 + i] = (uint8_t)(b >> (8 * i)); }
+        const int ok = firecode_ok(h);
+        flags[job.flag_off + r] = (uint8_t)ok;
+        const int k = r % 5;
+#pragma unroll
+        for (int q = 0; q < 5; q++) cnt[q] += (k == q) ? ok : 0;
+    }
 #pragma unroll
     for (int k = 0; k < 5; k++) {
 #pragma unroll
@@ -84,8 +113,8 @@ __global__ void __launch_bounds__(SF_ALIGN_THREADS) k_sf_align(const DabPlusJob*
         int best = -1, bc = 0;
         for (int k = 0; k < 5; k++) {
             int c = 0;
-            for (int w = 0; w < SF_ALIGN_THREADS / 32; w++) c += part[w][k];
-            if (c > bc) { bc = c; best = k; }
+            for (int w = 0; w < FIRE_THREADS / 32; w++) c += part[w][k];
+            if (c > bc) { bc = c; best = k; }           // first maximum
         }
         if (job.forced_phase >= 0) best = job.forced_phase % 5;
         s_best = best;
@@ -93,7 +122,7 @@ __global__ void __launch_bounds__(SF_ALIGN_THREADS) k_sf_align(const DabPlusJob*
     }
     __syncthreads();
     const int best = s_best;
-    for (int m = tid; m < job.max_sf; m += SF_ALIGN_THREADS) {
+    for (int m = tid; m < job.max_sf; m += FIRE_THREADS) {
         SfInfo* o = sf + job.sf_off + m;
         const int row = best + 5 * m;
         o->valid = (best >= 0 && row + 5 <= job.n_rows) ? 1 : 0;
@@ -103,60 +132,14 @@ __global__ void __launch_bounds__(SF_ALIGN_THREADS) k_sf_align(const DabPlusJob*
     }
 }
 
-// ---- GF(2^8) / 0x11D
-struct GfTables { uint8_t exp[512]; uint8_t log[256]; };
-__device__ __forceinline__ uint8_t gf_mul(const GfTables& g, uint8_t a, uint8_t b) { return (a && b) ? g.exp[g.log[a] + g.log[b]] : 0; }
-__device__ __forceinline__ uint8_t gf_inv(const GfTables& g, uint8_t a) { return g.exp[255 - g.log[a]]; }
-
-// one thread per RS codeword; grid (ceil(max_sf * s / 128), n_jobs), 128 threads
-__global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
-                                                   SfInfo* __restrict__ sf, const GfTables* __restrict__ gf_g)
+// RS(120,110) correction of codeword j (bytes j, j + s, j + 2 s, ... of the superframe in shared memory); corrected bytes go to
+// `buf` and to `glob`.  Returns the number of corrected bytes (bit errors in *bit_errors), or -1 if the word is uncorrectable.
+__device__ __noinline__ int rs_correct(uint8_t* buf, uint8_t* glob, int j, int s, uint32_t w0, uint32_t w1, uint32_t w2, const GfTables& gf, int* bit_errors)
 {
-    __shared__ GfTables gf;
-    __shared__ uint8_t gen[12];                 // g(x) = prod_{i < 10} (x - alpha^i) = x^10 + gen[9] x^9 + ... + gen[0]
-    __shared__ uint32_t fb[256][3];             // fb[t] = t * (gen[0..3] | gen[4..7] | gen[8..9]): what t * g(x) adds to the remainder
-    for (int i = threadIdx.x; i < (int)sizeof(GfTables); i += blockDim.x) reinterpret_cast<uint8_t*>(&gf)[i] = reinterpret_cast<const uint8_t*>(gf_g)[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint8_t g[12] = {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};           // g = 1, then times (x + alpha^i)
-        for (int i = 0; i < 10; i++) {
-            const uint8_t a = gf.exp[i];
-            for (int j = i + 1; j > 0; j--) g[j] = g[j - 1] ^ gf_mul(gf, g[j], a);
-            g[0] = gf_mul(gf, g[0], a);
-        }
-        for (int j = 0; j < 12; j++) gen[j] = j < 10 ? g[j] : 0;
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-        uint32_t w[3] = {0, 0, 0};
-        for (int j = 0; j < 10; j++) w[j >> 2] |= (uint32_t)gf_mul(gf, (uint8_t)t, gen[j]) << (8 * (j & 3));
-        fb[t][0] = w[0]; fb[t][1] = w[1]; fb[t][2] = w[2];
-    }
-    __syncthreads();
-    const DabPlusJob job = jobs[blockIdx.y];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= job.max_sf * job.s) return;
-    const int m = idx / job.s, j = idx - m * job.s;
-    SfInfo* info = sf + job.sf_off + m;
-    if (!info->valid) return;
-    uint8_t* base = frames + job.frames_off + (size_t)info->row * job.pitch;
-    const int s = job.s, n = 120, nroots = 10;
-    // Remainder of the received word modulo g(x), Horner style: R <- R x + c - t g(x) with t the coefficient that leaves at the top.
-    // The ten remainder bytes live in three words and t g(x) is one table row, so a received byte costs three shared-memory loads
-    // instead of the twenty of ten separate syndrome recursions.  R = 0 <=> all syndromes are 0 (the common case); otherwise the
-    // syndromes are R evaluated at alpha^i, since g(alpha^i) = 0.
-    uint32_t w0 = 0, w1 = 0, w2 = 0;
-    for (int k = 0; k < n; k++) {
-        const uint32_t c = base[j + s * k];
-        const uint32_t t = (w2 >> 8) & 0xffu;
-        w2 = ((w2 << 8) | (w1 >> 24)) & 0xffffu;
-        w1 = (w1 << 8) | (w0 >> 24);
-        w0 = (w0 << 8) | c;
-        w0 ^= fb[t][0]; w1 ^= fb[t][1]; w2 ^= fb[t][2];
-    }
-    if (!(w0 | w1 | w2)) return;
+    const int n = 120, nroots = 10;
     uint8_t S[10];
     {
+        // the syndromes are the remainder evaluated at alpha^i, since g(alpha^i) = 0
         uint8_t r[10];
 #pragma unroll
         for (int q = 0; q < 10; q++) r[q] = (uint8_t)((q < 4 ? w0 : q < 8 ? w1 : w2) >> (8 * (q & 3)));
@@ -184,7 +167,7 @@ __global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames,
         for (int i = 0; i + mm < 12; i++) Lm[i + mm] ^= gf_mul(gf, coef, B[i]);
         if (2 * el <= r) { el = r + 1 - el; for (int i = 0; i < 12; i++) B[i] = T[i]; bb = d; mm = 1; } else mm++;
     }
-    if (el > nroots / 2) { atomicAdd(&info->rs_uncorrectable, 1); return; }
+    if (el > nroots / 2) return -1;
     // Chien search over the 120 positions
     int pos[5], np = 0;
     for (int k = 0; k < n; k++) {
@@ -194,7 +177,7 @@ __global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames,
         for (int i = 0; i <= el; i++) { v ^= gf_mul(gf, Lm[i], xp); xp = gf_mul(gf, xp, xinv); }
         if (v == 0) { if (np < 5) pos[np] = k; np++; }
     }
-    if (np != el) { atomicAdd(&info->rs_uncorrectable, 1); return; }
+    if (np != el) return -1;
     // Forney (first root alpha^0): e = X * Omega(X^-1) / Lambda'(X^-1)
     uint8_t Om[10];
     for (int i = 0; i < nroots; i++) {
@@ -214,144 +197,180 @@ __global__ void __launch_bounds__(128) k_rs_decode(uint8_t* __restrict__ frames,
             for (int k = 0; k < i - 1; k++) pw = gf_mul(gf, pw, xinv);
             den ^= gf_mul(gf, Lm[i], pw);
         }
-        if (den == 0) { atomicAdd(&info->rs_uncorrectable, 1); return; }
+        if (den == 0) return -1;
         ev[e] = gf_mul(gf, gf_mul(gf, X, num), gf_inv(gf, den));
     }
     int be = 0;
-    for (int e = 0; e < np; e++) { base[j + s * pos[e]] ^= ev[e]; be += __popc((unsigned)ev[e]); }
-    atomicAdd(&info->rs_corrected, np);
-    atomicAdd(&info->rs_bit_errors, be);
+    for (int e = 0; e < np; e++) {
+        const int at = j + s * pos[e];
+        buf[at] ^= ev[e];
+        glob[at] = buf[at];
+        be += __popc((unsigned)ev[e]);
+    }
+    *bit_errors = be;
+    return np;
 }
 
-// one thread per superframe slot: firecode after RS, header parse -> AU offsets (the CRCs follow in k_au_crc)
-__global__ void __launch_bounds__(64) k_au_split(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs, SfInfo* __restrict__ sf)
+
+// Everything behind the alignment in ONE launch.  A CTA takes SF_PER_CTA superframe slots of one sub-channel: its warps stage the
+// 120 s bytes of their superframes in shared memory (coalesced); then, with the whole CTA re-divided for each phase so that the lanes
+// are full, (1) one thread per RS(120,110) codeword -- SF_PER_CTA x s of them -- computes the remainder modulo g(x) (three table words
+// per received byte) and runs Berlekamp-Massey / Chien / Forney only when it is non-zero; (2) one thread per superframe checks the
+// fire code again and parses the header into the access-unit table; (3) one thread per access unit checks its CRC (slicing by four,
+// straight from shared memory: the dependent loop no longer waits for global loads).  Was four launches (k_rs_decode, k_au_split,
+// k_au_crc + the statistics), each of them short and latency-bound at the very end of a step.
+#define SF_PER_CTA 8
+#define SF_MAX_BYTES (120 * 24)            /* s <= 24 (192 kbit/s) */
+__global__ void __launch_bounds__(32 * SF_PER_CTA) k_sf_decode(uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
+                                                                SfInfo* __restrict__ sf, const SfTables* __restrict__ tabs_g,
+                                                                int* __restrict__ naus, DabPlusTotals* __restrict__ totals)
 {
+    __shared__ SfTables tabs;
+    __shared__ __align__(16) uint8_t sfbuf[SF_PER_CTA][SF_MAX_BYTES];
+    __shared__ int s_tot[5];
+    __shared__ int s_valid[SF_PER_CTA], s_row[SF_PER_CTA], s_rs[SF_PER_CTA][3], s_num[SF_PER_CTA], s_st[SF_PER_CTA][7];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (t < 5) s_tot[t] = 0;
+    if (t < SF_PER_CTA) { s_rs[t][0] = s_rs[t][1] = s_rs[t][2] = 0; s_num[t] = 0; }
+    for (int i = t; i < (int)(sizeof(SfTables) / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(&tabs)[i] = __ldg(reinterpret_cast<const uint32_t*>(tabs_g) + i);
     const DabPlusJob job = jobs[blockIdx.y];
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= job.max_sf) return;
-    SfInfo* info = sf + job.sf_off + m;
-    if (!info->valid) return;
-    const uint8_t* p = frames + job.frames_off + (size_t)info->row * job.pitch;
-    const int s = job.s;
-    const uint16_t fc = crc16_ccitt_dev(p + 2, 9, 0, 0x782F);
-    const int fok = (fc == (uint16_t)((p[0] << 8) | p[1])) && ((p[0] | p[1] | p[2]) != 0);
-    info->firecode_ok = fok;
-    info->header = p[2];
-    if (!fok) return;
-    const int dac = (p[2] >> 6) & 1, sbr = (p[2] >> 5) & 1;
-    const int num = dac ? (sbr ? 3 : 6) : (sbr ? 2 : 4);
-    const int first = dac ? (sbr ? 6 : 11) : (sbr ? 5 : 8);
-    int st[7];
-    st[0] = first;
-    for (int i = 1; i < num; i++) {
-        const int bitpos = 24 + 12 * (i - 1), byte = bitpos >> 3;
-        st[i] = (bitpos & 7) ? (((p[byte] & 0x0F) << 8) | p[byte + 1]) : ((p[byte] << 4) | (p[byte + 1] >> 4));
-    }
-    st[num] = 110 * s;
-    for (int i = 0; i < num; i++) if (st[i + 1] <= st[i] + 2 || st[i + 1] > 110 * s) return;
-    for (int i = 0; i < num; i++) { info->au_off[i] = st[i]; info->au_len[i] = st[i + 1] - st[i] - 2; info->au_ok[i] = 0; }
-    info->n_aus = num;
-}
-
-// one thread per (superframe, access unit): table-driven CRC-16 (0x1021, init 0xFFFF, inverted) over the AU payload
-__global__ void __launch_bounds__(128) k_au_crc(const uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs, SfInfo* __restrict__ sf)
-{
-    // slicing by four: tbl[k][v] = CRC state after byte v followed by k zero bytes, so four message bytes are folded in with four
-    // independent look-ups instead of a chain of four
-    __shared__ uint16_t tbl[4][256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        uint32_t c = (uint32_t)i << 8;
-#pragma unroll
-        for (int b = 0; b < 8; b++) c = (c & 0x8000u) ? ((c << 1) ^ 0x1021u) & 0xffffu : (c << 1) & 0xffffu;
-        tbl[0][i] = (uint16_t)c;
-    }
-    __syncthreads();
-    for (int k = 1; k < 4; k++) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-            const uint32_t c = tbl[k - 1][i];
-            tbl[k][i] = (uint16_t)(((c << 8) & 0xffffu) ^ tbl[0][c >> 8]);
+    const int s = job.s, bytes = 120 * s;
+    const int m0 = blockIdx.x * SF_PER_CTA;
+    {   // phase 0: warp w stages superframe m0 + w (five consecutive logical frames)
+        const int m = m0 + warp;
+        int valid = 0, row = 0;
+        if (m < job.max_sf) { const SfInfo* info = sf + job.sf_off + m; valid = info->valid && s <= 24; row = info->row; }
+        if (lane == 0) { s_valid[warp] = valid; s_row[warp] = row; }
+        if (valid) {
+            const uint8_t* glob = frames + job.frames_off + (size_t)row * job.pitch;
+            for (int i = lane * 8; i < bytes; i += 256) *reinterpret_cast<uint2*>(sfbuf[warp] + i) = *reinterpret_cast<const uint2*>(glob + i);
         }
-        __syncthreads();
-    }
-    const DabPlusJob job = jobs[blockIdx.y];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int m = idx / 6, a = idx - 6 * m;
-    if (m >= job.max_sf) return;
-    SfInfo* info = sf + job.sf_off + m;
-    if (!info->valid || a >= info->n_aus) return;
-    const uint8_t* p = frames + job.frames_off + (size_t)info->row * job.pitch + info->au_off[a];
-    const int len = info->au_len[a];
-    uint32_t crc = 0xFFFF;
-    int i = 0;
-    for (; i + 4 <= len; i += 4)
-        crc = (uint32_t)tbl[3][((crc >> 8) ^ p[i]) & 0xff] ^ tbl[2][(crc ^ p[i + 1]) & 0xff] ^ tbl[1][p[i + 2]] ^ tbl[0][p[i + 3]];
-    for (; i < len; i++) crc = ((crc << 8) & 0xffffu) ^ tbl[0][((crc >> 8) ^ p[i]) & 0xff];
-    crc = (~crc) & 0xffffu;
-    info->au_ok[a] = crc == (uint32_t)((p[len] << 8) | p[len + 1]);
-}
-
-// Result records in the layout of the C ABI (b200dab_au_t: seven int32) and the totals the host used to add up from SfInfo.
-struct AuRecord { int subch_index, superframe, cif, offset, length, crc_ok, header; };
-struct DabPlusTotals { int n_aus, superframes, rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail, pad_[2]; };
-
-// Compaction in two small launches over all superframe slots in (job, superframe) order -- the order the host loop produced:
-// k_au_count: per CTA of 256 slots, the number of access units and the partial RS statistics;
-// k_au_write: prefix over the (<= a few dozen) CTA sums + scan inside the CTA, then every slot writes its records.
-__global__ void __launch_bounds__(256) k_au_count(const SfInfo* __restrict__ sf, int total_sf, int* __restrict__ block_sums)
-{
-    __shared__ int acc[6];
-    const int t = threadIdx.x, i = blockIdx.x * 256 + t;
-    if (t < 6) acc[t] = 0;
-    __syncthreads();
-    int v[6] = {0, 0, 0, 0, 0, 0};
-    if (i < total_sf && sf[i].valid) {
-        const SfInfo* p = sf + i;
-        v[0] = p->n_aus; v[1] = 1; v[2] = p->rs_corrected; v[3] = p->rs_bit_errors; v[4] = p->rs_uncorrectable; v[5] = p->firecode_ok ? 0 : 1;
-    }
-#pragma unroll
-    for (int q = 0; q < 6; q++) {
-        int x = v[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((t & 31) == 0 && x) atomicAdd(&acc[q], x);
     }
     __syncthreads();
-    if (t < 6) block_sums[blockIdx.x * 6 + t] = acc[t];
-}
-
-__global__ void __launch_bounds__(256) k_au_write(const DabPlusJob* __restrict__ jobs, int n_jobs, const SfInfo* __restrict__ sf, int total_sf,
-                                                  const int* __restrict__ block_sums, AuRecord* __restrict__ out, DabPlusTotals* __restrict__ totals)
-{
-    __shared__ int warp_tot[8];
-    __shared__ int job_off[65], job_pitch[64], job_sub[64];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, i = blockIdx.x * 256 + t;
-    if (n_jobs > 64) n_jobs = 64;
-    if (t < n_jobs) { job_off[t] = jobs[t].sf_off; job_pitch[t] = jobs[t].pitch; job_sub[t] = jobs[t].subch_index; }
-    if (t == n_jobs) job_off[t] = total_sf;
-    int base = 0;
-    for (int b = 0; b < (int)blockIdx.x; b++) base += block_sums[b * 6];
-    if (blockIdx.x == 0 && t == 0) {
-        DabPlusTotals r = {0, 0, 0, 0, 0, 0, {0, 0}};
-        for (int b = 0; b < (int)gridDim.x; b++) {
-            const int* q = block_sums + b * 6;
-            r.n_aus += q[0]; r.superframes += q[1]; r.rs_corrected += q[2]; r.rs_bit_errors += q[3]; r.rs_uncorrectable += q[4]; r.firecode_fail += q[5];
+    // phase 1: Reed-Solomon, one thread per codeword (w, j): bytes j, j + s, j + 2 s, ... of superframe w
+    if (t < SF_PER_CTA * s) {
+        const int w = t / s, j = t - w * s;
+        if (s_valid[w]) {
+            uint8_t* buf = sfbuf[w];
+            // Remainder of the received word modulo g(x), Horner style: R <- R x + c - t g(x) with t the coefficient that leaves at the
+            // top.  R = 0 <=> all syndromes are 0 (the common case).
+            uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll 4
+            for (int k = 0; k < 120; k++) {
+                const uint32_t c = buf[j + s * k];
+                const uint32_t tt = (w2 >> 8) & 0xffu;
+                w2 = ((w2 << 8) | (w1 >> 24)) & 0xffffu;
+                w1 = (w1 << 8) | (w0 >> 24);
+                w0 = (w0 << 8) | c;
+                w0 ^= tabs.fb[tt][0]; w1 ^= tabs.fb[tt][1]; w2 ^= tabs.fb[tt][2];
+            }
+            if (w0 | w1 | w2) {
+                int be = 0;
+                uint8_t* glob = frames + job.frames_off + (size_t)s_row[w] * job.pitch;
+                const int np = rs_correct(buf, glob, j, s, w0, w1, w2, tabs.gf, &be);
+                if (np < 0) atomicAdd(&s_rs[w][2], 1);
+                else { atomicAdd(&s_rs[w][0], np); atomicAdd(&s_rs[w][1], be); }
+            }
         }
-        *totals = r;
     }
-    SfInfo info;
-    int n = 0;
-    if (i < total_sf) { info = sf[i]; if (info.valid) n = info.n_aus; }
+    __syncthreads();                                    // corrections are in shared memory
+    // phase 2: fire code after RS, header -> access-unit table, one thread per superframe
+    if (t < SF_PER_CTA && m0 + t < job.max_sf) {
+        const int m = m0 + t;
+        SfInfo* info = sf + job.sf_off + m;
+        int num = 0;
+        if (s_valid[t]) {
+            const uint8_t* buf = sfbuf[t];
+            const int fok = firecode_ok(buf);
+            int st[7] = {0, 0, 0, 0, 0, 0, 0};
+            if (fok) {
+                const int dac = (buf[2] >> 6) & 1, sbr = (buf[2] >> 5) & 1;
+                num = dac ? (sbr ? 3 : 6) : (sbr ? 2 : 4);
+                st[0] = dac ? (sbr ? 6 : 11) : (sbr ? 5 : 8);
+#pragma unroll
+                for (int i = 1; i < 6; i++) {
+                    if (i < num) {
+                        const int bitpos = 24 + 12 * (i - 1), byte = bitpos >> 3;
+                        st[i] = (bitpos & 7) ? (((buf[byte] & 0x0F) << 8) | buf[byte + 1]) : ((buf[byte] << 4) | (buf[byte + 1] >> 4));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 7; i++) if (i == num) st[i] = 110 * s;
+                bool good = true;
+#pragma unroll
+                for (int i = 0; i < 6; i++) if (i < num && (st[i + 1] <= st[i] + 2 || st[i + 1] > 110 * s)) good = false;
+                if (!good) num = 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) s_st[t][i] = st[i];
+            s_num[t] = num;
+            info->rs_corrected = s_rs[t][0]; info->rs_bit_errors = s_rs[t][1]; info->rs_uncorrectable = s_rs[t][2];
+            info->firecode_ok = fok;
+            info->header = buf[2];
+            info->n_aus = num;
+            atomicAdd(&s_tot[0], 1);
+            if (s_rs[t][0]) atomicAdd(&s_tot[1], s_rs[t][0]);
+            if (s_rs[t][1]) atomicAdd(&s_tot[2], s_rs[t][1]);
+            if (s_rs[t][2]) atomicAdd(&s_tot[3], s_rs[t][2]);
+            if (!fok) atomicAdd(&s_tot[4], 1);
+        }
+        naus[job.sf_off + m] = num;
+    }
+    __syncthreads();
+    // phase 3: access-unit CRCs, one thread per (superframe, access unit)
+    if (t < SF_PER_CTA * 6) {
+        const int w = t / 6, a = t - 6 * w;
+        if (a < s_num[w]) {
+            SfInfo* info = sf + job.sf_off + m0 + w;
+            const int my_off = s_st[w][a], my_end = s_st[w][a + 1];
+            const uint8_t* p = sfbuf[w] + my_off;
+            const int len = my_end - my_off - 2;
+            uint32_t crc = 0xFFFF;
+            int i = 0;
+            for (; i + 4 <= len; i += 4)
+                crc = (uint32_t)tabs.crc[3][((crc >> 8) ^ p[i]) & 0xff] ^ tabs.crc[2][(crc ^ p[i + 1]) & 0xff] ^ tabs.crc[1][p[i + 2]] ^ tabs.crc[0][p[i + 3]];
+            for (; i < len; i++) crc = ((crc << 8) & 0xffffu) ^ tabs.crc[0][((crc >> 8) ^ p[i]) & 0xff];
+            crc = (~crc) & 0xffffu;
+            info->au_off[a] = my_off; info->au_len[a] = len;
+            info->au_ok[a] = crc == (uint32_t)((p[len] << 8) | p[len + 1]);
+        }
+    }
+    // RS statistics: one set of global atomics per CTA
+    if (t < 5 && s_tot[t]) atomicAdd(&totals->superframes + t, s_tot[t]);     // superframes, rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail
+}
+
+// Access-unit list in (sub-channel, superframe) order -- the layout of the result (b200dab_au_t): every CTA adds up the access-unit
+// counts of the slots in front of its own 256 (a coalesced read of a few KB), scans its own, and every thread writes the records of
+// its slot.  One short, fully parallel launch instead of a count / write pair whose second half walked the CTA sums serially.
+__global__ void __launch_bounds__(256) k_au_list(const DabPlusJob* __restrict__ jobs, int n_jobs, const SfInfo* __restrict__ sf, const int* __restrict__ naus,
+                                                 int total_sf, AuRecord* __restrict__ out, DabPlusTotals* __restrict__ totals)
+{
+    __shared__ int red[8];
+    __shared__ int s_base;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int first = blockIdx.x * 256, i = first + t;
+    int before = 0;
+    for (int k = t; k < first; k += 256) before += __ldg(naus + k);
+    const int n = i < total_sf ? __ldg(naus + i) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
     int incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) warp_tot[warp] = incl;
+    if (lane == 0) red[warp] = before;
     __syncthreads();
-    int pos = base + incl - n;
-    for (int w = 0; w < warp; w++) pos += warp_tot[w];
+    if (t == 0) { int b = 0; for (int w = 0; w < 8; w++) b += red[w]; s_base = b; }
+    __syncthreads();
+    if (lane == 31) red[warp] = incl;
+    __syncthreads();
+    int pos = s_base + incl - n;
+    for (int w = 0; w < warp; w++) pos += red[w];
+    if (t == 255) atomicAdd(&totals->n_aus, pos + n - s_base);
     if (n > 0) {
         int k = 0;
-        while (k + 1 < n_jobs && i >= job_off[k + 1]) k++;
-        const int m = i - job_off[k], pitch = job_pitch[k], sub = job_sub[k];
+        while (k + 1 < n_jobs && i >= jobs[k + 1].sf_off) k++;
+        const SfInfo info = sf[i];
+        const int m = i - jobs[k].sf_off, pitch = jobs[k].pitch, sub = jobs[k].subch_index;
         for (int a = 0; a < n; a++) {
             AuRecord r;
             r.subch_index = sub; r.superframe = m; r.cif = info.row;

@@ -7,12 +7,6 @@
 #pragma once
 #include "common.cuh"
 
-struct FrameInfo {
-    long long t_f;     // FFT window start of symbol 0 (PRS)
-    float cfo_hz;
-    int slot;          // frame slot in the soft-bit buffer (gaps = lost frames)
-};
-
 #define OFDM_SYMS_PER_CTA 19
 #define OFDM_GROUPS 4
 
@@ -41,10 +35,21 @@ __device__ __forceinline__ void fft_pass_d_scatter(const float2* __restrict__ wo
     __syncthreads();
 }
 
+// slots [first, end) hold no frame (lost frames in front of the one this CTA demodulates): they read as erasures; each of the
+// frame's four CTAs clears a quarter of them.  Rare, kept out of line so that it costs the demodulation loop no registers.
+__device__ __noinline__ void ofdm_clear_lost(int8_t* __restrict__ soft, int first, int end, int gi)
+{
+    for (int sl = first; sl < end; sl++) {
+        uint4* z = reinterpret_cast<uint4*>(soft + (size_t)sl * DAB_FRAME_SOFT) + gi * (DAB_FRAME_SOFT / 16 / OFDM_GROUPS);
+        for (int i = threadIdx.x; i < DAB_FRAME_SOFT / 16 / OFDM_GROUPS; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+    }
+}
+
 // fdi_inv[p], p < 2048: address inside the spectrum buffer of the FFT output at logical position p of the digit-reversed result
 // (0xffff = unused bin); fdi_inv[2048 + n]: address of QPSK symbol n (a conflict-free slot inside its group of 16, see init_tables)
 template <int FMT>
 __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+                                                    const ChainState* __restrict__ chain, int range_idx, int skip, int limit,
                                                     const float2* __restrict__ tw, const uint16_t* __restrict__ fdi_inv,
                                                     int8_t* __restrict__ soft, float* __restrict__ symstat)
 {
@@ -52,16 +57,23 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
     __shared__ float2 specA[DAB_NCARR];
     __shared__ float2 specB[DAB_NCARR];
     __shared__ float red[32];
+    float2* spec = specA;
+    float2* prev = specB;
     const int t = threadIdx.x;
-    const int fi = blockIdx.x / OFDM_GROUPS, gi = blockIdx.x % OFDM_GROUPS;
+    const int gi = blockIdx.x % OFDM_GROUPS;
+    // the frame list and its length live on the device (chained by k_fine_sync): the grid is an upper bound, CTAs beyond it leave
+    int fi, f_end;
+    chain_range(chain, range_idx, skip, limit, fi, f_end);
+    fi += blockIdx.x / OFDM_GROUPS;
+    if (fi >= f_end) return;
     const FrameInfo fr = frames[fi];
+    if (fi > 0 && frames[fi - 1].slot + 1 < fr.slot) ofdm_clear_lost(soft, frames[fi - 1].slot + 1, fr.slot, gi);
+    else if (fi == 0 && fr.slot > 0) ofdm_clear_lost(soft, 0, fr.slot, gi);
     const int l_ref = OFDM_SYMS_PER_CTA * gi;
     int l_end = l_ref + OFDM_SYMS_PER_CTA;
     if (l_end > DAB_NSYM - 1) l_end = DAB_NSYM - 1;
     const double cyc_per = (double)fr.cfo_hz / (double)DAB_FS;
     const float cpp = (float)cyc_per;
-    float2* cur = specA;
-    float2* prev = specB;
     int8_t* out_frame = soft + (size_t)fr.slot * DAB_FRAME_SOFT;
 
     // thread-invariant pieces hoisted out of the symbol loop: FFT plan (addresses + 21 twiddles), de-interleaver targets of the
@@ -99,14 +111,14 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
             if (inside) fetch_symbol_fast<FMT>(rs, raw, nx); else fetch_symbol<FMT>(rs, raw, nsamp, nx);
         }
         fft2048_planned_abc_regs(work, plan, x);
-        fft_pass_d_scatter(work, plan, cur, wp);
+        fft_pass_d_scatter(work, plan, spec, wp);
         if (l > l_ref) {
             // DQPSK against the previous symbol: thread handles QPSK symbols n = t + 256 j, stored at rp[j]
             float2 y[6];
             float sabs = 0.f, ssq = 0.f;
 #pragma unroll
             for (int j = 0; j < 6; j++) {
-                const float2 v = cmul_conj(cur[rp[j]], prev[rp[j]]);
+                const float2 v = cmul_conj(spec[rp[j]], prev[rp[j]]);
                 y[j] = v;
                 sabs += fabsf(v.x) + fabsf(v.y);
                 ssq += v.x * v.x + v.y * v.y;
@@ -131,7 +143,7 @@ __global__ void __launch_bounds__(256, 3) k_ofdm_demod(const void* __restrict__ 
                 o[DAB_NCARR + 256 * j] = (int8_t)b;
             }
         }
-        // no barrier needed here: the next writes into `prev` (as the new `cur`) come after the four barriers of the next FFT
-        float2* tmp = cur; cur = prev; prev = tmp;
+        // no barrier needed here: the next writes into `prev` (as the new `spec`) come after the four barriers of the next FFT
+        { float2* tmp = spec; spec = prev; prev = tmp; }
     }
 }

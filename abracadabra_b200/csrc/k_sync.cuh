@@ -3,10 +3,10 @@
 // Replaces, inside the closed reference core, "null-symbol/PRS time sync and coarse/fine CFO estimation"
 // (observable results: dabsdrNtfPeriodic_t.freqOffset, dabsdr.h:155, and sync level).
 // Unlike the reference's per-frame tracking loop, every stage here is stateless and batch-parallel:
-//   k_block_power  : one thread per 32-sample block                       (HBM-bound: reads the whole recording once)
-//   k_window_sum   : S[b] = sum of 83 block powers                        (tiny)
-//   k_candidates   : threshold + neighbourhood maximum of the energy step (tiny)
-//   k_fine_sync    : one CTA per candidate: CP correlation, PRS FFT, integer CFO, channel impulse response
+//   k_coarse       : power of 32-sample blocks, S[b] = sum of 83 block powers, threshold + neighbourhood maximum of the energy
+//                    step, sorted candidate list -- one launch (HBM-bound: reads the whole recording once)
+//   k_fine_sync    : one CTA per candidate: CP correlation, PRS FFT, integer CFO, channel impulse response; the last CTA chains
+//                    the frames (slot numbers, lost frames) on the device
 #pragma once
 #include "common.cuh"
 
@@ -20,11 +20,10 @@ struct FineOut {
     int pad_[2];
 };
 
+// power of one 32-sample block, summed in the order of the scalar checker
 template <int FMT>
-__global__ void __launch_bounds__(256) k_block_power(const void* __restrict__ raw, int64_t nblk, float* __restrict__ P)
+__device__ __forceinline__ float block_power_one(const void* __restrict__ raw, int64_t b)
 {
-    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblk) return;
     float acc = 0.f;
     if (FMT == B200DAB_FMT_U8) {
         const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(raw) + b * 64);
@@ -62,95 +61,145 @@ __global__ void __launch_bounds__(256) k_block_power(const void* __restrict__ ra
             acc += __fmaf_rn(w.z, w.z, __fmul_rn(w.w, w.w));
         }
     }
-    P[b] = acc;
+    return acc;
 }
 
-// Four consecutive outputs per thread: every block power is read from shared memory once and added into the (up to four)
-// running sums it belongs to.  Each sum still receives its 83 terms in ascending order, one __fadd_rn at a time, so the result is
-// bit-identical to the scalar checker; the kernel goes from 83 shared-memory reads per output to 21.5.
+template <int FMT>
+__global__ void __launch_bounds__(256) k_block_power(const void* __restrict__ raw, int64_t nblk, float* __restrict__ P)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblk) P[b] = block_power_one<FMT>(raw, b);
+}
+
+// Everything of the coarse synchronisation behind the block powers in ONE launch (was window sum -> candidates -> sort): a CTA owns
+// CO_TILE consecutive blocks, fetches their powers P plus the halo the candidate test looks at (83 blocks below, 415 above) into shared
+// memory, computes the window sums S over them and runs the candidate test for its own blocks.  Candidates of a tile are at least 84
+// blocks apart (neighbourhood maximum), so a tile holds at most CO_CAP of them; they leave the CTA in ascending order, and the last CTA
+// to finish strings the tiles together: the list is sorted by construction, no atomically appended list and no sort kernel.
+// Arithmetic and summation order are those of the kernels this replaces (and of the scalar checker): each S receives its 83 terms in
+// ascending order, one __fadd_rn at a time.
+#define CO_TILE 1024
+#define CO_S_LEN (CO_TILE + 4 * SYNC_WIN)               /* S[b0 - 83 .. b0 + 1024 + 249) */
+#define CO_P_LEN (CO_S_LEN + SYNC_WIN - 1)
+#define CO_CAP 16
 #define WSUM_PER_THREAD 4
 __device__ __forceinline__ int wsum_phys(int x) { return x + (x >> 5); }       // one pad word per 32: 4-word lane strides stay conflict-free
-__global__ void __launch_bounds__(256) k_window_sum(const float* __restrict__ P, int64_t nblk, float* __restrict__ S)
+__global__ void __launch_bounds__(256) k_coarse(const float* __restrict__ P, int64_t nblk, int64_t nsamp, float* __restrict__ S,
+                                                long long* __restrict__ cand_tile, int* __restrict__ cand_cnt, int* __restrict__ ticket,
+                                                long long* __restrict__ cand, int* __restrict__ n_cand, int max_cand)
 {
-    constexpr int TILE = 256 * WSUM_PER_THREAD, NEED = TILE + SYNC_WIN + WSUM_PER_THREAD - 1;
-    __shared__ float tile[NEED + NEED / 32 + 2];
-    const int64_t b0 = (int64_t)blockIdx.x * TILE;
-    for (int i = threadIdx.x; i < NEED; i += 256) tile[wsum_phys(i)] = (b0 + i < nblk) ? __ldg(P + b0 + i) : 0.f;
+    __shared__ float sP[CO_P_LEN + CO_P_LEN / 32 + 2];
+    __shared__ float sS[CO_S_LEN];
+    __shared__ int s_list[CO_CAP];
+    __shared__ int s_n, s_last;
+    const int t = threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * CO_TILE, g0 = b0 - SYNC_WIN;      // g0: global block index of sP[0] / sS[0]
+    if (t == 0) s_n = 0;
+    for (int i = t; i < CO_P_LEN; i += 256) {
+        const int64_t g = g0 + i;
+        sP[wsum_phys(i)] = (g >= 0 && g < nblk) ? __ldg(P + g) : 0.f;
+    }
     __syncthreads();
-    const int o = threadIdx.x * WSUM_PER_THREAD;               // thread t owns outputs b0 + 4 t .. + 3
-    float acc[WSUM_PER_THREAD] = {0.f, 0.f, 0.f, 0.f};
-    // term j = i - k of output k is tile[o + i]: j ascending for every output
+    for (int quad = t; quad * WSUM_PER_THREAD < CO_S_LEN; quad += 256) {
+        const int o = quad * WSUM_PER_THREAD;                  // outputs o .. o + 3; term j = i - k of output k is sP[o + i]
+        float acc[WSUM_PER_THREAD] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < WSUM_PER_THREAD - 1; i++) {            // head: outputs k <= i have started
-        const float p = tile[wsum_phys(o + i)];
+        for (int i = 0; i < WSUM_PER_THREAD - 1; i++) {        // head: outputs k <= i have started
+            const float p = sP[wsum_phys(o + i)];
 #pragma unroll
-        for (int k = 0; k <= i; k++) acc[k] = __fadd_rn(acc[k], p);
-    }
+            for (int k = 0; k <= i; k++) acc[k] = __fadd_rn(acc[k], p);
+        }
 #pragma unroll 4
-    for (int i = WSUM_PER_THREAD - 1; i < SYNC_WIN; i++) {     // body: all four
-        const float p = tile[wsum_phys(o + i)];
+        for (int i = WSUM_PER_THREAD - 1; i < SYNC_WIN; i++) { // body: all four
+            const float p = sP[wsum_phys(o + i)];
 #pragma unroll
-        for (int k = 0; k < WSUM_PER_THREAD; k++) acc[k] = __fadd_rn(acc[k], p);
-    }
+            for (int k = 0; k < WSUM_PER_THREAD; k++) acc[k] = __fadd_rn(acc[k], p);
+        }
 #pragma unroll
-    for (int i = SYNC_WIN; i < SYNC_WIN + WSUM_PER_THREAD - 1; i++) {   // tail: outputs k > i - 83 are still open
-        const float p = tile[wsum_phys(o + i)];
+        for (int i = SYNC_WIN; i < SYNC_WIN + WSUM_PER_THREAD - 1; i++) {   // tail: outputs k > i - 83 are still open
+            const float p = (o + i < CO_P_LEN) ? sP[wsum_phys(o + i)] : 0.f;
 #pragma unroll
-        for (int k = 0; k < WSUM_PER_THREAD; k++) if (k > i - SYNC_WIN) acc[k] = __fadd_rn(acc[k], p);
-    }
+            for (int k = 0; k < WSUM_PER_THREAD; k++) if (k > i - SYNC_WIN) acc[k] = __fadd_rn(acc[k], p);
+        }
 #pragma unroll
-    for (int k = 0; k < WSUM_PER_THREAD; k++) {
-        const int64_t b = b0 + o + k;
-        if (b < nblk) S[b] = (b + SYNC_WIN <= nblk) ? acc[k] : 0.f;
+        for (int k = 0; k < WSUM_PER_THREAD; k++) {
+            const int64_t g = g0 + o + k;
+            const float v = (g >= 0 && g + SYNC_WIN <= nblk) ? acc[k] : 0.f;
+            if (o + k < CO_S_LEN) sS[o + k] = v;
+            if (o + k >= SYNC_WIN && o + k < SYNC_WIN + CO_TILE && g < nblk) S[g] = v;
+        }
     }
-}
-
-__device__ __forceinline__ float energy_step(const float* __restrict__ S, int64_t nblk, int64_t b)
-{
-    return (b + 2 * SYNC_WIN <= nblk) ? __fsub_rn(__ldg(S + b + SYNC_WIN), __ldg(S + b)) : -1e30f;
-}
-
-__device__ __forceinline__ float ratio_k(const float* __restrict__ S, int64_t nblk, int64_t b, int k)
-{
-    if (b + (int64_t)(k + 1) * SYNC_WIN <= nblk) {
-        float den = __ldg(S + b + k * SYNC_WIN);
-        if (den > 0.f) return __fdiv_rn(__ldg(S + b), den);
+    __syncthreads();
+    // candidate test for the owned blocks: null/PRS energy ratios, then the maximum of the energy step in the +-83-block neighbourhood
+    auto Sg = [&](int64_t g) -> float { return sS[(int)(g - g0)]; };
+    auto estep = [&](int64_t g) -> float { return (g + 2 * SYNC_WIN <= nblk) ? __fsub_rn(Sg(g + SYNC_WIN), Sg(g)) : -1e30f; };
+    auto ratio = [&](int64_t g, int k) -> float {
+        if (g + (int64_t)(k + 1) * SYNC_WIN <= nblk) {
+            const float den = Sg(g + k * SYNC_WIN);
+            if (den > 0.f) return __fdiv_rn(Sg(g), den);
+        }
+        return 1e30f;
+    };
+    for (int i = t; i < CO_TILE; i += 256) {
+        const int64_t b = b0 + i;
+        if (b >= nblk) break;
+        if (!(ratio(b, 1) < SYNC_THR_ACQ && ratio(b, 2) < SYNC_THR_ACQ && ratio(b, 3) < SYNC_THR_ACQ)) continue;
+        if (b * SYNC_BLK + DAB_T_FRAME + SYNC_FRAME_MARGIN > nsamp) continue;
+        int64_t lo = b - SYNC_WIN, hi = b + SYNC_WIN;
+        if (lo < 0) lo = 0;
+        if (hi >= nblk) hi = nblk - 1;
+        const float d = estep(b);
+        bool is_max = true;
+        for (int64_t j = lo; j <= hi; j++) {
+            const float dj = estep(j);
+            if (dj > d || (dj == d && j < b)) { is_max = false; break; }
+        }
+        if (!is_max) continue;
+        const int slot = atomicAdd(&s_n, 1);
+        if (slot < CO_CAP) s_list[slot] = i;
     }
-    return 1e30f;
-}
-
-// appends candidate sample positions (unordered) to cand[]; sorted afterwards by k_sort_small
-__global__ void __launch_bounds__(256) k_candidates(const float* __restrict__ S, int64_t nblk, int64_t nsamp,
-                                                    long long* __restrict__ cand, int* __restrict__ n_cand, int max_cand)
-{
-    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblk) return;
-    if (!(ratio_k(S, nblk, b, 1) < SYNC_THR_ACQ && ratio_k(S, nblk, b, 2) < SYNC_THR_ACQ && ratio_k(S, nblk, b, 3) < SYNC_THR_ACQ)) return;
-    if (b * SYNC_BLK + DAB_T_FRAME + SYNC_FRAME_MARGIN > nsamp) return;
-    int64_t lo = b - SYNC_WIN, hi = b + SYNC_WIN;
-    if (lo < 0) lo = 0;
-    if (hi >= nblk) hi = nblk - 1;
-    const float d = energy_step(S, nblk, b);
-    for (int64_t i = lo; i <= hi; i++) {
-        float di = energy_step(S, nblk, i);
-        if (di > d || (di == d && i < b)) return;
+    __syncthreads();
+    if (t == 0) {
+        int n = min(s_n, CO_CAP);
+        for (int a = 1; a < n; a++) {                            // at most a couple of dozen entries
+            const int v = s_list[a];
+            int c = a - 1;
+            while (c >= 0 && s_list[c] > v) { s_list[c + 1] = s_list[c]; c--; }
+            s_list[c + 1] = v;
+        }
+        for (int a = 0; a < n; a++) cand_tile[(size_t)blockIdx.x * CO_CAP + a] = (b0 + s_list[a]) * SYNC_BLK;
+        cand_cnt[blockIdx.x] = n;
+        __threadfence();
+        const int tk = atomicAdd(ticket, 1);
+        s_last = (tk == (int)gridDim.x - 1);
+        if (s_last) *ticket = 0;
     }
-    int slot = atomicAdd(n_cand, 1);
-    if (slot < max_cand) cand[slot] = b * SYNC_BLK;
-}
-
-// rank sort of a short list (n <= a few thousand), single CTA
-__global__ void __launch_bounds__(256) k_sort_small(const long long* __restrict__ in, const int* __restrict__ n_in, int max_n,
-                                                    long long* __restrict__ out)
-{
-    int n = *n_in;
-    if (n > max_n) n = max_n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        long long v = in[i];
-        int rank = 0;
-        for (int j = 0; j < n; j++) rank += (in[j] < v) ? 1 : 0;
-        out[rank] = v;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the last CTA: tiles in order -> one sorted list
+    __shared__ int s_run;
+    if (t == 0) s_run = 0;
+    __syncthreads();
+    const int lane = t & 31, warp = t >> 5;
+    __shared__ int wtot[8];
+    for (int base = 0; base < (int)gridDim.x; base += 256) {
+        const int tile = base + t;
+        const int n = tile < (int)gridDim.x ? __ldcg(cand_cnt + tile) : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int pos = s_run + incl - n;
+        for (int w = 0; w < warp; w++) pos += wtot[w];
+        for (int a = 0; a < n; a++)
+            if (pos + a < max_cand) cand[pos + a] = __ldcg(cand_tile + (size_t)tile * CO_CAP + a);
+        __syncthreads();
+        if (t == 0) { int sum = 0; for (int w = 0; w < 8; w++) sum += wtot[w]; s_run += sum; }
+        __syncthreads();
     }
+    if (t == 0) *n_cand = s_run;
 }
 
 // carrier pairs (c, c+1) grouped by the PRS phase step between them (class q: PRS[c+1] = PRS[c] * exp(j pi/2 q));
@@ -162,10 +211,12 @@ template <int FMT>
 __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw, int64_t nsamp, const long long* __restrict__ cand,
                                                    const int* __restrict__ n_cand_p, int max_cand, const float2* __restrict__ tw,
                                                    const int8_t* __restrict__ prs_q, const uint16_t* __restrict__ cls_bin,
-                                                   FineOut* __restrict__ out)
+                                                   FineOut* __restrict__ out,
+                                                   long long range_off, int range_idx, int max_slots, ChainState* __restrict__ chain,
+                                                   FrameInfo* __restrict__ frames, float* __restrict__ frame_cir, int* __restrict__ ticket)
 {
-    __shared__ float2 X[FFT_BUF_LEN];
-    __shared__ float2 C[FFT_BUF_LEN];
+    __shared__ __align__(16) float2 X[FFT_BUF_LEN];
+    __shared__ __align__(16) float2 C[FFT_BUF_LEN];
     __shared__ float red[32];
     __shared__ float shift_m[2 * CFO_INT_RANGE + 1];
     __shared__ int s_best, s_peak;
@@ -173,12 +224,13 @@ __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw,
 
     int n_cand = *n_cand_p;
     if (n_cand > max_cand) n_cand = max_cand;
-    const int ci = blockIdx.x;
-    if (ci >= n_cand) return;
     const int t = threadIdx.x;
-    const int64_t null_start = cand[ci];
     FftPlan plan;
     fft_plan_init(plan, tw);
+    // a CTA takes candidates blockIdx.x, blockIdx.x + gridDim.x, ...: the grid is sized for the frames a range can hold, and a range
+    // with (many) more candidates than frames -- noise-like input -- is still looked at completely
+    for (int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {
+    const int64_t null_start = cand[ci];
 
     // (a) cyclic-prefix correlation over all 76 symbols -> fractional CFO
     float sr = 0.f, si = 0.f;
@@ -317,5 +369,143 @@ __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw,
         o.tau1 = (float)tau1;
         o.pad_[0] = o.pad_[1] = 0;
         out[ci] = o;
+    }
+    __syncthreads();                                    // shared buffers are reused by the next candidate
+    }
+    if (!chain) return;
+    // ---- chaining (last CTA to finish): candidates in ascending order; a candidate is a frame if its channel impulse response
+    //      stands out and it lies at least 0.9 frame periods behind the previous frame; the slot (frame number) advances by the
+    //      rounded distance to the previous frame, so gaps = lost frames = erasures, and a sample-clock offset that accumulates to
+    //      more than half a frame over a long recording cannot shift the CIF numbering.
+    __shared__ int s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const int tk = atomicAdd(ticket, 1);
+        s_is_last = (tk == (int)gridDim.x - 1);
+        if (s_is_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    // Candidates are taken 1024 at a time: (1) four consecutive candidates per thread, those whose impulse response stands out are
+    // compacted in order into shared memory; (2) if every one of them lies at least 0.9 frame periods behind its predecessor -- the
+    // normal case -- all are frames and their slots are a prefix sum of the rounded distances: fully parallel; (3) otherwise (a
+    // false candidate next to a frame) one thread walks the compacted list.
+    struct Ent { long long t; float cfo, cir; };                // 16 bytes
+    Ent* sE = reinterpret_cast<Ent*>(X);                        // FFT_BUF_LEN * 8 / 16 = 1152 entries
+    int* sSlot = reinterpret_cast<int*>(C);                     // slot of entry e (-1: not a frame)
+    __shared__ int c_frames, c_slot, s_wsum[8], s_carry;
+    __shared__ long long c_last;
+    const int lane = t & 31, warp = t >> 5;
+    auto excl_scan = [&](int v, int& total) -> int {            // exclusive prefix over the CTA in thread order
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        __syncthreads();
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const int x = s_wsum[w]; if (w < warp) before += x; tot += x; }
+        total = tot;
+        return before + incl - v;
+    };
+    auto frames_between = [](long long gap) -> int {            // rounded distance in frame periods
+        if (gap >= 0 && gap < (1ll << 30)) return (int)(((unsigned)gap + DAB_T_FRAME / 2) / (unsigned)DAB_T_FRAME);
+        return (int)((gap + DAB_T_FRAME / 2) / DAB_T_FRAME);
+    };
+    if (t == 0) { c_frames = chain->n_frames; c_last = chain->last_t; c_slot = c_frames > 0 ? frames[c_frames - 1].slot : -1; }
+    __syncthreads();
+    for (int base = 0; base < n_cand; base += 1024) {
+        Ent mine[4];
+        int nv = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = base + 4 * t + q;
+            if (i < n_cand) {
+                const FineOut* f = out + i;                             // written by other CTAs: read from L2
+                const float cir = __ldcg(&f->cir_ratio);
+                if (cir >= SYNC_CIR_MIN) {
+                    Ent e;
+                    e.t = __ldcg(&f->t_f) + range_off;
+                    e.cfo = __ldcg(&f->cfo_hz); e.cir = cir;
+                    mine[nv++] = e;
+                }
+            }
+        }
+        int n_valid;
+        const int at = excl_scan(nv, n_valid);
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (q < nv) sE[at + q] = mine[q];
+        __syncthreads();
+        const int nf0 = c_frames, slot0 = c_slot;
+        const long long last0 = c_last;
+        // (2) the parallel case
+        int ok = 1;
+        for (int e = t; e < n_valid; e += 256) {
+            const bool has_prev = e > 0 || nf0 > 0;
+            const long long prev = e > 0 ? sE[e - 1].t : last0;
+            if (has_prev && sE[e].t - prev < (long long)(DAB_T_FRAME * 9 / 10)) ok = 0;
+        }
+        if (__syncthreads_and(ok)) {
+            if (t == 0) s_carry = slot0;
+            __syncthreads();
+            for (int e0 = 0; e0 < n_valid; e0 += 256) {
+                const int e = e0 + t;
+                int inc = 0;
+                if (e < n_valid) {
+                    const bool has_prev = e > 0 || nf0 > 0;
+                    inc = has_prev ? frames_between(sE[e].t - (e > 0 ? sE[e - 1].t : last0)) : 1;       // the first frame of the call gets slot 0
+                }
+                int tot;
+                const int before = excl_scan(inc, tot);
+                if (e < n_valid) sSlot[e] = s_carry + before + inc;
+                __syncthreads();
+                if (t == 0) s_carry += tot;
+                __syncthreads();
+            }
+        } else {
+            // (3) sequential walk
+            if (t == 0) {
+                int nf = nf0, slot_prev = slot0;
+                long long last = last0;
+                for (int e = 0; e < n_valid; e++) {
+                    const long long t_abs = sE[e].t;
+                    if (nf > 0 && t_abs - last < (long long)(DAB_T_FRAME * 9 / 10)) { sSlot[e] = -1; continue; }   // seen already / too close
+                    const int slot = nf == 0 ? 0 : slot_prev + frames_between(t_abs - last);
+                    sSlot[e] = slot;
+                    nf++; slot_prev = slot; last = t_abs;
+                }
+            }
+            __syncthreads();
+        }
+        // frames = entries with a slot below max_slots (slots ascend, so what is cut off is a tail), written out in order
+        int acc = 0;
+        for (int e0 = 0; e0 < n_valid; e0 += 256) {
+            const int e = e0 + t;
+            const int is_frame = (e < n_valid && sSlot[e] >= 0 && sSlot[e] < max_slots) ? 1 : 0;
+            int tot;
+            const int before = excl_scan(is_frame, tot);
+            if (is_frame) {
+                FrameInfo fi;
+                fi.t_f = sE[e].t; fi.cfo_hz = sE[e].cfo; fi.slot = sSlot[e];
+                frames[nf0 + acc + before] = fi;
+                frame_cir[nf0 + acc + before] = sE[e].cir;
+            }
+            // the last frame of the chunk carries the chain on
+            if (is_frame && before == tot - 1) { c_last = sE[e].t; c_slot = sSlot[e]; }
+            acc += tot;
+            __syncthreads();
+        }
+        if (t == 0) c_frames = nf0 + acc;
+        __syncthreads();
+    }
+    if (t == 0) {
+        if (range_idx == 0) chain->range_first[0] = 0;
+        if (range_idx < CHAIN_MAX_RANGES) chain->range_first[range_idx + 1] = c_frames;
+        chain->n_frames = c_frames;
+        chain->last_t = c_last;
+        chain->n_candidates += n_cand;
     }
 }

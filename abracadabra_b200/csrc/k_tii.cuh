@@ -17,12 +17,17 @@ __constant__ float c_tii_gain[TII_SPECTRUM_BINS];
 // one CTA per frame: fold[f][2p+e] = sum over the 4 quarters of |N[k]|, k = 384 q + 2p + e ; norm[f] = rms PRS carrier magnitude
 template <int FMT>
 __global__ void __launch_bounds__(256) k_tii_fold(const void* __restrict__ raw, int64_t nsamp, const FrameInfo* __restrict__ frames,
+                                                  const ChainState* __restrict__ chain, int range_idx, int skip, int limit,
                                                   const float2* __restrict__ tw, float* __restrict__ fold, float* __restrict__ norm)
 {
     __shared__ float2 buf[FFT_BUF_LEN];
     __shared__ float red[32];
     const int t = threadIdx.x;
-    const FrameInfo fr = frames[blockIdx.x];
+    int fi, f_end;
+    chain_range(chain, range_idx, skip, limit, fi, f_end);   // the grid is an upper bound of the frames of the range
+    fi += blockIdx.x;
+    if (fi >= f_end) return;
+    const FrameInfo fr = frames[fi];
     const double cyc_per = (double)fr.cfo_hz / (double)DAB_FS;
     const float cpp = (float)cyc_per;
     // PRS symbol -> reference carrier magnitude

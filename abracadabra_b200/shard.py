@@ -164,7 +164,7 @@ def decode_chunked(iq, fmt: str, n_chunks: int, rx=None, device: int = 0, tii: b
                 fl[lo:hi] = f[lo - r0:hi - r0]
         cnt = [int(fl[k::5].sum()) for k in range(5)]
         if max(cnt) > 0:
-            best[i] = int(np.argmax(cnt))                 # first maximum = the strict '>' of k_sf_align
+            best[i] = int(np.argmax(cnt))                 # first maximum = the strict '>' of k_fire_align
     # a chunk whose own table differs could not contribute its flags above: decode it again first, then settle the alignment
     for c in order:
         if every[c]["key"] != gkey and slot0[order.index(c)] is not None:

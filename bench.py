@@ -243,8 +243,8 @@ def algorithmic_bytes(name: str, n_frames: int, subch, n_samples: int) -> float:
     steps = sum(s.bitrate * 24 + 6 for s in subch)
     if name == "k_block_power":
         return 2.0 * n_samples + 4.0 * n_samples / 32
-    if name.startswith("k_window_sum"):
-        return 3 * 4.0 * n_samples / 32
+    if name == "k_coarse":
+        return 2 * 4.0 * n_samples / 32
     if name == "k_fine_sync":
         return n_frames * (76 * 184 * 2 * 2 + 2048 * 2) * 1.0
     if name == "k_ofdm_demod":
@@ -266,7 +266,7 @@ def algorithmic_bytes(name: str, n_frames: int, subch, n_samples: int) -> float:
         return rows * (steps * 4 + steps * 8 + len(subch) * 2 * 64 * 2) * 1.0  # soft words in, decisions + meeting metrics out
     if name == "k_vit_trace(msc)":
         return rows * (steps * 8 + len(subch) * 2 * 64 * 2 + info / 8) * 1.0  # decisions + meeting metrics in, bytes out
-    if name == "k_rs_decode":
+    if name == "k_sf_decode":        # every byte of the DAB+ logical frames read once
         return rows * info / 8 * 1.0
     return 0.0
 
