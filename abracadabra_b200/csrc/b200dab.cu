@@ -108,6 +108,8 @@ struct b200dab_ctx {
         DevBuf d_vin, d_dec, d_meet;   // work buffers of the set: the FIC chain runs on its own stream next to the MSC chain
     } vit_tables[3];                   // [0] FIC, [1] MSC, [2] FIC of the first frames only (early sub-channel discovery)
     int vit_set = -1;                  // table set forced by the caller (-1: by job kind)
+    cudaEvent_t ev_first_trace = nullptr;   // set by the caller: recorded behind the first of two k_vit_trace launches (see run_viterbi)
+    bool first_trace_recorded = false;
     int vit4_min_steps = 0;            // codewords of at least this many trellis steps run in four-lane mode (k_viterbi.cuh); 0 = all
     // work items of k_viterbi for `groups` (sorted), longest dependent instruction chain first
     void build_items(const std::vector<VitJob>& jobs, const std::vector<VitGroup>& groups, std::vector<VitItem>& items) const
@@ -126,6 +128,9 @@ struct b200dab_ctx {
     cudaStream_t cur = nullptr;        // stream the helpers below launch on (nullptr: `stream`)
     cudaStream_t S() const { return cur ? cur : stream; }
     cudaStream_t fic_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;       // DAB+ half of the back end behind k_viterbi: trace + superframe kernels, next to the trace of the other sub-channels
+    cudaEvent_t ev_vit = nullptr, ev_aux = nullptr;
+    bool late_on_aux = false;
     cudaEvent_t ev_early_demod = nullptr, ev_early_done = nullptr, ev_early_fic = nullptr, ev_demod = nullptr, ev_fic_stream = nullptr;
     DevBuf d_fic_out_early, d_fib_ok_early;
     HostBuf h_fibs_early, h_fib_ok_early;
@@ -624,10 +629,30 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     k_viterbi<<<vit_grid(vt.n_items), 32 * VIT_CTA_WARPS, vit_dyn_smem(), stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg, vt.d_items.as<VitItem>(),
                                                                         (int)vt.n_items, d_vit_counter.as<int>() + st);
     prof_end();
-    prof_begin(st == 0 ? "k_vit_trace(fic)" : st == 2 ? "k_vit_trace(early fic)" : "k_vit_trace(msc)");
-    k_vit_trace<<<(unsigned)n_groups, 64, 0, stream>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_vit_counter.as<int>() + st);
-    prof_end();
-    launches += 3;
+    // Sub-channels whose logical frames are final after the trace (DAB / data) are traced first, so that their copy to the host runs
+    // under the trace of the DAB+ sub-channels and the superframe kernels behind it (ev_first_trace: recorded between the two launches).
+    bool any_late = false, any_early = false;
+    for (auto& j : vt.jobs_in) { if (j.late) any_late = true; else any_early = true; }
+    const bool two = any_late && any_early && ev_first_trace != nullptr;
+    const char* tname = st == 0 ? "k_vit_trace(fic)" : st == 2 ? "k_vit_trace(early fic)" : "k_vit_trace(msc)";
+    if (two) {
+        // the two halves run next to each other: both are chains of dependent steps that leave most of the GPU idle on their own
+        CK(cudaEventRecord(ev_vit, stream));
+        CK(cudaStreamWaitEvent(aux_stream, ev_vit, 0));
+    }
+    for (int ph = 0; ph < (two ? 2 : 1); ph++) {
+        cudaStream_t keep = cur;
+        if (two && ph == 1) cur = aux_stream;
+        prof_begin(tname);
+        k_vit_trace<<<(unsigned)n_groups, 64, 0, S()>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_vit_counter.as<int>() + st, two ? ph : -1);
+        prof_end();
+        cur = keep;
+        launches += 1;
+        if (two && ph == 0) CK(cudaEventRecord(ev_first_trace, stream));
+    }
+    late_on_aux = two;
+    first_trace_recorded = two;
+    launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
@@ -711,6 +736,7 @@ int b200dab_ctx::msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std
         }
         out_off[i] = off;
         jobs.push_back(make_job(subch[i], 1, n_rows, n_cif - 1, si_off, (long long)off));
+        jobs.back().late = subch[i].kind == 1 ? 1 : 0;       // DAB+: its frames are final only after the RS correction
         off += (size_t)((n_rows + 31) / 32 * 32) * (size_t)(subch[i].bitrate * 3);
     }
     *total = off;
@@ -735,17 +761,17 @@ int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int
     CK(d_totals.ensure(sizeof(DabPlusTotals)));
     CK(d_naus.ensure((size_t)total_sf * 4 + 64));
     prof_begin("k_fire_align");
-    k_fire_align<<<nj, FIRE_THREADS, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>(), d_totals.as<DabPlusTotals>());
+    k_fire_align<<<nj, FIRE_THREADS, 0, S()>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>(), d_totals.as<DabPlusTotals>());
     prof_end();
     // RS correction, fire code, access-unit table and access-unit CRCs of a superframe by one warp, in one launch
     prof_begin("k_sf_decode");
-    k_sf_decode<<<dim3((max_sf + SF_PER_CTA - 1) / SF_PER_CTA, nj), 32 * SF_PER_CTA, 0, stream>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<SfTables>(),
+    k_sf_decode<<<dim3((max_sf + SF_PER_CTA - 1) / SF_PER_CTA, nj), 32 * SF_PER_CTA, 0, S()>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<SfTables>(),
                                                                                               d_naus.as<int>(), d_totals.as<DabPlusTotals>());
     prof_end();
-    if (ev_rs) CK(cudaEventRecord(ev_rs, stream));        // the logical frames are final from here on: the caller starts their copy
+    if (ev_rs) CK(cudaEventRecord(ev_rs, S()));        // the logical frames are final from here on: the caller starts their copy
     // access-unit list and RS statistics in the layout of the result, put together on the device
     prof_begin("k_au_list");
-    k_au_list<<<(total_sf + 255) / 256, 256, 0, stream>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, d_sf.as<SfInfo>(), d_naus.as<int>(), total_sf, d_aus.as<AuRecord>(), d_totals.as<DabPlusTotals>());
+    k_au_list<<<(total_sf + 255) / 256, 256, 0, S()>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, d_sf.as<SfInfo>(), d_naus.as<int>(), total_sf, d_aus.as<AuRecord>(), d_totals.as<DabPlusTotals>());
     prof_end();
     launches += 3;
     CK(cudaGetLastError());
@@ -854,6 +880,8 @@ int b200dab_create(b200dab_ctx** out, int device)
     cudaEventCreateWithFlags(&ctx->ev_early_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_frames, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_demod, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_fic_stream, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_vit, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming);
     if (ctx->init_tables()) { fprintf(stderr, "b200dab: %s\n", ctx->err.c_str()); cudaStreamDestroy(ctx->stream); delete ctx; return -6; }
     *out = ctx;
     return 0;
@@ -872,12 +900,16 @@ void b200dab_destroy(b200dab_ctx* ctx)
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_chain, &ctx->h_frame_cir, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
                      &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_sfinfo, &ctx->h_flags, &ctx->h_residue};
+    cudaStreamSynchronize(ctx->fic_stream); if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto* b : hb) b->release();
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); cudaEventDestroy(ctx->ev_rs); cudaEventDestroy(ctx->ev_tii); }
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
     if (ctx->fic_stream) { cudaEventDestroy(ctx->ev_early_demod); cudaEventDestroy(ctx->ev_early_done); cudaEventDestroy(ctx->ev_early_fic); cudaEventDestroy(ctx->ev_demod); cudaEventDestroy(ctx->ev_fic_stream); cudaStreamDestroy(ctx->fic_stream); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_vit) { cudaEventDestroy(ctx->ev_vit); cudaEventDestroy(ctx->ev_aux); }
+    if (ctx->ev_chain) { cudaEventDestroy(ctx->ev_chain); cudaEventDestroy(ctx->ev_frames); }
     for (auto& set : ctx->prof_sets) for (auto& e : set) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1262,7 +1294,10 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
     };
     auto msc_block = [&]() -> int {
     if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
-        if (ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes)) return -1;
+        ctx->ev_first_trace = ctx->ev_msc;
+        const int msc_rc = ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes);
+        ctx->ev_first_trace = nullptr;
+        if (msc_rc) return -1;
         TRACE("msc submitted");
         for (size_t i = 0; i < ctx->r_subch.size(); i++) {
             if (ctx->r_subch[i].kind != 1) continue;
@@ -1290,14 +1325,19 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
             }
             return 0;
         };
-        const bool split = !dpjobs.empty();
+        static const bool no_split = getenv("B200DAB_NO_SPLIT_COPY") != nullptr;      // A/B switch (tools/ab_step.py)
+        const bool split = !dpjobs.empty() && !no_split;
         if (split) {
-            CKC(cudaEventRecord(ctx->ev_msc, ctx->stream));
+            if (!ctx->first_trace_recorded) CKC(cudaEventRecord(ctx->ev_msc, ctx->stream));      // (else: recorded between the two trace launches)
             CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_msc, 0));
             if (copy_class(false, ctx->copy_stream)) return -1;
             copies_pending = true;
         }
-        if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows)) return -1;
+        cudaStream_t back = ctx->late_on_aux ? ctx->aux_stream : ctx->stream;      // where the DAB+ half of the back end runs
+        ctx->cur = ctx->late_on_aux ? ctx->aux_stream : nullptr;
+        const int dp_rc = ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows);
+        ctx->cur = nullptr;
+        if (dp_rc) return -1;
         if (split) {
             CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rs, 0));
             if (copy_class(true, ctx->copy_stream)) return -1;
@@ -1305,15 +1345,16 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         if (total_sf > 0) {
             static_assert(sizeof(AuRecord) == sizeof(b200dab_au_t), "AU record layout");
             CKC(ctx->h_sf.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + sizeof(DabPlusTotals)));
-            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, ctx->stream));
-            CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, back));
+            CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, back));
             CKC(ctx->h_sfinfo.ensure((size_t)total_sf * sizeof(SfInfo)));
             CKC(ctx->h_flags.ensure((size_t)total_rows + 64));
             CKC(ctx->h_residue.ensure(dpjobs.size() * 4));
-            CKC(cudaMemcpyAsync(ctx->h_sfinfo.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
-            CKC(cudaMemcpyAsync(ctx->h_flags.p, ctx->d_flags.p, (size_t)total_rows, cudaMemcpyDeviceToHost, ctx->stream));
-            CKC(cudaMemcpyAsync(ctx->h_residue.p, ctx->d_residue.p, dpjobs.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CKC(cudaMemcpyAsync(ctx->h_sfinfo.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, back));
+            CKC(cudaMemcpyAsync(ctx->h_flags.p, ctx->d_flags.p, (size_t)total_rows, cudaMemcpyDeviceToHost, back));
+            CKC(cudaMemcpyAsync(ctx->h_residue.p, ctx->d_residue.p, dpjobs.size() * 4, cudaMemcpyDeviceToHost, back));
         }
+        if (ctx->late_on_aux) { CKC(cudaEventRecord(ctx->ev_aux, ctx->aux_stream)); CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0)); }
     }
     TRACE("msc+dab+ submitted");
     return 0;
@@ -1514,7 +1555,7 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     ctx->prof_end();
     ctx->prof_begin("k_vit_trace(stage)");
     k_vit_trace<<<ng, 64, 0, ctx->stream>>>(ctx->d_dec.as<uint2>(), ctx->d_meet.as<unsigned short>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
-                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3);
+                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1);
     ctx->prof_end();
     ctx->launches += 2;
     CKC(cudaGetLastError());

@@ -72,18 +72,18 @@ __global__ void __launch_bounds__(256) k_block_power(const void* __restrict__ ra
 }
 
 // Everything of the coarse synchronisation behind the block powers in ONE launch (was window sum -> candidates -> sort): a CTA owns
-// CO_TILE consecutive blocks, fetches their powers P plus the halo the candidate test looks at (83 blocks below, 415 above) into shared
+// CO_TILE (1712) consecutive blocks, fetches their powers P plus the halo the candidate test looks at (83 blocks below, 335 above) into shared
 // memory, computes the window sums S over them and runs the candidate test for its own blocks.  Candidates of a tile are at least 84
 // blocks apart (neighbourhood maximum), so a tile holds at most CO_CAP of them; they leave the CTA in ascending order, and the last CTA
 // to finish strings the tiles together: the list is sorted by construction, no atomically appended list and no sort kernel.
 // Arithmetic and summation order are those of the kernels this replaces (and of the scalar checker): each S receives its 83 terms in
 // ascending order, one __fadd_rn at a time.
-#define CO_TILE 1024
-#define CO_S_LEN (CO_TILE + 4 * SYNC_WIN)               /* S[b0 - 83 .. b0 + 1024 + 249) */
+#define WSUM_PER_THREAD 8                                /* outputs per thread: every block power is read once and added into up to eight running sums */
+#define CO_S_LEN 2048                                    /* window sums per CTA = 256 threads x 8: S[b0 - 83 .. b0 - 83 + 2048) */
+#define CO_TILE (CO_S_LEN - 4 * SYNC_WIN - 4)            /* blocks owned by a CTA: the test of block b looks at S[b - 83 .. b + 249] */
 #define CO_P_LEN (CO_S_LEN + SYNC_WIN - 1)
-#define CO_CAP 16
-#define WSUM_PER_THREAD 4
-__device__ __forceinline__ int wsum_phys(int x) { return x + (x >> 5); }       // one pad word per 32: 4-word lane strides stay conflict-free
+#define CO_CAP 24
+__device__ __forceinline__ int wsum_phys(int x) { return x + (x >> 5); }       // one pad word per 32: lane strides of 4 or 8 words stay conflict-free
 __global__ void __launch_bounds__(256) k_coarse(const float* __restrict__ P, int64_t nblk, int64_t nsamp, float* __restrict__ S,
                                                 long long* __restrict__ cand_tile, int* __restrict__ cand_cnt, int* __restrict__ ticket,
                                                 long long* __restrict__ cand, int* __restrict__ n_cand, int max_cand)
@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(256) k_coarse(const float* __restrict__ P, int
     __syncthreads();
     for (int quad = t; quad * WSUM_PER_THREAD < CO_S_LEN; quad += 256) {
         const int o = quad * WSUM_PER_THREAD;                  // outputs o .. o + 3; term j = i - k of output k is sP[o + i]
-        float acc[WSUM_PER_THREAD] = {0.f, 0.f, 0.f, 0.f};
+        float acc[WSUM_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < WSUM_PER_THREAD; k++) acc[k] = 0.f;
 #pragma unroll
         for (int i = 0; i < WSUM_PER_THREAD - 1; i++) {        // head: outputs k <= i have started
             const float p = sP[wsum_phys(o + i)];

@@ -29,7 +29,7 @@ struct VitJob {
     int out_pitch;         // bytes per decoded row = n_info / 8
     int kind;              // 0 FIC, 1 MSC
     int mode4;             // 1: four-lane survivor-word layout (set by the host together with the work items)
-    int pad_;
+    int late;              // 1: traced by the second k_vit_trace launch (DAB+ sub-channels; the others go first so that their copy to the host starts early)
 };
 struct VitGroup { int job; int g_in_job; };
 
@@ -547,11 +547,12 @@ __device__ __forceinline__ void vit_trace_run(const uint2* __restrict__ d, const
 }
 __global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec, const unsigned short* __restrict__ meet,
                                                   const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
-                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out, int* __restrict__ vit_counter)
+                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out, int* __restrict__ vit_counter, int phase)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) *vit_counter = 0;      // the work queue of the k_viterbi launch in front of this one
     const VitGroup grp = groups[blockIdx.x];
     const VitJob job = jobs[grp.job];
+    if (phase >= 0 && job.late != phase) return;                    // two launches: phase 0 = jobs whose output is final after the trace
     const int lane = threadIdx.x & 31, dir = threadIdx.x >> 5;
     const int steps = job.steps;
     const int m = ((steps >> 1) >> 5) << 5;

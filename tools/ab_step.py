@@ -13,7 +13,7 @@ import torch
 import bench
 from abracadabra_b200 import pipeline
 
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
+args = [a for a in sys.argv[1:] if ":" in a]
 secs = float(sys.argv[sys.argv.index("--seconds") + 1]) if "--seconds" in sys.argv else 60.0
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 12
 host = "--host" in sys.argv
