@@ -74,6 +74,13 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 static const bool g_trace = getenv("B200DAB_TRACE") != nullptr;
 #define TRACE(msg) do { if (g_trace) fprintf(stderr, "[trace] %-28s %.3f ms\n", msg, now_ms() - ctx->t_trace0); } while (0)
 
+// Host-to-device uploads of the receiver contexts sharing a GPU (ReceiverPool) are chained: the copy stream of a context waits for the
+// last chunk of the upload queued before it, so recordings cross PCIe one after the other, back to back -- not interleaved chunk by
+// chunk (every recording would arrive late) and without the copy engine idling between them.
+#include <mutex>
+static std::mutex g_upload_mu;
+static cudaEvent_t g_upload_last[64] = {};        // per device: event behind the last chunk of the most recently queued upload
+
 #define EARLY_FIC_FRAMES 16      /* frames of the early FIC slice: the first two prefixes (8, 16) of the sub-channel discovery */
 
 struct b200dab_ctx {
@@ -91,7 +98,9 @@ struct b200dab_ctx {
     // evenly however the SMs drain from the kernel in front (without it the block scheduler may pile four of them on the SMs that
     // are free first and leave others with one: the work queue evens out the items, not the issue slots).
     bool vit_smem_cap = true;
-    size_t vit_dyn_smem() const { return vit_smem_cap ? (size_t)(227 * 1024 / vit_ctas_per_sm) - sizeof(uint32_t) * VIT_CTA_WARPS * 2 * VIT_NORM_PERIOD * 32 - 2048 : 0; }
+    bool trace_pdl = true;             // k_vit_trace(msc) as a programmatic dependent launch next to k_viterbi (B200DAB_TRACE_PDL=0: behind it)
+    int vit_smem_slack = 4096;         // bytes per CTA left free below the cap: the trace CTAs running next to the recursions need 1 KB of (system) shared memory each
+    size_t vit_dyn_smem() const { return vit_smem_cap ? (size_t)(227 * 1024 / vit_ctas_per_sm) - sizeof(uint32_t) * VIT_CTA_WARPS * 2 * VIT_NORM_PERIOD * 32 - (size_t)vit_smem_slack : 0; }
     unsigned vit_grid(size_t n_items) const { return (unsigned)std::min<size_t>((size_t)n_sm * vit_ctas_per_sm, (n_items + VIT_CTA_WARPS - 1) / VIT_CTA_WARPS); }
     // constant tables on the device
     DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin, d_naus;   // d_gf: SfTables of k_sf_decode; d_naus: access units per superframe slot
@@ -106,24 +115,53 @@ struct b200dab_ctx {
         int max_steps = 0, vit4_min_steps = -1;
         DevBuf d_jobs, d_groups, d_stepinfo, d_items;
         DevBuf d_vin, d_dec, d_meet;   // work buffers of the set: the FIC chain runs on its own stream next to the MSC chain
+        DevBuf d_order, d_done;        // trace order (CTA -> group); finished recursions per group, cleared before every launch
     } vit_tables[3];                   // [0] FIC, [1] MSC, [2] FIC of the first frames only (early sub-channel discovery)
     int vit_set = -1;                  // table set forced by the caller (-1: by job kind)
     cudaEvent_t ev_first_trace = nullptr;   // set by the caller: recorded behind the first of two k_vit_trace launches (see run_viterbi)
     bool first_trace_recorded = false;
     int vit4_min_steps = 0;            // codewords of at least this many trellis steps run in four-lane mode (k_viterbi.cuh); 0 = all
-    // work items of k_viterbi for `groups` (sorted), longest dependent instruction chain first
-    void build_items(const std::vector<VitJob>& jobs, const std::vector<VitGroup>& groups, std::vector<VitItem>& items) const
+    // Work items of k_viterbi for `groups` (sorted), longest dependent instruction chain first.  trace_order (optional): the groups in
+    // the order in which a simulation of the kernel's own schedule (n_warps persistent warps, each taking the next item when it is
+    // through with its last) expects their recursions to be finished -- the order in which k_vit_trace, running next to k_viterbi as
+    // its programmatic dependent, takes them (ties: the longer trace first).
+    void build_items(const std::vector<VitJob>& jobs, const std::vector<VitGroup>& groups, std::vector<VitItem>& items,
+                     std::vector<int>* trace_order = nullptr, int n_warps = 1) const
     {
         items.clear();
         std::vector<std::pair<long long, VitItem>> tmp;
         for (size_t g = 0; g < groups.size(); g++) {
             const VitJob& j = jobs[groups[g].job];
-            // instructions per trellis step of one warp (tools/sass_loops.py): 185 (two lanes per codeword pair), 111 (four lanes)
-            if (j.mode4) for (int w = 0; w < 4; w++) tmp.push_back({(long long)j.steps * 111, VitItem{(int)g, 4 | w}});
-            else for (int w = 0; w < 2; w++) tmp.push_back({(long long)j.steps * 185, VitItem{(int)g, w}});
+            // instructions per trellis step of one warp (tools/sass_loops.py): 186 (two lanes per codeword pair), 107 (four lanes)
+            if (j.mode4) for (int w = 0; w < 4; w++) tmp.push_back({(long long)j.steps * 107, VitItem{(int)g, 4 | w}});
+            else for (int w = 0; w < 2; w++) tmp.push_back({(long long)j.steps * 186, VitItem{(int)g, w}});
         }
         std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<long long, VitItem>& a, const std::pair<long long, VitItem>& b) { return a.first > b.first; });
         for (auto& t : tmp) items.push_back(t.second);
+        if (!trace_order) return;
+        n_warps = std::max(n_warps, 1);
+        std::vector<int> left(groups.size());
+        std::vector<long long> ready_at(groups.size(), 0);
+        for (size_t g = 0; g < groups.size(); g++) left[g] = jobs[groups[g].job].mode4 ? 4 : 2;
+        typedef std::pair<long long, int> Ev;                      // (end time, group) of a busy warp; min-heap on the time
+        std::vector<Ev> heap;
+        auto later = [](const Ev& a, const Ev& b) { return a.first > b.first; };
+        long long now = 0;
+        auto retire = [&]() {
+            std::pop_heap(heap.begin(), heap.end(), later);
+            const Ev e = heap.back(); heap.pop_back();
+            now = e.first;
+            if (--left[e.second] == 0) ready_at[e.second] = e.first;
+        };
+        for (auto& t : tmp) {
+            if ((int)heap.size() >= n_warps) retire();
+            heap.push_back({now + t.first, t.second.group}); std::push_heap(heap.begin(), heap.end(), later);
+        }
+        while (!heap.empty()) retire();
+        trace_order->resize(groups.size());
+        for (size_t g = 0; g < groups.size(); g++) (*trace_order)[g] = (int)g;
+        std::stable_sort(trace_order->begin(), trace_order->end(), [&](int a, int b) {
+            return ready_at[a] != ready_at[b] ? ready_at[a] < ready_at[b] : jobs[groups[a].job].steps > jobs[groups[b].job].steps; });
     }
     cudaStream_t cur = nullptr;        // stream the helpers below launch on (nullptr: `stream`)
     cudaStream_t S() const { return cur ? cur : stream; }
@@ -140,7 +178,7 @@ struct b200dab_ctx {
     DevBuf d_tmp_a, d_tmp_b, d_spec;
     HostBuf h_spec;
     HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
-    HostBuf h_jobs[3], h_groups[3], h_stepinfo[3], h_items[3], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
+    HostBuf h_jobs[3], h_groups[3], h_stepinfo[3], h_items[3], h_order[3], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
     std::vector<int32_t> r_sign;
     std::vector<std::pair<b200dab_subch_t, std::vector<uint32_t>>> stepinfo_cache;   // de-puncturing tables by protection profile
     // result storage
@@ -593,8 +631,15 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
         if (groups.empty()) return 0;
         std::stable_sort(groups.begin(), groups.end(), [&](const VitGroup& a, const VitGroup& b) { return jobs[a.job].steps > jobs[b.job].steps; });
         std::vector<VitItem> items;
-        build_items(jobs, groups, items);
+        std::vector<int> order;
+        size_t n_it = 0;
+        for (auto& g : groups) n_it += jobs[g.job].mode4 ? 4 : 2;
+        build_items(jobs, groups, items, &order, (int)vit_grid(n_it) * VIT_CTA_WARPS);
         vt.n_items = items.size();
+        CK(h_order[st].ensure(order.size() * 4 + 16));
+        CK(vt.d_order.ensure(order.size() * 4 + 16));
+        memcpy(h_order[st].p, order.data(), order.size() * 4);
+        if (fetch(vt.d_order.p, h_order[st].p, order.size() * 4)) { set_error("k_fetch launch failed"); return -1; }
         // small tables go through pinned staging owned by the context (one set per call site), so no stream sync is needed here
         CK(h_items[st].ensure(items.size() * sizeof(VitItem) + 16));
         CK(vt.d_items.ensure(items.size() * sizeof(VitItem) + 16));
@@ -621,34 +666,60 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
     CK(d_meet.ensure(n_groups * VIT_MEET_WORDS * sizeof(unsigned short)));
     const VitJob* dj = vt.d_jobs.as<VitJob>();
     const VitGroup* dg = vt.d_groups.as<VitGroup>();
+    // k_vit_trace as a programmatic dependent of k_viterbi (MSC set): it starts while the recursions are still running and takes the
+    // groups as they finish (done[]: recursions finished per group, cleared here).  B200DAB_TRACE_PDL=0: plain launches (A/B).
+    const bool pdl = trace_pdl && st == 1;
+    if (pdl) {
+        CK(vt.d_done.ensure((n_groups + 1) * 4));               // + the work queue head of k_viterbi: the trace kernel, which clears it
+        CK(cudaMemsetAsync(vt.d_done.p, 0, (n_groups + 1) * 4, stream));   //   otherwise, now runs while the queue is in use
+    }
+    int* d_done = pdl ? vt.d_done.as<int>() : nullptr;
+    int* d_head = pdl ? vt.d_done.as<int>() + n_groups : d_vit_counter.as<int>() + st;
     dim3 ggrid((unsigned)n_groups, (unsigned)((vt.max_steps + GATHER_STEPS - 1) / GATHER_STEPS));
     prof_begin(st == 0 ? "k_gather(fic)" : st == 2 ? "k_gather(early fic)" : "k_gather(msc)");
     k_gather<<<ggrid, 256, 0, stream>>>(d_soft.as<int8_t>(), dj, dg, vt.d_stepinfo.as<uint32_t>(), d_vin.as<uint32_t>());
     prof_end();
     prof_begin(st == 0 ? "k_viterbi(fic)" : st == 2 ? "k_viterbi(early fic)" : "k_viterbi(msc)");
-    k_viterbi<<<vit_grid(vt.n_items), 32 * VIT_CTA_WARPS, vit_dyn_smem(), stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg, vt.d_items.as<VitItem>(),
-                                                                        (int)vt.n_items, d_vit_counter.as<int>() + st);
-    prof_end();
-    // Sub-channels whose logical frames are final after the trace (DAB / data) are traced first, so that their copy to the host runs
-    // under the trace of the DAB+ sub-channels and the superframe kernels behind it (ev_first_trace: recorded between the two launches).
-    bool any_late = false, any_early = false;
-    for (auto& j : vt.jobs_in) { if (j.late) any_late = true; else any_early = true; }
-    const bool two = any_late && any_early && ev_first_trace != nullptr;
+    k_viterbi<<<vit_grid(vt.n_items), 32 * VIT_CTA_WARPS, st == 1 ? vit_dyn_smem() : 0, stream>>>(d_vin.as<uint32_t>(), d_dec.as<uint32_t>(), d_meet.as<unsigned short>(), dj, dg, vt.d_items.as<VitItem>(),
+                                                                        (int)vt.n_items, d_head, d_done);
+    if (!pdl) prof_end();
     const char* tname = st == 0 ? "k_vit_trace(fic)" : st == 2 ? "k_vit_trace(early fic)" : "k_vit_trace(msc)";
-    if (two) {
-        // the two halves run next to each other: both are chains of dependent steps that leave most of the GPU idle on their own
-        CK(cudaEventRecord(ev_vit, stream));
-        CK(cudaStreamWaitEvent(aux_stream, ev_vit, 0));
-    }
-    for (int ph = 0; ph < (two ? 2 : 1); ph++) {
-        cudaStream_t keep = cur;
-        if (two && ph == 1) cur = aux_stream;
-        prof_begin(tname);
-        k_vit_trace<<<(unsigned)n_groups, 64, 0, S()>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_vit_counter.as<int>() + st, two ? ph : -1);
+    bool two = false;
+    if (pdl) {
+        // (profiling: one pair of events around both kernels -- an event between them would be a stream dependency and keep the
+        // trace from starting early)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_groups); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, k_vit_trace, (const uint2*)d_dec.as<uint2>(), (const unsigned short*)d_meet.as<unsigned short>(), dj, dg,
+                              (const uint32_t*)d_prbs_w.as<uint32_t>(), d_out, (int*)nullptr, -1, (const int*)vt.d_order.as<int>(), (const int*)d_done));
         prof_end();
-        cur = keep;
         launches += 1;
-        if (two && ph == 0) CK(cudaEventRecord(ev_first_trace, stream));
+    } else {
+        // Sub-channels whose logical frames are final after the trace (DAB / data) are traced first, so that their copy to the host runs
+        // under the trace of the DAB+ sub-channels and the superframe kernels behind it (ev_first_trace: recorded between the two launches).
+        bool any_late = false, any_early = false;
+        for (auto& j : vt.jobs_in) { if (j.late) any_late = true; else any_early = true; }
+        two = any_late && any_early && ev_first_trace != nullptr;
+        if (two) {
+            // the two halves run next to each other: both are chains of dependent steps that leave most of the GPU idle on their own
+            CK(cudaEventRecord(ev_vit, stream));
+            CK(cudaStreamWaitEvent(aux_stream, ev_vit, 0));
+        }
+        for (int ph = 0; ph < (two ? 2 : 1); ph++) {
+            cudaStream_t keep = cur;
+            if (two && ph == 1) cur = aux_stream;
+            prof_begin(tname);
+            k_vit_trace<<<(unsigned)n_groups, 64, 0, S()>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_head, two ? ph : -1,
+                                                            vt.d_order.as<int>(), nullptr);
+            prof_end();
+            cur = keep;
+            launches += 1;
+            if (two && ph == 0) CK(cudaEventRecord(ev_first_trace, stream));
+        }
     }
     late_on_aux = two;
     first_trace_recorded = two;
@@ -867,6 +938,8 @@ int b200dab_create(b200dab_ctx** out, int device)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return -5; }
     if (const char* e = getenv("B200DAB_VIT_CTAS")) ctx->vit_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("B200DAB_VIT_SMEMCAP")) ctx->vit_smem_cap = atoi(e) != 0;
+    if (const char* e = getenv("B200DAB_TRACE_PDL")) ctx->trace_pdl = atoi(e) != 0;
+    if (const char* e = getenv("B200DAB_VIT_SMEM_SLACK")) ctx->vit_smem_slack = std::max(0, atoi(e));
     cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (const char* e = getenv("B200DAB_VIT4_MIN_STEPS")) ctx->vit4_min_steps = atoi(e);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
@@ -895,14 +968,17 @@ void b200dab_destroy(b200dab_ctx* ctx)
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_naus, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_chain, &ctx->d_frame_cir, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
-                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->vit_tables[0].d_items, &ctx->vit_tables[1].d_items, &ctx->vit_tables[2].d_items, &ctx->d_items, &ctx->d_vit_counter, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
+                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->vit_tables[0].d_items, &ctx->vit_tables[1].d_items, &ctx->vit_tables[2].d_items, &ctx->vit_tables[0].d_done, &ctx->vit_tables[1].d_done, &ctx->vit_tables[2].d_done, &ctx->vit_tables[0].d_order, &ctx->vit_tables[1].d_order, &ctx->vit_tables[2].d_order, &ctx->d_items, &ctx->d_vit_counter, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
                     &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
     for (auto* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_chain, &ctx->h_frame_cir, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
-                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_sfinfo, &ctx->h_flags, &ctx->h_residue};
+                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_order[0], &ctx->h_order[1], &ctx->h_order[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_sfinfo, &ctx->h_flags, &ctx->h_residue};
     cudaStreamSynchronize(ctx->fic_stream); if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto* b : hb) b->release();
-    for (auto e : ctx->copy_events) cudaEventDestroy(e);
+    {
+        std::lock_guard<std::mutex> lk(g_upload_mu);
+        for (auto e : ctx->copy_events) { if (g_upload_last[ctx->device & 63] == e) g_upload_last[ctx->device & 63] = nullptr; cudaEventDestroy(e); }
+    }
     if (ctx->ev_msc) { cudaEventDestroy(ctx->ev_msc); cudaEventDestroy(ctx->ev_d2h); cudaEventDestroy(ctx->ev_rs); cudaEventDestroy(ctx->ev_tii); }
     if (ctx->ev_fic) cudaEventDestroy(ctx->ev_fic);
     if (ctx->fic_stream) { cudaEventDestroy(ctx->ev_early_demod); cudaEventDestroy(ctx->ev_early_done); cudaEventDestroy(ctx->ev_early_fic); cudaEventDestroy(ctx->ev_demod); cudaEventDestroy(ctx->ev_fic_stream); cudaStreamDestroy(ctx->fic_stream); }
@@ -1108,10 +1184,16 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         if (!ctx->copy_stream) CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         const int n_chunks = (int)((n + chunk - 1) / chunk);
         while ((int)ctx->copy_events.size() < n_chunks) { cudaEvent_t e; CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->copy_events.push_back(e); }
-        for (int c = 0; c < n_chunks; c++) {
-            const uint64_t a0 = (uint64_t)c * chunk, a1 = std::min<uint64_t>(n, a0 + chunk);
-            CKC(cudaMemcpyAsync((uint8_t*)ctx->d_raw.p + a0 * bps, (const uint8_t*)iq + a0 * bps, (size_t)(a1 - a0) * bps, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CKC(cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
+        {
+            std::lock_guard<std::mutex> lk(g_upload_mu);
+            cudaEvent_t& last = g_upload_last[ctx->device & 63];
+            if (last) CKC(cudaStreamWaitEvent(ctx->copy_stream, last, 0));
+            for (int c = 0; c < n_chunks; c++) {
+                const uint64_t a0 = (uint64_t)c * chunk, a1 = std::min<uint64_t>(n, a0 + chunk);
+                CKC(cudaMemcpyAsync((uint8_t*)ctx->d_raw.p + a0 * bps, (const uint8_t*)iq + a0 * bps, (size_t)(a1 - a0) * bps, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CKC(cudaEventRecord(ctx->copy_events[c], ctx->copy_stream));
+            }
+            last = ctx->copy_events[n_chunks - 1];
         }
         static const bool trace = getenv("B200DAB_TRACE") != nullptr;
         auto t_start = std::chrono::steady_clock::now();
@@ -1551,11 +1633,11 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     ctx->prof_begin("k_viterbi(stage)");
     k_viterbi<<<ctx->vit_grid(items.size()), 32 * VIT_CTA_WARPS, 0, ctx->stream>>>(ctx->d_vin.as<uint32_t>(), ctx->d_dec.as<uint32_t>(), ctx->d_meet.as<unsigned short>(),
                                                                                   ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(), ctx->d_items.as<VitItem>(),
-                                                                                  (int)items.size(), ctx->d_vit_counter.as<int>() + 3);
+                                                                                  (int)items.size(), ctx->d_vit_counter.as<int>() + 3, nullptr);
     ctx->prof_end();
     ctx->prof_begin("k_vit_trace(stage)");
     k_vit_trace<<<ng, 64, 0, ctx->stream>>>(ctx->d_dec.as<uint2>(), ctx->d_meet.as<unsigned short>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
-                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1);
+                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1, nullptr, nullptr);
     ctx->prof_end();
     ctx->launches += 2;
     CKC(cudaGetLastError());

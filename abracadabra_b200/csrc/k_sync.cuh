@@ -380,9 +380,8 @@ __global__ void __launch_bounds__(256) k_fine_sync(const void* __restrict__ raw,
     //      rounded distance to the previous frame, so gaps = lost frames = erasures, and a sample-clock offset that accumulates to
     //      more than half a frame over a long recording cannot shift the CIF numbering.
     __shared__ int s_is_last;
-    __threadfence();
-    __syncthreads();
     if (t == 0) {
+        __threadfence();                                // thread 0 wrote this CTA's results: one fence, not one per thread
         const int tk = atomicAdd(ticket, 1);
         s_is_last = (tk == (int)gridDim.x - 1);
         if (s_is_last) *ticket = 0;

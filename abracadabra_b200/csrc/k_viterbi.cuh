@@ -450,10 +450,13 @@ __device__ __forceinline__ void vit_run4(uint32_t (&ring)[2][VIT_NORM_PERIOD][32
 #define VIT_CTA_WARPS 4
 __global__ void __launch_bounds__(32 * VIT_CTA_WARPS) k_viterbi(const uint32_t* __restrict__ vin, uint32_t* __restrict__ dec, unsigned short* __restrict__ meet,
                                                                   const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
-                                                                  const VitItem* __restrict__ items, int n_items, int* __restrict__ counter)
+                                                                  const VitItem* __restrict__ items, int n_items, int* __restrict__ counter, int* __restrict__ done)
 {
     __shared__ uint32_t ring[VIT_CTA_WARPS][2][VIT_NORM_PERIOD][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Programmatic dependent launch: the trace kernel queued behind this one may start as soon as every CTA of this grid is running
+    // (its CTAs then wait for the groups they trace, see k_vit_trace); without the launch attribute this is a no-op.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(counter, 1);
@@ -464,6 +467,11 @@ __global__ void __launch_bounds__(32 * VIT_CTA_WARPS) k_viterbi(const uint32_t* 
         const VitJob job = jobs[grp.job];
         if (item.what & 4) vit_run4(ring[warp], vin, dec, meet, job, item.group, grp.g_in_job, item.what & 1, (item.what >> 1) & 1);
         else vit_run2(ring[warp], vin, dec, meet, job, item.group, grp.g_in_job, item.what & 1);
+        if (done) {
+            __threadfence();                            // every lane's decision words and metrics are out before the counter moves
+            __syncwarp();
+            if (lane == 0) atomicAdd(done + item.group, 1);
+        }
         __syncwarp();
     }
 }
@@ -494,7 +502,7 @@ __host__ __device__ __forceinline__ uint32_t vit4_dec_index_bwd(uint32_t s)
 __device__ __forceinline__ void vit_load_chunk(uint2 (&b)[32], const uint2* d, int c)
 {
 #pragma unroll
-    for (int i = 0; i < 32; i++) b[i] = __ldcs(d + (size_t)(32 * c + i) * 32);
+    for (int i = 0; i < 32; i++) b[i] = __ldcg(d + (size_t)(32 * c + i) * 32);        // L2: written by other SMs, possibly while this kernel is already running
 }
 // the 64 survivor bits of step i (0..31) of a chunk, two-lane layout: role 0's word | ~bit-reverse(role 1's word) << 32
 __device__ __forceinline__ unsigned long long vit_word2(const uint2 (&b)[32], int i)
@@ -545,24 +553,40 @@ __device__ __forceinline__ void vit_trace_run(const uint2* __restrict__ d, const
         }
     }
 }
-__global__ void __launch_bounds__(64) k_vit_trace(const uint2* __restrict__ dec, const unsigned short* __restrict__ meet,
+__global__ void __launch_bounds__(64) k_vit_trace(const uint2* dec, const unsigned short* meet,
                                                   const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
-                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out, int* __restrict__ vit_counter, int phase)
+                                                  const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out, int* __restrict__ vit_counter, int phase,
+                                                  const int* __restrict__ order, const int* done)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *vit_counter = 0;      // the work queue of the k_viterbi launch in front of this one
-    const VitGroup grp = groups[blockIdx.x];
+    if (vit_counter && blockIdx.x == 0 && threadIdx.x == 0) *vit_counter = 0;   // the work queue of the k_viterbi launch in front of this one (not when the two run side by side)
+    // order: CTA -> group, in the order in which the groups' recursions are expected to finish (host simulation of the k_viterbi
+    // schedule).  done: launched as a programmatic dependent of k_viterbi, this kernel runs NEXT TO it, on the registers and warp
+    // slots its persistent CTAs leave free: a CTA waits until the recursions of its group (two, or four in four-lane mode) have
+    // published their decisions, traces, and makes room for the next.  Every k_viterbi CTA is resident before the first CTA of this
+    // kernel starts, and the recursions wait for nothing: no deadlock.  What is left behind the end of k_viterbi is the trace of the
+    // groups that finished last instead of the whole 0.14 ms.
+    const int g = order ? order[blockIdx.x] : (int)blockIdx.x;
+    const VitGroup grp = groups[g];
     const VitJob job = jobs[grp.job];
     if (phase >= 0 && job.late != phase) return;                    // two launches: phase 0 = jobs whose output is final after the trace
+    if (done) {
+        if (threadIdx.x == 0) {
+            const int need = job.mode4 ? 4 : 2;
+            while (*reinterpret_cast<const volatile int*>(done + g) < need) __nanosleep(1000);
+            __threadfence();
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, dir = threadIdx.x >> 5;
     const int steps = job.steps;
     const int m = ((steps >> 1) >> 5) << 5;
     const uint2* d = dec + job.dec_off + ((size_t)grp.g_in_job * steps) * 32 + lane;
-    const unsigned short* mt = meet + (size_t)blockIdx.x * VIT_MEET_WORDS + lane;
+    const unsigned short* mt = meet + (size_t)g * VIT_MEET_WORDS + lane;
     uint32_t s = 0;
     int best = -1;
 #pragma unroll 8
     for (int q = 0; q < 64; q++) {
-        const int v = (int)mt[q * 32] + (int)mt[(64 + q) * 32];
+        const int v = (int)__ldcg(mt + q * 32) + (int)__ldcg(mt + (64 + q) * 32);
         if (v > best) { best = v; s = (uint32_t)q; }
     }
     const int row = grp.g_in_job * 32 + lane;
