@@ -36,7 +36,7 @@ def _reference_jobs(args, td):
     k = args.config
     if k == 2:
         raw, res, _ = bench.make_recording(args.seconds, 0)
-        n = min(raw.size // 2, int(args.cpu_sample_seconds * FS))
+        n = raw.size // 2 if args.cpu_sample_seconds >= args.seconds else min(raw.size // 2, int(args.cpu_sample_seconds * FS))   # the same file, lead-in and tail included
         p = os.path.join(td, "full.u8")
         raw[:2 * n].tofile(p)
         return [(p, "u8", len(res.ens.services), True)], int(2 * n), "the whole recording, all 12 audio services + TII"

@@ -87,5 +87,26 @@ def full(rep, prefix):
               f"elapsed {d.get('sm__cycles_elapsed.max', 0) / 1e6:.3f} M  smem wavefronts {d.get('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 0) / 1e6:.1f} M")
 
 
+def traffic(summary_json, dst):
+    """profiles/rNN_traffic.json for bench.py: DRAM bytes (read + written) per launch of the workload's main launches, from a _summary.json"""
+    rows = json.load(open(summary_json))
+    big = {}
+    for d in rows:                                   # the longest launch of every kernel = the one on the whole recording / the MSC set
+        k = d["kernel"]
+        if k not in big or d.get("gpu__time_duration.sum", 0) > big[k].get("gpu__time_duration.sum", 0):
+            big[k] = dict(d)
+    for k, b in big.items():                         # a launch split in two over the same grid (k_vit_trace: DAB / data and DAB+ halves): their sum
+        same = [d for d in rows if d["kernel"] == k and d["grid"] == b["grid"]]
+        if k == "k_vit_trace" and len(same) == 2:
+            b["dram_bytes"] = sum(d["dram_bytes"] for d in same)
+            b["gpu__time_duration.sum"] = sum(d.get("gpu__time_duration.sum", 0) for d in same)
+    name = {"k_viterbi": "k_viterbi(msc)", "k_gather": "k_gather(msc)", "k_vit_trace": "k_vit_trace(msc)"}
+    out = {"source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch ({summary_json}); k_ofdm_demod: the launch on frames 16.. (the first 16 frames are a second, small launch)",
+           "bytes_per_launch": {name.get(k, k): int(d["dram_bytes"]) for k, d in big.items()},
+           "ms_under_ncu": {name.get(k, k): round(d.get("gpu__time_duration.sum", 0) / 1e6, 4) for k, d in big.items()}}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
