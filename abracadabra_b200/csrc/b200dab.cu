@@ -261,6 +261,21 @@ struct b200dab_ctx {
     int early_fic(const void* d_iq, uint64_t n_visible, int fmt, bool want_stat, bool want_tii);
     int msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std::vector<size_t>& out_off, size_t* total);
     int dabplus(uint8_t* d_frames, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows);
+    // A DISCOVERED sub-channel whose description cannot be decoded (capacity units beyond the CIF, a protection profile that does not fit
+    // its size: what a FIB with a false-positive CRC at low SNR can produce) is left out -- the others are still decoded.  A table given
+    // by the caller is taken as is (msc() fails on an inconsistent entry).
+    int dropped_subch = 0;
+    void drop_undecodable(std::vector<b200dab_subch_t>& v)
+    {
+        size_t k = 0;
+        for (size_t i = 0; i < v.size(); i++) {
+            std::vector<uint32_t> t;
+            const int np = dabtab::build_stepinfo(v[i], t) >= 0 ? (int)(t.back() >> 4) : -1;
+            const bool ok = np >= 0 && np <= v[i].size_cu * 64 && v[i].start_cu >= 0 && v[i].start_cu + v[i].size_cu <= 864 && v[i].bitrate > 0;
+            if (ok) v[k++] = v[i]; else dropped_subch++;
+        }
+        v.resize(k);
+    }
 };
 
 static size_t fmt_bytes(int fmt) { return fmt == B200DAB_FMT_U8 ? 2 : fmt == B200DAB_FMT_S16 ? 4 : 8; }
@@ -1149,8 +1164,28 @@ int b200dab_parse_ensemble(const uint8_t* fibs, const uint8_t* fib_ok, int n_fib
 }
 
 // ------------------------------------------------------------------------------------------------ whole path
+static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int mem, const b200dab_subch_t* subch_in, int n_subch_in,
+                       uint32_t flags, b200dab_result_t* res);
+
 int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int mem, const b200dab_subch_t* subch_in, int n_subch_in,
                    uint32_t flags, b200dab_result_t* res)
+{
+    const int rc = decode_impl(ctx, iq, n, fmt, mem, subch_in, n_subch_in, flags, res);
+    if (rc != 0 && ctx) {
+        // An error exit may leave copies and kernels in flight on any of the context's streams: they read the caller's buffer and
+        // the context's pinned staging, which the caller / the next call are free to reuse once this returns.
+        const std::string keep = ctx->err;
+        cudaStream_t all[] = {ctx->stream, ctx->fic_stream, ctx->aux_stream, ctx->copy_stream};
+        for (cudaStream_t st : all) if (st) cudaStreamSynchronize(st);
+        cudaGetLastError();
+        ctx->err = keep;
+        ctx->cur = nullptr;
+    }
+    return rc;
+}
+
+static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int mem, const b200dab_subch_t* subch_in, int n_subch_in,
+                       uint32_t flags, b200dab_result_t* res)
 {
     if (!ctx || !iq || !res || fmt < 0 || fmt > 2) return -1;
     cudaSetDevice(ctx->device);
@@ -1312,6 +1347,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         }
         ctx->r_subch.resize(ns);
     }
+    if (!(subch_in && n_subch_in > 0)) ctx->drop_undecodable(ctx->r_subch);
     res->n_subch = (int)ctx->r_subch.size();
     res->subch = ctx->r_subch.data();
     TRACE("sub-channels known");
@@ -1452,6 +1488,7 @@ int b200dab_decode(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, int me
         std::vector<b200dab_subch_t> full(B200DAB_MAX_SUBCH);
         const int nf = parse_subch_impl(res->fibs, res->fib_ok, n_slots * 12, full.data(), B200DAB_MAX_SUBCH);
         full.resize(nf);
+        ctx->drop_undecodable(full);
         const bool same = full.size() == ctx->r_subch.size() && (full.empty() || !memcmp(full.data(), ctx->r_subch.data(), full.size() * sizeof(b200dab_subch_t)));
         if (!same) {
             TRACE("sub-channel table revised from the whole FIC");

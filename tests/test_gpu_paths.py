@@ -216,3 +216,20 @@ def test_chunked_decode_equals_single_pass(receiver):
             got = shard.decode_chunked(raw, fmt, n_chunks, rx=receiver, tii=True, stats=st)
             _same_decode(one, got)
         del raw
+
+
+def test_error_exit_leaves_the_context_usable(receiver):
+    """A caller-given sub-channel that does not fit the CIF makes b200dab_decode fail AFTER the front end and the FIC chain have been
+    queued on three streams.  The error exit has to drain them (the caller may free its buffer at once), and the next call on the
+    same context has to work and give the same result as before."""
+    raw, res = cases.config1(12, "u8", 30.0, 250.0, 21)
+    good = receiver.decode(raw, "u8", tii=True)
+    assert good.n_frames == 12 and len(good.subch) == 1
+    bad = pipeline.SubCh()
+    for name, _ in pipeline.SubCh._fields_:
+        setattr(bad, name, getattr(good.subch[0], name))
+    bad.start_cu = 860                                         # 860 + size > 864
+    with pytest.raises(RuntimeError):
+        receiver.decode(raw.copy(), "u8", subch=[bad])
+    again = receiver.decode(raw, "u8", tii=True)
+    _same(good, again)
