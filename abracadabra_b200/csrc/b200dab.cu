@@ -265,12 +265,30 @@ struct b200dab_ctx {
     // its size: what a FIB with a false-positive CRC at low SNR can produce) is left out -- the others are still decoded.  A table given
     // by the caller is taken as is (msc() fails on an inconsistent entry).
     int dropped_subch = 0;
+    // De-puncturing table of a sub-channel (nullptr: inconsistent protection profile).  It depends on the bitrate and the (L, PI) segments
+    // only, and ensembles rarely change between calls: built once per profile -- the sub-channel discovery sits between the early FIC
+    // and the MSC chain on the critical path of a step, and building the tables of a full ensemble takes 0.1 ms.  The pointer is valid
+    // until the next call.
+    bool stepinfo_cached = true;
+    const std::vector<uint32_t>* stepinfo_for(const b200dab_subch_t& q)
+    {
+        if (q.n_seg < 0 || q.n_seg > (int)(sizeof q.seg_len / sizeof q.seg_len[0])) return nullptr;
+        if (!stepinfo_cached) stepinfo_cache.clear();             // B200DAB_STEPINFO_CACHE=0: built every time (A/B)
+        for (auto& e : stepinfo_cache)
+            if (e.first.bitrate == q.bitrate && e.first.n_seg == q.n_seg && !memcmp(e.first.seg_len, q.seg_len, sizeof q.seg_len) &&
+                !memcmp(e.first.seg_pi, q.seg_pi, sizeof q.seg_pi)) return &e.second;
+        std::vector<uint32_t> t;
+        if (dabtab::build_stepinfo(q, t) < 0) return nullptr;
+        if (stepinfo_cache.size() > 64) stepinfo_cache.clear();
+        stepinfo_cache.emplace_back(q, std::move(t));
+        return &stepinfo_cache.back().second;
+    }
     void drop_undecodable(std::vector<b200dab_subch_t>& v)
     {
         size_t k = 0;
         for (size_t i = 0; i < v.size(); i++) {
-            std::vector<uint32_t> t;
-            const int np = dabtab::build_stepinfo(v[i], t) >= 0 ? (int)(t.back() >> 4) : -1;
+            const std::vector<uint32_t>* t = stepinfo_for(v[i]);
+            const int np = t ? (int)(t->back() >> 4) : -1;
             const bool ok = np >= 0 && np <= v[i].size_cu * 64 && v[i].start_cu >= 0 && v[i].start_cu + v[i].size_cu <= 864 && v[i].bitrate > 0;
             if (ok) v[k++] = v[i]; else dropped_subch++;
         }
@@ -800,22 +818,7 @@ int b200dab_ctx::msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std
     for (size_t i = 0; i < subch.size(); i++) {
         const int si_off = (int)si.size();
         int np = -1;
-        {   // the table depends on bitrate and the (L, PI) segments only; ensembles rarely change between calls
-            const b200dab_subch_t& q = subch[i];
-            const std::vector<uint32_t>* hit = nullptr;
-            for (auto& e : stepinfo_cache)
-                if (e.first.bitrate == q.bitrate && e.first.n_seg == q.n_seg && !memcmp(e.first.seg_len, q.seg_len, sizeof q.seg_len) &&
-                    !memcmp(e.first.seg_pi, q.seg_pi, sizeof q.seg_pi)) { hit = &e.second; break; }
-            if (!hit) {
-                std::vector<uint32_t> t;
-                if (dabtab::build_stepinfo(q, t) >= 0) {
-                    if (stepinfo_cache.size() > 64) stepinfo_cache.clear();
-                    stepinfo_cache.emplace_back(q, std::move(t));
-                    hit = &stepinfo_cache.back().second;
-                }
-            }
-            if (hit) { si.insert(si.end(), hit->begin(), hit->end()); np = (int)(hit->back() >> 4); }
-        }
+        if (const std::vector<uint32_t>* hit = stepinfo_for(subch[i])) { si.insert(si.end(), hit->begin(), hit->end()); np = (int)(hit->back() >> 4); }
         if (np < 0 || np > subch[i].size_cu * 64 || subch[i].start_cu < 0 || subch[i].start_cu + subch[i].size_cu > 864) {
             set_error("sub-channel protection profile inconsistent with its size");
             return -1;
@@ -955,6 +958,7 @@ int b200dab_create(b200dab_ctx** out, int device)
     if (const char* e = getenv("B200DAB_VIT_SMEMCAP")) ctx->vit_smem_cap = atoi(e) != 0;
     if (const char* e = getenv("B200DAB_TRACE_PDL")) ctx->trace_pdl = atoi(e) != 0;
     if (const char* e = getenv("B200DAB_VIT_SMEM_SLACK")) ctx->vit_smem_slack = std::max(0, atoi(e));
+    if (const char* e = getenv("B200DAB_STEPINFO_CACHE")) ctx->stepinfo_cached = atoi(e) != 0;
     cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (const char* e = getenv("B200DAB_VIT4_MIN_STEPS")) ctx->vit4_min_steps = atoi(e);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
