@@ -1534,6 +1534,7 @@ static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, in
             ctx->r_sf_flags.assign(ctx->r_subch.size(), nullptr);
             ctx->r_sf_phase.assign(ctx->r_subch.size(), -1);
             const SfInfo* si = ctx->h_sfinfo.as<SfInfo>();
+            ctx->r_sf.reserve((size_t)total_sf);
             for (size_t k = 0; k < dpjobs.size(); k++) {
                 const DabPlusJob& j = dpjobs[k];
                 ctx->r_sf_flags[j.subch_index] = ctx->h_flags.as<uint8_t>() + j.flag_off;
