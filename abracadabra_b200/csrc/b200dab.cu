@@ -83,6 +83,7 @@ static cudaEvent_t g_upload_last[64] = {};        // per device: event behind th
 
 #define EARLY_FIC_FRAMES 16      /* frames of the early FIC slice: the first two prefixes (8, 16) of the sub-channel discovery */
 
+#define RS_PATCH_PREFIX 8192       /* RS corrections copied to the host together with their count (64 KB) */
 struct b200dab_ctx {
     int device = 0;
     double t_trace0 = 0;
@@ -91,6 +92,27 @@ struct b200dab_ctx {
     int launches = 0;
     cudaEvent_t ev_msc = nullptr, ev_d2h = nullptr;   // ordering of the split device-to-host copy of the logical frames
     cudaEvent_t ev_rs = nullptr, ev_tii = nullptr;    // behind k_rs_decode (DAB+ frames final) / behind k_tii_detect
+    // Logical frames written to the host result buffer by k_vit_trace itself, group by group, next to the recursions that are still
+    // running (B200DAB_FRAME_EXPORT=0: one device-to-host copy per class of sub-channels behind the trace / the RS correction instead).
+    // The frames of the DAB+ sub-channels arrive as traced; what the RS decoder changes afterwards follows as a list of (offset, byte)
+    // that the host applies to its copy.  The list has room for every byte the decoder can change (five per codeword); its first
+    // rs_patch_prefix entries are copied blindly -- the count arrives with the totals -- and a recording with more corrections than that
+    // (close to the decoding threshold) gets its corrected DAB+ frames copied again.
+    bool frame_export = true;
+    bool export_frames = false;        // set by the caller of msc() for this call
+    bool frames_exported = false;      // answer of msc(): h_msc is being filled by the trace kernel
+    uint8_t* trace_host_out = nullptr;
+    size_t rs_patch_prefix = RS_PATCH_PREFIX;     // B200DAB_RS_PATCH_PREFIX: fewer entries copied blindly (tests of the overflow path)
+    bool rs_patch_mode = false;
+    size_t rs_patch_cap = 0;
+    // Everything the DAB+ kernels hand to the host lives in ONE device buffer and comes back in ONE copy (a small copy costs its latency,
+    // and five of them in a row sat at the very end of a step): totals | access-unit records | SfInfo | fire-code flags | alignment
+    // per sub-channel | RS patch list (only its first entries are copied).  Offsets in bytes, same layout in h_dpres.
+    struct DpLayout { size_t aus = 0, sf = 0, flags = 0, res = 0, patch = 0, end = 0; } dp;
+    DevBuf d_dpres;
+    HostBuf h_dpres;
+    template <typename T> T* dpp(size_t off) { return reinterpret_cast<T*>(d_dpres.as<uint8_t>() + off); }
+    template <typename T> const T* hpp(size_t off) { return reinterpret_cast<const T*>(h_dpres.as<uint8_t>() + off); }
     int vit_ctas_per_sm = 2;       // persistent k_viterbi CTAs (four warps, one per sub-partition) per SM (tools/vit_split_sweep.py sweeps this)
     int n_sm = 148;
     DevBuf d_vit_counter;          // work queue heads of k_viterbi, one per table set + one for the stage entry point; zero between launches
@@ -106,7 +128,7 @@ struct b200dab_ctx {
     DevBuf d_tw, d_fdi_pos, d_prs_q, d_prbs_w, d_gf, d_cls_bin, d_naus;   // d_gf: SfTables of k_sf_decode; d_naus: access units per superframe slot
     // pipeline buffers
     DevBuf d_raw, d_P, d_S, d_cand_raw, d_cand, d_ncand, d_fine, d_frames, d_soft, d_symstat;
-    DevBuf d_jobs, d_groups, d_items, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out, d_aus, d_totals;
+    DevBuf d_jobs, d_groups, d_items, d_stepinfo, d_vin, d_dec, d_meet, d_fic_out, d_fib_ok, d_msc_out;
     struct VitTables {              // device-resident job / group / step tables of one call site, kept between calls
         bool valid = false;
         std::vector<VitJob> jobs_in;
@@ -174,10 +196,10 @@ struct b200dab_ctx {
     HostBuf h_fibs_early, h_fib_ok_early;
     int early_frames = 0;              // > 0: front_end splits its first demodulation launch and starts the early FIC slice
     bool early_launched = false;
-    DevBuf d_dpjobs, d_flags, d_sf, d_residue, d_fold, d_norm, d_sign, d_windows, d_tii;
+    DevBuf d_dpjobs, d_fold, d_norm, d_sign, d_windows, d_tii;
     DevBuf d_tmp_a, d_tmp_b, d_spec;
     HostBuf h_spec;
-    HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_sf, h_tii, h_symstat, h_misc, h_fold, h_norm;
+    HostBuf h_fine, h_frames, h_fibs, h_fib_ok, h_msc, h_tii, h_symstat, h_misc, h_fold, h_norm;
     HostBuf h_jobs[3], h_groups[3], h_stepinfo[3], h_items[3], h_order[3], h_dpjobs, h_sign, h_windows;   // pinned staging of small uploads ([0] FIC, [1] MSC)
     std::vector<int32_t> r_sign;
     std::vector<std::pair<b200dab_subch_t, std::vector<uint32_t>>> stepinfo_cache;   // de-puncturing tables by protection profile
@@ -191,7 +213,6 @@ struct b200dab_ctx {
     std::vector<b200dab_sf_t> r_sf;
     std::vector<const uint8_t*> r_sf_flags;
     std::vector<int32_t> r_sf_phase, forced_phase;
-    HostBuf h_sfinfo, h_flags, h_residue;
     std::vector<b200dab_tii_t> r_tii;
 
     // optional per-kernel timing (CUDA events on `stream`), enabled by b200dab_set_profiling
@@ -728,7 +749,8 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         CK(cudaLaunchKernelEx(&cfg, k_vit_trace, (const uint2*)d_dec.as<uint2>(), (const unsigned short*)d_meet.as<unsigned short>(), dj, dg,
-                              (const uint32_t*)d_prbs_w.as<uint32_t>(), d_out, (int*)nullptr, -1, (const int*)vt.d_order.as<int>(), (const int*)d_done));
+                              (const uint32_t*)d_prbs_w.as<uint32_t>(), d_out, (int*)nullptr, -1, (const int*)vt.d_order.as<int>(), (const int*)d_done,
+                              st == 1 ? trace_host_out : (uint8_t*)nullptr));
         prof_end();
         launches += 1;
     } else {
@@ -747,7 +769,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
             if (two && ph == 1) cur = aux_stream;
             prof_begin(tname);
             k_vit_trace<<<(unsigned)n_groups, 64, 0, S()>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_head, two ? ph : -1,
-                                                            vt.d_order.as<int>(), nullptr);
+                                                            vt.d_order.as<int>(), nullptr, st == 1 ? trace_host_out : nullptr);
             prof_end();
             cur = keep;
             launches += 1;
@@ -830,37 +852,54 @@ int b200dab_ctx::msc(int n_slots, const std::vector<b200dab_subch_t>& subch, std
     }
     *total = off;
     CK(d_msc_out.ensure(off + 256));
-    return run_viterbi(jobs, si, d_msc_out.as<uint8_t>());
+    frames_exported = export_frames && off < (1ull << 32);     // (patch offsets are 32 bit)
+    if (frames_exported) {
+        if (off + 64 > h_msc.cap) CK(cudaDeviceSynchronize());    // growing the buffer frees it: nothing may still be writing into it
+        CK(h_msc.ensure(off + 64));
+        trace_host_out = h_msc.as<uint8_t>();
+    }
+    const int rc = run_viterbi(jobs, si, d_msc_out.as<uint8_t>());
+    trace_host_out = nullptr;
+    if (rc) frames_exported = false;
+    return rc;
 }
 
 int b200dab_ctx::dabplus(uint8_t* d_fr, const std::vector<DabPlusJob>& jobs, int total_sf, int total_rows)
 {
     if (jobs.empty() || total_sf <= 0) return 0;
     CK(d_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob) + 16));
-    CK(d_flags.ensure((size_t)total_rows + 64));
-    CK(d_sf.ensure((size_t)total_sf * sizeof(SfInfo)));
-    CK(d_residue.ensure(jobs.size() * 4));
     CK(h_dpjobs.ensure(jobs.size() * sizeof(DabPlusJob) + 16));
     memcpy(h_dpjobs.p, jobs.data(), jobs.size() * sizeof(DabPlusJob));
     if (fetch(d_dpjobs.p, h_dpjobs.p, jobs.size() * sizeof(DabPlusJob))) { set_error("k_fetch launch failed"); return -1; }
     int max_sf = 0;
     for (auto& j : jobs) { max_sf = std::max(max_sf, j.max_sf); if (j.s > 24 || j.s < 1 || j.pitch != 24 * j.s) { set_error("DAB+ sub-channel bitrate out of range"); return -1; } }
     const unsigned nj = (unsigned)jobs.size();
-    CK(d_aus.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + 64));
-    CK(d_totals.ensure(sizeof(DabPlusTotals)));
+    rs_patch_cap = 0;
+    if (rs_patch_mode) for (auto& j : jobs) rs_patch_cap += (size_t)j.max_sf * j.s * 5;
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    static_assert(sizeof(DabPlusTotals) == 32, "the access-unit records follow the totals at byte 32");
+    dp.aus = sizeof(DabPlusTotals);
+    dp.sf = al16(dp.aus + (size_t)total_sf * 6 * sizeof(AuRecord));
+    dp.flags = al16(dp.sf + (size_t)total_sf * sizeof(SfInfo));
+    dp.res = al16(dp.flags + (size_t)total_rows);
+    dp.patch = al16(dp.res + (size_t)nj * 4);
+    dp.end = dp.patch + rs_patch_cap * sizeof(RsPatch);
+    CK(d_dpres.ensure(dp.end + 64));
     CK(d_naus.ensure((size_t)total_sf * 4 + 64));
+    DabPlusTotals* d_tot = dpp<DabPlusTotals>(0);
     prof_begin("k_fire_align");
-    k_fire_align<<<nj, FIRE_THREADS, 0, S()>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_flags.as<uint8_t>(), d_sf.as<SfInfo>(), d_residue.as<int>(), d_totals.as<DabPlusTotals>());
+    k_fire_align<<<nj, FIRE_THREADS, 0, S()>>>(d_fr, d_dpjobs.as<DabPlusJob>(), dpp<uint8_t>(dp.flags), dpp<SfInfo>(dp.sf), dpp<int>(dp.res), d_tot);
     prof_end();
     // RS correction, fire code, access-unit table and access-unit CRCs of a superframe by one warp, in one launch
     prof_begin("k_sf_decode");
-    k_sf_decode<<<dim3((max_sf + SF_PER_CTA - 1) / SF_PER_CTA, nj), 32 * SF_PER_CTA, 0, S()>>>(d_fr, d_dpjobs.as<DabPlusJob>(), d_sf.as<SfInfo>(), d_gf.as<SfTables>(),
-                                                                                              d_naus.as<int>(), d_totals.as<DabPlusTotals>());
+    k_sf_decode<<<dim3((max_sf + SF_PER_CTA - 1) / SF_PER_CTA, nj), 32 * SF_PER_CTA, 0, S()>>>(d_fr, d_dpjobs.as<DabPlusJob>(), dpp<SfInfo>(dp.sf), d_gf.as<SfTables>(),
+                                                                                              d_naus.as<int>(), d_tot,
+                                                                                              rs_patch_mode ? dpp<RsPatch>(dp.patch) : nullptr, (int)std::min<size_t>(rs_patch_cap, 1u << 30));
     prof_end();
     if (ev_rs) CK(cudaEventRecord(ev_rs, S()));        // the logical frames are final from here on: the caller starts their copy
     // access-unit list and RS statistics in the layout of the result, put together on the device
     prof_begin("k_au_list");
-    k_au_list<<<(total_sf + 255) / 256, 256, 0, S()>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, d_sf.as<SfInfo>(), d_naus.as<int>(), total_sf, d_aus.as<AuRecord>(), d_totals.as<DabPlusTotals>());
+    k_au_list<<<(total_sf + 255) / 256, 256, 0, S()>>>(d_dpjobs.as<DabPlusJob>(), (int)nj, dpp<SfInfo>(dp.sf), d_naus.as<int>(), total_sf, dpp<AuRecord>(dp.aus), d_tot);
     prof_end();
     launches += 3;
     CK(cudaGetLastError());
@@ -958,6 +997,8 @@ int b200dab_create(b200dab_ctx** out, int device)
     if (const char* e = getenv("B200DAB_VIT_SMEMCAP")) ctx->vit_smem_cap = atoi(e) != 0;
     if (const char* e = getenv("B200DAB_TRACE_PDL")) ctx->trace_pdl = atoi(e) != 0;
     if (const char* e = getenv("B200DAB_VIT_SMEM_SLACK")) ctx->vit_smem_slack = std::max(0, atoi(e));
+    if (const char* e = getenv("B200DAB_FRAME_EXPORT")) ctx->frame_export = atoi(e) != 0;
+    if (const char* e = getenv("B200DAB_RS_PATCH_PREFIX")) ctx->rs_patch_prefix = (size_t)std::max(0, std::min(RS_PATCH_PREFIX, atoi(e)));
     if (const char* e = getenv("B200DAB_STEPINFO_CACHE")) ctx->stepinfo_cached = atoi(e) != 0;
     cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (const char* e = getenv("B200DAB_VIT4_MIN_STEPS")) ctx->vit4_min_steps = atoi(e);
@@ -987,11 +1028,11 @@ void b200dab_destroy(b200dab_ctx* ctx)
     DevBuf* db[] = {&ctx->d_tw, &ctx->d_fdi_pos, &ctx->d_prs_q, &ctx->d_prbs_w, &ctx->d_gf, &ctx->d_naus, &ctx->d_cls_bin, &ctx->d_raw, &ctx->d_P, &ctx->d_S, &ctx->d_cand_raw,
                     &ctx->d_cand, &ctx->d_ncand, &ctx->d_fine, &ctx->d_frames, &ctx->d_chain, &ctx->d_frame_cir, &ctx->d_soft, &ctx->d_symstat, &ctx->d_jobs, &ctx->d_groups,
                     &ctx->d_stepinfo, &ctx->vit_tables[0].d_jobs, &ctx->vit_tables[0].d_groups, &ctx->vit_tables[0].d_stepinfo, &ctx->vit_tables[1].d_jobs,
-                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->vit_tables[0].d_items, &ctx->vit_tables[1].d_items, &ctx->vit_tables[2].d_items, &ctx->vit_tables[0].d_done, &ctx->vit_tables[1].d_done, &ctx->vit_tables[2].d_done, &ctx->vit_tables[0].d_order, &ctx->vit_tables[1].d_order, &ctx->vit_tables[2].d_order, &ctx->d_items, &ctx->d_vit_counter, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_aus, &ctx->d_totals, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs, &ctx->d_flags,
-                    &ctx->d_sf, &ctx->d_residue, &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec};
+                    &ctx->vit_tables[1].d_groups, &ctx->vit_tables[1].d_stepinfo, &ctx->vit_tables[2].d_jobs, &ctx->vit_tables[2].d_groups, &ctx->vit_tables[2].d_stepinfo, &ctx->vit_tables[0].d_vin, &ctx->vit_tables[0].d_dec, &ctx->vit_tables[0].d_meet, &ctx->vit_tables[1].d_vin, &ctx->vit_tables[1].d_dec, &ctx->vit_tables[1].d_meet, &ctx->vit_tables[2].d_vin, &ctx->vit_tables[2].d_dec, &ctx->vit_tables[2].d_meet, &ctx->vit_tables[0].d_items, &ctx->vit_tables[1].d_items, &ctx->vit_tables[2].d_items, &ctx->vit_tables[0].d_done, &ctx->vit_tables[1].d_done, &ctx->vit_tables[2].d_done, &ctx->vit_tables[0].d_order, &ctx->vit_tables[1].d_order, &ctx->vit_tables[2].d_order, &ctx->d_items, &ctx->d_vit_counter, &ctx->d_fic_out_early, &ctx->d_fib_ok_early, &ctx->d_vin, &ctx->d_dec, &ctx->d_meet, &ctx->d_fic_out, &ctx->d_fib_ok, &ctx->d_msc_out, &ctx->d_dpjobs,
+                    &ctx->d_fold, &ctx->d_norm, &ctx->d_sign, &ctx->d_windows, &ctx->d_tii, &ctx->d_tmp_a, &ctx->d_tmp_b, &ctx->d_spec, &ctx->d_dpres};
     for (auto* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_chain, &ctx->h_frame_cir, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_sf, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
-                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_order[0], &ctx->h_order[1], &ctx->h_order[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_sfinfo, &ctx->h_flags, &ctx->h_residue};
+    HostBuf* hb[] = {&ctx->h_fine, &ctx->h_frames, &ctx->h_chain, &ctx->h_frame_cir, &ctx->h_fibs, &ctx->h_fib_ok, &ctx->h_msc, &ctx->h_tii, &ctx->h_symstat, &ctx->h_misc, &ctx->h_fold, &ctx->h_norm,
+                     &ctx->h_spec, &ctx->h_jobs[0], &ctx->h_jobs[1], &ctx->h_jobs[2], &ctx->h_groups[0], &ctx->h_groups[1], &ctx->h_groups[2], &ctx->h_stepinfo[0], &ctx->h_stepinfo[1], &ctx->h_stepinfo[2], &ctx->h_items[0], &ctx->h_items[1], &ctx->h_items[2], &ctx->h_order[0], &ctx->h_order[1], &ctx->h_order[2], &ctx->h_fibs_early, &ctx->h_fib_ok_early, &ctx->h_dpjobs, &ctx->h_sign, &ctx->h_windows, &ctx->h_dpres};
     cudaStreamSynchronize(ctx->fic_stream); if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto* b : hb) b->release();
     {
@@ -1414,12 +1455,19 @@ static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, in
     }
     return 0;
     };
+    bool exported = false;              // the trace kernel wrote the logical frames to the host buffer itself
+    bool patching = false;              // ... those of the DAB+ sub-channels as traced: the RS corrections are applied here
+    size_t n_patch_copied = 0;
     auto msc_block = [&]() -> int {
+    exported = false; patching = false; n_patch_copied = 0;
     if (!(flags & B200DAB_OPT_NO_MSC) && n_rows > 0 && !ctx->r_subch.empty()) {
         ctx->ev_first_trace = ctx->ev_msc;
+        ctx->export_frames = ctx->frame_export;
         const int msc_rc = ctx->msc(n_slots, ctx->r_subch, out_off, &msc_bytes);
+        ctx->export_frames = false;
         ctx->ev_first_trace = nullptr;
         if (msc_rc) return -1;
+        exported = ctx->frames_exported;
         TRACE("msc submitted");
         for (size_t i = 0; i < ctx->r_subch.size(); i++) {
             if (ctx->r_subch[i].kind != 1) continue;
@@ -1448,7 +1496,8 @@ static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, in
             return 0;
         };
         static const bool no_split = getenv("B200DAB_NO_SPLIT_COPY") != nullptr;      // A/B switch (tools/ab_step.py)
-        const bool split = !dpjobs.empty() && !no_split;
+        const bool split = !dpjobs.empty() && !no_split && !exported;
+        patching = exported && !dpjobs.empty() && total_sf > 0;
         if (split) {
             if (!ctx->first_trace_recorded) CKC(cudaEventRecord(ctx->ev_msc, ctx->stream));      // (else: recorded between the two trace launches)
             CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_msc, 0));
@@ -1457,24 +1506,25 @@ static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, in
         }
         cudaStream_t back = ctx->late_on_aux ? ctx->aux_stream : ctx->stream;      // where the DAB+ half of the back end runs
         ctx->cur = ctx->late_on_aux ? ctx->aux_stream : nullptr;
+        ctx->rs_patch_mode = patching;
         const int dp_rc = ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), dpjobs, total_sf, total_rows);
+        ctx->rs_patch_mode = false;
         ctx->cur = nullptr;
         if (dp_rc) return -1;
-        if (split) {
-            CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rs, 0));
-            if (copy_class(true, ctx->copy_stream)) return -1;
-        } else CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!patching) {
+            if (split) {
+                CKC(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rs, 0));
+                if (copy_class(true, ctx->copy_stream)) return -1;
+            } else if (!exported) CKC(cudaMemcpyAsync(ctx->h_msc.p, ctx->d_msc_out.p, msc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         if (total_sf > 0) {
+            // totals, access-unit records, superframe details, flags, alignments and (the frames being on the host already, as traced) the
+            // first RS corrections: one copy
             static_assert(sizeof(AuRecord) == sizeof(b200dab_au_t), "AU record layout");
-            CKC(ctx->h_sf.ensure((size_t)total_sf * 6 * sizeof(AuRecord) + sizeof(DabPlusTotals)));
-            CKC(cudaMemcpyAsync(ctx->h_sf.p, ctx->d_totals.p, sizeof(DabPlusTotals), cudaMemcpyDeviceToHost, back));
-            CKC(cudaMemcpyAsync((uint8_t*)ctx->h_sf.p + sizeof(DabPlusTotals), ctx->d_aus.p, (size_t)total_sf * 6 * sizeof(AuRecord), cudaMemcpyDeviceToHost, back));
-            CKC(ctx->h_sfinfo.ensure((size_t)total_sf * sizeof(SfInfo)));
-            CKC(ctx->h_flags.ensure((size_t)total_rows + 64));
-            CKC(ctx->h_residue.ensure(dpjobs.size() * 4));
-            CKC(cudaMemcpyAsync(ctx->h_sfinfo.p, ctx->d_sf.p, (size_t)total_sf * sizeof(SfInfo), cudaMemcpyDeviceToHost, back));
-            CKC(cudaMemcpyAsync(ctx->h_flags.p, ctx->d_flags.p, (size_t)total_rows, cudaMemcpyDeviceToHost, back));
-            CKC(cudaMemcpyAsync(ctx->h_residue.p, ctx->d_residue.p, dpjobs.size() * 4, cudaMemcpyDeviceToHost, back));
+            n_patch_copied = patching ? std::min<size_t>(ctx->rs_patch_cap, ctx->rs_patch_prefix) : 0;
+            const size_t len = ctx->dp.patch + n_patch_copied * sizeof(RsPatch);
+            CKC(ctx->h_dpres.ensure(len + 64));
+            CKC(cudaMemcpyAsync(ctx->h_dpres.p, ctx->d_dpres.p, len, cudaMemcpyDeviceToHost, back));
         }
         if (ctx->late_on_aux) { CKC(cudaEventRecord(ctx->ev_aux, ctx->aux_stream)); CKC(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0)); }
     }
@@ -1519,26 +1569,43 @@ static int decode_impl(b200dab_ctx* ctx, const void* iq, uint64_t n, int fmt, in
     TRACE("all submitted");
     CKC(cudaStreamSynchronize(ctx->stream));
     TRACE("final sync");
+    // ---- RS corrections of the DAB+ frames that reached the host as traced
+    if (patching && total_sf > 0) {
+        const int n_patches = ctx->hpp<DabPlusTotals>(0)->n_patches;
+        if (n_patches >= 0 && (size_t)n_patches <= n_patch_copied) {
+            const RsPatch* e = ctx->hpp<RsPatch>(ctx->dp.patch);
+            uint8_t* fr = ctx->h_msc.as<uint8_t>();
+            for (int i = 0; i < n_patches; i++) if (e[i].offset < msc_bytes) fr[e[i].offset] = (uint8_t)e[i].value;
+        } else {
+            // more corrections than the prefix that was copied (a recording close to the decoding threshold): the corrected frames themselves
+            for (size_t i = 0; i < ctx->r_subch.size(); i++) {
+                if (ctx->r_subch[i].kind != 1) continue;
+                const size_t a = out_off[i], b = (i + 1 < ctx->r_subch.size()) ? out_off[i + 1] : msc_bytes;
+                CKC(cudaMemcpyAsync((uint8_t*)ctx->h_msc.p + a, (const uint8_t*)ctx->d_msc_out.p + a, b - a, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            CKC(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     // ---- assemble the result
     if (msc_bytes > 0) {
         for (size_t i = 0; i < ctx->r_subch.size(); i++) { ctx->r_frames.push_back(ctx->h_msc.as<uint8_t>() + out_off[i]); ctx->r_rows.push_back(n_rows); }
         res->frames = ctx->r_frames.data(); res->frame_rows = ctx->r_rows.data();
         if (total_sf > 0) {
             // the access-unit list and the RS totals were put together on the device (k_au_compact)
-            const DabPlusTotals* tot = ctx->h_sf.as<DabPlusTotals>();
+            const DabPlusTotals* tot = ctx->hpp<DabPlusTotals>(0);
             res->superframes = tot->superframes; res->rs_corrected = tot->rs_corrected; res->rs_bit_errors = tot->rs_bit_errors;
             res->rs_uncorrectable = tot->rs_uncorrectable; res->firecode_fail = tot->firecode_fail;
             res->n_aus = tot->n_aus;
-            res->aus = reinterpret_cast<const b200dab_au_t*>(ctx->h_sf.as<uint8_t>() + sizeof(DabPlusTotals));
+            res->aus = ctx->hpp<b200dab_au_t>(ctx->dp.aus);
             // the superframe layer in detail
             ctx->r_sf_flags.assign(ctx->r_subch.size(), nullptr);
             ctx->r_sf_phase.assign(ctx->r_subch.size(), -1);
-            const SfInfo* si = ctx->h_sfinfo.as<SfInfo>();
+            const SfInfo* si = ctx->hpp<SfInfo>(ctx->dp.sf);
             ctx->r_sf.reserve((size_t)total_sf);
             for (size_t k = 0; k < dpjobs.size(); k++) {
                 const DabPlusJob& j = dpjobs[k];
-                ctx->r_sf_flags[j.subch_index] = ctx->h_flags.as<uint8_t>() + j.flag_off;
-                ctx->r_sf_phase[j.subch_index] = ctx->h_residue.as<int32_t>()[k];
+                ctx->r_sf_flags[j.subch_index] = ctx->hpp<uint8_t>(ctx->dp.flags) + j.flag_off;
+                ctx->r_sf_phase[j.subch_index] = ctx->hpp<int32_t>(ctx->dp.res)[k];
                 for (int m = 0; m < j.max_sf; m++) {
                     const SfInfo& q = si[j.sf_off + m];
                     if (!q.valid) continue;
@@ -1679,7 +1746,7 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     ctx->prof_end();
     ctx->prof_begin("k_vit_trace(stage)");
     k_vit_trace<<<ng, 64, 0, ctx->stream>>>(ctx->d_dec.as<uint2>(), ctx->d_meet.as<unsigned short>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
-                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1, nullptr, nullptr);
+                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1, nullptr, nullptr, nullptr);
     ctx->prof_end();
     ctx->launches += 2;
     CKC(cudaGetLastError());
@@ -1739,7 +1806,7 @@ int b200dab_stage_dabplus(b200dab_ctx* ctx, uint8_t* frames, int n_rows, int bit
     if (ctx->dabplus(ctx->d_msc_out.as<uint8_t>(), jobs, j.max_sf, n_rows)) return -1;
     std::vector<SfInfo> sf(j.max_sf);
     CKC(cudaMemcpyAsync(frames, ctx->d_msc_out.p, (size_t)n_rows * pitch, cudaMemcpyDeviceToHost, ctx->stream));
-    CKC(cudaMemcpyAsync(sf.data(), ctx->d_sf.p, sf.size() * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaMemcpyAsync(sf.data(), ctx->dpp<SfInfo>(ctx->dp.sf), sf.size() * sizeof(SfInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CKC(cudaStreamSynchronize(ctx->stream));
     int n = 0;
     int64_t st[5] = {0, 0, 0, 0, 0};

@@ -51,7 +51,11 @@ struct SfInfo {             // per superframe slot
 
 // Result records in the layout of the C ABI (b200dab_au_t: seven int32) and the totals the host used to add up from SfInfo.
 struct AuRecord { int subch_index, superframe, cif, offset, length, crc_ok, header; };
-struct DabPlusTotals { int n_aus, superframes, rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail, pad_[2]; };
+struct DabPlusTotals { int n_aus, superframes, rs_corrected, rs_bit_errors, rs_uncorrectable, firecode_fail, n_patches, pad_; };
+// One corrected byte: where it lies inside the logical-frame buffer and what it is now.  The host receives the logical frames of the DAB+
+// sub-channels as they were traced -- before the RS correction (k_vit_trace writes them to host memory) -- and applies this list to
+// its copy (b200dab_decode).
+struct RsPatch { uint32_t offset, value; };
 
 // ---- GF(2^8) / 0x11D
 struct GfTables { uint8_t exp[512]; uint8_t log[256]; };
@@ -134,7 +138,8 @@ __global__ void __launch_bounds__(FIRE_THREADS) k_fire_align(const uint8_t* __re
 
 // RS(120,110) correction of codeword j (bytes j, j + s, j + 2 s, ... of the superframe in shared memory); corrected bytes go to
 // `buf` and to `glob`.  Returns the number of corrected bytes (bit errors in *bit_errors), or -1 if the word is uncorrectable.
-__device__ __noinline__ int rs_correct(uint8_t* buf, uint8_t* glob, int j, int s, uint32_t w0, uint32_t w1, uint32_t w2, const GfTables& gf, int* bit_errors)
+__device__ __noinline__ int rs_correct(uint8_t* buf, uint8_t* glob, int j, int s, uint32_t w0, uint32_t w1, uint32_t w2, const GfTables& gf, int* bit_errors,
+                                       RsPatch* patches, int patch_cap, int* n_patches, uint32_t glob_off)
 {
     const int n = 120, nroots = 10;
     uint8_t S[10];
@@ -205,6 +210,10 @@ __device__ __noinline__ int rs_correct(uint8_t* buf, uint8_t* glob, int j, int s
         const int at = j + s * pos[e];
         buf[at] ^= ev[e];
         glob[at] = buf[at];
+        if (patches) {
+            const int idx = atomicAdd(n_patches, 1);
+            if (idx < patch_cap) patches[idx] = RsPatch{glob_off + (uint32_t)at, buf[at]};
+        }
         be += __popc((unsigned)ev[e]);
     }
     *bit_errors = be;
@@ -223,7 +232,8 @@ __device__ __noinline__ int rs_correct(uint8_t* buf, uint8_t* glob, int j, int s
 #define SF_MAX_BYTES (120 * 24)            /* s <= 24 (192 kbit/s) */
 __global__ void __launch_bounds__(32 * SF_PER_CTA) k_sf_decode(uint8_t* __restrict__ frames, const DabPlusJob* __restrict__ jobs,
                                                                 SfInfo* __restrict__ sf, const SfTables* __restrict__ tabs_g,
-                                                                int* __restrict__ naus, DabPlusTotals* __restrict__ totals)
+                                                                int* __restrict__ naus, DabPlusTotals* __restrict__ totals,
+                                                                RsPatch* __restrict__ patches, int patch_cap)
 {
     __shared__ SfTables tabs;
     __shared__ __align__(16) uint8_t sfbuf[SF_PER_CTA][SF_MAX_BYTES];
@@ -266,8 +276,8 @@ __global__ void __launch_bounds__(32 * SF_PER_CTA) k_sf_decode(uint8_t* __restri
             }
             if (w0 | w1 | w2) {
                 int be = 0;
-                uint8_t* glob = frames + job.frames_off + (size_t)s_row[w] * job.pitch;
-                const int np = rs_correct(buf, glob, j, s, w0, w1, w2, tabs.gf, &be);
+                const size_t goff = (size_t)job.frames_off + (size_t)s_row[w] * job.pitch;
+                const int np = rs_correct(buf, frames + goff, j, s, w0, w1, w2, tabs.gf, &be, patches, patch_cap, &totals->n_patches, (uint32_t)goff);
                 if (np < 0) atomicAdd(&s_rs[w][2], 1);
                 else { atomicAdd(&s_rs[w][0], np); atomicAdd(&s_rs[w][1], be); }
             }

@@ -233,3 +233,28 @@ def test_error_exit_leaves_the_context_usable(receiver):
         receiver.decode(raw.copy(), "u8", subch=[bad])
     again = receiver.decode(raw, "u8", tii=True)
     _same(good, again)
+
+
+def test_frames_written_by_the_trace_kernel_and_rs_patch_list(monkeypatch):
+    """By default k_vit_trace writes the logical frames to the host result buffer itself, group by group; those of the DAB+ sub-channels
+    arrive as traced, and the host applies the RS corrections from a list (offset, byte) that comes back with the other DAB+ results.
+    On a recording noisy enough for the RS decoder to work (full ensemble at 5 dB: hundreds of corrected bytes, some uncorrectable
+    words) frames, access units and counters must equal those of the plain order (device-to-host copies behind the trace and behind
+    the RS correction), also when the list is longer than the prefix that is copied blindly (corrected frames copied again)."""
+    ens = synth.full_ensemble(seed=77)
+    raw, res = synth.synthesize(ens, 24, "u8", synth.Impairments(snr_db=5.0, cfo_hz=140.0, seed=9, lead_in=30000), seed=9, tail=60000)
+    out = []
+    for env in ({"B200DAB_FRAME_EXPORT": "0"}, {}, {"B200DAB_RS_PATCH_PREFIX": "3"}, {"B200DAB_TRACE_PDL": "0"}):
+        for k in ("B200DAB_FRAME_EXPORT", "B200DAB_RS_PATCH_PREFIX", "B200DAB_TRACE_PDL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        rx = pipeline.Receiver(0)
+        out.append(rx.decode(raw, "u8", tii=True))
+        out.append(rx.decode(raw, "u8", tii=True))             # a second call on the same context: counters and lists start over
+        rx.close()
+    base = out[0]
+    assert base.n_frames == 24 and base.rs_corrected > 50, (base.n_frames, base.rs_corrected)
+    for d in out[1:]:
+        _same(base, d)
+        assert (d.rs_corrected, d.rs_bit_errors, d.rs_uncorrectable, d.firecode_fail) == (base.rs_corrected, base.rs_bit_errors, base.rs_uncorrectable, base.firecode_fail)
