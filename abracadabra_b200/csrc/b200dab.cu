@@ -102,6 +102,7 @@ struct b200dab_ctx {
     bool export_frames = false;        // set by the caller of msc() for this call
     bool frames_exported = false;      // answer of msc(): h_msc is being filled by the trace kernel
     uint8_t* trace_host_out = nullptr;
+    int export_vec = 16;               // bytes per lane of the trace kernel's stores to host memory (B200DAB_EXPORT_VEC: 8 or 16)
     size_t rs_patch_prefix = RS_PATCH_PREFIX;     // B200DAB_RS_PATCH_PREFIX: fewer entries copied blindly (tests of the overflow path)
     bool rs_patch_mode = false;
     size_t rs_patch_cap = 0;
@@ -750,7 +751,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
         cfg.attrs = at; cfg.numAttrs = 1;
         CK(cudaLaunchKernelEx(&cfg, k_vit_trace, (const uint2*)d_dec.as<uint2>(), (const unsigned short*)d_meet.as<unsigned short>(), dj, dg,
                               (const uint32_t*)d_prbs_w.as<uint32_t>(), d_out, (int*)nullptr, -1, (const int*)vt.d_order.as<int>(), (const int*)d_done,
-                              st == 1 ? trace_host_out : (uint8_t*)nullptr));
+                              st == 1 ? trace_host_out : (uint8_t*)nullptr, export_vec));
         prof_end();
         launches += 1;
     } else {
@@ -769,7 +770,7 @@ int b200dab_ctx::run_viterbi(const std::vector<VitJob>& jobs_in, const std::vect
             if (two && ph == 1) cur = aux_stream;
             prof_begin(tname);
             k_vit_trace<<<(unsigned)n_groups, 64, 0, S()>>>(d_dec.as<uint2>(), d_meet.as<unsigned short>(), dj, dg, d_prbs_w.as<uint32_t>(), d_out, d_head, two ? ph : -1,
-                                                            vt.d_order.as<int>(), nullptr, st == 1 ? trace_host_out : nullptr);
+                                                            vt.d_order.as<int>(), nullptr, st == 1 ? trace_host_out : nullptr, export_vec);
             prof_end();
             cur = keep;
             launches += 1;
@@ -998,6 +999,7 @@ int b200dab_create(b200dab_ctx** out, int device)
     if (const char* e = getenv("B200DAB_TRACE_PDL")) ctx->trace_pdl = atoi(e) != 0;
     if (const char* e = getenv("B200DAB_VIT_SMEM_SLACK")) ctx->vit_smem_slack = std::max(0, atoi(e));
     if (const char* e = getenv("B200DAB_FRAME_EXPORT")) ctx->frame_export = atoi(e) != 0;
+    if (const char* e = getenv("B200DAB_EXPORT_VEC")) ctx->export_vec = atoi(e) == 16 ? 16 : 8;
     if (const char* e = getenv("B200DAB_RS_PATCH_PREFIX")) ctx->rs_patch_prefix = (size_t)std::max(0, std::min(RS_PATCH_PREFIX, atoi(e)));
     if (const char* e = getenv("B200DAB_STEPINFO_CACHE")) ctx->stepinfo_cached = atoi(e) != 0;
     cudaFuncSetAttribute(k_viterbi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1746,7 +1748,7 @@ int b200dab_stage_viterbi(b200dab_ctx* ctx, const int8_t* soft4, int n_cw, int s
     ctx->prof_end();
     ctx->prof_begin("k_vit_trace(stage)");
     k_vit_trace<<<ng, 64, 0, ctx->stream>>>(ctx->d_dec.as<uint2>(), ctx->d_meet.as<unsigned short>(), ctx->d_jobs.as<VitJob>(), ctx->d_groups.as<VitGroup>(),
-                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1, nullptr, nullptr, nullptr);
+                                           ctx->d_tmp_a.as<uint32_t>(), ctx->d_tmp_b.as<uint8_t>(), ctx->d_vit_counter.as<int>() + 3, -1, nullptr, nullptr, nullptr, 0);
     ctx->prof_end();
     ctx->launches += 2;
     CKC(cudaGetLastError());

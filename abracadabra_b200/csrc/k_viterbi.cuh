@@ -556,7 +556,7 @@ __device__ __forceinline__ void vit_trace_run(const uint2* __restrict__ d, const
 __global__ void __launch_bounds__(64) k_vit_trace(const uint2* dec, const unsigned short* meet,
                                                   const VitJob* __restrict__ jobs, const VitGroup* __restrict__ groups,
                                                   const uint32_t* __restrict__ prbs_w, uint8_t* __restrict__ out, int* __restrict__ vit_counter, int phase,
-                                                  const int* __restrict__ order, const int* done, uint8_t* __restrict__ host_out)
+                                                  const int* __restrict__ order, const int* done, uint8_t* __restrict__ host_out, int host_vec)
 {
     if (vit_counter && blockIdx.x == 0 && threadIdx.x == 0) *vit_counter = 0;   // the work queue of the k_viterbi launch in front of this one (not when the two run side by side)
     // order: CTA -> group, in the order in which the groups' recursions are expected to finish (host simulation of the k_viterbi
@@ -597,18 +597,29 @@ __global__ void __launch_bounds__(64) k_vit_trace(const uint2* dec, const unsign
     // host_out: the logical frames go straight to the caller's (pinned, device-visible) result buffer, group by group, while the
     // recursions of the other groups are still running -- instead of one device-to-host copy of everything behind the last trace, on
     // the critical path of a step.  The group's rows are contiguous (32 x out_pitch bytes at the same offset in both buffers); the CTA
-    // re-reads what its lanes wrote row by row (L2) and stores it in pieces of 512 consecutive bytes, which cross PCIe as full packets.
+    // re-reads what its lanes wrote row by row (L2) and stores it in long consecutive pieces, which cross PCIe as full packets.
     if (host_out) {
         __syncthreads();                                            // both warps' rows are written
         const int r0 = grp.g_in_job * 32;
         const int rows_here = min(32, job.n_rows - r0);
         if (rows_here > 0) {
             const size_t boff = (size_t)job.out_off + (size_t)r0 * job.out_pitch;      // multiple of 768: out_pitch is a multiple of 24
-            const int nbytes = rows_here * job.out_pitch, n8 = nbytes >> 3;
-            const uint2* src = reinterpret_cast<const uint2*>(out + boff);
-            uint2* dst = reinterpret_cast<uint2*>(host_out + boff);
-            for (int i = threadIdx.x; i < n8; i += 64) dst[i] = __ldcg(src + i);
-            for (int i = (n8 << 3) + threadIdx.x; i < nbytes; i += 64) host_out[boff + i] = __ldcg(out + boff + i);
+            const int nbytes = rows_here * job.out_pitch;
+            int done_bytes = 0;
+            if (host_vec == 16) {                                   // a warp's store = 512 consecutive bytes
+                const int n16 = nbytes >> 4;
+                const uint4* src = reinterpret_cast<const uint4*>(out + boff);
+                uint4* dst = reinterpret_cast<uint4*>(host_out + boff);
+                for (int i = threadIdx.x; i < n16; i += 64) dst[i] = __ldcg(src + i);
+                done_bytes = n16 << 4;
+            } else {
+                const int n8 = nbytes >> 3;
+                const uint2* src = reinterpret_cast<const uint2*>(out + boff);
+                uint2* dst = reinterpret_cast<uint2*>(host_out + boff);
+                for (int i = threadIdx.x; i < n8; i += 64) dst[i] = __ldcg(src + i);
+                done_bytes = n8 << 3;
+            }
+            for (int i = done_bytes + threadIdx.x; i < nbytes; i += 64) host_out[boff + i] = __ldcg(out + boff + i);
         }
     }
 }
